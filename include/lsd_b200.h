@@ -1,0 +1,160 @@
+/* lsd_b200.h -- C ABI of the B200-native LSD-SLAM hot path (liblsd_b200.so).
+ *
+ * The reference application (apl-ocean-engineering/lsd-slam-pangolin-gui) has no FFI for this
+ * path: it links the C++ classes of the un-vendored `lsd-slam` core (fips.yml:1-4) and drives
+ * them through lsd_slam::SlamSystem (tools/LSD.cpp:102, lib/App/InputThread.cpp:71).  The
+ * drop-in boundary is therefore the set of lsd-slam core methods named in BASELINE.json;
+ * each entry point below cites the core method it replaces ([UP] = upstream lsd-slam file,
+ * source absent from /root/reference) and the reference-side line that evidences its contract.
+ * C++ adapters with the upstream class signatures sit on top of this ABI in
+ * lsd-slam-pangolin-gui_b200/host/ (see INTEGRATION.md).
+ *
+ * Conventions: every function returns 0 on success, <0 on error (no exceptions cross the ABI;
+ * lsd_last_error() gives the text).  Handles are opaque and owned by their context.  All host
+ * buffers are caller-owned.  Calls are blocking unless named *_async.  One context per calling
+ * thread (upstream runs tracking / mapping / constraint search concurrently); frame and
+ * reference handles may be shared read-only between contexts on the same device.
+ *
+ * Poses: SE3 = double[7] {qx,qy,qz,qw,tx,ty,tz} (Sophus::SE3d::data() order);
+ *        Sim3 = double[8] {qx,qy,qz,qw,tx,ty,tz,scale}.
+ */
+#ifndef LSD_B200_H
+#define LSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSD_PYRAMID_LEVELS 5
+
+typedef struct lsd_ctx lsd_ctx;           /* one device, one stream, one set of scratch buffers   */
+typedef struct lsd_frame lsd_frame;       /* [UP] lsd_slam::Frame -- device-resident pyramids       */
+typedef struct lsd_ref lsd_ref;           /* [UP] lsd_slam::TrackingReference -- per-level points   */
+typedef struct lsd_depthmap lsd_depthmap; /* [UP] lsd_slam::DepthMap -- SoA hypothesis planes       */
+
+enum lsd_status {
+  LSD_OK = 0,
+  LSD_ERR_ARG = -1,
+  LSD_ERR_CUDA = -2,
+  LSD_ERR_STATE = -3,
+  LSD_ERR_NOMEM = -4
+};
+
+/* Frame::image/gradients/maxGradients/idepth/idepthVar(level), refPixelWasGood()
+ * (read by the reference at lib/Pangolin_IOWrapper/PangolinOutputIOWrapper.cpp:56-79). */
+enum lsd_field {
+  LSD_FIELD_IMAGE = 0,      /* float  [h_l*w_l]                                  */
+  LSD_FIELD_GRADIENTS = 1,  /* float4 [h_l*w_l]  (gx, gy, I, 0)                  */
+  LSD_FIELD_MAXGRAD = 2,    /* float  [h_l*w_l]  (level 0 only is ever consumed)  */
+  LSD_FIELD_IDEPTH = 3,     /* float  [h_l*w_l]                                  */
+  LSD_FIELD_IDEPTHVAR = 4,  /* float  [h_l*w_l]                                  */
+  LSD_FIELD_MASK = 5        /* uint8  [(h>>1)*(w>>1)]  refPixelWasGood            */
+};
+
+/* Tracker tunables: [UP] DenseDepthTrackerSettings + the util/settings.h constants the kernels use. */
+typedef struct lsd_tracker_settings {
+  float lambdaSuccessFac, lambdaFailFac;
+  float stepSizeMin[LSD_PYRAMID_LEVELS];
+  float convergenceEps[LSD_PYRAMID_LEVELS];
+  int maxItsPerLvl[LSD_PYRAMID_LEVELS];
+  float lambdaInitial[LSD_PYRAMID_LEVELS];
+  float var_weight, huber_d;
+} lsd_tracker_settings;
+
+/* What [UP] SE3Tracker exposes as members after trackFrame. */
+typedef struct lsd_se3_result {
+  double frameToRef[7];
+  float lastResidual, lastMeanRes, pointUsage, lastGoodCount, lastBadCount;
+  float affine_a, affine_b, initialTrackedResidual;
+  int diverged, trackingWasGood;
+  int numResidualCalls[LSD_PYRAMID_LEVELS], numWarpUpdateCalls[LSD_PYRAMID_LEVELS];
+  int traceLen;
+} lsd_se3_result;
+
+/* One LM evaluation, recorded when a trace buffer is supplied (parity tests). */
+typedef struct lsd_trace_entry {
+  int level, accepted; /* -1 first evaluation of a level, 0 rejected, 1 accepted */
+  float error, lambda;
+  int bufSize;
+} lsd_trace_entry;
+#define LSD_TRACE_CAP 512
+
+/* ---- context ------------------------------------------------------------------------------- */
+const char *lsd_last_error(void);
+int lsd_version(void);
+/* stream: a cudaStream_t to run on (0/NULL: the context creates its own non-blocking stream).
+ * K = {fx, fy, cx, cy} at level 0 ([UP] Frame ctor takes the undistorted camera matrix; the
+ * reference passes undistorter->getCamera(), lib/App/InputThread.cpp:71). */
+int lsd_ctx_create(int device, int width, int height, const float K[4], void *stream, lsd_ctx **out);
+int lsd_ctx_destroy(lsd_ctx *ctx);
+int lsd_ctx_synchronize(lsd_ctx *ctx);
+void *lsd_ctx_stream(lsd_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py gpu_launches) */
+long long lsd_ctx_launch_count(lsd_ctx *ctx);
+int lsd_default_tracker_settings(lsd_tracker_settings *s);
+int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
+
+/* ---- Frame ---------------------------------------------------------------------------------- */
+#define LSD_BUILD_TRACKING 0u /* image L0-4 + gradients L1-4: what a tracked frame needs        */
+#define LSD_BUILD_MAXGRAD0 1u /* + maxGradients(0): what a keyframe / stereo KF needs            */
+#define LSD_BUILD_GRAD0 2u    /* + gradients(0)                                                  */
+/* [UP] Frame::Frame(id, w, h, K, timestamp, const unsigned char* image) + buildImage /
+ * buildGradients / buildMaxGradients for all levels.  `image` is the 8-bit grey frame the
+ * reference hands SlamSystem::nextImage (lib/App/InputThread.cpp:59,65,71); pitch in bytes. */
+int lsd_frame_create(lsd_ctx *ctx, int id, const uint8_t *image, size_t pitch, unsigned flags, lsd_frame **out);
+/* batch form: n frames from n host images in one pass (pinned staging, one launch per stage) */
+int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *const *images, size_t pitch,
+                           unsigned flags, lsd_frame **out);
+/* same, source images already in device memory (contiguous n * h * w bytes) */
+int lsd_frame_create_batch_device(lsd_ctx *ctx, int n, const int *ids, const void *d_images, unsigned flags,
+                                  lsd_frame **out);
+int lsd_frame_release(lsd_ctx *ctx, lsd_frame *f);
+int lsd_frame_release_batch(lsd_ctx *ctx, int n, lsd_frame **f);
+/* lazily builds whatever `field` at `level` needs, then copies it to host memory */
+int lsd_frame_read(lsd_ctx *ctx, lsd_frame *f, int field, int level, void *dst);
+int lsd_frame_num_mappable_pixels(lsd_ctx *ctx, lsd_frame *f, int *out); /* [UP] Frame::numMappablePixels */
+/* [UP] Frame::setDepthFromGroundTruth(const float* depth, float cov_scale) */
+int lsd_frame_set_depth_from_gt(lsd_ctx *ctx, lsd_frame *f, const float *depth, float cov_scale);
+/* install level-0 idepth / idepthVar planes directly (what Frame::setDepth leaves behind) */
+int lsd_frame_set_idepth(lsd_ctx *ctx, lsd_frame *f, const float *idepth, const float *idepthVar);
+int lsd_frame_set_idepth_batch_device(lsd_ctx *ctx, int n, lsd_frame *const *f, const void *d_idepth,
+                                      const void *d_idepthVar);
+int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *numPoints);
+
+/* ---- TrackingReference ---------------------------------------------------------------------- */
+/* [UP] TrackingReference::importFrame + makePointCloud(level) for levels 1..4 */
+int lsd_ref_create(lsd_ctx *ctx, lsd_frame *keyframe, lsd_ref **out);
+int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_ref **out);
+int lsd_ref_release(lsd_ctx *ctx, lsd_ref *r);
+int lsd_ref_num_data(lsd_ctx *ctx, lsd_ref *r, int level, int *out); /* [UP] numData[level] */
+/* copies the level's point cloud in the reference's layout (pos 3f, grad 2f, colorAndVar 2f, idx);
+ * emission order is row-major here (upstream: column-major) -- see DESIGN.md */
+int lsd_ref_read(lsd_ctx *ctx, lsd_ref *r, int level, float *pos, float *grad, float *colorAndVar, int *idx);
+
+/* ---- SE3Tracker ----------------------------------------------------------------------------- */
+/* [UP] SE3Tracker::trackFrame(TrackingReference*, Frame*, const SE3& frameToReference_initialEstimate).
+ * Writes refPixelWasGood of `frame`, frame->initialTrackedResidual, pose->thisToParent_raw. */
+int lsd_se3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[7], lsd_se3_result *result,
+                  lsd_trace_entry *trace /* LSD_TRACE_CAP entries or NULL */);
+/* n independent (ref, frame) pairs in ONE persistent launch (config 2 of BASELINE.json) */
+int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames,
+                        const double *init_frameToRef /* n*7 */, lsd_se3_result *results,
+                        lsd_trace_entry *traces /* n*LSD_TRACE_CAP or NULL */);
+/* host images in, poses out: ingest (H2D + pyramids) and tracking pipelined over two streams */
+int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const uint8_t *const *images, size_t pitch,
+                               const double *init_frameToRef, lsd_se3_result *results);
+/* one fused LM evaluation (calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate)
+ * at a fixed pose; A36/b6 as after NormalEquationsLeastSquares::finish(); scalars[12] =
+ * {error, meanSqRes, bufSize, good, bad, pointUsage, meanRes, a_lastIt, b_lastIt, lsError, 0, 0} */
+int lsd_se3_eval(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float affine_a,
+                 float affine_b, float *A36, float *b6, float *scalars);
+/* algorithmic bytes and evaluation count of the last lsd_se3_track* call on this ctx */
+int lsd_se3_last_stats(lsd_ctx *ctx, double *algorithmic_bytes, long long *evaluations, float *kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSD_B200_H */

@@ -1,0 +1,652 @@
+// api.cu -- extern "C" surface of liblsd_b200.so (include/lsd_b200.h): contexts, device-resident
+// frames, tracking references and the SE3 tracker entry points.  No CPU fallback exists: every
+// entry point either runs the sm_100a kernels or returns an error.
+#include <cstring>
+
+#include "ctx.cuh"
+
+namespace lsd {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void make_intrinsics(int w, int h, const float K[4], Intrinsics &I) {
+  for (int l = 0; l < NL; l++) {
+    I.w[l] = w >> l;
+    I.h[l] = h >> l;
+    if (l == 0) {
+      I.fx[0] = K[0]; I.fy[0] = K[1]; I.cx[0] = K[2]; I.cy[0] = K[3];
+    } else {
+      // Frame::initialize: fx_l = fx_{l-1} * 0.5; cx_l = (cx_0 + 0.5) / 2^l - 0.5 (double literals, rounded on store)
+      I.fx[l] = (float)(I.fx[l - 1] * 0.5);
+      I.fy[l] = (float)(I.fy[l - 1] * 0.5);
+      I.cx[l] = (float)((I.cx[0] + 0.5) / ((int)1 << l) - 0.5);
+      I.cy[l] = (float)((I.cy[0] + 0.5) / ((int)1 << l) - 0.5);
+    }
+    I.fxi[l] = 1.0f / I.fx[l];
+    I.fyi[l] = 1.0f / I.fy[l];
+    I.cxi[l] = -I.cx[l] / I.fx[l];
+    I.cyi[l] = -I.cy[l] / I.fy[l];
+  }
+}
+
+static void make_layout(const Intrinsics &I, FrameLayout &L) {
+  size_t off = 0;
+  for (int l = 0; l < NL; l++) { L.img[l] = off; off = align_up(off + (size_t)I.w[l] * I.h[l] * 4, 256); }
+  for (int l = 0; l < NL; l++) { L.grad[l] = off; off = align_up(off + (size_t)I.w[l] * I.h[l] * 16, 256); }
+  L.maxgrad = off; off = align_up(off + (size_t)I.w[0] * I.h[0] * 4, 256);
+  for (int l = 0; l < NL; l++) { L.idepth[l] = off; off = align_up(off + (size_t)I.w[l] * I.h[l] * 4, 256); }
+  for (int l = 0; l < NL; l++) { L.idvar[l] = off; off = align_up(off + (size_t)I.w[l] * I.h[l] * 4, 256); }
+  L.mask = off; off = align_up(off + (size_t)I.w[1] * I.h[1], 256);
+  off += 256;  // tail: counters (numMappablePixels at total-16)
+  L.total = off;
+}
+
+int ensure_stage(lsd_ctx *ctx, size_t hostBytes, size_t devBytes) {
+  if (hostBytes > ctx->h_stageBytes) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stageBytes = 0;
+    LSD_CUDA(cudaMallocHost(&ctx->h_stage, hostBytes));
+    ctx->h_stageBytes = hostBytes;
+  }
+  if (devBytes > ctx->d_stageBytes) {
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->d_stageBytes = 0;
+    LSD_CUDA(cudaMalloc(&ctx->d_stage, devBytes));
+    ctx->d_stageBytes = devBytes;
+  }
+  return LSD_OK;
+}
+
+int ensure_table(lsd_ctx *ctx, size_t bytes) {
+  if (bytes > ctx->tableBytes) {
+    if (ctx->h_table) cudaFreeHost(ctx->h_table);
+    if (ctx->d_table) cudaFree(ctx->d_table);
+    ctx->h_table = ctx->d_table = nullptr;
+    ctx->tableBytes = 0;
+    size_t nb = align_up(bytes < 4096 ? 4096 : bytes * 2, 4096);
+    LSD_CUDA(cudaMallocHost(&ctx->h_table, nb));
+    LSD_CUDA(cudaMalloc(&ctx->d_table, nb));
+    ctx->tableBytes = nb;
+  }
+  return LSD_OK;
+}
+
+static int alloc_frame_slab(lsd_ctx *ctx, uint8_t **out) {
+  if (!ctx->frameSlabPool.empty()) {
+    *out = ctx->frameSlabPool.back();
+    ctx->frameSlabPool.pop_back();
+    return LSD_OK;
+  }
+  LSD_CUDA(cudaMalloc(out, ctx->lay.total));
+  return LSD_OK;
+}
+
+static lsd_frame *new_frame(int id, uint8_t *slab) {
+  lsd_frame *f = new lsd_frame();
+  std::memset(f, 0, sizeof(*f));
+  f->id = id;
+  f->slab = slab;
+  f->numMappable = -1;
+  f->trackingParentId = -1;
+  f->thisToParent_raw[3] = 1.0;
+  f->thisToParent_raw[7] = 1.0;
+  f->meanIdepth = 1.0f;
+  return f;
+}
+
+// upload a pointer list to d_table (blocking: h_table is reused)
+static int upload_ptrs(lsd_ctx *ctx, const std::vector<void *> &v, cudaStream_t st, size_t tableOffset = 0) {
+  int rc = ensure_table(ctx, tableOffset + v.size() * sizeof(void *));
+  if (rc) return rc;
+  std::memcpy((char *)ctx->h_table + tableOffset, v.data(), v.size() * sizeof(void *));
+  LSD_CUDA(cudaMemcpyAsync((char *)ctx->d_table + tableOffset, (char *)ctx->h_table + tableOffset, v.size() * sizeof(void *),
+                           cudaMemcpyHostToDevice, st));
+  return LSD_OK;
+}
+
+// builds the requested planes of n frames whose slabs are listed in d_table[0..n)
+static void build_planes(lsd_ctx *ctx, int n, unsigned flags, cudaStream_t st) {
+  uint8_t *const *d_slabs = reinterpret_cast<uint8_t *const *>(ctx->d_table);
+  launch_gradients(ctx, d_slabs, n, (flags & LSD_BUILD_GRAD0) ? 0 : 1, NL - 1, st);
+  if (flags & LSD_BUILD_MAXGRAD0) launch_maxgrad0(ctx, d_slabs, n, st);
+}
+
+static int ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need) {
+  const unsigned missing = need & ~f->built;
+  if (!missing) return LSD_OK;
+  cudaStream_t st = ctx->stream;
+  std::vector<void *> v{f->slab};
+  int rc = upload_ptrs(ctx, v, st);
+  if (rc) return rc;
+  uint8_t *const *d_slabs = reinterpret_cast<uint8_t *const *>(ctx->d_table);
+  if (missing & FB_GRAD0) {
+    launch_gradients(ctx, d_slabs, 1, 0, 0, st);
+    f->built |= FB_GRAD0;
+  }
+  if (missing & FB_MAXGRAD0) {
+    launch_maxgrad0(ctx, d_slabs, 1, st);
+    f->built |= FB_MAXGRAD0;
+  }
+  if (missing & FB_IDEPTH_PYR) {
+    if (!(f->built & FB_IDEPTH0)) {
+      set_error("frame has no depth (hasIDepthBeenSet() == false)");
+      return LSD_ERR_STATE;
+    }
+    launch_idepth_pyramid(ctx, d_slabs, 1, st);
+    f->built |= FB_IDEPTH_PYR;
+  }
+  if (missing & FB_MASK) {
+    launch_mask_init(ctx, d_slabs, 1, st);
+    f->built |= FB_MASK;
+  }
+  LSD_CUDA(cudaStreamSynchronize(st));
+  return LSD_OK;
+}
+
+}  // namespace lsd
+
+using namespace lsd;
+
+extern "C" {
+
+const char *lsd_last_error(void) { return g_err.c_str(); }
+int lsd_version(void) { return 100; }
+
+int lsd_default_tracker_settings(lsd_tracker_settings *s) {
+  LSD_ARG(s);
+  s->lambdaSuccessFac = 0.5f;
+  s->lambdaFailFac = 2.0f;
+  const int its[NL] = {5, 20, 50, 100, 100};
+  for (int l = 0; l < NL; l++) {
+    s->stepSizeMin[l] = 1e-8f;
+    s->convergenceEps[l] = 0.999f;
+    s->maxItsPerLvl[l] = its[l];
+    s->lambdaInitial[l] = 0;
+  }
+  s->var_weight = 1.0f;
+  s->huber_d = 3.0f;
+  return LSD_OK;
+}
+
+int lsd_ctx_create(int device, int width, int height, const float K[4], void *stream, lsd_ctx **out) {
+  LSD_ARG(out && K);
+  LSD_ARG(width > 0 && height > 0 && width % 16 == 0 && height % 16 == 0);
+  LSD_ARG(width <= 65535 && height <= 65535);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (liblsd_b200 has no CPU fallback)");
+    return LSD_ERR_CUDA;
+  }
+  LSD_ARG(device >= 0 && device < ndev);
+  LSD_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LSD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("liblsd_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    return LSD_ERR_CUDA;
+  }
+  lsd_ctx *ctx = new lsd_ctx();
+  ctx->device = device;
+  ctx->numSMs = prop.multiProcessorCount;
+  ctx->w = width;
+  ctx->h = height;
+  make_intrinsics(width, height, K, ctx->K);
+  make_layout(ctx->K, ctx->lay);
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+    ctx->ownStream = false;
+  } else {
+    LSD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->ownStream = true;
+  }
+  LSD_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  LSD_CUDA(cudaEventCreate(&ctx->evA));
+  LSD_CUDA(cudaEventCreate(&ctx->evB));
+  for (int i = 0; i < 4; i++) LSD_CUDA(cudaEventCreateWithFlags(&ctx->evPipe[i], cudaEventDisableTiming));
+  ctx->launches = 0;
+  lsd_default_tracker_settings(&ctx->se3);
+  ctx->refSlabBytes = 0;
+  ctx->h_stage = ctx->d_stage = nullptr;
+  ctx->h_stageBytes = ctx->d_stageBytes = 0;
+  ctx->h_table = ctx->d_table = nullptr;
+  ctx->tableBytes = 0;
+  ctx->se3s = nullptr;
+  ctx->lastAlgBytes = 0;
+  ctx->lastEvals = 0;
+  ctx->lastKernelMs = 0;
+  *out = ctx;
+  return LSD_OK;
+}
+
+int lsd_ctx_destroy(lsd_ctx *ctx) {
+  if (!ctx) return LSD_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  se3_scratch_free(ctx);
+  for (auto p : ctx->frameSlabPool) cudaFree(p);
+  for (auto p : ctx->refSlabPool) cudaFree(p);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->h_table) cudaFreeHost(ctx->h_table);
+  if (ctx->d_table) cudaFree(ctx->d_table);
+  cudaEventDestroy(ctx->evA);
+  cudaEventDestroy(ctx->evB);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->evPipe[i]);
+  cudaStreamDestroy(ctx->copyStream);
+  if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return LSD_OK;
+}
+
+int lsd_ctx_synchronize(lsd_ctx *ctx) {
+  LSD_ARG(ctx);
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LSD_OK;
+}
+void *lsd_ctx_stream(lsd_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+long long lsd_ctx_launch_count(lsd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s) {
+  LSD_ARG(ctx && s);
+  ctx->se3 = *s;
+  return LSD_OK;
+}
+
+// ---- frames ---------------------------------------------------------------------------------
+
+int lsd_frame_create_batch_device(lsd_ctx *ctx, int n, const int *ids, const void *d_images, unsigned flags, lsd_frame **out) {
+  LSD_ARG(ctx && out && d_images && n >= 0);
+  if (n == 0) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  std::vector<void *> slabs(n);
+  for (int i = 0; i < n; i++) {
+    uint8_t *s = nullptr;
+    int rc = alloc_frame_slab(ctx, &s);
+    if (rc) return rc;
+    slabs[i] = s;
+    out[i] = new_frame(ids ? ids[i] : i, s);
+  }
+  int rc = upload_ptrs(ctx, slabs, st);
+  if (rc) return rc;
+  launch_ingest(ctx, (const uint8_t *)d_images, ctx->w, (size_t)ctx->w * ctx->h, reinterpret_cast<uint8_t *const *>(ctx->d_table), n,
+                st);
+  build_planes(ctx, n, flags, st);
+  LSD_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; i++)
+    out[i]->built = FB_TRACKING | ((flags & LSD_BUILD_MAXGRAD0) ? FB_MAXGRAD0 : 0) | ((flags & LSD_BUILD_GRAD0) ? FB_GRAD0 : 0);
+  return LSD_OK;
+}
+
+int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *const *images, size_t pitch, unsigned flags,
+                           lsd_frame **out) {
+  LSD_ARG(ctx && out && images && n >= 0);
+  LSD_ARG(pitch >= (size_t)ctx->w);
+  if (n == 0) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  const size_t fbytes = (size_t)ctx->w * ctx->h;
+  // stage in chunks of <= 64 frames so pinned/device staging stays small
+  const int CH = 64;
+  int rc = ensure_stage(ctx, fbytes * (n < CH ? n : CH), fbytes * (n < CH ? n : CH));
+  if (rc) return rc;
+  for (int i0 = 0; i0 < n; i0 += CH) {
+    const int m = (n - i0) < CH ? (n - i0) : CH;
+    for (int i = 0; i < m; i++) {
+      const uint8_t *src = images[i0 + i];
+      LSD_ARG(src);
+      uint8_t *dst = ctx->h_stage + fbytes * i;
+      if (pitch == (size_t)ctx->w) std::memcpy(dst, src, fbytes);
+      else for (int y = 0; y < ctx->h; y++) std::memcpy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
+    }
+    LSD_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, fbytes * m, cudaMemcpyHostToDevice, ctx->stream));
+    rc = lsd_frame_create_batch_device(ctx, m, ids ? ids + i0 : nullptr, ctx->d_stage, flags, out + i0);
+    if (rc) return rc;
+    if (!ids) for (int i = 0; i < m; i++) out[i0 + i]->id = i0 + i;
+  }
+  return LSD_OK;
+}
+
+int lsd_frame_create(lsd_ctx *ctx, int id, const uint8_t *image, size_t pitch, unsigned flags, lsd_frame **out) {
+  const uint8_t *imgs[1] = {image};
+  return lsd_frame_create_batch(ctx, 1, &id, imgs, pitch, flags, out);
+}
+
+int lsd_frame_release(lsd_ctx *ctx, lsd_frame *f) {
+  LSD_ARG(ctx);
+  if (!f) return LSD_OK;
+  ctx->frameSlabPool.push_back(f->slab);
+  delete f;
+  return LSD_OK;
+}
+
+int lsd_frame_release_batch(lsd_ctx *ctx, int n, lsd_frame **f) {
+  LSD_ARG(ctx && (f || n == 0));
+  for (int i = 0; i < n; i++) {
+    lsd_frame_release(ctx, f[i]);
+    f[i] = nullptr;
+  }
+  return LSD_OK;
+}
+
+int lsd_frame_read(lsd_ctx *ctx, lsd_frame *f, int field, int level, void *dst) {
+  LSD_ARG(ctx && f && dst);
+  LSD_ARG(level >= 0 && level < NL);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  const size_t N = (size_t)ctx->K.w[level] * ctx->K.h[level];
+  const FrameLayout &L = ctx->lay;
+  const uint8_t *src = nullptr;
+  size_t bytes = 0;
+  int rc = LSD_OK;
+  switch (field) {
+    case LSD_FIELD_IMAGE: src = f->slab + L.img[level]; bytes = N * 4; break;
+    case LSD_FIELD_GRADIENTS:
+      if (level == 0) rc = ensure_built(ctx, f, FB_GRAD0);
+      src = f->slab + L.grad[level]; bytes = N * 16; break;
+    case LSD_FIELD_MAXGRAD:
+      LSD_ARG(level == 0);
+      rc = ensure_built(ctx, f, FB_MAXGRAD0);
+      src = f->slab + L.maxgrad; bytes = N * 4; break;
+    case LSD_FIELD_IDEPTH:
+    case LSD_FIELD_IDEPTHVAR:
+      if (!(f->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
+      if (level > 0) rc = ensure_built(ctx, f, FB_IDEPTH_PYR);
+      src = f->slab + (field == LSD_FIELD_IDEPTH ? L.idepth[level] : L.idvar[level]); bytes = N * 4; break;
+    case LSD_FIELD_MASK:
+      rc = ensure_built(ctx, f, FB_MASK);
+      src = f->slab + L.mask; bytes = (size_t)ctx->K.w[1] * ctx->K.h[1]; break;
+    default: LSD_ARG(!"unknown field");
+  }
+  if (rc) return rc;
+  LSD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LSD_OK;
+}
+
+int lsd_frame_num_mappable_pixels(lsd_ctx *ctx, lsd_frame *f, int *out) {
+  LSD_ARG(ctx && f && out);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_built(ctx, f, FB_MAXGRAD0);
+  if (rc) return rc;
+  if (f->numMappable < 0) {
+    LSD_CUDA(cudaMemcpyAsync(&f->numMappable, f->slab + ctx->lay.total - 16, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  *out = f->numMappable;
+  return LSD_OK;
+}
+
+int lsd_frame_set_depth_from_gt(lsd_ctx *ctx, lsd_frame *f, const float *depth, float cov_scale) {
+  LSD_ARG(ctx && f && depth);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->w * ctx->h * 4;
+  int rc = ensure_stage(ctx, bytes, bytes);
+  if (rc) return rc;
+  std::memcpy(ctx->h_stage, depth, bytes);
+  LSD_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  launch_set_depth_gt(ctx, f->slab, reinterpret_cast<const float *>(ctx->d_stage), cov_scale, ctx->stream);
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  f->built = (f->built | FB_IDEPTH0) & ~FB_IDEPTH_PYR;
+  return LSD_OK;
+}
+
+int lsd_frame_set_idepth(lsd_ctx *ctx, lsd_frame *f, const float *idepth, const float *idepthVar) {
+  LSD_ARG(ctx && f && idepth && idepthVar);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->w * ctx->h * 4;
+  int rc = ensure_stage(ctx, 2 * bytes, 0);
+  if (rc) return rc;
+  std::memcpy(ctx->h_stage, idepth, bytes);
+  std::memcpy(ctx->h_stage + bytes, idepthVar, bytes);
+  LSD_CUDA(cudaMemcpyAsync(f->slab + ctx->lay.idepth[0], ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  LSD_CUDA(cudaMemcpyAsync(f->slab + ctx->lay.idvar[0], ctx->h_stage + bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  f->built = (f->built | FB_IDEPTH0) & ~FB_IDEPTH_PYR;
+  return LSD_OK;
+}
+
+int lsd_frame_set_idepth_batch_device(lsd_ctx *ctx, int n, lsd_frame *const *f, const void *d_idepth, const void *d_idepthVar) {
+  LSD_ARG(ctx && f && d_idepth && d_idepthVar);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->w * ctx->h * 4;
+  for (int i = 0; i < n; i++) {
+    LSD_CUDA(cudaMemcpyAsync(f[i]->slab + ctx->lay.idepth[0], (const char *)d_idepth + bytes * i, bytes, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    LSD_CUDA(cudaMemcpyAsync(f[i]->slab + ctx->lay.idvar[0], (const char *)d_idepthVar + bytes * i, bytes, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    f[i]->built = (f[i]->built | FB_IDEPTH0) & ~FB_IDEPTH_PYR;
+  }
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LSD_OK;
+}
+
+int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *numPoints) {
+  LSD_ARG(ctx && f);
+  if (!(f->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_table(ctx, 64);
+  if (rc) return rc;
+  launch_idepth_stats(ctx, f->slab, reinterpret_cast<float *>(ctx->d_table), ctx->stream);
+  float h[2];
+  LSD_CUDA(cudaMemcpyAsync(h, ctx->d_table, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  f->meanIdepth = h[0];
+  std::memcpy(&f->numPoints, &h[1], 4);
+  if (meanIdepth) *meanIdepth = f->meanIdepth;
+  if (numPoints) *numPoints = f->numPoints;
+  return LSD_OK;
+}
+
+// ---- tracking references ----------------------------------------------------------------------
+
+int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_ref **out) {
+  LSD_ARG(ctx && keyframes && out && n >= 0);
+  if (n == 0) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // slab layout: per level RefPoint[N_l] then float2[N_l], then int[NL] counters
+  size_t offPts[NL], offGrad[NL], off = 0;
+  for (int l = 0; l < NL; l++) {
+    const size_t N = (l == 0) ? 0 : (size_t)ctx->K.w[l] * ctx->K.h[l];
+    offPts[l] = off; off = align_up(off + N * sizeof(RefPoint), 256);
+    offGrad[l] = off; off = align_up(off + N * sizeof(float2), 256);
+  }
+  const size_t offNum = off;
+  off += 256;
+  ctx->refSlabBytes = off;
+  // frames that still need their idepth pyramid
+  std::vector<void *> needPyr;
+  for (int i = 0; i < n; i++) {
+    LSD_ARG(keyframes[i]);
+    if (!(keyframes[i]->built & FB_IDEPTH0)) { set_error("keyframe has no depth"); return LSD_ERR_STATE; }
+    if (!(keyframes[i]->built & FB_IDEPTH_PYR)) needPyr.push_back(keyframes[i]->slab);
+  }
+  if (!needPyr.empty()) {
+    int rc = upload_ptrs(ctx, needPyr, st);
+    if (rc) return rc;
+    launch_idepth_pyramid(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), (int)needPyr.size(), st);
+    LSD_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) keyframes[i]->built |= FB_IDEPTH_PYR;
+  }
+  std::vector<void *> tab(3 * (size_t)n);
+  for (int i = 0; i < n; i++) {
+    uint8_t *slab = nullptr;
+    if (!ctx->refSlabPool.empty()) {
+      slab = ctx->refSlabPool.back();
+      ctx->refSlabPool.pop_back();
+    } else {
+      LSD_CUDA(cudaMalloc(&slab, ctx->refSlabBytes));
+    }
+    lsd_ref *r = new lsd_ref();
+    r->keyframe = keyframes[i];
+    r->frameID = keyframes[i]->id;
+    r->slab = slab;
+    for (int l = 0; l < NL; l++) { r->offPts[l] = offPts[l]; r->offGrad[l] = offGrad[l]; r->num[l] = 0; }
+    r->d_num = reinterpret_cast<int *>(slab + offNum);
+    r->numValid = false;
+    out[i] = r;
+    tab[i] = keyframes[i]->slab;
+    tab[n + i] = slab;
+    tab[2 * (size_t)n + i] = r->d_num;
+  }
+  int rc = upload_ptrs(ctx, tab, st);
+  if (rc) return rc;
+  void **d = reinterpret_cast<void **>(ctx->d_table);
+  for (int i = 0; i < n; i++) LSD_CUDA(cudaMemsetAsync(out[i]->d_num, 0, sizeof(int) * NL, st));
+  launch_make_pointcloud(ctx, reinterpret_cast<uint8_t *const *>(d), reinterpret_cast<uint8_t *const *>(d + n),
+                         reinterpret_cast<int *const *>(d + 2 * (size_t)n), n, offPts, offGrad, st);
+  LSD_CUDA(cudaStreamSynchronize(st));
+  return LSD_OK;
+}
+
+int lsd_ref_create(lsd_ctx *ctx, lsd_frame *keyframe, lsd_ref **out) { return lsd_ref_create_batch(ctx, 1, &keyframe, out); }
+
+int lsd_ref_release(lsd_ctx *ctx, lsd_ref *r) {
+  LSD_ARG(ctx);
+  if (!r) return LSD_OK;
+  ctx->refSlabPool.push_back(r->slab);
+  delete r;
+  return LSD_OK;
+}
+
+static int ref_fetch_nums(lsd_ctx *ctx, lsd_ref *r) {
+  if (r->numValid) return LSD_OK;
+  LSD_CUDA(cudaMemcpyAsync(r->num, r->d_num, sizeof(int) * NL, cudaMemcpyDeviceToHost, ctx->stream));
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  r->numValid = true;
+  return LSD_OK;
+}
+
+int lsd_ref_num_data(lsd_ctx *ctx, lsd_ref *r, int level, int *out) {
+  LSD_ARG(ctx && r && out && level >= 1 && level < NL);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  int rc = ref_fetch_nums(ctx, r);
+  if (rc) return rc;
+  *out = r->num[level];
+  return LSD_OK;
+}
+
+int lsd_ref_read(lsd_ctx *ctx, lsd_ref *r, int level, float *pos, float *grad, float *colorAndVar, int *idx) {
+  LSD_ARG(ctx && r && level >= 1 && level < NL);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  int rc = ref_fetch_nums(ctx, r);
+  if (rc) return rc;
+  const int n = r->num[level];
+  std::vector<RefPoint> pts(n);
+  std::vector<float2> g(n);
+  LSD_CUDA(cudaMemcpyAsync(pts.data(), r->slab + r->offPts[level], sizeof(RefPoint) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  LSD_CUDA(cudaMemcpyAsync(g.data(), r->slab + r->offGrad[level], sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  const float fxi = ctx->K.fxi[level], fyi = ctx->K.fyi[level], cxi = ctx->K.cxi[level], cyi = ctx->K.cyi[level];
+  const int W = ctx->K.w[level];
+  for (int i = 0; i < n; i++) {
+    const int x = pts[i].xy & 0xffff, y = pts[i].xy >> 16;
+    if (pos) {  // same operations as the kernel (and upstream makePointCloud)
+      volatile float inv = 1.0f / pts[i].idepth;
+      volatile float ax = fxi * x, ay = fyi * y;
+      volatile float bx = ax + cxi, by = ay + cyi;
+      pos[3 * i] = inv * bx;
+      pos[3 * i + 1] = inv * by;
+      pos[3 * i + 2] = inv * 1.0f;
+    }
+    if (grad) { grad[2 * i] = g[i].x; grad[2 * i + 1] = g[i].y; }
+    if (colorAndVar) { colorAndVar[2 * i] = pts[i].color; colorAndVar[2 * i + 1] = pts[i].var; }
+    if (idx) idx[i] = x + y * W;
+  }
+  return LSD_OK;
+}
+
+// ---- SE3 tracker --------------------------------------------------------------------------------
+
+int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init_frameToRef,
+                        lsd_se3_result *results, lsd_trace_entry *traces) {
+  LSD_ARG(ctx && refs && frames && init_frameToRef && results && n >= 0);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  return se3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, results, traces, ctx->stream, true);
+}
+
+int lsd_se3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[7], lsd_se3_result *result,
+                  lsd_trace_entry *trace) {
+  return lsd_se3_track_batch(ctx, 1, &ref, &frame, init_frameToRef, result, trace);
+}
+
+int lsd_se3_eval(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float affine_a,
+                 float affine_b, float *A36, float *b6, float *scalars) {
+  LSD_ARG(ctx && ref && frame && refToFrame && A36 && b6 && scalars);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  return se3_eval_impl(ctx, ref, frame, refToFrame, level, affine_a, affine_b, A36, b6, scalars);
+}
+
+int lsd_se3_last_stats(lsd_ctx *ctx, double *algorithmic_bytes, long long *evaluations, float *kernel_ms) {
+  LSD_ARG(ctx);
+  if (algorithmic_bytes) *algorithmic_bytes = ctx->lastAlgBytes;
+  if (evaluations) *evaluations = ctx->lastEvals;
+  if (kernel_ms) *kernel_ms = ctx->lastKernelMs;
+  return LSD_OK;
+}
+
+// Host images in, poses out.  Chunks of frames are uploaded on the copy stream while the previous
+// chunk is ingested and tracked on the compute stream (two staging halves, event-ordered).
+int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const uint8_t *const *images, size_t pitch,
+                               const double *init_frameToRef, lsd_se3_result *results) {
+  LSD_ARG(ctx && refs && images && init_frameToRef && results && n >= 0);
+  LSD_ARG(pitch >= (size_t)ctx->w);
+  if (n == 0) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  const size_t fbytes = (size_t)ctx->w * ctx->h;
+  const int CH = n < 256 ? n : 256;
+  int rc = ensure_stage(ctx, 0, 2 * fbytes * CH);
+  if (rc) return rc;
+  std::vector<lsd_frame *> fr(n, nullptr);
+  std::vector<void *> slabs;
+  const int nChunks = (n + CH - 1) / CH;
+  auto issue_copy = [&](int c) -> int {
+    const int i0 = c * CH, m = (n - i0) < CH ? (n - i0) : CH;
+    uint8_t *dst = ctx->d_stage + (size_t)(c & 1) * fbytes * CH;
+    // the half must have been consumed by the ingest of chunk c-2
+    if (c >= 2) LSD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evPipe[2 + (c & 1)], 0));
+    for (int i = 0; i < m; i++)
+      LSD_CUDA(cudaMemcpy2DAsync(dst + fbytes * i, ctx->w, images[i0 + i], pitch, ctx->w, ctx->h, cudaMemcpyHostToDevice,
+                                 ctx->copyStream));
+    LSD_CUDA(cudaEventRecord(ctx->evPipe[c & 1], ctx->copyStream));
+    return LSD_OK;
+  };
+  rc = issue_copy(0);
+  if (rc) return rc;
+  for (int c = 0; c < nChunks; c++) {
+    const int i0 = c * CH, m = (n - i0) < CH ? (n - i0) : CH;
+    if (c + 1 < nChunks) {
+      rc = issue_copy(c + 1);
+      if (rc) return rc;
+    }
+    slabs.assign(m, nullptr);
+    for (int i = 0; i < m; i++) {
+      uint8_t *s = nullptr;
+      rc = alloc_frame_slab(ctx, &s);
+      if (rc) return rc;
+      slabs[i] = s;
+      fr[i0 + i] = new_frame(i0 + i, s);
+      fr[i0 + i]->built = FB_TRACKING;
+    }
+    rc = upload_ptrs(ctx, slabs, ctx->stream);
+    if (rc) return rc;
+    LSD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evPipe[c & 1], 0));
+    const uint8_t *src = ctx->d_stage + (size_t)(c & 1) * fbytes * CH;
+    launch_ingest(ctx, src, ctx->w, fbytes, reinterpret_cast<uint8_t *const *>(ctx->d_table), m, ctx->stream);
+    LSD_CUDA(cudaEventRecord(ctx->evPipe[2 + (c & 1)], ctx->stream));
+    launch_gradients(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), m, 1, NL - 1, ctx->stream);
+    LSD_CUDA(cudaStreamSynchronize(ctx->stream));  // d_table is reused by the tracker below
+    rc = se3_track_batch_impl(ctx, m, refs + i0, fr.data() + i0, init_frameToRef + 7 * (size_t)i0, results + i0, nullptr,
+                              ctx->stream, true);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < n; i++) lsd_frame_release(ctx, fr[i]);
+  return LSD_OK;
+}
+
+}  // extern "C"

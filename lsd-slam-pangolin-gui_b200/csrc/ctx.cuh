@@ -1,0 +1,66 @@
+// ctx.cuh -- lsd_ctx definition and kernel-launcher prototypes (internal).
+#pragma once
+#include "common.cuh"
+
+struct SE3Scratch;  // se3_track.cu
+struct DepthScratch;
+
+struct lsd_ctx {
+  int device;
+  int numSMs;
+  int w, h;
+  lsd::Intrinsics K;
+  lsd::FrameLayout lay;
+  cudaStream_t stream;
+  bool ownStream;
+  cudaStream_t copyStream;  // second stream for the pipelined host-image path
+  cudaEvent_t evA, evB, evPipe[4];
+  long long launches;
+  lsd_tracker_settings se3;
+  // pools
+  std::vector<uint8_t *> frameSlabPool;
+  std::vector<uint8_t *> refSlabPool;
+  size_t refSlabBytes;
+  // staging for uploads
+  uint8_t *h_stage;  // pinned
+  size_t h_stageBytes;
+  uint8_t *d_stage;
+  size_t d_stageBytes;
+  // small pinned / device tables for batched pointer lists
+  void *h_table;
+  void *d_table;
+  size_t tableBytes;
+  SE3Scratch *se3s;
+  // last-call stats
+  double lastAlgBytes;
+  long long lastEvals;
+  float lastKernelMs;
+};
+
+namespace lsd {
+
+int ensure_stage(lsd_ctx *ctx, size_t hostBytes, size_t devBytes);
+int ensure_table(lsd_ctx *ctx, size_t bytes);
+
+// pyramid.cu
+void launch_ingest(lsd_ctx *ctx, const uint8_t *d_src, size_t srcPitch, size_t srcFrameStride, uint8_t *const *d_slabs, int n,
+                   cudaStream_t st);
+void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st);
+void launch_maxgrad0(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
+void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
+void launch_set_depth_gt(lsd_ctx *ctx, uint8_t *slab, const float *d_depth, float cov, cudaStream_t st);
+void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
+void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st);
+
+// trackref.cu
+void launch_make_pointcloud(lsd_ctx *ctx, uint8_t *const *d_kfSlabs, uint8_t *const *d_refSlabs, int *const *d_nums, int n,
+                            const size_t *offPts, const size_t *offGrad, cudaStream_t st);
+
+// se3_track.cu
+int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
+                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st, bool sync);
+int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
+                  float *A36, float *b6, float *scalars);
+void se3_scratch_free(lsd_ctx *ctx);
+
+}  // namespace lsd

@@ -1,0 +1,381 @@
+// pyramid.cu -- Frame pyramids on device, batched over frames.
+//
+// Replaces [UP] Frame::Frame(u8 image) + Frame::buildImage / buildGradients / buildMaxGradients /
+// buildIDepthAndIDepthVar (lsd-slam core DataStructures/Frame.cpp; the reference consumes the
+// results at lib/Pangolin_IOWrapper/PangolinOutputIOWrapper.cpp:56-79).  All results are
+// bit-exact against the oracle: box means of u8 data are exact in fp32, gradients are exact,
+// |g| uses IEEE sqrt and the file is compiled with -fmad=false so dx*dx+dy*dy is not contracted.
+#include "ctx.cuh"
+
+namespace lsd {
+
+#define TILE_W 64
+#define TILE_H 16
+
+// ---------------------------------------------------------------------------------------
+// k_ingest: u8 level 0 -> float image levels 0..4 in one pass (one 64x16 tile per CTA).
+// Each thread converts 4 adjacent pixels (uchar4 load, float4 store); levels 1..4 are
+// reduced hierarchically in shared memory, so the u8 source is read exactly once.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ingest(const uint8_t *__restrict__ src, size_t srcPitch, size_t srcFrameStride,
+                                                uint8_t *const *__restrict__ slabs, FrameLayout lay, int W, int H) {
+  __shared__ float s0[TILE_H][TILE_W];
+  __shared__ float s1[TILE_H / 2][TILE_W / 2];
+  __shared__ float s2[TILE_H / 4][TILE_W / 4];
+  __shared__ float s3[TILE_H / 8][TILE_W / 8];
+  const int f = blockIdx.z;
+  const uint8_t *img = src + (size_t)f * srcFrameStride;
+  uint8_t *slab = slabs[f];
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+  const int t = threadIdx.x;
+  {
+    const int tx = (t & 15) * 4, ty = t >> 4;  // 16 threads x 4 px per row, 16 rows
+    const int x = x0 + tx, y = y0 + ty;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (x < W && y < H) {
+      const uchar4 p = *reinterpret_cast<const uchar4 *>(img + (size_t)y * srcPitch + x);
+      v = make_float4((float)p.x, (float)p.y, (float)p.z, (float)p.w);
+      *reinterpret_cast<float4 *>(reinterpret_cast<float *>(slab + lay.img[0]) + (size_t)y * W + x) = v;
+    }
+    s0[ty][tx] = v.x; s0[ty][tx + 1] = v.y; s0[ty][tx + 2] = v.z; s0[ty][tx + 3] = v.w;
+  }
+  __syncthreads();
+  {  // level 1: 32 x 8 = 256 px
+    const int tx = t & 31, ty = t >> 5;
+    const float v = (s0[2 * ty][2 * tx] + s0[2 * ty][2 * tx + 1] + s0[2 * ty + 1][2 * tx] + s0[2 * ty + 1][2 * tx + 1]) * 0.25f;
+    s1[ty][tx] = v;
+    const int x = (x0 >> 1) + tx, y = (y0 >> 1) + ty;
+    if (x < (W >> 1) && y < (H >> 1)) reinterpret_cast<float *>(slab + lay.img[1])[(size_t)y * (W >> 1) + x] = v;
+  }
+  __syncthreads();
+  if (t < 64) {  // level 2: 16 x 4
+    const int tx = t & 15, ty = t >> 4;
+    const float v = (s1[2 * ty][2 * tx] + s1[2 * ty][2 * tx + 1] + s1[2 * ty + 1][2 * tx] + s1[2 * ty + 1][2 * tx + 1]) * 0.25f;
+    s2[ty][tx] = v;
+    const int x = (x0 >> 2) + tx, y = (y0 >> 2) + ty;
+    if (x < (W >> 2) && y < (H >> 2)) reinterpret_cast<float *>(slab + lay.img[2])[(size_t)y * (W >> 2) + x] = v;
+  }
+  __syncthreads();
+  if (t < 16) {  // level 3: 8 x 2
+    const int tx = t & 7, ty = t >> 3;
+    const float v = (s2[2 * ty][2 * tx] + s2[2 * ty][2 * tx + 1] + s2[2 * ty + 1][2 * tx] + s2[2 * ty + 1][2 * tx + 1]) * 0.25f;
+    s3[ty][tx] = v;
+    const int x = (x0 >> 3) + tx, y = (y0 >> 3) + ty;
+    if (x < (W >> 3) && y < (H >> 3)) reinterpret_cast<float *>(slab + lay.img[3])[(size_t)y * (W >> 3) + x] = v;
+  }
+  __syncthreads();
+  if (t < 4) {  // level 4: 4 x 1
+    const int tx = t;
+    const float v = (s3[0][2 * tx] + s3[0][2 * tx + 1] + s3[1][2 * tx] + s3[1][2 * tx + 1]) * 0.25f;
+    const int x = (x0 >> 4) + tx, y = (y0 >> 4);
+    if (x < (W >> 4) && y < (H >> 4)) reinterpret_cast<float *>(slab + lay.img[4])[(size_t)y * (W >> 4) + x] = v;
+  }
+}
+
+void launch_ingest(lsd_ctx *ctx, const uint8_t *d_src, size_t srcPitch, size_t srcFrameStride, uint8_t *const *d_slabs, int n,
+                   cudaStream_t st) {
+  dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
+  k_ingest<<<grid, 256, 0, st>>>(d_src, srcPitch, srcFrameStride, d_slabs, ctx->lay, ctx->w, ctx->h);
+  ctx->launches++;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_gradients: (gx, gy, I, 0) for the LINEAR index range [w, w(h-1)); rows 0 and h-1 are
+// zero (upstream leaves them unwritten); x=0 / x=w-1 use the wrapped linear neighbours.
+// One launch covers levels lvlLo..lvlHi of n frames.
+// ---------------------------------------------------------------------------------------
+struct LevelSpan {
+  int start[NL + 1];  // prefix of pixel counts over the covered levels
+  int lvlLo, lvlHi;
+};
+
+__global__ void __launch_bounds__(256) k_gradients(uint8_t *const *__restrict__ slabs, FrameLayout lay, Intrinsics K, LevelSpan sp) {
+  const int f = blockIdx.y;
+  uint8_t *slab = slabs[f];
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= sp.start[sp.lvlHi - sp.lvlLo + 1]) return;
+  int l = sp.lvlLo;
+  while (g >= sp.start[l - sp.lvlLo + 1]) l++;
+  const int i = g - sp.start[l - sp.lvlLo];
+  const int W = K.w[l], H = K.h[l];
+  const float *I = reinterpret_cast<const float *>(slab + lay.img[l]);
+  float4 out = make_float4(0, 0, 0, 0);
+  if (i >= W && i < W * (H - 1)) {
+    out.x = 0.5f * (__ldg(I + i + 1) - __ldg(I + i - 1));
+    out.y = 0.5f * (__ldg(I + i + W) - __ldg(I + i - W));
+    out.z = __ldg(I + i);
+  }
+  reinterpret_cast<float4 *>(slab + lay.grad[l])[i] = out;
+}
+
+void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st) {
+  LevelSpan sp;
+  sp.lvlLo = lvlLo;
+  sp.lvlHi = lvlHi;
+  int acc = 0;
+  for (int l = lvlLo; l <= lvlHi; l++) {
+    sp.start[l - lvlLo] = acc;
+    acc += ctx->K.w[l] * ctx->K.h[l];
+  }
+  sp.start[lvlHi - lvlLo + 1] = acc;
+  dim3 grid((acc + 255) / 256, n);
+  k_gradients<<<grid, 256, 0, st>>>(d_slabs, ctx->lay, ctx->K, sp);
+  ctx->launches++;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_maxgrad0: |g| -> vertical 3-max -> horizontal 3-max, fused through shared memory, with
+// the upstream linear-index ranges ([w, w(h-1)) for |g|; [w+1, w(h-1)-1) for both max
+// passes; everything unwritten is 0).  Counts numMappablePixels (out >= 5 inside the range).
+// ---------------------------------------------------------------------------------------
+#define MG_TX 32
+#define MG_TY 8
+
+__device__ __forceinline__ float absgrad_lin(const float *__restrict__ I, int k, int W, int H) {
+  if (k < W || k >= W * (H - 1)) return 0.0f;
+  const float dx = 0.5f * (__ldg(I + k + 1) - __ldg(I + k - 1));
+  const float dy = 0.5f * (__ldg(I + k + W) - __ldg(I + k - W));
+  return sqrtf(dx * dx + dy * dy);
+}
+
+__global__ void __launch_bounds__(MG_TX *MG_TY) k_maxgrad0(uint8_t *const *__restrict__ slabs, FrameLayout lay, int W, int H) {
+  __shared__ float sm[MG_TY + 2][MG_TX + 2];
+  __shared__ float st[MG_TY][MG_TX + 2];
+  const int f = blockIdx.z;
+  uint8_t *slab = slabs[f];
+  const float *I = reinterpret_cast<const float *>(slab + lay.img[0]);
+  float *out = reinterpret_cast<float *>(slab + lay.maxgrad);
+  const int x0 = blockIdx.x * MG_TX, y0 = blockIdx.y * MG_TY;
+  const int t = threadIdx.y * MG_TX + threadIdx.x;
+  const int lo = W + 1, hi = W * (H - 1) - 1;  // [lo, hi)
+  for (int c = t; c < (MG_TY + 2) * (MG_TX + 2); c += MG_TX * MG_TY) {
+    const int cy = c / (MG_TX + 2), cx = c % (MG_TX + 2);
+    const int k = (y0 + cy - 1) * W + (x0 + cx - 1);  // linear semantics: cx-1 == -1 wraps to the previous row
+    sm[cy][cx] = absgrad_lin(I, k, W, H);
+  }
+  __syncthreads();
+  for (int c = t; c < MG_TY * (MG_TX + 2); c += MG_TX * MG_TY) {
+    const int cy = c / (MG_TX + 2), cx = c % (MG_TX + 2);
+    const int k = (y0 + cy) * W + (x0 + cx - 1);
+    float v = 0.0f;
+    if (k >= lo && k < hi) {
+      float g1 = sm[cy][cx];
+      const float g2 = sm[cy + 1][cx];
+      if (g1 < g2) g1 = g2;
+      const float g3 = sm[cy + 2][cx];
+      v = (g1 < g3) ? g3 : g1;
+    }
+    st[cy][cx] = v;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  int mappable = 0;
+  if (x < W && y < H) {
+    const int i = y * W + x;
+    float r;
+    if (i >= lo && i < hi) {
+      float g1 = st[threadIdx.y][threadIdx.x];
+      const float g2 = st[threadIdx.y][threadIdx.x + 1];
+      if (g1 < g2) g1 = g2;
+      const float g3 = st[threadIdx.y][threadIdx.x + 2];
+      r = (g1 < g3) ? g3 : g1;
+      mappable = r >= LSD_MIN_USE_GRAD;
+    } else {
+      r = sm[threadIdx.y + 1][threadIdx.x + 1];  // i == w or i == w(h-1)-1 keep |g|; border rows are 0
+    }
+    out[i] = r;
+  }
+  const int cnt = __syncthreads_count(mappable);
+  if (t == 0 && cnt) atomicAdd(reinterpret_cast<int *>(slab + lay.total - 16), cnt);
+}
+
+__global__ void k_zero_counters(uint8_t *const *__restrict__ slabs, FrameLayout lay, int n) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < n) *reinterpret_cast<int *>(slabs[f] + lay.total - 16) = 0;
+}
+
+void launch_maxgrad0(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st) {
+  k_zero_counters<<<(n + 127) / 128, 128, 0, st>>>(d_slabs, ctx->lay, n);
+  dim3 grid((ctx->w + MG_TX - 1) / MG_TX, (ctx->h + MG_TY - 1) / MG_TY, n);
+  k_maxgrad0<<<grid, dim3(MG_TX, MG_TY), 0, st>>>(d_slabs, ctx->lay, ctx->w, ctx->h);
+  ctx->launches += 2;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_idepth_pyramid: Frame::buildIDepthAndIDepthVar for levels 1..4 in one pass (64x16 tile).
+// Children order (2x,2y),(2x+1,2y),(2x,2y+1),(2x+1,2y+1); only var > 0 children fuse.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void fuse4(const float id[4], const float var[4], float &oid, float &ovar) {
+  float idepthSumsSum = 0, ivarSumsSum = 0;
+  int num = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (var[k] > 0) {
+      const float ivar = 1.0f / var[k];
+      ivarSumsSum += ivar;
+      idepthSumsSum += ivar * id[k];
+      num++;
+    }
+  }
+  if (num > 0) {
+    const float depth = ivarSumsSum / idepthSumsSum;
+    oid = 1.0f / depth;
+    ovar = num / ivarSumsSum;
+  } else {
+    oid = -1;
+    ovar = -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restrict__ slabs, FrameLayout lay, int W, int H) {
+  __shared__ float a1[TILE_H / 2][TILE_W / 2], b1[TILE_H / 2][TILE_W / 2];
+  __shared__ float a2[TILE_H / 4][TILE_W / 4], b2[TILE_H / 4][TILE_W / 4];
+  __shared__ float a3[TILE_H / 8][TILE_W / 8], b3[TILE_H / 8][TILE_W / 8];
+  const int f = blockIdx.z;
+  uint8_t *slab = slabs[f];
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+  const int t = threadIdx.x;
+  {
+    const int tx = t & 31, ty = t >> 5;
+    const int x = (x0 >> 1) + tx, y = (y0 >> 1) + ty;
+    float oid = -1, ovar = -1;
+    if (x < (W >> 1) && y < (H >> 1)) {
+      const float *ID = reinterpret_cast<const float *>(slab + lay.idepth[0]);
+      const float *VR = reinterpret_cast<const float *>(slab + lay.idvar[0]);
+      const size_t base = (size_t)(2 * y) * W + 2 * x;
+      const float2 i0 = *reinterpret_cast<const float2 *>(ID + base), i1 = *reinterpret_cast<const float2 *>(ID + base + W);
+      const float2 v0 = *reinterpret_cast<const float2 *>(VR + base), v1 = *reinterpret_cast<const float2 *>(VR + base + W);
+      const float id[4] = {i0.x, i0.y, i1.x, i1.y}, var[4] = {v0.x, v0.y, v1.x, v1.y};
+      fuse4(id, var, oid, ovar);
+      reinterpret_cast<float *>(slab + lay.idepth[1])[(size_t)y * (W >> 1) + x] = oid;
+      reinterpret_cast<float *>(slab + lay.idvar[1])[(size_t)y * (W >> 1) + x] = ovar;
+    }
+    a1[ty][tx] = oid;
+    b1[ty][tx] = ovar;
+  }
+  __syncthreads();
+  if (t < 64) {
+    const int tx = t & 15, ty = t >> 4;
+    const float id[4] = {a1[2 * ty][2 * tx], a1[2 * ty][2 * tx + 1], a1[2 * ty + 1][2 * tx], a1[2 * ty + 1][2 * tx + 1]};
+    const float var[4] = {b1[2 * ty][2 * tx], b1[2 * ty][2 * tx + 1], b1[2 * ty + 1][2 * tx], b1[2 * ty + 1][2 * tx + 1]};
+    float oid, ovar;
+    fuse4(id, var, oid, ovar);
+    a2[ty][tx] = oid;
+    b2[ty][tx] = ovar;
+    const int x = (x0 >> 2) + tx, y = (y0 >> 2) + ty;
+    if (x < (W >> 2) && y < (H >> 2)) {
+      reinterpret_cast<float *>(slab + lay.idepth[2])[(size_t)y * (W >> 2) + x] = oid;
+      reinterpret_cast<float *>(slab + lay.idvar[2])[(size_t)y * (W >> 2) + x] = ovar;
+    }
+  }
+  __syncthreads();
+  if (t < 16) {
+    const int tx = t & 7, ty = t >> 3;
+    const float id[4] = {a2[2 * ty][2 * tx], a2[2 * ty][2 * tx + 1], a2[2 * ty + 1][2 * tx], a2[2 * ty + 1][2 * tx + 1]};
+    const float var[4] = {b2[2 * ty][2 * tx], b2[2 * ty][2 * tx + 1], b2[2 * ty + 1][2 * tx], b2[2 * ty + 1][2 * tx + 1]};
+    float oid, ovar;
+    fuse4(id, var, oid, ovar);
+    a3[ty][tx] = oid;
+    b3[ty][tx] = ovar;
+    const int x = (x0 >> 3) + tx, y = (y0 >> 3) + ty;
+    if (x < (W >> 3) && y < (H >> 3)) {
+      reinterpret_cast<float *>(slab + lay.idepth[3])[(size_t)y * (W >> 3) + x] = oid;
+      reinterpret_cast<float *>(slab + lay.idvar[3])[(size_t)y * (W >> 3) + x] = ovar;
+    }
+  }
+  __syncthreads();
+  if (t < 4) {
+    const int tx = t;
+    const float id[4] = {a3[0][2 * tx], a3[0][2 * tx + 1], a3[1][2 * tx], a3[1][2 * tx + 1]};
+    const float var[4] = {b3[0][2 * tx], b3[0][2 * tx + 1], b3[1][2 * tx], b3[1][2 * tx + 1]};
+    float oid, ovar;
+    fuse4(id, var, oid, ovar);
+    const int x = (x0 >> 4) + tx, y = (y0 >> 4);
+    if (x < (W >> 4) && y < (H >> 4)) {
+      reinterpret_cast<float *>(slab + lay.idepth[4])[(size_t)y * (W >> 4) + x] = oid;
+      reinterpret_cast<float *>(slab + lay.idvar[4])[(size_t)y * (W >> 4) + x] = ovar;
+    }
+  }
+}
+
+void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st) {
+  dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
+  k_idepth_pyramid<<<grid, 256, 0, st>>>(d_slabs, ctx->lay, ctx->w, ctx->h);
+  ctx->launches++;
+}
+
+// Frame::setDepthFromGroundTruth
+__global__ void k_set_depth_gt(uint8_t *slab, FrameLayout lay, const float *__restrict__ depth, float var, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float d = depth[i];
+  float id = -1, v = -1;
+  if (d > 0) {
+    id = 1.0f / d;
+    v = var;
+  }
+  reinterpret_cast<float *>(slab + lay.idepth[0])[i] = id;
+  reinterpret_cast<float *>(slab + lay.idvar[0])[i] = v;
+}
+
+void launch_set_depth_gt(lsd_ctx *ctx, uint8_t *slab, const float *d_depth, float cov, cudaStream_t st) {
+  const int N = ctx->w * ctx->h;
+  k_set_depth_gt<<<(N + 255) / 256, 256, 0, st>>>(slab, ctx->lay, d_depth, LSD_VAR_GT_INIT_INITIAL * cov, N);
+  ctx->launches++;
+}
+
+// Frame::refPixelWasGood(): created as 0xFF
+__global__ void k_mask_init(uint8_t *const *__restrict__ slabs, FrameLayout lay, int words) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < words) reinterpret_cast<uint32_t *>(slabs[blockIdx.y] + lay.mask)[i] = 0xFFFFFFFFu;
+}
+
+void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st) {
+  const int words = (ctx->K.w[1] * ctx->K.h[1] + 3) / 4;
+  dim3 grid((words + 255) / 256, n);
+  k_mask_init<<<grid, 256, 0, st>>>(d_slabs, ctx->lay, words);
+  ctx->launches++;
+}
+
+// meanIdepth / numPoints of a level-0 idepth plane (Frame::setDepth bookkeeping): single CTA,
+// fixed-order tree => deterministic.
+__global__ void __launch_bounds__(1024) k_idepth_stats(const uint8_t *slab, FrameLayout lay, int N, float *out2) {
+  __shared__ float ssum[32];
+  __shared__ int scnt[32];
+  const float *ID = reinterpret_cast<const float *>(slab + lay.idepth[0]);
+  const float *VR = reinterpret_cast<const float *>(slab + lay.idvar[0]);
+  float s = 0;
+  int c = 0;
+  for (int i = threadIdx.x; i < N; i += 1024) {
+    if (VR[i] > 0) {
+      s += ID[i];
+      c++;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    c += __shfl_down_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ssum[threadIdx.x >> 5] = s;
+    scnt[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float S = 0;
+    int Cn = 0;
+    for (int k = 0; k < 32; k++) {
+      S += ssum[k];
+      Cn += scnt[k];
+    }
+    out2[0] = S / (float)Cn;
+    out2[1] = __int_as_float(Cn);
+  }
+}
+
+void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st) {
+  k_idepth_stats<<<1, 1024, 0, st>>>(slab, ctx->lay, ctx->w * ctx->h, d_out2);
+  ctx->launches++;
+}
+
+}  // namespace lsd

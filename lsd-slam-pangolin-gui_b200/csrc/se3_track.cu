@@ -1,0 +1,776 @@
+// se3_track.cu -- [UP] SE3Tracker::trackFrame as ONE persistent cooperative kernel over a batch
+// of independent (TrackingReference, Frame) pairs (BASELINE.json config 2).
+//
+// Reference structure (lsd-slam core Tracking/SE3Tracker.cpp, un-vendored): per LM evaluation three
+// CPU passes -- calcResidualAndBuffers (8 SoA buffers out), calcWeightsAndResidual, and (per outer
+// iteration) calculateWarpUpdate -- with a 6x6 LDLT + SE3 exp on the host in between.
+//
+// B200 structure: the three passes are fused into one per-point evaluation that never
+// materialises the buffers; every evaluation also reduces the 21+6 normal-equation terms (they are
+// only CONSUMED if the step is accepted, exactly when upstream would call calculateWarpUpdate on the
+// same buffers).  Work items are (pair, 1024-point chunk); a grid-resident kernel pulls items from a
+// device work list; the CTA that completes a pair's last chunk sums the per-chunk partials in chunk
+// order (deterministic), runs the LM accept/reject logic, the 6x6 LDL^T solve and SE3 exp on device
+// and appends the pair's next evaluation to the next round's list.  Rounds are separated by one
+// grid.sync(); the host is not involved until every pair has finished.
+//
+// Compiled with -fmad=false: per-point values are bit-identical to the oracle's
+// (-ffp-contract=off); only the summation order differs.
+#include <cooperative_groups.h>
+
+#include <cstring>
+
+#include "ctx.cuh"
+#include "lie_dev.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lsd {
+
+#define SE3_CH 1024       // points per work item
+#define SE3_THREADS 256   // threads per CTA
+#define SE3_NRED 40       // floats per partial record (38 used)
+
+// indices inside a partial record
+enum { R_A = 0, R_B = 21, R_SUMRES = 27, R_SUMUNW = 28, R_SUMSGN = 29, R_SXX = 30, R_SYY = 31, R_SX = 32, R_SY = 33, R_SW = 34,
+       R_USAGE = 35, R_GOOD = 36, R_BAD = 37 };
+
+// Immutable while the persistent kernel runs (host + k_se3_init write it): read with plain loads.
+struct SE3Pair {
+  const RefPoint *pts[NL];
+  const float4 *fgrad[NL];
+  const int *d_num;  // ref numData[NL] on device
+  uint8_t *mask;
+  float q0[4], t0[3];  // initial referenceToFrame (float)
+  int n[NL];
+};
+
+// Mutable LM state: other SMs update it between rounds, so inside the persistent kernel it is only
+// read through L2 (__ldcg) -- never through a possibly stale L1 line.
+struct __align__(16) SE3State {
+  float R[9], t[3];  // pose of the evaluation in flight
+  float q_try[4];
+  float q_cur[4], t_cur[3];
+  float aff_a, aff_b;
+  int level, phase, iteration, incTry;
+  float lambda, lastErr, last_residual;
+  float A[21], b[6], inc[6];
+  int nChunks;
+  unsigned done;
+  int finished, diverged, trackingWasGood;
+  // stats of the last evaluation
+  float pointUsage, good, bad, meanRes, aff_a_lastIt, aff_b_lastIt;
+  int bufSize;
+  int nResCalls[NL], nWarpCalls[NL];
+  int traceLen;
+  float outq[4], outt[3];  // frameToRef (float)
+  float initialTrackedResidual;
+  int n[NL];  // copy of numData for the host
+  int pad_[3];
+};
+static_assert(sizeof(SE3State) % 16 == 0, "SE3State must be int4-copyable");
+
+__device__ __forceinline__ void state_load(SE3State *dst, const SE3State *src) {
+  const int4 *s4 = reinterpret_cast<const int4 *>(src);
+  int4 *d4 = reinterpret_cast<int4 *>(dst);
+#pragma unroll 4
+  for (int i = 0; i < (int)(sizeof(SE3State) / 16); i++) d4[i] = __ldcg(s4 + i);
+}
+__device__ __forceinline__ void state_store(SE3State *dst, const SE3State *src) {
+  const int4 *s4 = reinterpret_cast<const int4 *>(src);
+  int4 *d4 = reinterpret_cast<int4 *>(dst);
+#pragma unroll 4
+  for (int i = 0; i < (int)(sizeof(SE3State) / 16); i++) d4[i] = s4[i];
+}
+
+struct SE3Params {
+  Intrinsics K;
+  lsd_tracker_settings s;
+  int maxChunks;
+  int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
+};
+
+__device__ __forceinline__ float ldcg_f(const float *p) { return __ldcg(p); }
+__device__ __forceinline__ int ldcg_i(const int *p) { return __ldcg(p); }
+
+// Append the chunks of the pair's next evaluation to list `nxt`.
+__device__ void push_items(const SE3Pair *P, SE3State *S, int pairIdx, int level, int *list, int *count) {
+  const int n = P->n[level];
+  const int nch = (n + SE3_CH - 1) / SE3_CH;
+  S->nChunks = nch;
+  S->done = 0;
+  const int base = atomicAdd(count, nch);
+  for (int c = 0; c < nch; c++) list[base + c] = (pairIdx << 12) | c;
+}
+
+__device__ void set_eval_pose(SE3State *S, const float q[4], const float t[3]) {
+  QuatT<float> qq = {q[0], q[1], q[2], q[3]};
+  float R[9];
+  qtoR(qq, R);
+  for (int i = 0; i < 9; i++) S->R[i] = R[i];
+  for (int i = 0; i < 3; i++) S->t[i] = t[i];
+}
+
+__device__ void mark_diverged(SE3State *S) {
+  S->diverged = 1;
+  S->trackingWasGood = 0;
+  S->outq[0] = S->outq[1] = S->outq[2] = 0; S->outq[3] = 1;  // upstream returns SE3()
+  S->outt[0] = S->outt[1] = S->outt[2] = 0;
+  S->finished = 1;
+}
+
+__device__ void finish_pair(SE3State *S, const SE3Params &prm) {
+  // trackingWasGood / outputs exactly as at the end of SE3Tracker::trackFrame
+  const int l1 = prm.minLevel;
+  const float lastGood = S->good, lastBad = S->bad;
+  S->trackingWasGood = !S->diverged && lastGood / (prm.K.w[l1] * prm.K.h[l1]) > LSD_MIN_GOODPERALL_PIXEL &&
+                       lastGood / (lastGood + lastBad) > LSD_MIN_GOODPERGOODBAD_PIXEL;
+  S->initialTrackedResidual = S->last_residual / S->pointUsage;
+  // frameToRef = referenceToFrame.inverse()  (float)
+  QuatT<float> qc = {-S->q_cur[0], -S->q_cur[1], -S->q_cur[2], S->q_cur[3]};
+  float R[9], nt[3] = {-S->t_cur[0], -S->t_cur[1], -S->t_cur[2]}, ot[3];
+  qtoR(qc, R);
+  mat3vec(R, nt, ot);
+  S->outq[0] = qc.x; S->outq[1] = qc.y; S->outq[2] = qc.z; S->outq[3] = qc.w;
+  S->outt[0] = ot[0]; S->outt[1] = ot[1]; S->outt[2] = ot[2];
+  S->finished = 1;
+}
+
+// S is a thread-local copy; the caller stores it back to global memory afterwards.
+__device__ void start_level(const SE3Pair *P, SE3State *S, int pairIdx, int level, int *list, int *count) {
+  S->level = level;
+  S->phase = 0;
+  set_eval_pose(S, S->q_cur, S->t_cur);
+  if (P->n[level] == 0) {  // calcResidualAndBuffers on an empty cloud: buf_warped_size 0 < 1% => diverged
+    mark_diverged(S);
+    return;
+  }
+  push_items(P, S, pairIdx, level, list, count);
+}
+
+// The LM state machine, run by one thread after the last chunk of an evaluation (tot = summed partials).
+__device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float *tot, const SE3Params &prm, int *list,
+                        int *count, lsd_trace_entry *trace) {
+  const int lvl = S->level;
+  const float good = tot[R_GOOD], bad = tot[R_BAD];
+  const int size = (int)(good + bad);
+  S->bufSize = size;
+  S->good = good;
+  S->bad = bad;
+  S->pointUsage = tot[R_USAGE] / (float)P->n[lvl];
+  S->meanRes = tot[R_SUMSGN] / good;
+  const float sxx = tot[R_SXX], syy = tot[R_SYY], sx = tot[R_SX], sy = tot[R_SY], sw = tot[R_SW];
+  const float aL = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+  const float bL = (sy - aL * sx) / sw;
+  S->aff_a_lastIt = aL;
+  S->aff_b_lastIt = bL;
+
+  if (size < LSD_MIN_GOODPERALL_PIXEL_ABSMIN * prm.K.w[lvl] * prm.K.h[lvl]) {
+    mark_diverged(S);
+    return;
+  }
+  const float error = tot[R_SUMRES] / (float)size;
+  S->nResCalls[lvl]++;
+
+  bool takeNormalEq = false;  // begin a new outer iteration with this evaluation's A, b
+  if (S->phase == 0) {
+    S->aff_a = aL;
+    S->aff_b = bL;
+    S->lastErr = error;
+    S->lambda = prm.s.lambdaInitial[lvl];
+    S->iteration = 0;
+    if (trace && S->traceLen < LSD_TRACE_CAP) trace[S->traceLen] = {lvl, -1, error, 0.0f, size};
+    S->traceLen++;
+    takeNormalEq = true;
+  } else {
+    if (error < S->lastErr) {
+      if (trace && S->traceLen < LSD_TRACE_CAP) trace[S->traceLen] = {lvl, 1, error, S->lambda, size};
+      S->traceLen++;
+      for (int i = 0; i < 4; i++) S->q_cur[i] = S->q_try[i];
+      for (int i = 0; i < 3; i++) S->t_cur[i] = S->t[i];
+      S->aff_a = aL;
+      S->aff_b = bL;
+      if (error / S->lastErr > prm.s.convergenceEps[lvl]) S->iteration = prm.s.maxItsPerLvl[lvl];
+      S->last_residual = S->lastErr = error;
+      if (S->lambda <= 0.2f) S->lambda = 0; else S->lambda *= prm.s.lambdaSuccessFac;
+      S->iteration++;
+      takeNormalEq = true;
+    } else {
+      if (trace && S->traceLen < LSD_TRACE_CAP) trace[S->traceLen] = {lvl, 0, error, S->lambda, size};
+      S->traceLen++;
+      float inc2 = 0;
+      for (int i = 0; i < 6; i++) inc2 += S->inc[i] * S->inc[i];
+      if (!(inc2 > prm.s.stepSizeMin[lvl])) {
+        S->iteration = prm.s.maxItsPerLvl[lvl] + 1;  // level ends
+      } else {
+        if (S->lambda == 0) S->lambda = 0.2f; else S->lambda *= powf(prm.s.lambdaFailFac, (float)S->incTry);
+      }
+    }
+  }
+
+  if (S->iteration >= prm.s.maxItsPerLvl[lvl]) {
+    if (lvl - 1 < prm.minLevel) finish_pair(S, prm);
+    else start_level(P, S, pairIdx, lvl - 1, list, count);
+    return;
+  }
+  if (takeNormalEq) {  // NormalEquationsLeastSquares::finish(): divide by num_constraints
+    const float nf = (float)size;
+    for (int k = 0; k < 21; k++) S->A[k] = tot[R_A + k] / nf;
+    for (int k = 0; k < 6; k++) S->b[k] = tot[R_B + k] / nf;
+    S->nWarpCalls[lvl]++;
+    S->incTry = 0;
+  }
+  // solve (A + lambda*diag(A)) inc = b   (b already holds +sum w r J / n, i.e. "-ls.b")
+  float Al[36], rhs[6], inc[6];
+  {
+    int k = 0;
+    for (int a = 0; a < 6; a++)
+      for (int c = a; c < 6; c++) {
+        Al[a * 6 + c] = Al[c * 6 + a] = S->A[k++];
+      }
+    for (int a = 0; a < 6; a++) {
+      Al[a * 6 + a] *= 1 + S->lambda;
+      rhs[a] = S->b[a];
+    }
+  }
+  ldlt_solve<float, 6>(Al, rhs, inc);
+  S->incTry++;
+  for (int i = 0; i < 6; i++) S->inc[i] = inc[i];
+  QuatT<float> qc = {S->q_cur[0], S->q_cur[1], S->q_cur[2], S->q_cur[3]}, qn;
+  float tn[3];
+  se3_exp_compose<float>(inc, qc, S->t_cur, qn, tn);
+  S->q_try[0] = qn.x; S->q_try[1] = qn.y; S->q_try[2] = qn.z; S->q_try[3] = qn.w;
+  set_eval_pose(S, S->q_try, tn);
+  S->phase = 1;
+  push_items(P, S, pairIdx, lvl, list, count);
+}
+
+// Fused calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate for one point.
+struct EvalConst {
+  float R[9], t[3];
+  float a, b;
+  float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
+  float var_weight, huber_half;
+  int W, H;
+};
+
+__device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c, const float4 *__restrict__ G,
+                                           uint8_t *__restrict__ mask, float acc[38]) {
+  const int x = p.xy & 0xffff, y = p.xy >> 16;
+  const float inv = 1.0f / p.idepth;
+  const float px = inv * (c.fxi * x + c.cxi);
+  const float py = inv * (c.fyi * y + c.cyi);
+  const float pz = inv * 1.0f;
+  const float Wx = (c.R[0] * px + c.R[1] * py + c.R[2] * pz) + c.t[0];
+  const float Wy = (c.R[3] * px + c.R[4] * py + c.R[5] * pz) + c.t[1];
+  const float Wz = (c.R[6] * px + c.R[7] * py + c.R[8] * pz) + c.t[2];
+  const float u_new = (Wx / Wz) * c.fx + c.cx;
+  const float v_new = (Wy / Wz) * c.fy + c.cy;
+  if (!(u_new > 1 && v_new > 1 && u_new < c.W - 2 && v_new < c.H - 2)) {
+    if (mask) mask[x + y * c.W] = 0;
+    return;
+  }
+  // getInterpolatedElement43
+  const int ix = (int)u_new, iy = (int)v_new;
+  const float dx = u_new - ix, dy = v_new - iy, dxdy = dx * dy;
+  const float4 *bp = G + ix + iy * c.W;
+  const float4 p00 = __ldg(bp), p10 = __ldg(bp + 1), p01 = __ldg(bp + c.W), p11 = __ldg(bp + 1 + c.W);
+  const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+  const float gxI = w11 * p11.x + w01 * p01.x + w10 * p10.x + w00 * p00.x;
+  const float gyI = w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y;
+  const float cI = w11 * p11.z + w01 * p01.z + w10 * p10.z + w00 * p00.z;
+
+  const float c1 = c.a * p.color + c.b;
+  const float c2 = cI;
+  const float residual = c1 - c2;
+  const float weight = fabsf(residual) < 5.0f ? 1 : 5.0f / fabsf(residual);
+  acc[R_SXX] += c1 * c1 * weight;
+  acc[R_SYY] += c2 * c2 * weight;
+  acc[R_SX] += c1 * weight;
+  acc[R_SY] += c2 * weight;
+  acc[R_SW] += weight;
+  const bool isGood = residual * residual / (LSD_MAX_DIFF_CONSTANT + LSD_MAX_DIFF_GRAD_MULT * (gxI * gxI + gyI * gyI)) < 1;
+  if (mask) mask[x + y * c.W] = isGood;
+  if (isGood) {
+    acc[R_SUMUNW] += residual * residual;
+    acc[R_SUMSGN] += residual;
+    acc[R_GOOD] += 1.0f;
+  } else {
+    acc[R_BAD] += 1.0f;
+  }
+  const float depthChange = pz / Wz;
+  acc[R_USAGE] += depthChange < 1 ? depthChange : 1;
+
+  // calcWeightsAndResidual
+  const float gx = c.fx * gxI, gy = c.fy * gyI;
+  const float d = 1.0f / pz;
+  const float s = c.var_weight * p.var;
+  const float g0 = (c.t[0] * Wz - c.t[2] * Wx) / (Wz * Wz * d);
+  const float g1 = (c.t[1] * Wz - c.t[2] * Wy) / (Wz * Wz * d);
+  const float drpdd = gx * g0 + gy * g1;
+  const float w_p = 1.0f / (LSD_CAMERA_PIXEL_NOISE2 + s * drpdd * drpdd);
+  const float weighted_rp = fabsf(residual * sqrtf(w_p));
+  const float wh = fabsf(weighted_rp < c.huber_half ? 1 : c.huber_half / weighted_rp);
+  acc[R_SUMRES] += wh * w_p * residual * residual;
+  const float wgt = wh * w_p;
+
+  // calculateWarpUpdate (the two rows with upstream's `1.0 +` double literals are evaluated in fp64)
+  const float z = 1.0f / Wz;
+  const float z_sqr = 1.0f / (Wz * Wz);
+  float v[6];
+  v[0] = z * gx + 0;
+  v[1] = 0 + z * gy;
+  v[2] = (-Wx * z_sqr) * gx + (-Wy * z_sqr) * gy;
+  v[3] = (float)((double)((-Wx * Wy * z_sqr) * gx) + (-(1.0 + (double)(Wy * Wy * z_sqr))) * (double)gy);
+  v[4] = (float)((1.0 + (double)(Wx * Wx * z_sqr)) * (double)gx + (double)((Wx * Wy * z_sqr) * gy));
+  v[5] = (-Wy * z) * gx + (Wx * z) * gy;
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    const float wa = v[a] * wgt;
+#pragma unroll
+    for (int cc = a; cc < 6; cc++) acc[R_A + (k++)] += wa * v[cc];
+  }
+  const float rw = residual * wgt;
+#pragma unroll
+  for (int a = 0; a < 6; a++) acc[R_B + a] += v[a] * rw;
+}
+
+__device__ __forceinline__ void block_reduce_store(float acc[38], float *__restrict__ dst, float (*sred)[SE3_NRED]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 38; j++) {
+    float v = acc[j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sred[wid][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 38) {
+    float s = sred[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < SE3_THREADS / 32; w++) s += sred[w][threadIdx.x];
+    dst[threadIdx.x] = s;
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_eval_const(const SE3State *P, int level, const SE3Params &prm, EvalConst &c) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) c.R[i] = ldcg_f(&P->R[i]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) c.t[i] = ldcg_f(&P->t[i]);
+  c.a = ldcg_f(&P->aff_a);
+  c.b = ldcg_f(&P->aff_b);
+  c.fx = prm.K.fx[level]; c.fy = prm.K.fy[level]; c.cx = prm.K.cx[level]; c.cy = prm.K.cy[level];
+  c.fxi = prm.K.fxi[level]; c.fyi = prm.K.fyi[level]; c.cxi = prm.K.cxi[level]; c.cyi = prm.K.cyi[level];
+  c.var_weight = prm.s.var_weight;
+  c.huber_half = prm.s.huber_d / 2;
+  c.W = prm.K.w[level];
+  c.H = prm.K.h[level];
+}
+
+__global__ void __launch_bounds__(SE3_THREADS, 2)
+k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials, int *lists, int listCap, int *counts,
+            const __grid_constant__ SE3Params prm, lsd_trace_entry *traces) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ float sred[SE3_THREADS / 32][SE3_NRED];
+  __shared__ float stot[SE3_NRED];
+  __shared__ int sIsLast;
+
+  for (int round = 0;; round++) {
+    const int cur = round % 3, nxt = (round + 1) % 3, clr = (round + 2) % 3;
+    const int cnt = ldcg_i(&counts[cur]);
+    if (cnt == 0) break;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[clr] = 0;
+    const int *list = lists + (size_t)cur * listCap;
+    for (int item = blockIdx.x; item < cnt; item += gridDim.x) {
+      const int code = ldcg_i(&list[item]);
+      const int pairIdx = code >> 12, chunk = code & 0xfff;
+      const SE3Pair *P = pairs + pairIdx;
+      SE3State *S = states + pairIdx;
+      const int level = ldcg_i(&S->level);
+      EvalConst c;
+      load_eval_const(S, level, prm, c);
+      const int n = P->n[level];
+      const RefPoint *__restrict__ pts = P->pts[level];
+      const float4 *__restrict__ G = P->fgrad[level];
+      uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
+
+      float acc[38];
+#pragma unroll
+      for (int j = 0; j < 38; j++) acc[j] = 0.0f;
+      const int base = chunk * SE3_CH + threadIdx.x;
+#pragma unroll
+      for (int k = 0; k < SE3_CH / SE3_THREADS; k++) {
+        const int i = base + k * SE3_THREADS;
+        if (i < n) {
+          const float4 raw = __ldg(reinterpret_cast<const float4 *>(pts) + i);
+          RefPoint p;
+          p.xy = __float_as_uint(raw.x);
+          p.idepth = raw.y;
+          p.color = raw.z;
+          p.var = raw.w;
+          eval_point(p, c, G, mask, acc);
+        }
+      }
+      float *dst = partials + ((size_t)pairIdx * prm.maxChunks + chunk) * SE3_NRED;
+      block_reduce_store(acc, dst, sred);
+      if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(&S->done, 1u);
+        sIsLast = (ticket == (unsigned)(ldcg_i(&S->nChunks) - 1));
+      }
+      __syncthreads();
+      if (sIsLast) {
+        __threadfence();
+        const int nch = ldcg_i(&S->nChunks);
+        if (threadIdx.x < 38) {
+          const float *src = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED + threadIdx.x;
+          float s = 0.0f;
+          for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
+          stot[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          SE3State L;
+          state_load(&L, S);
+          lm_step(P, &L, pairIdx, stot, prm, lists + (size_t)nxt * listCap, &counts[nxt],
+                  traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
+          state_store(S, &L);
+        }
+      }
+      __syncthreads();
+    }
+    grid.sync();
+  }
+}
+
+// Build the initial state of every pair and the first work list (level maxLevel).
+__global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, int *__restrict__ lists,
+                           int *__restrict__ counts, SE3Params prm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SE3Pair *P = pairs + i;
+  SE3State L;
+  memset(&L, 0, sizeof(L));
+  for (int l = 0; l < NL; l++) {
+    P->n[l] = P->d_num[l];
+    L.n[l] = P->n[l];
+  }
+  for (int k = 0; k < 4; k++) L.q_cur[k] = P->q0[k];
+  for (int k = 0; k < 3; k++) L.t_cur[k] = P->t0[k];
+  L.aff_a = 1;
+  L.aff_a_lastIt = 1;
+  L.trackingWasGood = 1;
+  start_level(P, &L, i, prm.maxLevel, lists, &counts[0]);
+  state_store(states + i, &L);
+}
+
+struct SE3ScratchImpl {
+  SE3Pair *d_pairs = nullptr;
+  SE3Pair *h_pairs = nullptr;  // pinned
+  SE3State *d_states = nullptr;
+  SE3State *h_states = nullptr;  // pinned
+  int cap = 0;
+  float *d_partials = nullptr;
+  size_t partialsBytes = 0;
+  int *d_lists = nullptr;
+  int listCap = 0;
+  int *d_counts = nullptr;
+  lsd_trace_entry *d_traces = nullptr;
+  size_t tracesBytes = 0;
+  int gridBlocks = 0;
+};
+
+}  // namespace lsd
+
+struct SE3Scratch : lsd::SE3ScratchImpl {};
+
+namespace lsd {
+
+void se3_scratch_free(lsd_ctx *ctx) {
+  SE3Scratch *s = ctx->se3s;
+  if (!s) return;
+  cudaFree(s->d_pairs);
+  cudaFreeHost(s->h_pairs);
+  cudaFree(s->d_states);
+  cudaFreeHost(s->h_states);
+  cudaFree(s->d_partials);
+  cudaFree(s->d_lists);
+  cudaFree(s->d_counts);
+  cudaFree(s->d_traces);
+  delete s;
+  ctx->se3s = nullptr;
+}
+
+static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
+  if (!ctx->se3s) ctx->se3s = new SE3Scratch();
+  SE3Scratch *s = ctx->se3s;
+  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_CH - 1) / SE3_CH;
+  if (n > s->cap) {
+    cudaFree(s->d_pairs);
+    cudaFreeHost(s->h_pairs);
+    cudaFree(s->d_states);
+    cudaFreeHost(s->h_states);
+    cudaFree(s->d_partials);
+    cudaFree(s->d_lists);
+    int cap = n < 16 ? 16 : n;
+    LSD_CUDA(cudaMalloc(&s->d_pairs, sizeof(SE3Pair) * cap));
+    LSD_CUDA(cudaMallocHost(&s->h_pairs, sizeof(SE3Pair) * cap));
+    LSD_CUDA(cudaMalloc(&s->d_states, sizeof(SE3State) * cap));
+    LSD_CUDA(cudaMallocHost(&s->h_states, sizeof(SE3State) * cap));
+    s->partialsBytes = (size_t)cap * maxChunks * SE3_NRED * sizeof(float);
+    LSD_CUDA(cudaMalloc(&s->d_partials, s->partialsBytes));
+    s->listCap = cap * maxChunks;
+    LSD_CUDA(cudaMalloc(&s->d_lists, sizeof(int) * 3 * (size_t)s->listCap));
+    s->cap = cap;
+    if (s->d_traces) {
+      cudaFree(s->d_traces);
+      s->d_traces = nullptr;
+      s->tracesBytes = 0;
+    }
+  }
+  if (!s->d_counts) LSD_CUDA(cudaMalloc(&s->d_counts, sizeof(int) * 4));
+  if (wantTrace && s->tracesBytes < sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)s->cap) {
+    cudaFree(s->d_traces);
+    s->tracesBytes = sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)s->cap;
+    LSD_CUDA(cudaMalloc(&s->d_traces, s->tracesBytes));
+  }
+  if (!s->gridBlocks) {
+    int perSM = 0;
+    LSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_se3_track, SE3_THREADS, 0));
+    if (perSM < 1) {
+      set_error("k_se3_track cannot be resident");
+      return LSD_ERR_CUDA;
+    }
+    s->gridBlocks = perSM * ctx->numSMs;
+  }
+  return LSD_OK;
+}
+
+static SE3Params make_params(lsd_ctx *ctx) {
+  SE3Params prm;
+  prm.K = ctx->K;
+  prm.s = ctx->se3;
+  prm.maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_CH - 1) / SE3_CH;
+  prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
+  prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
+  return prm;
+}
+
+// double frameToRef (Sophus data order) -> float referenceToFrame (q, t): inverse in fp64, then cast
+static void invert_pose_to_float(const double p[7], float q[4], float t[3]) {
+  QuatT<double> qc = {-p[0], -p[1], -p[2], p[3]};
+  double R[9], nt[3] = {-p[4], -p[5], -p[6]}, ot[3];
+  qtoR(qc, R);
+  mat3vec(R, nt, ot);
+  q[0] = (float)qc.x; q[1] = (float)qc.y; q[2] = (float)qc.z; q[3] = (float)qc.w;
+  t[0] = (float)ot[0]; t[1] = (float)ot[1]; t[2] = (float)ot[2];
+}
+
+static double alg_bytes_level(const lsd_ctx *ctx, int l, int n) {
+  // 20 n + 16 min(4n, N_l) + (idx 4n + isGood n at level 1) + 108
+  const double N = (double)ctx->K.w[l] * ctx->K.h[l];
+  double taps = 4.0 * n < N ? 4.0 * n : N;
+  return 20.0 * n + 16.0 * taps + (l == LSD_SE3TRACKING_MIN_LEVEL ? 5.0 * n : 0.0) + 108.0;
+}
+
+int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
+                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st, bool sync) {
+  if (n == 0) return LSD_OK;
+  int rc = se3_scratch_ensure(ctx, n, traces != nullptr);
+  if (rc) return rc;
+  SE3Scratch *s = ctx->se3s;
+  const FrameLayout &lay = ctx->lay;
+  for (int i = 0; i < n; i++) {
+    LSD_ARG(refs[i] && frames[i]);
+    LSD_ARG(frames[i]->built & FB_TRACKING);
+    SE3Pair &P = s->h_pairs[i];
+    std::memset(&P, 0, sizeof(P));
+    for (int l = 0; l < NL; l++) {
+      P.pts[l] = reinterpret_cast<const RefPoint *>(refs[i]->slab + refs[i]->offPts[l]);
+      P.fgrad[l] = reinterpret_cast<const float4 *>(frames[i]->slab + lay.grad[l]);
+    }
+    P.d_num = refs[i]->d_num;
+    P.mask = frames[i]->slab + lay.mask;
+    invert_pose_to_float(init + 7 * i, P.q0, P.t0);
+  }
+  // masks are created 0xFF on first use (Frame::refPixelWasGood())
+  {
+    std::vector<uint8_t *> need;
+    for (int i = 0; i < n; i++)
+      if (!(frames[i]->built & FB_MASK)) {
+        need.push_back(frames[i]->slab);
+        frames[i]->built |= FB_MASK;
+      }
+    if (!need.empty()) {
+      rc = ensure_table(ctx, need.size() * sizeof(void *));
+      if (rc) return rc;
+      std::memcpy(ctx->h_table, need.data(), need.size() * sizeof(void *));
+      LSD_CUDA(cudaMemcpyAsync(ctx->d_table, ctx->h_table, need.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
+      launch_mask_init(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), (int)need.size(), st);
+      LSD_CUDA(cudaStreamSynchronize(st));  // h_table is reused by callers
+    }
+  }
+  LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
+  LSD_CUDA(cudaMemsetAsync(s->d_counts, 0, sizeof(int) * 4, st));
+  SE3Params prm = make_params(ctx);
+  LSD_CUDA(cudaEventRecord(ctx->evA, st));
+  k_se3_init<<<(n + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, n, s->d_lists, s->d_counts, prm);
+  lsd_trace_entry *d_tr = traces ? s->d_traces : nullptr;
+  int listCap = s->listCap;
+  void *args[] = {&s->d_pairs, &s->d_states, &s->d_partials, &s->d_lists, &listCap, &s->d_counts, &prm, &d_tr};
+  LSD_CUDA(cudaLaunchCooperativeKernel((void *)k_se3_track, dim3(s->gridBlocks), dim3(SE3_THREADS), args, 0, st));
+  ctx->launches += 2;
+  LSD_CUDA(cudaEventRecord(ctx->evB, st));
+  LSD_CUDA(cudaMemcpyAsync(s->h_states, s->d_states, sizeof(SE3State) * n, cudaMemcpyDeviceToHost, st));
+  if (traces)
+    LSD_CUDA(cudaMemcpyAsync(traces, s->d_traces, sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)n, cudaMemcpyDeviceToHost, st));
+  (void)sync;
+  LSD_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
+  ctx->lastKernelMs = ms;
+  double bytes = 0;
+  long long evals = 0;
+  for (int i = 0; i < n; i++) {
+    const SE3State &P = s->h_states[i];
+    lsd_se3_result &r = results[i];
+    r.frameToRef[0] = P.outq[0]; r.frameToRef[1] = P.outq[1]; r.frameToRef[2] = P.outq[2]; r.frameToRef[3] = P.outq[3];
+    r.frameToRef[4] = P.outt[0]; r.frameToRef[5] = P.outt[1]; r.frameToRef[6] = P.outt[2];
+    r.lastResidual = P.last_residual;
+    r.lastMeanRes = P.meanRes;
+    r.pointUsage = P.pointUsage;
+    r.lastGoodCount = P.good;
+    r.lastBadCount = P.bad;
+    r.affine_a = P.aff_a;
+    r.affine_b = P.aff_b;
+    r.initialTrackedResidual = P.initialTrackedResidual;
+    r.diverged = P.diverged;
+    r.trackingWasGood = P.trackingWasGood;
+    for (int l = 0; l < NL; l++) {
+      r.numResidualCalls[l] = P.nResCalls[l];
+      r.numWarpUpdateCalls[l] = P.nWarpCalls[l];
+      bytes += P.nResCalls[l] * alg_bytes_level(ctx, l, P.n[l]);
+      evals += P.nResCalls[l];
+      refs[i]->num[l] = P.n[l];
+    }
+    refs[i]->numValid = true;
+    r.traceLen = P.traceLen;
+    // Frame bookkeeping done by SE3Tracker::trackFrame
+    lsd_frame *f = frames[i];
+    if (!P.diverged) {
+      f->initialTrackedResidual = P.initialTrackedResidual;
+      for (int k = 0; k < 7; k++) f->thisToParent_raw[k] = r.frameToRef[k];
+      f->thisToParent_raw[7] = 1.0;
+      f->trackingParentId = refs[i]->frameID;
+    }
+    if (P.trackingWasGood) refs[i]->keyframe->numFramesTrackedOnThis++;
+  }
+  ctx->lastAlgBytes = bytes;
+  ctx->lastEvals = evals;
+  return LSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Single fused evaluation at a fixed pose (parity probe for B3+B4+B5).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SE3_THREADS)
+k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, float *__restrict__ partials, int level,
+                const __grid_constant__ SE3Params prm) {
+  __shared__ float sred[SE3_THREADS / 32][SE3_NRED];
+  EvalConst c;
+  load_eval_const(S, level, prm, c);
+  const int n = P->d_num[level];
+  const RefPoint *pts = P->pts[level];
+  const float4 *G = P->fgrad[level];
+  uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
+  float acc[38];
+#pragma unroll
+  for (int j = 0; j < 38; j++) acc[j] = 0.0f;
+  const int base = blockIdx.x * SE3_CH + threadIdx.x;
+  for (int k = 0; k < SE3_CH / SE3_THREADS; k++) {
+    const int i = base + k * SE3_THREADS;
+    if (i < n) {
+      const float4 raw = __ldg(reinterpret_cast<const float4 *>(pts) + i);
+      RefPoint p;
+      p.xy = __float_as_uint(raw.x); p.idepth = raw.y; p.color = raw.z; p.var = raw.w;
+      eval_point(p, c, G, mask, acc);
+    }
+  }
+  block_reduce_store(acc, partials + (size_t)blockIdx.x * SE3_NRED, sred);
+}
+
+int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
+                  float *A36, float *b6, float *scalars) {
+  LSD_ARG(level >= 1 && level < NL);
+  int rc = se3_scratch_ensure(ctx, 1, false);
+  if (rc) return rc;
+  SE3Scratch *s = ctx->se3s;
+  cudaStream_t st = ctx->stream;
+  const FrameLayout &lay = ctx->lay;
+  if (!(frame->built & FB_MASK)) {
+    rc = ensure_table(ctx, sizeof(void *));
+    if (rc) return rc;
+    *reinterpret_cast<uint8_t **>(ctx->h_table) = frame->slab;
+    LSD_CUDA(cudaMemcpyAsync(ctx->d_table, ctx->h_table, sizeof(void *), cudaMemcpyHostToDevice, st));
+    launch_mask_init(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), 1, st);
+    LSD_CUDA(cudaStreamSynchronize(st));
+    frame->built |= FB_MASK;
+  }
+  SE3Pair &P = s->h_pairs[0];
+  std::memset(&P, 0, sizeof(P));
+  for (int l = 0; l < NL; l++) {
+    P.pts[l] = reinterpret_cast<const RefPoint *>(ref->slab + ref->offPts[l]);
+    P.fgrad[l] = reinterpret_cast<const float4 *>(frame->slab + lay.grad[l]);
+  }
+  P.d_num = ref->d_num;
+  P.mask = frame->slab + lay.mask;
+  SE3State &S = s->h_states[0];
+  std::memset(&S, 0, sizeof(S));
+  QuatT<float> q = {(float)refToFrame[0], (float)refToFrame[1], (float)refToFrame[2], (float)refToFrame[3]};
+  qtoR(q, S.R);
+  for (int k = 0; k < 3; k++) S.t[k] = (float)refToFrame[4 + k];
+  S.aff_a = a;
+  S.aff_b = b;
+  LSD_CUDA(cudaMemcpyAsync(s->d_pairs, &P, sizeof(SE3Pair), cudaMemcpyHostToDevice, st));
+  LSD_CUDA(cudaMemcpyAsync(s->d_states, &S, sizeof(SE3State), cudaMemcpyHostToDevice, st));
+  SE3Params prm = make_params(ctx);
+  const int nblk = prm.maxChunks;
+  k_se3_eval_once<<<nblk, SE3_THREADS, 0, st>>>(s->d_pairs, s->d_states, s->d_partials, level, prm);
+  ctx->launches++;
+  std::vector<float> h((size_t)nblk * SE3_NRED);
+  int hnum[NL];
+  LSD_CUDA(cudaMemcpyAsync(h.data(), s->d_partials, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaMemcpyAsync(hnum, ref->d_num, sizeof(hnum), cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaStreamSynchronize(st));
+  float tot[SE3_NRED] = {0};
+  const int nch = (hnum[level] + SE3_CH - 1) / SE3_CH;
+  for (int cidx = 0; cidx < nch; cidx++)
+    for (int j = 0; j < 38; j++) tot[j] += h[(size_t)cidx * SE3_NRED + j];
+  const float size = tot[R_GOOD] + tot[R_BAD];
+  int k = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) {
+      A36[i * 6 + j] = A36[j * 6 + i] = tot[R_A + k] / size;
+      k++;
+    }
+  for (int i = 0; i < 6; i++) b6[i] = -tot[R_B + i] / size;
+  const float sxx = tot[R_SXX], syy = tot[R_SYY], sx = tot[R_SX], sy = tot[R_SY], sw = tot[R_SW];
+  const float aL = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+  scalars[0] = tot[R_SUMRES] / size;
+  scalars[1] = tot[R_SUMUNW] / tot[R_GOOD];
+  scalars[2] = size;
+  scalars[3] = tot[R_GOOD];
+  scalars[4] = tot[R_BAD];
+  scalars[5] = tot[R_USAGE] / (float)hnum[level];
+  scalars[6] = tot[R_SUMSGN] / tot[R_GOOD];
+  scalars[7] = aL;
+  scalars[8] = (sy - aL * sx) / sw;
+  scalars[9] = tot[R_SUMRES] / size;
+  scalars[10] = scalars[11] = 0;
+  return LSD_OK;
+}
+
+}  // namespace lsd

@@ -1,0 +1,320 @@
+"""ctypes binding of liblsd_b200.so (include/lsd_b200.h).
+
+Thin host-side mirror of the lsd-slam core classes the reference application links
+(/root/reference/tools/LSD.cpp:102, lib/App/InputThread.cpp:71): Frame, TrackingReference,
+SE3Tracker.  There is NO CPU fallback: if the CUDA library is missing or no sm_100 device is
+present every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "liblsd_b200.so")
+
+NL = 5
+TRACE_CAP = 512
+FIELD_IMAGE, FIELD_GRADIENTS, FIELD_MAXGRAD, FIELD_IDEPTH, FIELD_IDEPTHVAR, FIELD_MASK = range(6)
+BUILD_TRACKING, BUILD_MAXGRAD0, BUILD_GRAD0 = 0, 1, 2
+
+
+class LsdError(RuntimeError):
+    pass
+
+
+class TrackerSettings(C.Structure):
+    _fields_ = [("lambdaSuccessFac", C.c_float), ("lambdaFailFac", C.c_float),
+                ("stepSizeMin", C.c_float * NL), ("convergenceEps", C.c_float * NL),
+                ("maxItsPerLvl", C.c_int * NL), ("lambdaInitial", C.c_float * NL),
+                ("var_weight", C.c_float), ("huber_d", C.c_float)]
+
+
+class SE3Result(C.Structure):
+    _fields_ = [("frameToRef", C.c_double * 7),
+                ("lastResidual", C.c_float), ("lastMeanRes", C.c_float), ("pointUsage", C.c_float),
+                ("lastGoodCount", C.c_float), ("lastBadCount", C.c_float),
+                ("affine_a", C.c_float), ("affine_b", C.c_float), ("initialTrackedResidual", C.c_float),
+                ("diverged", C.c_int), ("trackingWasGood", C.c_int),
+                ("numResidualCalls", C.c_int * NL), ("numWarpUpdateCalls", C.c_int * NL),
+                ("traceLen", C.c_int)]
+
+
+class TraceEntry(C.Structure):
+    _fields_ = [("level", C.c_int), ("accepted", C.c_int), ("error", C.c_float), ("lam", C.c_float), ("bufSize", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/lsd_b200.h declares: name -> (restype, argtypes)
+_vp, _ip, _fp, _dp, _sz, _u = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_uint
+SYMBOLS = {
+    "lsd_last_error": (C.c_char_p, []),
+    "lsd_version": (_ip, []),
+    "lsd_ctx_create": (_ip, [_ip, _ip, _ip, _vp, _vp, _vp]),
+    "lsd_ctx_destroy": (_ip, [_vp]),
+    "lsd_ctx_synchronize": (_ip, [_vp]),
+    "lsd_ctx_stream": (_vp, [_vp]),
+    "lsd_ctx_launch_count": (C.c_longlong, [_vp]),
+    "lsd_default_tracker_settings": (_ip, [_vp]),
+    "lsd_ctx_set_se3_settings": (_ip, [_vp, _vp]),
+    "lsd_frame_create": (_ip, [_vp, _ip, _vp, _sz, _u, _vp]),
+    "lsd_frame_create_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _u, _vp]),
+    "lsd_frame_create_batch_device": (_ip, [_vp, _ip, _vp, _vp, _u, _vp]),
+    "lsd_frame_release": (_ip, [_vp, _vp]),
+    "lsd_frame_release_batch": (_ip, [_vp, _ip, _vp]),
+    "lsd_frame_read": (_ip, [_vp, _vp, _ip, _ip, _vp]),
+    "lsd_frame_num_mappable_pixels": (_ip, [_vp, _vp, _vp]),
+    "lsd_frame_set_depth_from_gt": (_ip, [_vp, _vp, _vp, _fp]),
+    "lsd_frame_set_idepth": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_frame_set_idepth_batch_device": (_ip, [_vp, _ip, _vp, _vp, _vp]),
+    "lsd_frame_mean_idepth": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_ref_create": (_ip, [_vp, _vp, _vp]),
+    "lsd_ref_create_batch": (_ip, [_vp, _ip, _vp, _vp]),
+    "lsd_ref_release": (_ip, [_vp, _vp]),
+    "lsd_ref_num_data": (_ip, [_vp, _vp, _ip, _vp]),
+    "lsd_ref_read": (_ip, [_vp, _vp, _ip, _vp, _vp, _vp, _vp]),
+    "lsd_se3_track": (_ip, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "lsd_se3_track_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _vp, _vp]),
+    "lsd_se3_track_images_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _vp, _vp]),
+    "lsd_se3_eval": (_ip, [_vp, _vp, _vp, _vp, _ip, _fp, _fp, _vp, _vp, _vp]),
+    "lsd_se3_last_stats": (_ip, [_vp, _vp, _vp, _vp]),
+}
+
+
+def load():
+    """dlopen liblsd_b200.so; raises loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LsdError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"(liblsd_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        raise LsdError(f"liblsd_b200 error {rc}: {load().lsd_last_error().decode()}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One device + stream + scratch (SlamSystem's tracking / mapping threads each own one)."""
+
+    def __init__(self, width, height, K, device=0, stream=None):
+        self.L = load()
+        self.w, self.h = width, height
+        self.K = tuple(float(k) for k in K)
+        karr = (C.c_float * 4)(*self.K)
+        p = C.c_void_p()
+        _chk(self.L.lsd_ctx_create(device, width, height, karr, C.c_void_p(stream or 0), C.byref(p)))
+        self.p = p
+
+    def close(self):
+        if self.p:
+            self.L.lsd_ctx_destroy(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _chk(self.L.lsd_ctx_synchronize(self.p))
+
+    def launch_count(self):
+        return int(self.L.lsd_ctx_launch_count(self.p))
+
+    def default_settings(self):
+        s = TrackerSettings()
+        _chk(self.L.lsd_default_tracker_settings(C.byref(s)))
+        return s
+
+    def set_se3_settings(self, s):
+        _chk(self.L.lsd_ctx_set_se3_settings(self.p, C.byref(s)))
+
+    # ---- frames
+    def create_frames(self, images, ids=None, flags=BUILD_TRACKING):
+        """images: list of (h, w) uint8 arrays or one (n, h, w) array (host)."""
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        n = len(imgs)
+        for im in imgs:
+            assert im.shape == (self.h, self.w)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        idarr = None
+        if ids is not None:
+            idarr = (C.c_int * n)(*ids)
+        out = (C.c_void_p * n)()
+        _chk(self.L.lsd_frame_create_batch(self.p, n, idarr, ptrs, self.w, flags, out))
+        return [Frame(self, out[i], ids[i] if ids is not None else i) for i in range(n)]
+
+    def create_frames_device(self, d_ptr, n, ids=None, flags=BUILD_TRACKING):
+        idarr = (C.c_int * n)(*ids) if ids is not None else None
+        out = (C.c_void_p * n)()
+        _chk(self.L.lsd_frame_create_batch_device(self.p, n, idarr, C.c_void_p(d_ptr), flags, out))
+        return [Frame(self, out[i], ids[i] if ids is not None else i) for i in range(n)]
+
+    def create_frame(self, image, fid=0, flags=BUILD_TRACKING):
+        return self.create_frames([image], [fid], flags)[0]
+
+    def create_refs(self, keyframes):
+        n = len(keyframes)
+        kp = (C.c_void_p * n)(*[k.p for k in keyframes])
+        out = (C.c_void_p * n)()
+        _chk(self.L.lsd_ref_create_batch(self.p, n, kp, out))
+        return [Ref(self, out[i], keyframes[i]) for i in range(n)]
+
+    def set_idepth_batch_device(self, frames, d_idepth, d_var):
+        n = len(frames)
+        fp = (C.c_void_p * n)(*[f.p for f in frames])
+        _chk(self.L.lsd_frame_set_idepth_batch_device(self.p, n, fp, C.c_void_p(d_idepth), C.c_void_p(d_var)))
+
+    # ---- SE3 tracking
+    def se3_track_batch(self, refs, frames, inits, want_trace=False):
+        n = len(refs)
+        rp = (C.c_void_p * n)(*[r.p for r in refs])
+        fp = (C.c_void_p * n)(*[f.p for f in frames])
+        init = np.ascontiguousarray(inits, np.float64).reshape(n, 7)
+        res = (SE3Result * n)()
+        tr = (TraceEntry * (TRACE_CAP * n))() if want_trace else None
+        _chk(self.L.lsd_se3_track_batch(self.p, n, rp, fp, _ptr(init), res, tr))
+        if want_trace:
+            traces = []
+            for i in range(n):
+                m = min(res[i].traceLen, TRACE_CAP)
+                traces.append([(tr[i * TRACE_CAP + k].level, tr[i * TRACE_CAP + k].accepted, tr[i * TRACE_CAP + k].error,
+                                tr[i * TRACE_CAP + k].lam, tr[i * TRACE_CAP + k].bufSize) for k in range(m)])
+            return res, traces
+        return res
+
+    def se3_track(self, ref, frame, init7, want_trace=False):
+        out = self.se3_track_batch([ref], [frame], [init7], want_trace)
+        if want_trace:
+            return out[0][0], out[1][0]
+        return out[0]
+
+    def se3_track_images_batch(self, refs, image_ptrs, pitch, inits):
+        """image_ptrs: list of host addresses (pinned memory recommended)."""
+        n = len(refs)
+        rp = (C.c_void_p * n)(*[r.p for r in refs])
+        ip = (C.c_void_p * n)(*image_ptrs)
+        init = np.ascontiguousarray(inits, np.float64).reshape(n, 7)
+        res = (SE3Result * n)()
+        _chk(self.L.lsd_se3_track_images_batch(self.p, n, rp, ip, pitch, _ptr(init), res))
+        return res
+
+    def se3_eval(self, ref, frame, refToFrame7, level, a=1.0, b=0.0):
+        A = np.zeros((6, 6), np.float32)
+        bb = np.zeros(6, np.float32)
+        sc = np.zeros(12, np.float32)
+        p = np.ascontiguousarray(refToFrame7, np.float64)
+        _chk(self.L.lsd_se3_eval(self.p, ref.p, frame.p, _ptr(p), level, a, b, _ptr(A), _ptr(bb), _ptr(sc)))
+        return A, bb, sc
+
+    def se3_last_stats(self):
+        b = C.c_double()
+        e = C.c_longlong()
+        ms = C.c_float()
+        _chk(self.L.lsd_se3_last_stats(self.p, C.byref(b), C.byref(e), C.byref(ms)))
+        return b.value, e.value, ms.value
+
+
+class Frame:
+    """[UP] lsd_slam::Frame: device-resident pyramids; accessors copy to host on demand."""
+
+    def __init__(self, ctx: Context, p, fid):
+        self.ctx, self.p, self.id = ctx, p, fid
+
+    def release(self):
+        if self.p:
+            self.ctx.L.lsd_frame_release(self.ctx.p, self.p)
+            self.p = None
+
+    def read(self, field, level):
+        w, h = self.ctx.w >> level, self.ctx.h >> level
+        if field == FIELD_GRADIENTS:
+            out = np.empty((h, w, 4), np.float32)
+        elif field == FIELD_MASK:
+            out = np.empty((self.ctx.h >> 1, self.ctx.w >> 1), np.uint8)
+        else:
+            out = np.empty((h, w), np.float32)
+        _chk(self.ctx.L.lsd_frame_read(self.ctx.p, self.p, field, level, _ptr(out)))
+        return out
+
+    def image(self, level=0):
+        return self.read(FIELD_IMAGE, level)
+
+    def gradients(self, level=0):
+        return self.read(FIELD_GRADIENTS, level)
+
+    def maxGradients(self, level=0):
+        return self.read(FIELD_MAXGRAD, level)
+
+    def idepth(self, level=0):
+        return self.read(FIELD_IDEPTH, level)
+
+    def idepthVar(self, level=0):
+        return self.read(FIELD_IDEPTHVAR, level)
+
+    def refPixelWasGood(self):
+        return self.read(FIELD_MASK, 1)
+
+    def num_mappable_pixels(self):
+        v = C.c_int()
+        _chk(self.ctx.L.lsd_frame_num_mappable_pixels(self.ctx.p, self.p, C.byref(v)))
+        return v.value
+
+    def set_depth_from_gt(self, depth, cov_scale=1.0):
+        d = np.ascontiguousarray(depth, np.float32)
+        _chk(self.ctx.L.lsd_frame_set_depth_from_gt(self.ctx.p, self.p, _ptr(d), cov_scale))
+
+    def set_idepth(self, idepth, var):
+        a = np.ascontiguousarray(idepth, np.float32)
+        b = np.ascontiguousarray(var, np.float32)
+        _chk(self.ctx.L.lsd_frame_set_idepth(self.ctx.p, self.p, _ptr(a), _ptr(b)))
+
+    def mean_idepth(self):
+        m = C.c_float()
+        n = C.c_int()
+        _chk(self.ctx.L.lsd_frame_mean_idepth(self.ctx.p, self.p, C.byref(m), C.byref(n)))
+        return m.value, n.value
+
+
+class Ref:
+    """[UP] lsd_slam::TrackingReference."""
+
+    def __init__(self, ctx: Context, p, kf: Frame):
+        self.ctx, self.p, self.kf = ctx, p, kf
+
+    def release(self):
+        if self.p:
+            self.ctx.L.lsd_ref_release(self.ctx.p, self.p)
+            self.p = None
+
+    def num_data(self, level):
+        v = C.c_int()
+        _chk(self.ctx.L.lsd_ref_num_data(self.ctx.p, self.p, level, C.byref(v)))
+        return v.value
+
+    def read(self, level):
+        n = self.num_data(level)
+        pos = np.empty((n, 3), np.float32)
+        grad = np.empty((n, 2), np.float32)
+        cv = np.empty((n, 2), np.float32)
+        idx = np.empty((n,), np.int32)
+        _chk(self.ctx.L.lsd_ref_read(self.ctx.p, self.p, level, _ptr(pos), _ptr(grad), _ptr(cv), _ptr(idx)))
+        return pos, grad, cv, idx

@@ -1,0 +1,237 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liblsd_oracle*.so).
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/lsd_oracle.hpp).  Importable only from
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+IMAGE, GRADIENTS, MAXGRAD, IDEPTH, IDEPTHVAR, MASK = range(6)
+
+
+class SE3Result(C.Structure):
+    _fields_ = [("frameToRef", C.c_double * 7),
+                ("lastResidual", C.c_float), ("lastMeanRes", C.c_float), ("pointUsage", C.c_float),
+                ("lastGoodCount", C.c_float), ("lastBadCount", C.c_float),
+                ("affine_a", C.c_float), ("affine_b", C.c_float), ("initialTrackedResidual", C.c_float),
+                ("diverged", C.c_int), ("trackingWasGood", C.c_int),
+                ("numResidualCalls", C.c_int * 5), ("numWarpUpdateCalls", C.c_int * 5),
+                ("traceLen", C.c_int)]
+
+
+class TraceEntry(C.Structure):
+    _fields_ = [("level", C.c_int), ("accepted", C.c_int), ("error", C.c_float), ("lam", C.c_float), ("bufSize", C.c_int)]
+
+
+class Sim3Result(C.Structure):
+    _fields_ = [("frameToRef", C.c_double * 8),
+                ("hessian", C.c_float * 49),
+                ("lastResidual", C.c_float), ("lastDepthResidual", C.c_float), ("lastPhotometricResidual", C.c_float),
+                ("pointUsage", C.c_float), ("affine_a", C.c_float), ("affine_b", C.c_float),
+                ("diverged", C.c_int), ("traceLen", C.c_int)]
+
+
+class Hypothesis(C.Structure):
+    _fields_ = [("isValid", C.c_bool), ("blacklisted", C.c_int), ("nextStereoFrameMinID", C.c_float),
+                ("validity_counter", C.c_int), ("idepth", C.c_float), ("idepth_var", C.c_float),
+                ("idepth_smoothed", C.c_float), ("idepth_var_smoothed", C.c_float)]
+
+
+HYP_DTYPE = np.dtype([("isValid", np.uint8), ("_pad", np.uint8, (3,)), ("blacklisted", np.int32),
+                      ("nextStereoFrameMinID", np.float32), ("validity_counter", np.int32), ("idepth", np.float32),
+                      ("idepth_var", np.float32), ("idepth_smoothed", np.float32), ("idepth_var_smoothed", np.float32)])
+assert HYP_DTYPE.itemsize == 32
+
+_libs = {}
+
+
+def build(force: bool = False):
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    out = os.path.join(HERE, "_build", "liblsd_oracle.so")
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cpp", ".hpp"))]
+    if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.check_call(["make", "-C", HERE, "-s"])
+    return out
+
+
+def lib(fast: bool = False):
+    key = "fast" if fast else "parity"
+    if key in _libs:
+        return _libs[key]
+    path = os.path.join(HERE, "_build", "liblsd_oracle_fast.so" if fast else "liblsd_oracle.so")
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    vp, ip, fp, dp = C.c_void_p, C.c_int, C.c_float, C.c_double
+    L.lsdo_frame_create.restype = vp
+    L.lsdo_frame_create.argtypes = [ip, ip, ip, fp, fp, fp, fp, vp]
+    L.lsdo_frame_destroy.argtypes = [vp]
+    L.lsdo_frame_build_pyramids.argtypes = [vp]
+    L.lsdo_frame_get.argtypes = [vp, ip, ip, vp]
+    L.lsdo_frame_num_mappable.argtypes = [vp]
+    L.lsdo_frame_mean_idepth.argtypes = [vp]
+    L.lsdo_frame_mean_idepth.restype = fp
+    L.lsdo_frame_num_points.argtypes = [vp]
+    L.lsdo_frame_set_idepth.argtypes = [vp, vp, vp]
+    L.lsdo_frame_set_depth_gt.argtypes = [vp, vp, fp]
+    L.lsdo_frame_set_track_meta.argtypes = [vp, fp, ip, vp]
+    L.lsdo_frame_set_mask.argtypes = [vp, vp]
+    L.lsdo_frame_set_counters.argtypes = [vp, ip, ip]
+    L.lsdo_ref_create.restype = vp
+    L.lsdo_ref_create.argtypes = [vp]
+    L.lsdo_ref_destroy.argtypes = [vp]
+    L.lsdo_ref_num.argtypes = [vp, ip]
+    L.lsdo_ref_get.argtypes = [vp, ip, vp, vp, vp, vp]
+    L.lsdo_se3_track.argtypes = [vp, vp, vp, ip, vp, vp, ip]
+    L.lsdo_se3_eval.argtypes = [vp, vp, vp, ip, fp, fp, ip, vp, vp, vp]
+    L.lsdo_se3_track_batch.restype = dp
+    L.lsdo_se3_track_batch.argtypes = [ip, vp, vp, vp, ip, ip, vp]
+    L.lsdo_hardware_threads.restype = ip
+    for name, res, args in [
+        ("lsdo_sim3_track", ip, [vp, vp, vp, ip, ip, ip, vp, vp, ip]),
+        ("lsdo_sim3_track_batch", dp, [ip, vp, vp, vp, ip, ip, ip, ip, vp]),
+        ("lsdo_depthmap_create", vp, [ip, ip, fp, fp, fp, fp, ip]),
+        ("lsdo_depthmap_destroy", None, [vp]),
+        ("lsdo_depthmap_init_gt", None, [vp, vp]),
+        ("lsdo_depthmap_init_map", None, [vp, vp, vp]),
+        ("lsdo_depthmap_read", None, [vp, vp]),
+        ("lsdo_depthmap_write", None, [vp, vp]),
+        ("lsdo_depthmap_update_keyframe", dp, [vp, ip, vp, vp]),
+        ("lsdo_depthmap_create_keyframe", dp, [vp, vp]),
+        ("lsdo_depthmap_finalize", None, [vp]),
+        ("lsdo_depthmap_stage", dp, [vp, ip, ip, ip, vp]),
+        ("lsdo_depthmap_debug_rgb", None, [vp, vp]),
+        ("lsdo_line_stereo", fp, [vp, vp, fp, fp, fp, fp, fp, fp, fp, vp]),
+    ]:
+        if hasattr(L, name):
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+    _libs[key] = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Frame:
+    def __init__(self, fid, img_u8: np.ndarray, K, fast=False):
+        self.L = lib(fast)
+        img_u8 = np.ascontiguousarray(img_u8, dtype=np.uint8)
+        self.h, self.w = img_u8.shape
+        self.K = K
+        self.p = self.L.lsdo_frame_create(fid, self.w, self.h, K[0], K[1], K[2], K[3], _ptr(img_u8))
+        self.id = fid
+
+    def __del__(self):
+        try:
+            self.L.lsdo_frame_destroy(self.p)
+        except Exception:
+            pass
+
+    def build_pyramids(self):
+        self.L.lsdo_frame_build_pyramids(self.p)
+
+    def get(self, field, level):
+        w, h = self.w >> level, self.h >> level
+        if field == GRADIENTS:
+            out = np.empty((h, w, 4), np.float32)
+        elif field == MASK:
+            out = np.empty((self.h >> 1, self.w >> 1), np.uint8)
+        else:
+            out = np.empty((h, w), np.float32)
+        rc = self.L.lsdo_frame_get(self.p, field, level, _ptr(out))
+        if rc != 0:
+            raise RuntimeError(f"lsdo_frame_get rc={rc}")
+        return out
+
+    def num_mappable(self):
+        return self.L.lsdo_frame_num_mappable(self.p)
+
+    def set_idepth(self, idepth, var):
+        idepth = np.ascontiguousarray(idepth, np.float32)
+        var = np.ascontiguousarray(var, np.float32)
+        self.L.lsdo_frame_set_idepth(self.p, _ptr(idepth), _ptr(var))
+
+    def set_depth_gt(self, depth, cov=1.0):
+        depth = np.ascontiguousarray(depth, np.float32)
+        self.L.lsdo_frame_set_depth_gt(self.p, _ptr(depth), cov)
+
+    def set_track_meta(self, initialTrackedResidual, parent_id, toParent8):
+        a = np.ascontiguousarray(toParent8, np.float64)
+        self.L.lsdo_frame_set_track_meta(self.p, float(initialTrackedResidual), int(parent_id), _ptr(a))
+
+    def set_mask(self, mask):
+        m = np.ascontiguousarray(mask, np.uint8)
+        self.L.lsdo_frame_set_mask(self.p, _ptr(m))
+
+    def set_counters(self, tracked, mapped):
+        self.L.lsdo_frame_set_counters(self.p, tracked, mapped)
+
+    def mean_idepth(self):
+        return self.L.lsdo_frame_mean_idepth(self.p)
+
+    def num_points(self):
+        return self.L.lsdo_frame_num_points(self.p)
+
+
+class Ref:
+    def __init__(self, kf: Frame):
+        self.L = kf.L
+        self.kf = kf
+        self.p = self.L.lsdo_ref_create(kf.p)
+
+    def __del__(self):
+        try:
+            self.L.lsdo_ref_destroy(self.p)
+        except Exception:
+            pass
+
+    def num(self, level):
+        return self.L.lsdo_ref_num(self.p, level)
+
+    def get(self, level):
+        n = self.num(level)
+        pos = np.empty((n, 3), np.float32)
+        grad = np.empty((n, 2), np.float32)
+        cv = np.empty((n, 2), np.float32)
+        idx = np.empty((n,), np.int32)
+        self.L.lsdo_ref_get(self.p, level, _ptr(pos), _ptr(grad), _ptr(cv), _ptr(idx))
+        return pos, grad, cv, idx
+
+
+def se3_track(ref: Ref, frame: Frame, init7, mode=0, trace_cap=2048):
+    res = SE3Result()
+    tr = (TraceEntry * trace_cap)()
+    init = np.ascontiguousarray(init7, np.float64)
+    ref.L.lsdo_se3_track(ref.p, frame.p, _ptr(init), mode, C.byref(res), tr, trace_cap)
+    trace = [(tr[i].level, tr[i].accepted, tr[i].error, tr[i].lam, tr[i].bufSize) for i in range(min(res.traceLen, trace_cap))]
+    return res, trace
+
+
+def se3_eval(ref: Ref, frame: Frame, refToFrame7, level, a=1.0, b=0.0, mode=0):
+    A = np.zeros((6, 6), np.float32)
+    bb = np.zeros(6, np.float32)
+    sc = np.zeros(12, np.float32)
+    p = np.ascontiguousarray(refToFrame7, np.float64)
+    ref.L.lsdo_se3_eval(ref.p, frame.p, _ptr(p), level, a, b, mode, _ptr(A), _ptr(bb), _ptr(sc))
+    return A, bb, sc
+
+
+def se3_track_batch(refs, frames, inits, mode=0, threads=1):
+    n = len(refs)
+    L = refs[0].L
+    rp = (C.c_void_p * n)(*[r.p for r in refs])
+    fp = (C.c_void_p * n)(*[f.p for f in frames])
+    init = np.ascontiguousarray(inits, np.float64).reshape(n, 7)
+    outs = (SE3Result * n)()
+    secs = L.lsdo_se3_track_batch(n, rp, fp, _ptr(init), mode, threads, outs)
+    return secs, outs

@@ -1,0 +1,44 @@
+"""CPU checks of the drop-in boundary: the library loads and exports every symbol include/lsd_b200.h
+declares (no compute calls: there is no GPU here)."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "lsd_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lsd_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported_and_bound(lsd):
+    L = lsd.load()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/lsd_b200.h but not exported"
+        assert n in lsd.SYMBOLS, f"{n} not bound in lsd_b200/binding.py"
+    for n in lsd.SYMBOLS:
+        assert n in names, f"{n} bound but not declared"
+
+
+def test_no_cpu_fallback_without_device(lsd):
+    """On a box without a GPU every compute entry point must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    import pytest
+    with pytest.raises(lsd.LsdError):
+        lsd.Context(640, 480, (525, 525, 319.5, 239.5))
+
+
+def test_product_never_touches_oracle():
+    pkg = os.path.join(ROOT, "lsd-slam-pangolin-gui_b200")
+    for d, _, files in os.walk(pkg):
+        if "build" in d.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".py")) or f == "Makefile":
+                src = open(os.path.join(d, f), errors="ignore").read()
+                assert "pyoracle" not in src and "lsd_oracle" not in src and "oracle/" not in src.replace("the oracle", ""), f
