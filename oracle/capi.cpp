@@ -133,7 +133,7 @@ int lsdo_se3_track(void *refp, void *framep, const double init[7], int mode, lsd
   auto *ref = (TrackingReference *)refp;
   Frame *frame = (Frame *)framep;
   SE3Tracker t(frame->w[0], frame->h[0]);
-  t.mode = mode ? ReduceMode::SSE4 : ReduceMode::SCALAR;
+  t.mode = (ReduceMode)mode;
   const SE3<double> res = t.trackFrame(ref, frame, pose_in(init));
   fill_result(t, frame, res, out);
   if (trace)
@@ -149,7 +149,7 @@ int lsdo_se3_eval(void *refp, void *framep, const double refToFrame[7], int leve
   auto *ref = (TrackingReference *)refp;
   Frame *frame = (Frame *)framep;
   SE3Tracker t(frame->w[0], frame->h[0]);
-  t.mode = mode ? ReduceMode::SSE4 : ReduceMode::SCALAR;
+  t.mode = (ReduceMode)mode;
   t.affineEstimation_a = affine_a;
   t.affineEstimation_b = affine_b;
   ref->makePointCloud(level);
@@ -189,7 +189,7 @@ double lsdo_se3_track_batch(int n, void **refs, void **frames, const double *ini
       if (n == 0) return;
       Frame *f0 = (Frame *)frames[0];
       SE3Tracker t(f0->w[0], f0->h[0]);
-      t.mode = mode ? ReduceMode::SSE4 : ReduceMode::SCALAR;
+      t.mode = (ReduceMode)mode;
       for (int i = tid; i < n; i += threads) {
         Frame *frame = (Frame *)frames[i];
         const SE3<double> res = t.trackFrame((TrackingReference *)refs[i], frame, pose_in(inits + 7 * i));

@@ -169,7 +169,21 @@ struct TrackingReference {
   void invalidate();
 };
 
-enum class ReduceMode { SCALAR = 0, SSE4 = 1 };
+// SCALAR: sequential fp32 sums in emission order (upstream's scalar build).
+// SSE4:   4 interleaved fp32 lanes + scalar tail (lane ORDER of upstream's -DENABLE_SSE build).
+// EXACT:  identical per-point fp32 values, but every cross-point sum accumulated in fp64 and rounded
+//         once -- the order-independent definition of the same algorithm.  Used to separate the
+//         oracle's own fp32 summation noise from genuine differences (tests/test_gpu_se3.py).
+enum class ReduceMode { SCALAR = 0, SSE4 = 1, EXACT = 2 };
+
+struct Acc {  // one running sum in the selected mode
+  float f = 0;
+  double d = 0;
+  bool exact;
+  explicit Acc(bool e = false) : exact(e) {}
+  inline void add(float v) { if (exact) d += (double)v; else f += v; }
+  inline float get() const { return exact ? (float)d : f; }
+};
 
 struct LMTraceEntry {  // one LM evaluation (B3+B4), for per-iteration parity checks
   int level;

@@ -77,12 +77,13 @@ float SE3Tracker::calcResidualAndBuffers(const float *refPoint, const float *ref
   const float *frame_gradients = frame->grad[level].data();
 
   int idx = 0;
-  float sumResUnweighted = 0;
+  const bool ex = (mode == ReduceMode::EXACT);
+  Acc sumResUnweighted(ex);
   uint8_t *isGoodOutBuffer = idxBuf != nullptr ? frame->refPixelWasGoodBuf() : nullptr;
   int goodCount = 0, badCount = 0;
-  float sumSignedRes = 0;
-  float sxx = 0, syy = 0, sx = 0, sy = 0, sw = 0;
-  float usageCount = 0;
+  Acc sumSignedRes(ex);
+  Acc sxx_(ex), syy_(ex), sx_(ex), sy_(ex), sw_(ex);
+  Acc usageCount(ex);
 
   for (int i = 0; i < refNum; i++) {
     const Vec3<float> p(refPoint[3 * i], refPoint[3 * i + 1], refPoint[3 * i + 2]);
@@ -100,11 +101,11 @@ float SE3Tracker::calcResidualAndBuffers(const float *refPoint, const float *ref
     const float c2 = resInterp[2];
     const float residual = c1 - c2;
     const float weight = fabsf(residual) < 5.0f ? 1 : 5.0f / fabsf(residual);
-    sxx += c1 * c1 * weight;
-    syy += c2 * c2 * weight;
-    sx += c1 * weight;
-    sy += c2 * weight;
-    sw += weight;
+    sxx_.add(c1 * c1 * weight);
+    syy_.add(c2 * c2 * weight);
+    sx_.add(c1 * weight);
+    sy_.add(c2 * weight);
+    sw_.add(weight);
     const bool isGood = residual * residual /
                             (MAX_DIFF_CONSTANT + MAX_DIFF_GRAD_MULT * (resInterp[0] * resInterp[0] + resInterp[1] * resInterp[1])) <
                         1;
@@ -119,23 +120,24 @@ float SE3Tracker::calcResidualAndBuffers(const float *refPoint, const float *ref
     buf_idepthVar[idx] = refColVar[2 * i + 1];
     idx++;
     if (isGood) {
-      sumResUnweighted += residual * residual;
-      sumSignedRes += residual;
+      sumResUnweighted.add(residual * residual);
+      sumSignedRes.add(residual);
       goodCount++;
     } else {
       badCount++;
     }
     const float depthChange = p.z / Wxp.z;  // larger depth => pixel "smaller" => count it less
-    usageCount += depthChange < 1 ? depthChange : 1;
+    usageCount.add(depthChange < 1 ? depthChange : 1);
   }
+  const float sxx = sxx_.get(), syy = syy_.get(), sx = sx_.get(), sy = sy_.get(), sw = sw_.get();
   buf_warped_size = idx;
-  pointUsage = usageCount / (float)refNum;
+  pointUsage = usageCount.get() / (float)refNum;
   lastGoodCount = goodCount;
   lastBadCount = badCount;
-  lastMeanRes = sumSignedRes / goodCount;
+  lastMeanRes = sumSignedRes.get() / goodCount;
   affineEstimation_a_lastIt = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
   affineEstimation_b_lastIt = (sy - affineEstimation_a_lastIt * sx) / sw;
-  return sumResUnweighted / goodCount;
+  return sumResUnweighted.get() / goodCount;
 }
 
 // SE3Tracker::calcWeightsAndResidual.  ReduceMode::SSE4 mirrors the lane order of the SSE
@@ -145,6 +147,7 @@ float SE3Tracker::calcWeightsAndResidual(const SE3<float> &referenceToFrame) {
   const float tx = referenceToFrame.t.x, ty = referenceToFrame.t.y, tz = referenceToFrame.t.z;
   float lanes[4] = {0, 0, 0, 0};
   float sumRes = 0;
+  double sumResD = 0;
   const int n = buf_warped_size;
   const int n4 = (mode == ReduceMode::SSE4) ? (n & ~3) : 0;
   for (int i = 0; i < n; i++) {
@@ -160,9 +163,11 @@ float SE3Tracker::calcWeightsAndResidual(const SE3<float> &referenceToFrame) {
     const float weighted_rp = fabsf(rp * sqrtf(w_p));
     const float wh = fabsf(weighted_rp < (settings.huber_d / 2) ? 1 : (settings.huber_d / 2) / weighted_rp);
     const float term = wh * w_p * rp * rp;
-    if (i < n4) lanes[i & 3] += term; else sumRes += term;
+    if (mode == ReduceMode::EXACT) sumResD += (double)term;
+    else if (i < n4) lanes[i & 3] += term; else sumRes += term;
     buf_weight_p[i] = wh * w_p;
   }
+  if (mode == ReduceMode::EXACT) sumRes = (float)sumResD;
   if (mode == ReduceMode::SSE4) sumRes = (((lanes[0] + lanes[1]) + lanes[2]) + lanes[3]) + sumRes;
   return sumRes / n;
 }
@@ -174,6 +179,8 @@ void SE3Tracker::calculateWarpUpdate(float A[6][6], float b[6], float *error) {
   const int nl = (mode == ReduceMode::SSE4) ? 4 : 1;
   const int n4 = (mode == ReduceMode::SSE4) ? (n & ~3) : 0;
   float Aacc[5][21], bacc[5][6], eacc[5];
+  double Ad[21] = {0}, bd[6] = {0}, ed = 0;
+  const bool ex = (mode == ReduceMode::EXACT);
   std::memset(Aacc, 0, sizeof(Aacc));
   std::memset(bacc, 0, sizeof(bacc));
   std::memset(eacc, 0, sizeof(eacc));
@@ -194,13 +201,27 @@ void SE3Tracker::calculateWarpUpdate(float A[6][6], float b[6], float *error) {
     const float wgt = buf_weight_p[i];
     const int lane = (i < n4) ? (i & 3) : (nl == 4 ? 4 : 0);
     int k = 0;
+    const float rw = r * wgt;
+    if (ex) {
+      for (int a = 0; a < 6; a++) {
+        const float wa = v[a] * wgt;
+        for (int c = a; c < 6; c++) Ad[k++] += (double)(wa * v[c]);
+      }
+      for (int a = 0; a < 6; a++) bd[a] -= (double)(v[a] * rw);
+      ed += (double)(r * r * wgt);
+      continue;
+    }
     for (int a = 0; a < 6; a++) {
       const float wa = v[a] * wgt;
       for (int c = a; c < 6; c++) Aacc[lane][k++] += wa * v[c];
     }
-    const float rw = r * wgt;
     for (int a = 0; a < 6; a++) bacc[lane][a] -= v[a] * rw;
     eacc[lane] += r * r * wgt;
+  }
+  if (ex) {
+    for (int k = 0; k < 21; k++) Aacc[0][k] = (float)Ad[k];
+    for (int k = 0; k < 6; k++) bacc[0][k] = (float)bd[k];
+    eacc[0] = (float)ed;
   }
   float Asum[21], bsum[6], esum;
   if (nl == 4) {

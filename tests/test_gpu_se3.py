@@ -26,6 +26,13 @@ def _gpu_pair(lsd, d, w, h):
 
 @pytest.mark.parametrize("level", [1, 2, 3, 4])
 def test_fused_evaluation_matches_three_reference_passes(lsd, oracle, level):
+    """One fused GPU evaluation == calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate.
+
+    EXACT (mode 2) is the oracle with fp64 accumulators: the order-independent value of every sum.
+    The GPU (fp32 tree sums) must be within 1e-4 of it; the oracle's own fp32 modes (0 scalar,
+    1 sse4-order) carry sequential-summation noise, so against them the bound is the triangle
+    inequality |gpu - mode| <= |mode - exact| + tol.
+    """
     w, h = 640, 480
     d = make_oracle_pair(41, w, h)
     ctx, kf, fr, ref = _gpu_pair(lsd, d, w, h)
@@ -33,57 +40,84 @@ def test_fused_evaluation_matches_three_reference_passes(lsd, oracle, level):
     pose = _inv_pose7(d["pr"]["frameToRef"])  # refToFrame near the optimum
     for (a, b) in [(1.0, 0.0), (1.02, -1.5)]:
         gA, gb, gs = ctx.se3_eval(ref, fr, pose, level, a, b)
+        eA, eb, es = oracle.se3_eval(d["oref"], d["ofr"], pose, level, a, b, 2)
+        assert gs[2] == es[2] and gs[3] == es[3] and gs[4] == es[4], "bufSize / good / bad (bit-exact)"
+        assert np.allclose(gs[[0, 1, 5, 6]], es[[0, 1, 5, 6]], rtol=RES_RTOL, atol=1e-6)
+        # affine-lighting estimate sqrt((syy - sy^2/sw)/(sxx - sx^2/sw)) amplifies fp32 rounding of the sums
+        # ~20x (a) / ~100x (b): compare a at 2e-4 and the fitted line a*mean+b (what enters residuals) tightly
+        mean_c = float(d["okf"].get(oracle.IMAGE, level).mean())
+        assert abs(gs[7] - es[7]) <= 2e-4 * abs(es[7])
+        assert abs((gs[7] - es[7]) * mean_c + (gs[8] - es[8])) <= 2e-3
+        assert np.allclose(gA, eA, rtol=1e-4, atol=1e-5 * np.abs(eA).max())
+        assert np.allclose(gb, eb, rtol=1e-4, atol=1e-5 * np.abs(eb).max())
         for mode in (0, 1):
             oA, ob, os_ = oracle.se3_eval(d["oref"], d["ofr"], pose, level, a, b, mode)
-            # integer-valued outputs: exact
-            assert gs[2] == os_[2] and gs[3] == os_[3] and gs[4] == os_[4], "bufSize / good / bad"
-            assert np.allclose(gs[[0, 1, 5, 6]], os_[[0, 1, 5, 6]], rtol=RES_RTOL, atol=1e-6)
-            # affine-lighting estimate: sqrt((syy - sy^2/sw)/(sxx - sx^2/sw)) cancels ~20x (a) and ~100x (b) in
-            # fp32, so the ORACLE's sequential 30k-term sums limit it; compare a loosely and the fitted line
-            # a*mean + b (what enters the residual) tightly.
-            assert abs(gs[7] - os_[7]) <= 2e-3 * abs(os_[7])
-            mean_c = float(d["okf"].get(oracle.IMAGE, level).mean())
-            assert abs((gs[7] - os_[7]) * mean_c + (gs[8] - os_[8])) <= 2e-2
-            scale = np.abs(oA).max()
-            assert np.allclose(gA, oA, rtol=1e-4, atol=1e-5 * scale)
-            assert np.allclose(gb, ob, rtol=1e-4, atol=1e-5 * np.abs(ob).max())
+            assert gs[2] == os_[2] and gs[3] == os_[3] and gs[4] == os_[4]
+            for k in (0, 1, 5, 6, 7):
+                assert abs(gs[k] - os_[k]) <= abs(os_[k] - es[k]) + RES_RTOL * abs(es[k]) + 1e-6, (k, gs[k], os_[k], es[k])
+            assert np.all(np.abs(gA - oA) <= np.abs(oA - eA) + 1e-4 * np.abs(eA) + 1e-5 * np.abs(eA).max())
         if level == 1:
             assert np.array_equal(fr.refPixelWasGood(), d["ofr"].get(oracle.MASK, 1)), "refPixelWasGood mask"
     ctx.close()
 
 
+def _agreeing_prefix(*traces):
+    n = 0
+    for rows in zip(*traces):
+        if any((r[0], r[1]) != (rows[0][0], rows[0][1]) for r in rows):
+            break
+        n += 1
+    return n
+
+
 @pytest.mark.parametrize("seed,wh", [(41, (640, 480)), (42, (640, 480)), (43, (320, 240)), (44, (1280, 960))])
 def test_track_frame_matches_oracle(lsd, oracle, seed, wh):
+    """SE3Tracker::trackFrame through the C ABI vs the oracle.
+
+    vs EXACT (fp64 accumulators): per-iteration residual <= 1e-4 relative while the accept/reject
+    sequences agree, final SE3 <= 1e-5.  vs the fp32 SCALAR / SSE4-order modes: no farther than those
+    modes are from EXACT, plus the same tolerance (their sequential fp32 sums are the noisier side).
+    """
     w, h = wh
     d = make_oracle_pair(seed, w, h)
     ctx, kf, fr, ref = _gpu_pair(lsd, d, w, h)
     init = np.array([0, 0, 0, 1, 0, 0, 0.0])
     gres, gtrace = ctx.se3_track(ref, fr, init, want_trace=True)
     gpose = np.array(gres.frameToRef)
+    gmask = fr.refPixelWasGood()
+    eres, etrace = oracle.se3_track(d["oref"], d["ofr"], init, 2)
+    emask = d["ofr"].get(oracle.MASK, 1).copy()
+    epose = np.array(eres.frameToRef)
+
+    agree = _agreeing_prefix(gtrace, etrace)
+    assert agree >= 4
+    for k in range(agree):
+        g, e = gtrace[k], etrace[k]
+        assert g[4] == e[4], f"buf_warped_size differs at evaluation {k}"
+        assert abs(g[2] - e[2]) <= RES_RTOL * abs(e[2]), f"residual at evaluation {k}: {g[2]} vs {e[2]}"
+    assert np.linalg.norm(gpose[4:] - epose[4:]) <= POSE_TOL, (gpose, epose, agree, len(gtrace), len(etrace))
+    assert quat_angle(gpose[:4], epose[:4]) <= POSE_TOL
+    assert gres.diverged == eres.diverged and gres.trackingWasGood == eres.trackingWasGood
+    if agree == len(etrace) == len(gtrace):
+        assert gres.lastGoodCount == eres.lastGoodCount and gres.lastBadCount == eres.lastBadCount
+        assert list(gres.numResidualCalls) == list(eres.numResidualCalls)
+        assert list(gres.numWarpUpdateCalls) == list(eres.numWarpUpdateCalls)
+        assert np.isclose(gres.pointUsage, eres.pointUsage, rtol=1e-5)
+        assert np.isclose(gres.lastResidual, eres.lastResidual, rtol=RES_RTOL)
+        assert np.isclose(gres.initialTrackedResidual, eres.initialTrackedResidual, rtol=RES_RTOL)
+        assert np.mean(gmask != emask) <= 1e-4  # identical up to isGood threshold ties
+
     for mode in (0, 1):
         ores, otrace = oracle.se3_track(d["oref"], d["ofr"], init, mode)
         opose = np.array(ores.frameToRef)
-        # per-iteration residuals while the accept/reject sequences agree
-        agree = 0
-        for g, o in zip(gtrace, otrace):
-            if g[0] != o[0] or g[1] != o[1]:
-                break
-            assert g[4] == o[4], f"buf_warped_size differs at evaluation {agree}"
-            assert abs(g[2] - o[2]) <= RES_RTOL * abs(o[2]), f"residual at evaluation {agree}: {g[2]} vs {o[2]}"
-            agree += 1
-        assert agree >= 4
-        assert np.linalg.norm(gpose[4:] - opose[4:]) <= POSE_TOL, (gpose, opose, agree, len(gtrace), len(otrace))
-        assert quat_angle(gpose[:4], opose[:4]) <= POSE_TOL
-        assert gres.diverged == ores.diverged and gres.trackingWasGood == ores.trackingWasGood
-        if agree == len(otrace) == len(gtrace):
-            assert gres.lastGoodCount == ores.lastGoodCount and gres.lastBadCount == ores.lastBadCount
-            assert list(gres.numResidualCalls) == list(ores.numResidualCalls)
-            assert list(gres.numWarpUpdateCalls) == list(ores.numWarpUpdateCalls)
-            assert np.isclose(gres.pointUsage, ores.pointUsage, rtol=1e-5)
-            assert np.isclose(gres.lastResidual, ores.lastResidual, rtol=RES_RTOL)
-            assert np.isclose(gres.initialTrackedResidual, ores.initialTrackedResidual, rtol=RES_RTOL)
-            if mode == 0:
-                assert np.array_equal(fr.refPixelWasGood(), d["ofr"].get(oracle.MASK, 1))
+        n3 = _agreeing_prefix(gtrace, etrace, otrace)
+        for k in range(n3):
+            g, e, o = gtrace[k], etrace[k], otrace[k]
+            assert abs(g[2] - o[2]) <= abs(o[2] - e[2]) + RES_RTOL * abs(e[2]), f"mode {mode} evaluation {k}"
+        dt_oe = np.linalg.norm(opose[4:] - epose[4:])
+        dr_oe = quat_angle(opose[:4], epose[:4])
+        assert np.linalg.norm(gpose[4:] - opose[4:]) <= dt_oe + POSE_TOL
+        assert quat_angle(gpose[:4], opose[:4]) <= dr_oe + POSE_TOL
     ctx.close()
 
 
@@ -105,7 +139,7 @@ def test_batch_equals_single_and_is_deterministic(lsd, oracle):
     for i in range(6):
         rs = ctx.se3_track(refs[i], frs[i], inits[i])
         assert np.array_equal(np.array(rs.frameToRef), p1[i]), "batch result must not depend on batch composition"
-        ores, _ = oracle.se3_track(ds[i]["oref"], ds[i]["ofr"], inits[i], 0)
+        ores, _ = oracle.se3_track(ds[i]["oref"], ds[i]["ofr"], inits[i], 2)
         assert np.linalg.norm(p1[i][4:] - np.array(ores.frameToRef)[4:]) <= POSE_TOL
     ctx.close()
 
