@@ -29,11 +29,16 @@ namespace lsd {
 
 #define SE3_CH 1024       // points per work item
 #define SE3_THREADS 256   // threads per CTA
-#define SE3_NRED 40       // floats per partial record (38 used)
+#define SE3_NRED 44       // floats per partial record: 5 doubles (affine sums) + 33 floats + pad
+#define SE3_NF 33         // fp32 sums per record
+#define SE3_ND 5          // fp64 sums per record
 
-// indices inside a partial record
-enum { R_A = 0, R_B = 21, R_SUMRES = 27, R_SUMUNW = 28, R_SUMSGN = 29, R_SXX = 30, R_SYY = 31, R_SX = 32, R_SY = 33, R_SW = 34,
-       R_USAGE = 35, R_GOOD = 36, R_BAD = 37 };
+// fp32 sums (index into acc[] / the float part of a record, which starts at float offset 2*SE3_ND)
+enum { R_A = 0, R_B = 21, R_SUMRES = 27, R_SUMUNW = 28, R_SUMSGN = 29, R_USAGE = 30, R_GOOD = 31, R_BAD = 32 };
+// fp64 sums: the affine-lighting estimate sqrt((syy - sy^2/sw)/(sxx - sx^2/sw)) cancels ~20x (a) and
+// ~100x (b = mean_y - a*mean_x), so its five sums are carried in fp64 end to end (10 DADD per point);
+// everything else is consumed without cancellation and stays fp32.
+enum { D_SXX = 0, D_SYY = 1, D_SX = 2, D_SY = 3, D_SW = 4 };
 
 // Immutable while the persistent kernel runs (host + k_se3_init write it): read with plain loads.
 struct SE3Pair {
@@ -149,8 +154,8 @@ __device__ void start_level(const SE3Pair *P, SE3State *S, int pairIdx, int leve
 }
 
 // The LM state machine, run by one thread after the last chunk of an evaluation (tot = summed partials).
-__device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float *tot, const SE3Params &prm, int *list,
-                        int *count, lsd_trace_entry *trace) {
+__device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float *tot, const double *dtot,
+                        const SE3Params &prm, int *list, int *count, lsd_trace_entry *trace) {
   const int lvl = S->level;
   const float good = tot[R_GOOD], bad = tot[R_BAD];
   const int size = (int)(good + bad);
@@ -159,7 +164,8 @@ __device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float 
   S->bad = bad;
   S->pointUsage = tot[R_USAGE] / (float)P->n[lvl];
   S->meanRes = tot[R_SUMSGN] / good;
-  const float sxx = tot[R_SXX], syy = tot[R_SYY], sx = tot[R_SX], sy = tot[R_SY], sw = tot[R_SW];
+  const float sxx = (float)dtot[D_SXX], syy = (float)dtot[D_SYY], sx = (float)dtot[D_SX], sy = (float)dtot[D_SY],
+              sw = (float)dtot[D_SW];
   const float aL = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
   const float bL = (sy - aL * sx) / sw;
   S->aff_a_lastIt = aL;
@@ -255,7 +261,7 @@ struct EvalConst {
 };
 
 __device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c, const float4 *__restrict__ G,
-                                           uint8_t *__restrict__ mask, float acc[38]) {
+                                           uint8_t *__restrict__ mask, float acc[SE3_NF], double dacc[SE3_ND]) {
   const int x = p.xy & 0xffff, y = p.xy >> 16;
   const float inv = 1.0f / p.idepth;
   const float px = inv * (c.fxi * x + c.cxi);
@@ -284,11 +290,11 @@ __device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c,
   const float c2 = cI;
   const float residual = c1 - c2;
   const float weight = fabsf(residual) < 5.0f ? 1 : 5.0f / fabsf(residual);
-  acc[R_SXX] += c1 * c1 * weight;
-  acc[R_SYY] += c2 * c2 * weight;
-  acc[R_SX] += c1 * weight;
-  acc[R_SY] += c2 * weight;
-  acc[R_SW] += weight;
+  dacc[D_SXX] += (double)(c1 * c1 * weight);
+  dacc[D_SYY] += (double)(c2 * c2 * weight);
+  dacc[D_SX] += (double)(c1 * weight);
+  dacc[D_SY] += (double)(c2 * weight);
+  dacc[D_SW] += (double)weight;
   const bool isGood = residual * residual / (LSD_MAX_DIFF_CONSTANT + LSD_MAX_DIFF_GRAD_MULT * (gxI * gxI + gyI * gyI)) < 1;
   if (mask) mask[x + y * c.W] = isGood;
   if (isGood) {
@@ -336,21 +342,36 @@ __device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c,
   for (int a = 0; a < 6; a++) acc[R_B + a] += v[a] * rw;
 }
 
-__device__ __forceinline__ void block_reduce_store(float acc[38], float *__restrict__ dst, float (*sred)[SE3_NRED]) {
+__device__ __forceinline__ void block_reduce_store(float acc[SE3_NF], double dacc[SE3_ND], float *__restrict__ dst,
+                                                   float (*sred)[SE3_NRED]) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 38; j++) {
+  for (int j = 0; j < SE3_ND; j++) {
+    double v = dacc[j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) reinterpret_cast<double *>(sred[wid])[j] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < SE3_NF; j++) {
     float v = acc[j];
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) sred[wid][j] = v;
+    if (lane == 0) sred[wid][2 * SE3_ND + j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 38) {
-    float s = sred[0][threadIdx.x];
+  if (threadIdx.x < SE3_ND) {
+    double s = reinterpret_cast<double *>(sred[0])[threadIdx.x];
 #pragma unroll
-    for (int w = 1; w < SE3_THREADS / 32; w++) s += sred[w][threadIdx.x];
-    dst[threadIdx.x] = s;
+    for (int w = 1; w < SE3_THREADS / 32; w++) s += reinterpret_cast<double *>(sred[w])[threadIdx.x];
+    reinterpret_cast<double *>(dst)[threadIdx.x] = s;
+    __threadfence();
+  } else if (threadIdx.x < SE3_ND + SE3_NF) {
+    const int j = 2 * SE3_ND + (threadIdx.x - SE3_ND);
+    float s = sred[0][j];
+#pragma unroll
+    for (int w = 1; w < SE3_THREADS / 32; w++) s += sred[w][j];
+    dst[j] = s;
     __threadfence();
   }
   __syncthreads();
@@ -375,8 +396,9 @@ __global__ void __launch_bounds__(SE3_THREADS, 2)
 k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials, int *lists, int listCap, int *counts,
             const __grid_constant__ SE3Params prm, lsd_trace_entry *traces) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ float sred[SE3_THREADS / 32][SE3_NRED];
-  __shared__ float stot[SE3_NRED];
+  __shared__ __align__(16) float sred[SE3_THREADS / 32][SE3_NRED];
+  __shared__ float stot[SE3_NF];
+  __shared__ double sdtot[SE3_ND];
   __shared__ int sIsLast;
 
   for (int round = 0;; round++) {
@@ -398,9 +420,12 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
       const float4 *__restrict__ G = P->fgrad[level];
       uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
 
-      float acc[38];
+      float acc[SE3_NF];
+      double dacc[SE3_ND];
 #pragma unroll
-      for (int j = 0; j < 38; j++) acc[j] = 0.0f;
+      for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
       const int base = chunk * SE3_CH + threadIdx.x;
 #pragma unroll
       for (int k = 0; k < SE3_CH / SE3_THREADS; k++) {
@@ -412,11 +437,11 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
           p.idepth = raw.y;
           p.color = raw.z;
           p.var = raw.w;
-          eval_point(p, c, G, mask, acc);
+          eval_point(p, c, G, mask, acc, dacc);
         }
       }
       float *dst = partials + ((size_t)pairIdx * prm.maxChunks + chunk) * SE3_NRED;
-      block_reduce_store(acc, dst, sred);
+      block_reduce_store(acc, dacc, dst, sred);
       if (threadIdx.x == 0) {
         const unsigned ticket = atomicAdd(&S->done, 1u);
         sIsLast = (ticket == (unsigned)(ldcg_i(&S->nChunks) - 1));
@@ -425,17 +450,24 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
       if (sIsLast) {
         __threadfence();
         const int nch = ldcg_i(&S->nChunks);
-        if (threadIdx.x < 38) {
-          const float *src = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED + threadIdx.x;
+        const float *rec0 = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED;
+        if (threadIdx.x < SE3_ND) {
+          const double *src = reinterpret_cast<const double *>(rec0) + threadIdx.x;
+          double s = 0.0;
+          for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * (SE3_NRED / 2));
+          sdtot[threadIdx.x] = s;
+        } else if (threadIdx.x < SE3_ND + SE3_NF) {
+          const int j = threadIdx.x - SE3_ND;
+          const float *src = rec0 + 2 * SE3_ND + j;
           float s = 0.0f;
           for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
-          stot[threadIdx.x] = s;
+          stot[j] = s;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
           SE3State L;
           state_load(&L, S);
-          lm_step(P, &L, pairIdx, stot, prm, lists + (size_t)nxt * listCap, &counts[nxt],
+          lm_step(P, &L, pairIdx, stot, sdtot, prm, lists + (size_t)nxt * listCap, &counts[nxt],
                   traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
           state_store(S, &L);
         }
@@ -679,16 +711,19 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
 __global__ void __launch_bounds__(SE3_THREADS)
 k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, float *__restrict__ partials, int level,
                 const __grid_constant__ SE3Params prm) {
-  __shared__ float sred[SE3_THREADS / 32][SE3_NRED];
+  __shared__ __align__(16) float sred[SE3_THREADS / 32][SE3_NRED];
   EvalConst c;
   load_eval_const(S, level, prm, c);
   const int n = P->d_num[level];
   const RefPoint *pts = P->pts[level];
   const float4 *G = P->fgrad[level];
   uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
-  float acc[38];
+  float acc[SE3_NF];
+  double dacc[SE3_ND];
 #pragma unroll
-  for (int j = 0; j < 38; j++) acc[j] = 0.0f;
+  for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
   const int base = blockIdx.x * SE3_CH + threadIdx.x;
   for (int k = 0; k < SE3_CH / SE3_THREADS; k++) {
     const int i = base + k * SE3_THREADS;
@@ -696,10 +731,10 @@ k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, f
       const float4 raw = __ldg(reinterpret_cast<const float4 *>(pts) + i);
       RefPoint p;
       p.xy = __float_as_uint(raw.x); p.idepth = raw.y; p.color = raw.z; p.var = raw.w;
-      eval_point(p, c, G, mask, acc);
+      eval_point(p, c, G, mask, acc, dacc);
     }
   }
-  block_reduce_store(acc, partials + (size_t)blockIdx.x * SE3_NRED, sred);
+  block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sred);
 }
 
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
@@ -745,10 +780,13 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   LSD_CUDA(cudaMemcpyAsync(h.data(), s->d_partials, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
   LSD_CUDA(cudaMemcpyAsync(hnum, ref->d_num, sizeof(hnum), cudaMemcpyDeviceToHost, st));
   LSD_CUDA(cudaStreamSynchronize(st));
-  float tot[SE3_NRED] = {0};
+  float tot[SE3_NF] = {0};
+  double dtot[SE3_ND] = {0};
   const int nch = (hnum[level] + SE3_CH - 1) / SE3_CH;
-  for (int cidx = 0; cidx < nch; cidx++)
-    for (int j = 0; j < 38; j++) tot[j] += h[(size_t)cidx * SE3_NRED + j];
+  for (int cidx = 0; cidx < nch; cidx++) {
+    for (int j = 0; j < SE3_ND; j++) dtot[j] += reinterpret_cast<const double *>(&h[(size_t)cidx * SE3_NRED])[j];
+    for (int j = 0; j < SE3_NF; j++) tot[j] += h[(size_t)cidx * SE3_NRED + 2 * SE3_ND + j];
+  }
   const float size = tot[R_GOOD] + tot[R_BAD];
   int k = 0;
   for (int i = 0; i < 6; i++)
@@ -757,7 +795,8 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
       k++;
     }
   for (int i = 0; i < 6; i++) b6[i] = -tot[R_B + i] / size;
-  const float sxx = tot[R_SXX], syy = tot[R_SYY], sx = tot[R_SX], sy = tot[R_SY], sw = tot[R_SW];
+  const float sxx = (float)dtot[D_SXX], syy = (float)dtot[D_SYY], sx = (float)dtot[D_SX], sy = (float)dtot[D_SY],
+              sw = (float)dtot[D_SW];
   const float aL = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
   scalars[0] = tot[R_SUMRES] / size;
   scalars[1] = tot[R_SUMUNW] / tot[R_GOOD];

@@ -201,6 +201,23 @@ class Context:
             return res, traces
         return res
 
+    def prepare_batch(self, refs, frames, inits):
+        """Pre-marshal a batch so repeated calls cost no Python work (bench.py)."""
+        n = len(refs)
+        rp = (C.c_void_p * n)(*[r.p for r in refs])
+        fp = (C.c_void_p * n)(*[f.p for f in frames]) if frames is not None else None
+        init = np.ascontiguousarray(inits, np.float64).reshape(n, 7)
+        res = (SE3Result * n)()
+        return dict(n=n, rp=rp, fp=fp, init=init, res=res)
+
+    def se3_track_prepared(self, b):
+        _chk(self.L.lsd_se3_track_batch(self.p, b["n"], b["rp"], b["fp"], _ptr(b["init"]), b["res"], None))
+        return b["res"]
+
+    def se3_track_images_prepared(self, b, ip, pitch):
+        _chk(self.L.lsd_se3_track_images_batch(self.p, b["n"], b["rp"], ip, pitch, _ptr(b["init"]), b["res"]))
+        return b["res"]
+
     def se3_track(self, ref, frame, init7, want_trace=False):
         out = self.se3_track_batch([ref], [frame], [init7], want_trace)
         if want_trace:

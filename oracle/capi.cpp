@@ -202,6 +202,30 @@ double lsdo_se3_track_batch(int n, void **refs, void **frames, const double *ini
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Builds n (keyframe, frame, reference) triples on `threads` host threads (setup for the timed baseline):
+// pyramids for both frames, keyframe idepth installed, point clouds of levels 1..4 prebuilt.
+void lsdo_make_pairs(int n, const uint8_t *const *kf_imgs, const uint8_t *const *fr_imgs, const float *const *idepth,
+                     const float *const *var, int w, int h, const float K[4], int threads, void **out_kf, void **out_fr,
+                     void **out_ref) {
+  if (threads < 1) threads = 1;
+  std::vector<std::thread> pool;
+  for (int tid = 0; tid < threads; tid++) {
+    pool.emplace_back([=]() {
+      for (int i = tid; i < n; i += threads) {
+        Frame *kf = new Frame(2 * i, w, h, K[0], K[1], K[2], K[3], kf_imgs[i]);
+        Frame *fr = new Frame(2 * i + 1, w, h, K[0], K[1], K[2], K[3], fr_imgs[i]);
+        for (int l = 0; l < NL; l++) { kf->requireImage(l); kf->requireGradients(l); fr->requireImage(l); fr->requireGradients(l); }
+        kf->setIDepthRaw(idepth[i], var[i]);
+        auto *r = new TrackingReference();
+        r->importFrame(kf);
+        for (int l = 1; l < NL; l++) r->makePointCloud(l);
+        out_kf[i] = kf; out_fr[i] = fr; out_ref[i] = r;
+      }
+    });
+  }
+  for (auto &th : pool) th.join();
+}
+
 int lsdo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

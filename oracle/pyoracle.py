@@ -94,6 +94,7 @@ def lib(fast: bool = False):
     L.lsdo_se3_track_batch.restype = dp
     L.lsdo_se3_track_batch.argtypes = [ip, vp, vp, vp, ip, ip, vp]
     L.lsdo_hardware_threads.restype = ip
+    L.lsdo_make_pairs.argtypes = [ip, vp, vp, vp, vp, ip, ip, vp, ip, vp, vp, vp]
     for name, res, args in [
         ("lsdo_sim3_track", ip, [vp, vp, vp, ip, ip, ip, vp, vp, ip]),
         ("lsdo_sim3_track_batch", dp, [ip, vp, vp, vp, ip, ip, ip, ip, vp]),
@@ -235,3 +236,34 @@ def se3_track_batch(refs, frames, inits, mode=0, threads=1):
     outs = (SE3Result * n)()
     secs = L.lsdo_se3_track_batch(n, rp, fp, _ptr(init), mode, threads, outs)
     return secs, outs
+
+
+class RawBatch:
+    """n prepared (ref, frame) pairs living in the oracle library (bench.py cpu_baseline / --impl reference)."""
+
+    def __init__(self, kf_imgs, fr_imgs, idepths, vars_, K, threads, fast=True):
+        self.L = lib(fast)
+        n = len(kf_imgs)
+        self.n = n
+        h, w = kf_imgs[0].shape
+        keep = [np.ascontiguousarray(a) for a in kf_imgs], [np.ascontiguousarray(a) for a in fr_imgs], \
+               [np.ascontiguousarray(a, np.float32) for a in idepths], [np.ascontiguousarray(a, np.float32) for a in vars_]
+        arr = [(C.c_void_p * n)(*[a.ctypes.data for a in lst]) for lst in keep]
+        self.kf = (C.c_void_p * n)()
+        self.fr = (C.c_void_p * n)()
+        self.ref = (C.c_void_p * n)()
+        Kc = (C.c_float * 4)(*K)
+        self.L.lsdo_make_pairs(n, arr[0], arr[1], arr[2], arr[3], w, h, Kc, threads, self.kf, self.fr, self.ref)
+
+    def track(self, inits, mode=0, threads=1):
+        init = np.ascontiguousarray(inits, np.float64).reshape(self.n, 7)
+        outs = (SE3Result * self.n)()
+        secs = self.L.lsdo_se3_track_batch(self.n, self.ref, self.fr, _ptr(init), mode, threads, outs)
+        return secs, outs
+
+    def free(self):
+        for i in range(self.n):
+            self.L.lsdo_ref_destroy(self.ref[i])
+            self.L.lsdo_frame_destroy(self.kf[i])
+            self.L.lsdo_frame_destroy(self.fr[i])
+        self.n = 0
