@@ -18,6 +18,7 @@
 // (-ffp-contract=off); only the summation order differs.
 #include <cooperative_groups.h>
 
+#include <cmath>
 #include <cstring>
 
 #include "ctx.cuh"
@@ -164,10 +165,11 @@ __device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float 
   S->bad = bad;
   S->pointUsage = tot[R_USAGE] / (float)P->n[lvl];
   S->meanRes = tot[R_SUMSGN] / good;
-  const float sxx = (float)dtot[D_SXX], syy = (float)dtot[D_SYY], sx = (float)dtot[D_SX], sy = (float)dtot[D_SY],
-              sw = (float)dtot[D_SW];
-  const float aL = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
-  const float bL = (sy - aL * sx) / sw;
+  // closed form evaluated in fp64 (upstream: fp32; mathematically identical, see DESIGN.md "affine lighting")
+  const double sxx = dtot[D_SXX], syy = dtot[D_SYY], sx = dtot[D_SX], sy = dtot[D_SY], sw = dtot[D_SW];
+  const double aLd = sqrt((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+  const float aL = (float)aLd;
+  const float bL = (float)((sy - aLd * sx) / sw);
   S->aff_a_lastIt = aL;
   S->aff_b_lastIt = bL;
 
@@ -795,9 +797,8 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
       k++;
     }
   for (int i = 0; i < 6; i++) b6[i] = -tot[R_B + i] / size;
-  const float sxx = (float)dtot[D_SXX], syy = (float)dtot[D_SYY], sx = (float)dtot[D_SX], sy = (float)dtot[D_SY],
-              sw = (float)dtot[D_SW];
-  const float aL = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+  const double sxx = dtot[D_SXX], syy = dtot[D_SYY], sx = dtot[D_SX], sy = dtot[D_SY], sw = dtot[D_SW];
+  const double aL = std::sqrt((syy - sy * sy / sw) / (sxx - sx * sx / sw));
   scalars[0] = tot[R_SUMRES] / size;
   scalars[1] = tot[R_SUMUNW] / tot[R_GOOD];
   scalars[2] = size;
@@ -805,8 +806,8 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   scalars[4] = tot[R_BAD];
   scalars[5] = tot[R_USAGE] / (float)hnum[level];
   scalars[6] = tot[R_SUMSGN] / tot[R_GOOD];
-  scalars[7] = aL;
-  scalars[8] = (sy - aL * sx) / sw;
+  scalars[7] = (float)aL;
+  scalars[8] = (float)((sy - aL * sx) / sw);
   scalars[9] = tot[R_SUMRES] / size;
   scalars[10] = scalars[11] = 0;
   return LSD_OK;

@@ -135,8 +135,16 @@ float SE3Tracker::calcResidualAndBuffers(const float *refPoint, const float *ref
   lastGoodCount = goodCount;
   lastBadCount = badCount;
   lastMeanRes = sumSignedRes.get() / goodCount;
-  affineEstimation_a_lastIt = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
-  affineEstimation_b_lastIt = (sy - affineEstimation_a_lastIt * sx) / sw;
+  if (ex) {
+    // EXACT: the closed form cancels ~20x (a) / ~100x (b); evaluate it in fp64 from the fp64 sums, round once
+    const double Sxx = sxx_.d, Syy = syy_.d, Sx = sx_.d, Sy = sy_.d, Sw = sw_.d;
+    const double a = std::sqrt((Syy - Sy * Sy / Sw) / (Sxx - Sx * Sx / Sw));
+    affineEstimation_a_lastIt = (float)a;
+    affineEstimation_b_lastIt = (float)((Sy - a * Sx) / Sw);
+  } else {
+    affineEstimation_a_lastIt = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+    affineEstimation_b_lastIt = (sy - affineEstimation_a_lastIt * sx) / sw;
+  }
   return sumResUnweighted.get() / goodCount;
 }
 
