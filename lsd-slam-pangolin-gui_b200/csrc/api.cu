@@ -567,7 +567,7 @@ int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *co
                         lsd_se3_result *results, lsd_trace_entry *traces) {
   LSD_ARG(ctx && refs && frames && init_frameToRef && results && n >= 0);
   LSD_CUDA(cudaSetDevice(ctx->device));
-  return se3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, results, traces, ctx->stream, true);
+  return se3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, results, traces, ctx->stream, false);
 }
 
 int lsd_se3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[7], lsd_se3_result *result,
@@ -605,6 +605,9 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
   std::vector<lsd_frame *> fr(n, nullptr);
   std::vector<void *> slabs;
   const int nChunks = (n + CH - 1) / CH;
+  ctx->lastAlgBytes = 0;
+  ctx->lastEvals = 0;
+  ctx->lastKernelMs = 0;
   auto issue_copy = [&](int c) -> int {
     const int i0 = c * CH, m = (n - i0) < CH ? (n - i0) : CH;
     uint8_t *dst = ctx->d_stage + (size_t)(c & 1) * fbytes * CH;

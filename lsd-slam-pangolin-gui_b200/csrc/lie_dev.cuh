@@ -70,7 +70,9 @@ template <typename S> __host__ __device__ inline void hat2(const S om[3], S Om[9
   Om[0] = 0; Om[1] = -om[2]; Om[2] = om[1];
   Om[3] = om[2]; Om[4] = 0; Om[5] = -om[0];
   Om[6] = -om[1]; Om[7] = om[0]; Om[8] = 0;
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) Om2[3 * i + j] = Om[3 * i] * Om[j] + Om[3 * i + 1] * Om[3 + j] + Om[3 * i + 2] * Om[6 + j];
 }
 
@@ -87,6 +89,7 @@ __host__ __device__ inline void se3_exp_compose(const S inc[6], const QuatT<S> &
   } else {
     const S t2 = theta * theta;
     const S a = (S(1) - cos(theta)) / t2, b = (theta - sin(theta)) / (t2 * theta);
+#pragma unroll
     for (int i = 0; i < 9; i++) V[i] = ((i % 4 == 0) ? S(1) : S(0)) + Om[i] * a + Om2[i] * b;
   }
   const S ups[3] = {inc[0], inc[1], inc[2]};
@@ -129,6 +132,7 @@ __host__ __device__ inline void sim3_exp_compose(const S inc[7], const QuatT<S> 
       B = (Cc - ((b - S(1)) * sigma + a * theta) / c) * S(1) / t2;
     }
   }
+#pragma unroll
   for (int i = 0; i < 9; i++) Wm[i] = Om[i] * A + Om2[i] * B + ((i % 4 == 0) ? Cc : S(0));
   const S ups[3] = {inc[0], inc[1], inc[2]};
   S dt[3];
@@ -146,25 +150,34 @@ __host__ __device__ inline void sim3_exp_compose(const S inc[7], const QuatT<S> 
 template <typename S, int N> __host__ __device__ inline void ldlt_solve(const S *A, const S *b, S *x) {
   S L[N * N];
   S D[N];
+#pragma unroll
   for (int j = 0; j < N; j++) {
     S d = A[j * N + j];
+#pragma unroll
     for (int k = 0; k < j; k++) d -= L[j * N + k] * L[j * N + k] * D[k];
     D[j] = d;
+#pragma unroll
     for (int i = j + 1; i < N; i++) {
       S v = A[i * N + j];
+#pragma unroll
       for (int k = 0; k < j; k++) v -= L[i * N + k] * L[j * N + k] * D[k];
       L[i * N + j] = v / d;
     }
   }
   S y[N];
+#pragma unroll
   for (int i = 0; i < N; i++) {
     S v = b[i];
+#pragma unroll
     for (int k = 0; k < i; k++) v -= L[i * N + k] * y[k];
     y[i] = v;
   }
+#pragma unroll
   for (int i = 0; i < N; i++) y[i] = y[i] / D[i];
+#pragma unroll
   for (int i = N - 1; i >= 0; i--) {
     S v = y[i];
+#pragma unroll
     for (int k = i + 1; k < N; k++) v -= L[k * N + i] * x[k];
     x[i] = v;
   }

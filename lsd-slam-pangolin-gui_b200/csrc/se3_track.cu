@@ -1,35 +1,35 @@
-// se3_track.cu -- [UP] SE3Tracker::trackFrame as ONE persistent cooperative kernel over a batch
-// of independent (TrackingReference, Frame) pairs (BASELINE.json config 2).
+// se3_track.cu -- [UP] SE3Tracker::trackFrame as ONE persistent kernel over a batch of independent
+// (TrackingReference, Frame) pairs (BASELINE.json config 2).
 //
 // Reference structure (lsd-slam core Tracking/SE3Tracker.cpp, un-vendored): per LM evaluation three
 // CPU passes -- calcResidualAndBuffers (8 SoA buffers out), calcWeightsAndResidual, and (per outer
 // iteration) calculateWarpUpdate -- with a 6x6 LDLT + SE3 exp on the host in between.
 //
-// B200 structure: the three passes are fused into one per-point evaluation that never
-// materialises the buffers; every evaluation also reduces the 21+6 normal-equation terms (they are
-// only CONSUMED if the step is accepted, exactly when upstream would call calculateWarpUpdate on the
-// same buffers).  Work items are (pair, 1024-point chunk); a grid-resident kernel pulls items from a
-// device work list; the CTA that completes a pair's last chunk sums the per-chunk partials in chunk
-// order (deterministic), runs the LM accept/reject logic, the 6x6 LDL^T solve and SE3 exp on device
-// and appends the pair's next evaluation to the next round's list.  Rounds are separated by one
-// grid.sync(); the host is not involved until every pair has finished.
+// B200 structure:
+//  * the three passes are fused into one per-point evaluation that never materialises the buffers;
+//    every evaluation also reduces the 21+6 normal-equation terms (they are only CONSUMED if the step
+//    is accepted, exactly when upstream would call calculateWarpUpdate on the same buffers);
+//  * work items are (pair, chunk of points); a grid-resident kernel pulls items from a device ring
+//    queue.  The CTA that completes a pair's last chunk sums the per-chunk partials in chunk order
+//    (deterministic, independent of scheduling), runs the LM accept/reject logic, the 6x6 LDL^T solve
+//    and the SE3 exponential on device, and pushes the pair's next evaluation into the queue.  Pairs
+//    advance independently: no host round trip and no grid-wide barrier anywhere in a track;
+//  * results are bit-reproducible run to run and independent of the batch composition.
 //
-// Compiled with -fmad=false: per-point values are bit-identical to the oracle's
-// (-ffp-contract=off); only the summation order differs.
-#include <cooperative_groups.h>
-
+// Compiled with -fmad=false: per-point values (warp, residual, weights, Jacobian rows) are
+// bit-identical to the oracle's (-ffp-contract=off); only summation order differs.  Accumulations use
+// explicit fmaf (an accumulation's rounding is order noise anyway).
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 
 #include "ctx.cuh"
 #include "lie_dev.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace lsd {
 
-#define SE3_CH 1024       // points per work item
 #define SE3_THREADS 256   // threads per CTA
+#define SE3_P 2           // points in flight per thread (loads of a batch are issued before any math)
 #define SE3_NRED 44       // floats per partial record: 5 doubles (affine sums) + 33 floats + pad
 #define SE3_NF 33         // fp32 sums per record
 #define SE3_ND 5          // fp64 sums per record
@@ -37,7 +37,7 @@ namespace lsd {
 // fp32 sums (index into acc[] / the float part of a record, which starts at float offset 2*SE3_ND)
 enum { R_A = 0, R_B = 21, R_SUMRES = 27, R_SUMUNW = 28, R_SUMSGN = 29, R_USAGE = 30, R_GOOD = 31, R_BAD = 32 };
 // fp64 sums: the affine-lighting estimate sqrt((syy - sy^2/sw)/(sxx - sx^2/sw)) cancels ~20x (a) and
-// ~100x (b = mean_y - a*mean_x), so its five sums are carried in fp64 end to end (10 DADD per point);
+// ~100x (b = mean_y - a*mean_x), so its five sums are carried in fp64 end to end (5 DADD per point);
 // everything else is consumed without cancellation and stays fp32.
 enum { D_SXX = 0, D_SYY = 1, D_SX = 2, D_SY = 3, D_SW = 4 };
 
@@ -51,20 +51,22 @@ struct SE3Pair {
   int n[NL];
 };
 
-// Mutable LM state: other SMs update it between rounds, so inside the persistent kernel it is only
-// read through L2 (__ldcg) -- never through a possibly stale L1 line.
+// Mutable LM state: other SMs update it between evaluations, so inside the persistent kernel it is
+// only read through L2 (__ldcg) -- never through a possibly stale L1 line.
 struct __align__(16) SE3State {
+  // --- evaluation header: what every CTA working on this pair's current evaluation needs (64 B) ---
   float R[9], t[3];  // pose of the evaluation in flight
+  float aff_a, aff_b;
+  int level;
+  int nChunks;
+  // --- LM bookkeeping (touched only by the thread running the LM step) ---
   float q_try[4];
   float q_cur[4], t_cur[3];
-  float aff_a, aff_b;
-  int level, phase, iteration, incTry;
+  int phase, iteration, incTry;
   float lambda, lastErr, last_residual;
   float A[21], b[6], inc[6];
-  int nChunks;
   unsigned done;
   int finished, diverged, trackingWasGood;
-  // stats of the last evaluation
   float pointUsage, good, bad, meanRes, aff_a_lastIt, aff_b_lastIt;
   int bufSize;
   int nResCalls[NL], nWarpCalls[NL];
@@ -72,48 +74,61 @@ struct __align__(16) SE3State {
   float outq[4], outt[3];  // frameToRef (float)
   float initialTrackedResidual;
   int n[NL];  // copy of numData for the host
-  int pad_[3];
+  int pad_[2];
 };
 static_assert(sizeof(SE3State) % 16 == 0, "SE3State must be int4-copyable");
+static_assert(offsetof(SE3State, q_try) == 64, "evaluation header must be the first 64 bytes");
 
 __device__ __forceinline__ void state_load(SE3State *dst, const SE3State *src) {
   const int4 *s4 = reinterpret_cast<const int4 *>(src);
   int4 *d4 = reinterpret_cast<int4 *>(dst);
-#pragma unroll 4
+#pragma unroll
   for (int i = 0; i < (int)(sizeof(SE3State) / 16); i++) d4[i] = __ldcg(s4 + i);
 }
 __device__ __forceinline__ void state_store(SE3State *dst, const SE3State *src) {
   const int4 *s4 = reinterpret_cast<const int4 *>(src);
   int4 *d4 = reinterpret_cast<int4 *>(dst);
-#pragma unroll 4
+#pragma unroll
   for (int i = 0; i < (int)(sizeof(SE3State) / 16); i++) d4[i] = s4[i];
 }
+
+// Device work queue: ring of 64-bit slots {sequence : 32, item code : 32}.  A slot is valid for ticket T
+// when its sequence equals T / cap + 1.  At most n * maxChunks items are outstanding (one evaluation per
+// pair), and cap >= that, so a slot is never overwritten before it has been consumed.
+struct SE3Queue {
+  unsigned long long *slots;
+  unsigned *head;  // consumer tickets
+  unsigned *tail;  // producer reservations
+  int *remaining;  // pairs not finished yet
+  unsigned cap;    // power of two
+};
 
 struct SE3Params {
   Intrinsics K;
   lsd_tracker_settings s;
-  int maxChunks;
+  int maxChunks;           // per-pair stride of the partial records
+  int chunk;               // points per work item (multiple of SE3_THREADS * SE3_P)
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
 };
 
-__device__ __forceinline__ float ldcg_f(const float *p) { return __ldcg(p); }
-__device__ __forceinline__ int ldcg_i(const int *p) { return __ldcg(p); }
-
-// Append the chunks of the pair's next evaluation to list `nxt`.
-__device__ void push_items(const SE3Pair *P, SE3State *S, int pairIdx, int level, int *list, int *count) {
-  const int n = P->n[level];
-  const int nch = (n + SE3_CH - 1) / SE3_CH;
-  S->nChunks = nch;
-  S->done = 0;
-  const int base = atomicAdd(count, nch);
-  for (int c = 0; c < nch; c++) list[base + c] = (pairIdx << 12) | c;
+// Publish the chunks of the pair's next evaluation.  The caller has stored the pair's state already.
+__device__ void q_push(const SE3Queue &q, int pairIdx, int nch) {
+  __threadfence();  // state (and everything before) visible before any consumer can see the items
+  const unsigned base = atomicAdd(q.tail, (unsigned)nch);
+  for (int c = 0; c < nch; c++) {
+    const unsigned t = base + c;
+    const unsigned long long v = ((unsigned long long)(t / q.cap + 1) << 32) | (unsigned)((pairIdx << 12) | c);
+    *reinterpret_cast<volatile unsigned long long *>(&q.slots[t & (q.cap - 1)]) = v;
+  }
 }
 
-__device__ void set_eval_pose(SE3State *S, const float q[4], const float t[3]) {
+__device__ __forceinline__ void set_eval_pose(SE3State *S, const float q[4], const float t[3]) {
   QuatT<float> qq = {q[0], q[1], q[2], q[3]};
   float R[9];
   qtoR(qq, R);
+#pragma unroll
   for (int i = 0; i < 9; i++) S->R[i] = R[i];
+#pragma unroll
   for (int i = 0; i < 3; i++) S->t[i] = t[i];
 }
 
@@ -142,21 +157,24 @@ __device__ void finish_pair(SE3State *S, const SE3Params &prm) {
   S->finished = 1;
 }
 
-// S is a thread-local copy; the caller stores it back to global memory afterwards.
-__device__ void start_level(const SE3Pair *P, SE3State *S, int pairIdx, int level, int *list, int *count) {
+// S is a thread-local copy.  Returns the number of chunks to publish (0: the pair is finished).
+__device__ int start_level(const SE3Pair *P, SE3State *S, int level, const SE3Params &prm) {
   S->level = level;
   S->phase = 0;
   set_eval_pose(S, S->q_cur, S->t_cur);
   if (P->n[level] == 0) {  // calcResidualAndBuffers on an empty cloud: buf_warped_size 0 < 1% => diverged
     mark_diverged(S);
-    return;
+    return 0;
   }
-  push_items(P, S, pairIdx, level, list, count);
+  S->nChunks = (P->n[level] + prm.chunk - 1) / prm.chunk;
+  S->done = 0;
+  return S->nChunks;
 }
 
 // The LM state machine, run by one thread after the last chunk of an evaluation (tot = summed partials).
-__device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float *tot, const double *dtot,
-                        const SE3Params &prm, int *list, int *count, lsd_trace_entry *trace) {
+// Returns the number of chunks of the next evaluation (0: pair finished).
+__device__ int lm_step(const SE3Pair *P, SE3State *S, const float *tot, const double *dtot, const SE3Params &prm,
+                       lsd_trace_entry *trace) {
   const int lvl = S->level;
   const float good = tot[R_GOOD], bad = tot[R_BAD];
   const int size = (int)(good + bad);
@@ -175,55 +193,67 @@ __device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float 
 
   if (size < LSD_MIN_GOODPERALL_PIXEL_ABSMIN * prm.K.w[lvl] * prm.K.h[lvl]) {
     mark_diverged(S);
-    return;
+    return 0;
   }
   const float error = tot[R_SUMRES] / (float)size;
   S->nResCalls[lvl]++;
+  const int maxIts = prm.s.maxItsPerLvl[lvl];
 
   bool takeNormalEq = false;  // begin a new outer iteration with this evaluation's A, b
+  int accepted;
+  float traceLambda = S->lambda;
   if (S->phase == 0) {
     S->aff_a = aL;
     S->aff_b = bL;
     S->lastErr = error;
     S->lambda = prm.s.lambdaInitial[lvl];
     S->iteration = 0;
-    if (trace && S->traceLen < LSD_TRACE_CAP) trace[S->traceLen] = {lvl, -1, error, 0.0f, size};
-    S->traceLen++;
+    accepted = -1;
+    traceLambda = 0.0f;
+    takeNormalEq = true;
+  } else if (error < S->lastErr) {
+    accepted = 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) S->q_cur[i] = S->q_try[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) S->t_cur[i] = S->t[i];
+    S->aff_a = aL;
+    S->aff_b = bL;
+    if (error / S->lastErr > prm.s.convergenceEps[lvl]) S->iteration = maxIts;
+    S->last_residual = S->lastErr = error;
+    if (S->lambda <= 0.2f) S->lambda = 0; else S->lambda *= prm.s.lambdaSuccessFac;
+    S->iteration++;
     takeNormalEq = true;
   } else {
-    if (error < S->lastErr) {
-      if (trace && S->traceLen < LSD_TRACE_CAP) trace[S->traceLen] = {lvl, 1, error, S->lambda, size};
-      S->traceLen++;
-      for (int i = 0; i < 4; i++) S->q_cur[i] = S->q_try[i];
-      for (int i = 0; i < 3; i++) S->t_cur[i] = S->t[i];
-      S->aff_a = aL;
-      S->aff_b = bL;
-      if (error / S->lastErr > prm.s.convergenceEps[lvl]) S->iteration = prm.s.maxItsPerLvl[lvl];
-      S->last_residual = S->lastErr = error;
-      if (S->lambda <= 0.2f) S->lambda = 0; else S->lambda *= prm.s.lambdaSuccessFac;
-      S->iteration++;
-      takeNormalEq = true;
+    accepted = 0;
+    float inc2 = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) inc2 += S->inc[i] * S->inc[i];
+    if (!(inc2 > prm.s.stepSizeMin[lvl])) {
+      S->iteration = maxIts + 1;  // level ends
+    } else if (S->lambda == 0) {
+      S->lambda = 0.2f;
     } else {
-      if (trace && S->traceLen < LSD_TRACE_CAP) trace[S->traceLen] = {lvl, 0, error, S->lambda, size};
-      S->traceLen++;
-      float inc2 = 0;
-      for (int i = 0; i < 6; i++) inc2 += S->inc[i] * S->inc[i];
-      if (!(inc2 > prm.s.stepSizeMin[lvl])) {
-        S->iteration = prm.s.maxItsPerLvl[lvl] + 1;  // level ends
-      } else {
-        if (S->lambda == 0) S->lambda = 0.2f; else S->lambda *= powf(prm.s.lambdaFailFac, (float)S->incTry);
-      }
+      float f = 1.0f;  // std::pow(lambdaFailFac, incTry): exact for the default factor 2
+      for (int k = 0; k < S->incTry; k++) f *= prm.s.lambdaFailFac;
+      S->lambda *= f;
     }
   }
+  if (trace && S->traceLen < LSD_TRACE_CAP) trace[S->traceLen] = {lvl, accepted, error, traceLambda, size};
+  S->traceLen++;
 
-  if (S->iteration >= prm.s.maxItsPerLvl[lvl]) {
-    if (lvl - 1 < prm.minLevel) finish_pair(S, prm);
-    else start_level(P, S, pairIdx, lvl - 1, list, count);
-    return;
+  if (S->iteration >= maxIts) {
+    if (lvl - 1 < prm.minLevel) {
+      finish_pair(S, prm);
+      return 0;
+    }
+    return start_level(P, S, lvl - 1, prm);
   }
   if (takeNormalEq) {  // NormalEquationsLeastSquares::finish(): divide by num_constraints
     const float nf = (float)size;
+#pragma unroll
     for (int k = 0; k < 21; k++) S->A[k] = tot[R_A + k] / nf;
+#pragma unroll
     for (int k = 0; k < 6; k++) S->b[k] = tot[R_B + k] / nf;
     S->nWarpCalls[lvl]++;
     S->incTry = 0;
@@ -232,17 +262,22 @@ __device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float 
   float Al[36], rhs[6], inc[6];
   {
     int k = 0;
+#pragma unroll
     for (int a = 0; a < 6; a++)
+#pragma unroll
       for (int c = a; c < 6; c++) {
         Al[a * 6 + c] = Al[c * 6 + a] = S->A[k++];
       }
+    const float lam1 = 1 + S->lambda;
+#pragma unroll
     for (int a = 0; a < 6; a++) {
-      Al[a * 6 + a] *= 1 + S->lambda;
+      Al[a * 6 + a] *= lam1;
       rhs[a] = S->b[a];
     }
   }
   ldlt_solve<float, 6>(Al, rhs, inc);
   S->incTry++;
+#pragma unroll
   for (int i = 0; i < 6; i++) S->inc[i] = inc[i];
   QuatT<float> qc = {S->q_cur[0], S->q_cur[1], S->q_cur[2], S->q_cur[3]}, qn;
   float tn[3];
@@ -250,10 +285,14 @@ __device__ void lm_step(const SE3Pair *P, SE3State *S, int pairIdx, const float 
   S->q_try[0] = qn.x; S->q_try[1] = qn.y; S->q_try[2] = qn.z; S->q_try[3] = qn.w;
   set_eval_pose(S, S->q_try, tn);
   S->phase = 1;
-  push_items(P, S, pairIdx, lvl, list, count);
+  S->done = 0;  // same level => same nChunks
+  return S->nChunks;
 }
 
-// Fused calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate for one point.
+// ---------------------------------------------------------------------------------------------
+// Fused calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate, split in two phases so
+// that the bilinear taps of SE3_P points are in flight before any dependent math starts.
+// ---------------------------------------------------------------------------------------------
 struct EvalConst {
   float R[9], t[3];
   float a, b;
@@ -262,33 +301,49 @@ struct EvalConst {
   int W, H;
 };
 
-__device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c, const float4 *__restrict__ G,
-                                           uint8_t *__restrict__ mask, float acc[SE3_NF], double dacc[SE3_ND]) {
-  const int x = p.xy & 0xffff, y = p.xy >> 16;
-  const float inv = 1.0f / p.idepth;
+struct Warped {  // phase-A result of one point
+  float Wx, Wy, Wz, pz, dx, dy;
+  int off;   // tap base offset (float4 units); -1 when the point projects outside; -2 past the end
+  int midx;  // x + y*W (mask index)
+};
+
+__device__ __forceinline__ void warp_point(const float4 raw, const EvalConst &c, Warped &w) {
+  const uint32_t xy = __float_as_uint(raw.x);
+  const int x = xy & 0xffff, y = xy >> 16;
+  const float inv = 1.0f / raw.y;  // pos = (1/idepth) * (fxi*x+cxi, fyi*y+cyi, 1): TrackingReference::makePointCloud
   const float px = inv * (c.fxi * x + c.cxi);
   const float py = inv * (c.fyi * y + c.cyi);
   const float pz = inv * 1.0f;
-  const float Wx = (c.R[0] * px + c.R[1] * py + c.R[2] * pz) + c.t[0];
-  const float Wy = (c.R[3] * px + c.R[4] * py + c.R[5] * pz) + c.t[1];
-  const float Wz = (c.R[6] * px + c.R[7] * py + c.R[8] * pz) + c.t[2];
-  const float u_new = (Wx / Wz) * c.fx + c.cx;
-  const float v_new = (Wy / Wz) * c.fy + c.cy;
-  if (!(u_new > 1 && v_new > 1 && u_new < c.W - 2 && v_new < c.H - 2)) {
-    if (mask) mask[x + y * c.W] = 0;
+  w.Wx = (c.R[0] * px + c.R[1] * py + c.R[2] * pz) + c.t[0];
+  w.Wy = (c.R[3] * px + c.R[4] * py + c.R[5] * pz) + c.t[1];
+  w.Wz = (c.R[6] * px + c.R[7] * py + c.R[8] * pz) + c.t[2];
+  w.pz = pz;
+  const float u_new = (w.Wx / w.Wz) * c.fx + c.cx;
+  const float v_new = (w.Wy / w.Wz) * c.fy + c.cy;
+  w.midx = x + y * c.W;
+  if (!(u_new > 1 && v_new > 1 && u_new < c.W - 2 && v_new < c.H - 2)) {  // inverse test excludes NaN
+    w.off = -1;
+    w.dx = w.dy = 0;
     return;
   }
-  // getInterpolatedElement43
   const int ix = (int)u_new, iy = (int)v_new;
-  const float dx = u_new - ix, dy = v_new - iy, dxdy = dx * dy;
-  const float4 *bp = G + ix + iy * c.W;
-  const float4 p00 = __ldg(bp), p10 = __ldg(bp + 1), p01 = __ldg(bp + c.W), p11 = __ldg(bp + 1 + c.W);
-  const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+  w.dx = u_new - ix;
+  w.dy = v_new - iy;
+  w.off = ix + iy * c.W;
+}
+
+__device__ __forceinline__ void accumulate_point(const float4 raw, const Warped &w, const float4 p00, const float4 p10,
+                                                 const float4 p01, const float4 p11, const EvalConst &c,
+                                                 uint8_t *__restrict__ mask, float acc[SE3_NF], double dacc[SE3_ND]) {
+  // getInterpolatedElement43 (this exact weight form and summation order)
+  const float dxdy = w.dx * w.dy;
+  const float w11 = dxdy, w01 = w.dy - dxdy, w10 = w.dx - dxdy, w00 = 1 - w.dx - w.dy + dxdy;
   const float gxI = w11 * p11.x + w01 * p01.x + w10 * p10.x + w00 * p00.x;
   const float gyI = w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y;
   const float cI = w11 * p11.z + w01 * p01.z + w10 * p10.z + w00 * p00.z;
+  const float Wx = w.Wx, Wy = w.Wy, Wz = w.Wz, pz = w.pz;
 
-  const float c1 = c.a * p.color + c.b;
+  const float c1 = c.a * raw.z + c.b;
   const float c2 = cI;
   const float residual = c1 - c2;
   const float weight = fabsf(residual) < 5.0f ? 1 : 5.0f / fabsf(residual);
@@ -298,7 +353,7 @@ __device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c,
   dacc[D_SY] += (double)(c2 * weight);
   dacc[D_SW] += (double)weight;
   const bool isGood = residual * residual / (LSD_MAX_DIFF_CONSTANT + LSD_MAX_DIFF_GRAD_MULT * (gxI * gxI + gyI * gyI)) < 1;
-  if (mask) mask[x + y * c.W] = isGood;
+  if (mask) mask[w.midx] = isGood;
   if (isGood) {
     acc[R_SUMUNW] += residual * residual;
     acc[R_SUMSGN] += residual;
@@ -312,7 +367,7 @@ __device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c,
   // calcWeightsAndResidual
   const float gx = c.fx * gxI, gy = c.fy * gyI;
   const float d = 1.0f / pz;
-  const float s = c.var_weight * p.var;
+  const float s = c.var_weight * raw.w;
   const float g0 = (c.t[0] * Wz - c.t[2] * Wx) / (Wz * Wz * d);
   const float g1 = (c.t[1] * Wz - c.t[2] * Wy) / (Wz * Wz * d);
   const float drpdd = gx * g0 + gy * g1;
@@ -337,55 +392,99 @@ __device__ __forceinline__ void eval_point(const RefPoint p, const EvalConst &c,
   for (int a = 0; a < 6; a++) {
     const float wa = v[a] * wgt;
 #pragma unroll
-    for (int cc = a; cc < 6; cc++) acc[R_A + (k++)] += wa * v[cc];
+    for (int cc = a; cc < 6; cc++) {
+      acc[R_A + k] = fmaf(wa, v[cc], acc[R_A + k]);
+      k++;
+    }
   }
   const float rw = residual * wgt;
 #pragma unroll
-  for (int a = 0; a < 6; a++) acc[R_B + a] += v[a] * rw;
+  for (int a = 0; a < 6; a++) acc[R_B + a] = fmaf(v[a], rw, acc[R_B + a]);
 }
 
-__device__ __forceinline__ void block_reduce_store(float acc[SE3_NF], double dacc[SE3_ND], float *__restrict__ dst,
-                                                   float (*sred)[SE3_NRED]) {
+// All points [begin, end) of one evaluation handled by this CTA: SE3_P points per thread per step.
+__device__ __forceinline__ void eval_range(const RefPoint *__restrict__ pts, int begin, int end, const float4 *__restrict__ G,
+                                           uint8_t *__restrict__ mask, const EvalConst &c, float acc[SE3_NF],
+                                           double dacc[SE3_ND]) {
+  const float4 *pts4 = reinterpret_cast<const float4 *>(pts);
+  for (int i0 = begin + threadIdx.x; i0 < end; i0 += SE3_THREADS * SE3_P) {
+    float4 raw[SE3_P];
+    Warped w[SE3_P];
+    float4 tap[SE3_P][4];
+#pragma unroll
+    for (int k = 0; k < SE3_P; k++) {
+      const int i = i0 + k * SE3_THREADS;
+      raw[k] = (i < end) ? __ldg(pts4 + i) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < SE3_P; k++) {
+      const int i = i0 + k * SE3_THREADS;
+      if (i < end) {
+        warp_point(raw[k], c, w[k]);
+      } else {
+        w[k].off = -2;
+        w[k].midx = 0;
+      }
+      if (w[k].off >= 0) {
+        const float4 *bp = G + w[k].off;
+        tap[k][0] = __ldg(bp);
+        tap[k][1] = __ldg(bp + 1);
+        tap[k][2] = __ldg(bp + c.W);
+        tap[k][3] = __ldg(bp + 1 + c.W);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SE3_P; k++) {
+      if (w[k].off >= 0) accumulate_point(raw[k], w[k], tap[k][0], tap[k][1], tap[k][2], tap[k][3], c, mask, acc, dacc);
+      else if (w[k].off == -1 && mask) mask[w[k].midx] = 0;
+    }
+  }
+}
+
+// Block reduction through shared memory: every thread parks its 38 sums (column = thread), then warp w
+// reduces rows w, w+8, ...: 8 conflict-free LDS + one shuffle tree per row.  Fixed order => deterministic.
+struct SE3Smem {
+  float f[SE3_NF][SE3_THREADS];
+  double d[SE3_ND][SE3_THREADS];
+};
+
+__device__ __forceinline__ void block_reduce_store(const float acc[SE3_NF], const double dacc[SE3_ND], float *__restrict__ dst,
+                                                   SE3Smem &sm) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < SE3_ND; j++) {
-    double v = dacc[j];
+  for (int j = 0; j < SE3_NF; j++) sm.f[j][threadIdx.x] = acc[j];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) reinterpret_cast<double *>(sred[wid])[j] = v;
-  }
-#pragma unroll
-  for (int j = 0; j < SE3_NF; j++) {
-    float v = acc[j];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) sred[wid][2 * SE3_ND + j] = v;
-  }
+  for (int j = 0; j < SE3_ND; j++) sm.d[j][threadIdx.x] = dacc[j];
   __syncthreads();
-  if (threadIdx.x < SE3_ND) {
-    double s = reinterpret_cast<double *>(sred[0])[threadIdx.x];
+  for (int row = wid; row < SE3_NF + SE3_ND; row += SE3_THREADS / 32) {
+    if (row < SE3_NF) {
+      float v = 0.0f;
 #pragma unroll
-    for (int w = 1; w < SE3_THREADS / 32; w++) s += reinterpret_cast<double *>(sred[w])[threadIdx.x];
-    reinterpret_cast<double *>(dst)[threadIdx.x] = s;
-    __threadfence();
-  } else if (threadIdx.x < SE3_ND + SE3_NF) {
-    const int j = 2 * SE3_ND + (threadIdx.x - SE3_ND);
-    float s = sred[0][j];
+      for (int k = 0; k < SE3_THREADS / 32; k++) v += sm.f[row][lane + 32 * k];
 #pragma unroll
-    for (int w = 1; w < SE3_THREADS / 32; w++) s += sred[w][j];
-    dst[j] = s;
-    __threadfence();
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) dst[2 * SE3_ND + row] = v;
+    } else {
+      const int r = row - SE3_NF;
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < SE3_THREADS / 32; k++) v += sm.d[r][lane + 32 * k];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) reinterpret_cast<double *>(dst)[r] = v;
+    }
   }
+  __threadfence();  // partial record visible device-wide before this CTA's completion ticket
   __syncthreads();
 }
 
-__device__ __forceinline__ void load_eval_const(const SE3State *P, int level, const SE3Params &prm, EvalConst &c) {
-#pragma unroll
-  for (int i = 0; i < 9; i++) c.R[i] = ldcg_f(&P->R[i]);
-#pragma unroll
-  for (int i = 0; i < 3; i++) c.t[i] = ldcg_f(&P->t[i]);
-  c.a = ldcg_f(&P->aff_a);
-  c.b = ldcg_f(&P->aff_b);
+__device__ __forceinline__ void load_eval_const(const SE3Params &prm, int level, const int4 h0, const int4 h1, const int4 h2,
+                                                const int4 h3, EvalConst &c) {
+  c.R[0] = __int_as_float(h0.x); c.R[1] = __int_as_float(h0.y); c.R[2] = __int_as_float(h0.z); c.R[3] = __int_as_float(h0.w);
+  c.R[4] = __int_as_float(h1.x); c.R[5] = __int_as_float(h1.y); c.R[6] = __int_as_float(h1.z); c.R[7] = __int_as_float(h1.w);
+  c.R[8] = __int_as_float(h2.x); c.t[0] = __int_as_float(h2.y); c.t[1] = __int_as_float(h2.z); c.t[2] = __int_as_float(h2.w);
+  c.a = __int_as_float(h3.x);
+  c.b = __int_as_float(h3.y);
   c.fx = prm.K.fx[level]; c.fy = prm.K.fy[level]; c.cx = prm.K.cx[level]; c.cy = prm.K.cy[level];
   c.fxi = prm.K.fxi[level]; c.fyi = prm.K.fyi[level]; c.cxi = prm.K.cxi[level]; c.cyi = prm.K.cyi[level];
   c.var_weight = prm.s.var_weight;
@@ -395,94 +494,97 @@ __device__ __forceinline__ void load_eval_const(const SE3State *P, int level, co
 }
 
 __global__ void __launch_bounds__(SE3_THREADS, 2)
-k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials, int *lists, int listCap, int *counts,
+k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials, const SE3Queue q,
             const __grid_constant__ SE3Params prm, lsd_trace_entry *traces) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ __align__(16) float sred[SE3_THREADS / 32][SE3_NRED];
+  __shared__ SE3Smem sm;
   __shared__ float stot[SE3_NF];
   __shared__ double sdtot[SE3_ND];
-  __shared__ int sIsLast;
+  __shared__ int sCode, sIsLast;
 
-  for (int round = 0;; round++) {
-    const int cur = round % 3, nxt = (round + 1) % 3, clr = (round + 2) % 3;
-    const int cnt = ldcg_i(&counts[cur]);
-    if (cnt == 0) break;
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts[clr] = 0;
-    const int *list = lists + (size_t)cur * listCap;
-    for (int item = blockIdx.x; item < cnt; item += gridDim.x) {
-      const int code = ldcg_i(&list[item]);
-      const int pairIdx = code >> 12, chunk = code & 0xfff;
-      const SE3Pair *P = pairs + pairIdx;
-      SE3State *S = states + pairIdx;
-      const int level = ldcg_i(&S->level);
-      EvalConst c;
-      load_eval_const(S, level, prm, c);
-      const int n = P->n[level];
-      const RefPoint *__restrict__ pts = P->pts[level];
-      const float4 *__restrict__ G = P->fgrad[level];
-      uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
-
-      float acc[SE3_NF];
-      double dacc[SE3_ND];
-#pragma unroll
-      for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
-#pragma unroll
-      for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-      const int base = chunk * SE3_CH + threadIdx.x;
-#pragma unroll
-      for (int k = 0; k < SE3_CH / SE3_THREADS; k++) {
-        const int i = base + k * SE3_THREADS;
-        if (i < n) {
-          const float4 raw = __ldg(reinterpret_cast<const float4 *>(pts) + i);
-          RefPoint p;
-          p.xy = __float_as_uint(raw.x);
-          p.idepth = raw.y;
-          p.color = raw.z;
-          p.var = raw.w;
-          eval_point(p, c, G, mask, acc, dacc);
+  unsigned ticket = 0;
+  if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
+  for (;;) {
+    // ---- fetch the next work item (thread 0 spins on its ticket's slot) ----
+    if (threadIdx.x == 0) {
+      const unsigned slot = ticket & (q.cap - 1), seq = ticket / q.cap + 1;
+      const volatile unsigned long long *sp = reinterpret_cast<const volatile unsigned long long *>(&q.slots[slot]);
+      int code = -1;
+      for (;;) {
+        const unsigned long long v = *sp;
+        if ((unsigned)(v >> 32) == seq) {
+          code = (int)(unsigned)v;
+          break;
         }
+        if (*reinterpret_cast<const volatile int *>(q.remaining) <= 0) break;
+        __nanosleep(40);
       }
-      float *dst = partials + ((size_t)pairIdx * prm.maxChunks + chunk) * SE3_NRED;
-      block_reduce_store(acc, dacc, dst, sred);
-      if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&S->done, 1u);
-        sIsLast = (ticket == (unsigned)(ldcg_i(&S->nChunks) - 1));
-      }
-      __syncthreads();
-      if (sIsLast) {
-        __threadfence();
-        const int nch = ldcg_i(&S->nChunks);
-        const float *rec0 = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED;
-        if (threadIdx.x < SE3_ND) {
-          const double *src = reinterpret_cast<const double *>(rec0) + threadIdx.x;
-          double s = 0.0;
-          for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * (SE3_NRED / 2));
-          sdtot[threadIdx.x] = s;
-        } else if (threadIdx.x < SE3_ND + SE3_NF) {
-          const int j = threadIdx.x - SE3_ND;
-          const float *src = rec0 + 2 * SE3_ND + j;
-          float s = 0.0f;
-          for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
-          stot[j] = s;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          SE3State L;
-          state_load(&L, S);
-          lm_step(P, &L, pairIdx, stot, sdtot, prm, lists + (size_t)nxt * listCap, &counts[nxt],
-                  traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
-          state_store(S, &L);
-        }
-      }
-      __syncthreads();
+      sCode = code;
+      if (code >= 0) ticket = atomicAdd(q.head, 1u);  // next ticket is requested now, consumed after this item
     }
-    grid.sync();
+    __syncthreads();
+    const int code = sCode;
+    if (code < 0) break;
+    const int pairIdx = code >> 12, chunk = code & 0xfff;
+    const SE3Pair *P = pairs + pairIdx;
+    SE3State *S = states + pairIdx;
+    // evaluation header: 4 x LDG.128 through L2
+    const int4 *hp = reinterpret_cast<const int4 *>(S);
+    const int4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1), h2 = __ldcg(hp + 2), h3 = __ldcg(hp + 3);
+    const int level = h3.z, nch = h3.w;
+    EvalConst c;
+    load_eval_const(prm, level, h0, h1, h2, h3, c);
+    const int n = P->n[level];
+    uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
+
+    float acc[SE3_NF];
+    double dacc[SE3_ND];
+#pragma unroll
+    for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
+    const int begin = chunk * prm.chunk;
+    const int end = min(n, begin + prm.chunk);
+    eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc);
+
+    float *dst = partials + ((size_t)pairIdx * prm.maxChunks + chunk) * SE3_NRED;
+    block_reduce_store(acc, dacc, dst, sm);
+    if (threadIdx.x == 0) sIsLast = (atomicAdd(&S->done, 1u) == (unsigned)(nch - 1));
+    __syncthreads();
+    if (sIsLast) {
+      __threadfence();
+      const float *rec0 = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED;
+      if (threadIdx.x < SE3_ND) {
+        const double *src = reinterpret_cast<const double *>(rec0) + threadIdx.x;
+        double s = 0.0;
+        for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * (SE3_NRED / 2));
+        sdtot[threadIdx.x] = s;
+      } else if (threadIdx.x < SE3_ND + SE3_NF) {
+        const int j = threadIdx.x - SE3_ND;
+        const float *src = rec0 + 2 * SE3_ND + j;
+        float s = 0.0f;
+        for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
+        stot[j] = s;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        SE3State L;
+        state_load(&L, S);
+        const int next = lm_step(P, &L, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
+        state_store(S, &L);
+        if (next > 0) {
+          q_push(q, pairIdx, next);
+        } else {
+          __threadfence();
+          atomicSub(q.remaining, 1);
+        }
+      }
+    }
+    __syncthreads();  // sCode / sIsLast / sm are reused by the next item
   }
 }
 
-// Build the initial state of every pair and the first work list (level maxLevel).
-__global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, int *__restrict__ lists,
-                           int *__restrict__ counts, SE3Params prm) {
+// Build the initial state of every pair and publish the first evaluations (level maxLevel).
+__global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, const SE3Queue q, SE3Params prm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   SE3Pair *P = pairs + i;
@@ -497,8 +599,10 @@ __global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ s
   L.aff_a = 1;
   L.aff_a_lastIt = 1;
   L.trackingWasGood = 1;
-  start_level(P, &L, i, prm.maxLevel, lists, &counts[0]);
+  const int next = start_level(P, &L, prm.maxLevel, prm);
   state_store(states + i, &L);
+  if (next > 0) q_push(q, i, next);
+  else atomicSub(q.remaining, 1);
 }
 
 struct SE3ScratchImpl {
@@ -508,10 +612,10 @@ struct SE3ScratchImpl {
   SE3State *h_states = nullptr;  // pinned
   int cap = 0;
   float *d_partials = nullptr;
-  size_t partialsBytes = 0;
-  int *d_lists = nullptr;
-  int listCap = 0;
-  int *d_counts = nullptr;
+  int maxChunks = 0;
+  unsigned long long *d_slots = nullptr;
+  unsigned qcap = 0;
+  unsigned *d_ctrs = nullptr;  // head, tail, remaining, pad
   lsd_trace_entry *d_traces = nullptr;
   size_t tracesBytes = 0;
   int gridBlocks = 0;
@@ -531,33 +635,37 @@ void se3_scratch_free(lsd_ctx *ctx) {
   cudaFree(s->d_states);
   cudaFreeHost(s->h_states);
   cudaFree(s->d_partials);
-  cudaFree(s->d_lists);
-  cudaFree(s->d_counts);
+  cudaFree(s->d_slots);
+  cudaFree(s->d_ctrs);
   cudaFree(s->d_traces);
   delete s;
   ctx->se3s = nullptr;
 }
 
+#define SE3_MIN_CHUNK (SE3_THREADS * SE3_P)
+
 static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
   if (!ctx->se3s) ctx->se3s = new SE3Scratch();
   SE3Scratch *s = ctx->se3s;
-  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_CH - 1) / SE3_CH;
+  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_MIN_CHUNK - 1) / SE3_MIN_CHUNK;
   if (n > s->cap) {
     cudaFree(s->d_pairs);
     cudaFreeHost(s->h_pairs);
     cudaFree(s->d_states);
     cudaFreeHost(s->h_states);
     cudaFree(s->d_partials);
-    cudaFree(s->d_lists);
+    cudaFree(s->d_slots);
     int cap = n < 16 ? 16 : n;
     LSD_CUDA(cudaMalloc(&s->d_pairs, sizeof(SE3Pair) * cap));
     LSD_CUDA(cudaMallocHost(&s->h_pairs, sizeof(SE3Pair) * cap));
     LSD_CUDA(cudaMalloc(&s->d_states, sizeof(SE3State) * cap));
     LSD_CUDA(cudaMallocHost(&s->h_states, sizeof(SE3State) * cap));
-    s->partialsBytes = (size_t)cap * maxChunks * SE3_NRED * sizeof(float);
-    LSD_CUDA(cudaMalloc(&s->d_partials, s->partialsBytes));
-    s->listCap = cap * maxChunks;
-    LSD_CUDA(cudaMalloc(&s->d_lists, sizeof(int) * 3 * (size_t)s->listCap));
+    LSD_CUDA(cudaMalloc(&s->d_partials, (size_t)cap * maxChunks * SE3_NRED * sizeof(float)));
+    s->maxChunks = maxChunks;
+    unsigned need = (unsigned)cap * (unsigned)maxChunks + 4096u, qcap = 1;
+    while (qcap < need) qcap <<= 1;
+    LSD_CUDA(cudaMalloc(&s->d_slots, sizeof(unsigned long long) * qcap));
+    s->qcap = qcap;
     s->cap = cap;
     if (s->d_traces) {
       cudaFree(s->d_traces);
@@ -565,7 +673,7 @@ static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
       s->tracesBytes = 0;
     }
   }
-  if (!s->d_counts) LSD_CUDA(cudaMalloc(&s->d_counts, sizeof(int) * 4));
+  if (!s->d_ctrs) LSD_CUDA(cudaMalloc(&s->d_ctrs, sizeof(unsigned) * 4));
   if (wantTrace && s->tracesBytes < sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)s->cap) {
     cudaFree(s->d_traces);
     s->tracesBytes = sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)s->cap;
@@ -578,16 +686,19 @@ static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
       set_error("k_se3_track cannot be resident");
       return LSD_ERR_CUDA;
     }
-    s->gridBlocks = perSM * ctx->numSMs;
+    s->gridBlocks = perSM * ctx->numSMs;  // every CTA resident: spinning consumers never starve producers
   }
   return LSD_OK;
 }
 
-static SE3Params make_params(lsd_ctx *ctx) {
+static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   SE3Params prm;
   prm.K = ctx->K;
   prm.s = ctx->se3;
-  prm.maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_CH - 1) / SE3_CH;
+  prm.maxChunks = ctx->se3s->maxChunks;
+  // Work-item size: small items spread ONE pair over many SMs (latency of a live sequence); large
+  // items amortise the per-item reduction when the batch alone fills the machine.
+  prm.chunk = nPairs >= 256 ? 4 * SE3_MIN_CHUNK : (nPairs >= 32 ? 2 * SE3_MIN_CHUNK : SE3_MIN_CHUNK);
   prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
   prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
   return prm;
@@ -610,9 +721,28 @@ static double alg_bytes_level(const lsd_ctx *ctx, int l, int n) {
   return 20.0 * n + 16.0 * taps + (l == LSD_SE3TRACKING_MIN_LEVEL ? 5.0 * n : 0.0) + 108.0;
 }
 
+static int init_masks(lsd_ctx *ctx, int n, lsd_frame *const *frames, cudaStream_t st) {
+  // masks are created 0xFF on first use (Frame::refPixelWasGood())
+  std::vector<uint8_t *> need;
+  for (int i = 0; i < n; i++)
+    if (!(frames[i]->built & FB_MASK)) {
+      need.push_back(frames[i]->slab);
+      frames[i]->built |= FB_MASK;
+    }
+  if (need.empty()) return LSD_OK;
+  int rc = ensure_table(ctx, need.size() * sizeof(void *));
+  if (rc) return rc;
+  std::memcpy(ctx->h_table, need.data(), need.size() * sizeof(void *));
+  LSD_CUDA(cudaMemcpyAsync(ctx->d_table, ctx->h_table, need.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
+  launch_mask_init(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), (int)need.size(), st);
+  LSD_CUDA(cudaStreamSynchronize(st));  // h_table is reused by callers
+  return LSD_OK;
+}
+
 int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
-                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st, bool sync) {
+                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st, bool accumulateStats) {
   if (n == 0) return LSD_OK;
+  LSD_ARG(n < (1 << 19));
   int rc = se3_scratch_ensure(ctx, n, traces != nullptr);
   if (rc) return rc;
   SE3Scratch *s = ctx->se3s;
@@ -630,42 +760,33 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
     P.mask = frames[i]->slab + lay.mask;
     invert_pose_to_float(init + 7 * i, P.q0, P.t0);
   }
-  // masks are created 0xFF on first use (Frame::refPixelWasGood())
-  {
-    std::vector<uint8_t *> need;
-    for (int i = 0; i < n; i++)
-      if (!(frames[i]->built & FB_MASK)) {
-        need.push_back(frames[i]->slab);
-        frames[i]->built |= FB_MASK;
-      }
-    if (!need.empty()) {
-      rc = ensure_table(ctx, need.size() * sizeof(void *));
-      if (rc) return rc;
-      std::memcpy(ctx->h_table, need.data(), need.size() * sizeof(void *));
-      LSD_CUDA(cudaMemcpyAsync(ctx->d_table, ctx->h_table, need.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
-      launch_mask_init(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), (int)need.size(), st);
-      LSD_CUDA(cudaStreamSynchronize(st));  // h_table is reused by callers
-    }
-  }
+  rc = init_masks(ctx, n, frames, st);
+  if (rc) return rc;
+  SE3Params prm = make_params(ctx, n);
+  SE3Queue q;
+  q.slots = s->d_slots;
+  q.head = s->d_ctrs;
+  q.tail = s->d_ctrs + 1;
+  q.remaining = reinterpret_cast<int *>(s->d_ctrs + 2);
+  q.cap = s->qcap;
+  unsigned *ctr0 = reinterpret_cast<unsigned *>(s->h_states);  // pinned scratch, rewritten by the D2H below
+  ctr0[0] = 0u; ctr0[1] = 0u; ctr0[2] = (unsigned)n; ctr0[3] = 0u;
   LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
-  LSD_CUDA(cudaMemsetAsync(s->d_counts, 0, sizeof(int) * 4, st));
-  SE3Params prm = make_params(ctx);
+  LSD_CUDA(cudaMemcpyAsync(s->d_ctrs, ctr0, sizeof(unsigned) * 4, cudaMemcpyHostToDevice, st));
+  LSD_CUDA(cudaMemsetAsync(s->d_slots, 0, sizeof(unsigned long long) * q.cap, st));
   LSD_CUDA(cudaEventRecord(ctx->evA, st));
-  k_se3_init<<<(n + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, n, s->d_lists, s->d_counts, prm);
+  k_se3_init<<<(n + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, n, q, prm);
   lsd_trace_entry *d_tr = traces ? s->d_traces : nullptr;
-  int listCap = s->listCap;
-  void *args[] = {&s->d_pairs, &s->d_states, &s->d_partials, &s->d_lists, &listCap, &s->d_counts, &prm, &d_tr};
-  LSD_CUDA(cudaLaunchCooperativeKernel((void *)k_se3_track, dim3(s->gridBlocks), dim3(SE3_THREADS), args, 0, st));
+  k_se3_track<<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs, s->d_states, s->d_partials, q, prm, d_tr);
+  LSD_CUDA(cudaGetLastError());
   ctx->launches += 2;
   LSD_CUDA(cudaEventRecord(ctx->evB, st));
   LSD_CUDA(cudaMemcpyAsync(s->h_states, s->d_states, sizeof(SE3State) * n, cudaMemcpyDeviceToHost, st));
   if (traces)
     LSD_CUDA(cudaMemcpyAsync(traces, s->d_traces, sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)n, cudaMemcpyDeviceToHost, st));
-  (void)sync;
   LSD_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
-  ctx->lastKernelMs = ms;
   double bytes = 0;
   long long evals = 0;
   for (int i = 0; i < n; i++) {
@@ -702,8 +823,15 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
     }
     if (P.trackingWasGood) refs[i]->keyframe->numFramesTrackedOnThis++;
   }
-  ctx->lastAlgBytes = bytes;
-  ctx->lastEvals = evals;
+  if (accumulateStats) {
+    ctx->lastAlgBytes += bytes;
+    ctx->lastEvals += evals;
+    ctx->lastKernelMs += ms;
+  } else {
+    ctx->lastAlgBytes = bytes;
+    ctx->lastEvals = evals;
+    ctx->lastKernelMs = ms;
+  }
   return LSD_OK;
 }
 
@@ -713,12 +841,12 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
 __global__ void __launch_bounds__(SE3_THREADS)
 k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, float *__restrict__ partials, int level,
                 const __grid_constant__ SE3Params prm) {
-  __shared__ __align__(16) float sred[SE3_THREADS / 32][SE3_NRED];
+  __shared__ SE3Smem sm;
+  const int4 *hp = reinterpret_cast<const int4 *>(S);
+  const int4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1), h2 = __ldcg(hp + 2), h3 = __ldcg(hp + 3);
   EvalConst c;
-  load_eval_const(S, level, prm, c);
+  load_eval_const(prm, level, h0, h1, h2, h3, c);
   const int n = P->d_num[level];
-  const RefPoint *pts = P->pts[level];
-  const float4 *G = P->fgrad[level];
   uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
   float acc[SE3_NF];
   double dacc[SE3_ND];
@@ -726,17 +854,10 @@ k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, f
   for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
   for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-  const int base = blockIdx.x * SE3_CH + threadIdx.x;
-  for (int k = 0; k < SE3_CH / SE3_THREADS; k++) {
-    const int i = base + k * SE3_THREADS;
-    if (i < n) {
-      const float4 raw = __ldg(reinterpret_cast<const float4 *>(pts) + i);
-      RefPoint p;
-      p.xy = __float_as_uint(raw.x); p.idepth = raw.y; p.color = raw.z; p.var = raw.w;
-      eval_point(p, c, G, mask, acc, dacc);
-    }
-  }
-  block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sred);
+  const int begin = blockIdx.x * prm.chunk;
+  const int end = min(n, begin + prm.chunk);
+  eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc);
+  block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sm);
 }
 
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
@@ -747,15 +868,8 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   SE3Scratch *s = ctx->se3s;
   cudaStream_t st = ctx->stream;
   const FrameLayout &lay = ctx->lay;
-  if (!(frame->built & FB_MASK)) {
-    rc = ensure_table(ctx, sizeof(void *));
-    if (rc) return rc;
-    *reinterpret_cast<uint8_t **>(ctx->h_table) = frame->slab;
-    LSD_CUDA(cudaMemcpyAsync(ctx->d_table, ctx->h_table, sizeof(void *), cudaMemcpyHostToDevice, st));
-    launch_mask_init(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), 1, st);
-    LSD_CUDA(cudaStreamSynchronize(st));
-    frame->built |= FB_MASK;
-  }
+  rc = init_masks(ctx, 1, &frame, st);
+  if (rc) return rc;
   SE3Pair &P = s->h_pairs[0];
   std::memset(&P, 0, sizeof(P));
   for (int l = 0; l < NL; l++) {
@@ -773,7 +887,7 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   S.aff_b = b;
   LSD_CUDA(cudaMemcpyAsync(s->d_pairs, &P, sizeof(SE3Pair), cudaMemcpyHostToDevice, st));
   LSD_CUDA(cudaMemcpyAsync(s->d_states, &S, sizeof(SE3State), cudaMemcpyHostToDevice, st));
-  SE3Params prm = make_params(ctx);
+  SE3Params prm = make_params(ctx, 1);
   const int nblk = prm.maxChunks;
   k_se3_eval_once<<<nblk, SE3_THREADS, 0, st>>>(s->d_pairs, s->d_states, s->d_partials, level, prm);
   ctx->launches++;
@@ -784,7 +898,7 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   LSD_CUDA(cudaStreamSynchronize(st));
   float tot[SE3_NF] = {0};
   double dtot[SE3_ND] = {0};
-  const int nch = (hnum[level] + SE3_CH - 1) / SE3_CH;
+  const int nch = (hnum[level] + prm.chunk - 1) / prm.chunk;
   for (int cidx = 0; cidx < nch; cidx++) {
     for (int j = 0; j < SE3_ND; j++) dtot[j] += reinterpret_cast<const double *>(&h[(size_t)cidx * SE3_NRED])[j];
     for (int j = 0; j < SE3_NF; j++) tot[j] += h[(size_t)cidx * SE3_NRED + 2 * SE3_ND + j];
