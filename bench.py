@@ -40,7 +40,7 @@ W, H = 640, 480
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=1000, help="frame pairs per GPU per step")
@@ -50,44 +50,81 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md "clocks" line).
+
+    NVML is polled from a thread every few ms (the timed region of this microbench is tens of ms, shorter than
+    one `nvidia-smi -lms` period); if NVML cannot be loaded the nvidia-smi loop from the recipe is used instead."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.mx, self.reasons, self.power = [], None, set(), []
+        self.proc = self.th = self.h = None
+        self.stop_flag = False
+        self.how = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid else N.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.how = "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.h = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi -lms 20"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        N = self.N
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                self.power.append(N.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 9 and r[1].replace(".", "").isdigit():
+                self.sm.append(float(r[1]))
+                self.mx = float(r[2]) if r[2].replace(".", "").isdigit() else self.mx
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.th:
+            self.th.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how,
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def make_inputs(n, seed0, device):
@@ -220,7 +257,7 @@ def main():
     # ---- value: device-resident inputs ---------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         ctx.se3_track_prepared(b_res)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, "GPU-" + str(torch.cuda.get_device_properties(dev).uuid))
     barrier()
     sampler.start()
     l0 = ctx.launch_count()
@@ -237,7 +274,6 @@ def main():
     barrier()
     launches = ctx.launch_count() - l0
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     res = b_res["res"]
     poses = np.array([list(res[i].frameToRef) for i in range(n)])
     n_div = sum(res[i].diverged for i in range(n))
@@ -256,6 +292,7 @@ def main():
     f1.record()
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))  # host work included
+    clocks = sampler.stop()  # sampled over both timed regions (value and e2e)
     res2 = b_e2e["res"]
     e2e_same = all(list(res2[i].frameToRef) == list(res[i].frameToRef) for i in range(n))
 

@@ -96,6 +96,9 @@ void *lsd_ctx_stream(lsd_ctx *ctx);
 long long lsd_ctx_launch_count(lsd_ctx *ctx);
 int lsd_default_tracker_settings(lsd_tracker_settings *s);
 int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
+/* scheduling knob of the persistent tracker: 1024-point records per work item (0 = automatic).  Never
+ * changes a result (the summation order is fixed by the records), only latency vs throughput. */
+int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
 
 /* ---- Frame ---------------------------------------------------------------------------------- */
 #define LSD_BUILD_TRACKING 0u /* image L0-4 + gradients L1-4: what a tracked frame needs        */

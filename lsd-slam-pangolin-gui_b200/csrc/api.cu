@@ -211,6 +211,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   for (int i = 0; i < 4; i++) LSD_CUDA(cudaEventCreateWithFlags(&ctx->evPipe[i], cudaEventDisableTiming));
   ctx->launches = 0;
   lsd_default_tracker_settings(&ctx->se3);
+  ctx->se3RecsPerItem = 0;
   ctx->refSlabBytes = 0;
   ctx->h_stage = ctx->d_stage = nullptr;
   ctx->h_stageBytes = ctx->d_stageBytes = 0;
@@ -255,6 +256,12 @@ long long lsd_ctx_launch_count(lsd_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s) {
   LSD_ARG(ctx && s);
   ctx->se3 = *s;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records) {
+  LSD_ARG(ctx && records >= 0 && records <= 64);
+  ctx->se3RecsPerItem = records;
   return LSD_OK;
 }
 

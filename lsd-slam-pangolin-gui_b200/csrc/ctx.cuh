@@ -17,6 +17,7 @@ struct lsd_ctx {
   cudaEvent_t evA, evB, evPipe[4];
   long long launches;
   lsd_tracker_settings se3;
+  int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
   // pools
   std::vector<uint8_t *> frameSlabPool;
   std::vector<uint8_t *> refSlabPool;

@@ -9,9 +9,13 @@
 //  * the three passes are fused into one per-point evaluation that never materialises the buffers;
 //    every evaluation also reduces the 21+6 normal-equation terms (they are only CONSUMED if the step
 //    is accepted, exactly when upstream would call calculateWarpUpdate on the same buffers);
-//  * work items are (pair, chunk of points); a grid-resident kernel pulls items from a device ring
-//    queue.  The CTA that completes a pair's last chunk sums the per-chunk partials in chunk order
-//    (deterministic, independent of scheduling), runs the LM accept/reject logic, the 6x6 LDL^T solve
+//  * an evaluation is cut into RECORDS of SE3_REC consecutive points; every record is reduced by one CTA
+//    in a fixed order (thread-strided partial sums, then a fixed shared-memory tree) and the records are
+//    summed in record order, so every sum is a pure function of the inputs: bit-reproducible run to
+//    run and independent of batch size, work-item size and scheduling;
+//  * work items are (pair, run of consecutive records); a grid-resident kernel pulls items from a device
+//    ring queue.  The CTA that completes a pair's last item sums the records,
+//    runs the LM accept/reject logic, the 6x6 LDL^T solve
 //    and the SE3 exponential on device, and pushes the pair's next evaluation into the queue.  Pairs
 //    advance independently: no host round trip and no grid-wide barrier anywhere in a track;
 //  * results are bit-reproducible run to run and independent of the batch composition.
@@ -30,6 +34,7 @@ namespace lsd {
 
 #define SE3_THREADS 256   // threads per CTA
 #define SE3_P 2           // points in flight per thread (loads of a batch are issued before any math)
+#define SE3_REC 1024      // points per partial record: FIXED, it defines the summation order (see above)
 #define SE3_NRED 44       // floats per partial record: 5 doubles (affine sums) + 33 floats + pad
 #define SE3_NF 33         // fp32 sums per record
 #define SE3_ND 5          // fp64 sums per record
@@ -106,8 +111,8 @@ struct SE3Queue {
 struct SE3Params {
   Intrinsics K;
   lsd_tracker_settings s;
-  int maxChunks;           // per-pair stride of the partial records
-  int chunk;               // points per work item (multiple of SE3_THREADS * SE3_P)
+  int maxChunks;           // per-pair stride of the partial records (records of the largest tracked level)
+  int recsPerItem;         // records per work item: scheduling granularity only, never changes a result
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
 };
 
@@ -166,7 +171,8 @@ __device__ int start_level(const SE3Pair *P, SE3State *S, int level, const SE3Pa
     mark_diverged(S);
     return 0;
   }
-  S->nChunks = (P->n[level] + prm.chunk - 1) / prm.chunk;
+  const int nRecs = (P->n[level] + SE3_REC - 1) / SE3_REC;
+  S->nChunks = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;  // work items of this evaluation
   S->done = 0;
   return S->nChunks;
 }
@@ -542,27 +548,36 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
     for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
     for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-    const int begin = chunk * prm.chunk;
-    const int end = min(n, begin + prm.chunk);
-    eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc);
-
-    float *dst = partials + ((size_t)pairIdx * prm.maxChunks + chunk) * SE3_NRED;
-    block_reduce_store(acc, dacc, dst, sm);
+    const int nRecs = (n + SE3_REC - 1) / SE3_REC;
+    const int rec0 = chunk * prm.recsPerItem, rec1 = min(nRecs, rec0 + prm.recsPerItem);
+    for (int rec = rec0; rec < rec1; rec++) {
+      if (rec > rec0) {
+#pragma unroll
+        for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
+      }
+      const int begin = rec * SE3_REC;
+      const int end = min(n, begin + SE3_REC);
+      eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc);
+      float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
+      block_reduce_store(acc, dacc, dst, sm);
+    }
     if (threadIdx.x == 0) sIsLast = (atomicAdd(&S->done, 1u) == (unsigned)(nch - 1));
     __syncthreads();
     if (sIsLast) {
       __threadfence();
-      const float *rec0 = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED;
+      const float *recBase = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED;
       if (threadIdx.x < SE3_ND) {
-        const double *src = reinterpret_cast<const double *>(rec0) + threadIdx.x;
+        const double *src = reinterpret_cast<const double *>(recBase) + threadIdx.x;
         double s = 0.0;
-        for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * (SE3_NRED / 2));
+        for (int cidx = 0; cidx < nRecs; cidx++) s += __ldcg(src + (size_t)cidx * (SE3_NRED / 2));
         sdtot[threadIdx.x] = s;
       } else if (threadIdx.x < SE3_ND + SE3_NF) {
         const int j = threadIdx.x - SE3_ND;
-        const float *src = rec0 + 2 * SE3_ND + j;
+        const float *src = recBase + 2 * SE3_ND + j;
         float s = 0.0f;
-        for (int cidx = 0; cidx < nch; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
+        for (int cidx = 0; cidx < nRecs; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
         stot[j] = s;
       }
       __syncthreads();
@@ -642,12 +657,10 @@ void se3_scratch_free(lsd_ctx *ctx) {
   ctx->se3s = nullptr;
 }
 
-#define SE3_MIN_CHUNK (SE3_THREADS * SE3_P)
-
 static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
   if (!ctx->se3s) ctx->se3s = new SE3Scratch();
   SE3Scratch *s = ctx->se3s;
-  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_MIN_CHUNK - 1) / SE3_MIN_CHUNK;
+  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_REC - 1) / SE3_REC;
   if (n > s->cap) {
     cudaFree(s->d_pairs);
     cudaFreeHost(s->h_pairs);
@@ -696,9 +709,9 @@ static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   prm.K = ctx->K;
   prm.s = ctx->se3;
   prm.maxChunks = ctx->se3s->maxChunks;
-  // Work-item size: small items spread ONE pair over many SMs (latency of a live sequence); large
-  // items amortise the per-item reduction when the batch alone fills the machine.
-  prm.chunk = nPairs >= 256 ? 4 * SE3_MIN_CHUNK : (nPairs >= 32 ? 2 * SE3_MIN_CHUNK : SE3_MIN_CHUNK);
+  // Work-item size: single-record items spread ONE pair over many SMs (latency of a live sequence);
+  // longer items amortise the queue round trip when the batch alone fills the machine.
+  prm.recsPerItem = ctx->se3RecsPerItem > 0 ? ctx->se3RecsPerItem : (nPairs >= 256 ? 4 : (nPairs >= 32 ? 2 : 1));
   prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
   prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
   return prm;
@@ -854,8 +867,8 @@ k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, f
   for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
   for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-  const int begin = blockIdx.x * prm.chunk;
-  const int end = min(n, begin + prm.chunk);
+  const int begin = blockIdx.x * SE3_REC;
+  const int end = min(n, begin + SE3_REC);
   eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc);
   block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sm);
 }
@@ -898,7 +911,7 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   LSD_CUDA(cudaStreamSynchronize(st));
   float tot[SE3_NF] = {0};
   double dtot[SE3_ND] = {0};
-  const int nch = (hnum[level] + prm.chunk - 1) / prm.chunk;
+  const int nch = (hnum[level] + SE3_REC - 1) / SE3_REC;
   for (int cidx = 0; cidx < nch; cidx++) {
     for (int j = 0; j < SE3_ND; j++) dtot[j] += reinterpret_cast<const double *>(&h[(size_t)cidx * SE3_NRED])[j];
     for (int j = 0; j < SE3_NF; j++) tot[j] += h[(size_t)cidx * SE3_NRED + 2 * SE3_ND + j];

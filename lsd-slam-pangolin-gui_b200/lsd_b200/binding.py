@@ -60,6 +60,7 @@ SYMBOLS = {
     "lsd_ctx_launch_count": (C.c_longlong, [_vp]),
     "lsd_default_tracker_settings": (_ip, [_vp]),
     "lsd_ctx_set_se3_settings": (_ip, [_vp, _vp]),
+    "lsd_ctx_set_se3_work_item_records": (_ip, [_vp, _ip]),
     "lsd_frame_create": (_ip, [_vp, _ip, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch_device": (_ip, [_vp, _ip, _vp, _vp, _u, _vp]),
@@ -146,6 +147,9 @@ class Context:
 
     def set_se3_settings(self, s):
         _chk(self.L.lsd_ctx_set_se3_settings(self.p, C.byref(s)))
+
+    def set_se3_work_item_records(self, n):
+        _chk(self.L.lsd_ctx_set_se3_work_item_records(self.p, int(n)))
 
     # ---- frames
     def create_frames(self, images, ids=None, flags=BUILD_TRACKING):

@@ -23,6 +23,7 @@
 //         timing  g++ -O3 -march=x86-64-v3                   (mirrors the reference's Release
 //                 flags -O3 -march=native -DENABLE_SSE, /root/reference/CMakeLists.txt:59)
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <deque>
 #include <functional>
@@ -247,9 +248,9 @@ struct Sim3Tracker {
   Sim3Tracker(int w, int h);
   Sim3<double> trackFrameSim3(TrackingReference *ref, Frame *frame, const Sim3<double> &frameToReference_initialEstimate,
                               int startLevel, int finalLevel);
-  void calcSim3Buffers(TrackingReference *ref, Frame *frame, const Sim3<float> &referenceToFrame, int level);
-  Sim3ResidualStruct calcSim3WeightsAndResidual(const Sim3<float> &referenceToFrame);
-  void calcSim3LGS(float A[7][7], float b[7]);
+  void calcSim3Buffers(TrackingReference *ref, Frame *frame, const Sim3<double> &referenceToFrame, int level);
+  Sim3ResidualStruct calcSim3WeightsAndResidual(const Sim3<double> &referenceToFrame);
+  void calcSim3LGS(float A[7][7], float b[7], int *numConstraints);
 };
 
 // ---- DepthMap (DepthEstimation/DepthMap.cpp) -----------------------------------------
@@ -257,7 +258,18 @@ struct DepthMapStats {
   int created = 0, updated = 0, killed = 0, skipped = 0;
 };
 
+// util/settings.h thresholds that SURVEY.md 8a-K and the published upstream header disagree on (see the
+// DECISION note at the top of depthmap.cpp): run-time settings, defaults = published upstream values.
+struct DepthSettings {
+  int valSumMinForCreate = 30;       // VAL_SUM_MIN_FOR_CREATE
+  int valSumMinForKeep = 24;         // VAL_SUM_MIN_FOR_KEEP
+  int valSumMinForUnblacklist = 100; // VAL_SUM_MIN_FOR_UNBLACKLIST
+  int minBlacklist = -1;             // MIN_BLACKLIST
+};
+
 struct DepthMap {
+  DepthSettings settings;
+  float lastRescaleFactor = 1;
   int width, height;
   float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
   std::vector<Hypothesis> currentDepthMap, otherDepthMap;
@@ -271,6 +283,7 @@ struct DepthMap {
 
   DepthMap(int w, int h, float fx, float fy, float cx, float cy);
   void initializeFromGTDepth(Frame *new_frame);
+  void initializeRandomly(Frame *new_frame);
   void initializeFromMap(Frame *kf, const Hypothesis *map);  // DECISION: inject an explicit map (replaces rand())
   void updateKeyframe(const std::deque<Frame *> &referenceFrames);
   void createKeyFrame(Frame *new_keyframe);

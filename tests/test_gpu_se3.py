@@ -136,6 +136,11 @@ def test_batch_equals_single_and_is_deterministic(lsd, oracle):
     r2 = ctx.se3_track_batch(refs, frs, inits)
     p2 = np.array([list(r.frameToRef) for r in r2])
     assert np.array_equal(p1, p2), "batched tracking must be run-to-run deterministic"
+    for recs in (1, 3, 8):  # work-item size is a scheduling knob only: results must not move by one bit
+        ctx.set_se3_work_item_records(recs)
+        r3 = ctx.se3_track_batch(refs, frs, inits)
+        assert np.array_equal(np.array([list(r.frameToRef) for r in r3]), p1), f"result depends on work-item size {recs}"
+    ctx.set_se3_work_item_records(0)
     for i in range(6):
         rs = ctx.se3_track(refs[i], frs[i], inits[i])
         assert np.array_equal(np.array(rs.frameToRef), p1[i]), "batch result must not depend on batch composition"
