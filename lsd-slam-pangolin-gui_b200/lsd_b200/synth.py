@@ -217,3 +217,31 @@ def semidense_idepth(kf_depth: torch.Tensor, max_grad: np.ndarray, var: float = 
     idv = np.where(valid, idepth, np.float32(-1)).astype(np.float32)
     vv = np.where(valid, np.float32(var), np.float32(-1)).astype(np.float32)
     return idv, vv
+
+
+def make_depth_scene(seed: int, w: int, h: int, n_refs: int = 10, K=None, device="cpu", step=0.01, sigma=1.0,
+                     rot_step=math.radians(0.15)):
+    """Config-3 style scene: one keyframe plus n_refs reference frames on a smooth path with
+    baselines step, 2*step, ... (metres) and a slowly growing rotation.
+
+    Returns dict: kf_img/kf_depth (torch), refs = list of dict(img, depth, toKf = pose7 refToKf (GT)), K.
+    """
+    K = K or default_K(w, h)
+    rng = np.random.default_rng(seed)
+    room = make_room(seed, device)
+    R0, t0 = random_camera(rng)
+    dirv = rng.normal(size=3)
+    dirv[2] *= 0.3  # mostly sideways motion: good stereo baselines
+    dirv /= np.linalg.norm(dirv)
+    axis = rng.normal(size=3)
+    axis /= np.linalg.norm(axis)
+    kf_img, kf_depth = render(room, w, h, K, R0, t0, noise_seed=1000 * seed, sigma=sigma)
+    refs = []
+    for i in range(1, n_refs + 1):
+        dR = rodrigues(axis * rot_step * i)
+        dt = dirv * step * i
+        R1 = R0 @ dR
+        t1 = t0 + R0 @ dt
+        img, depth = render(room, w, h, K, R1, t1, noise_seed=1000 * seed + i, sigma=sigma)
+        refs.append(dict(img=img, depth=depth, toKf=pose7(dR, dt), R_w=R1, t_w=t1))
+    return dict(kf_img=kf_img, kf_depth=kf_depth, refs=refs, K=K, R_w_kf=R0, t_w_kf=t0, room=room)

@@ -1,6 +1,8 @@
 // oracle/capi.cpp -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see lsd_oracle.hpp).
 // Flat C entry points so tests / bench.py's cpu_baseline leg can drive the oracle via ctypes.
 #include <chrono>
+#include <cstdlib>
+#include <deque>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -225,6 +227,180 @@ void lsdo_make_pairs(int n, const uint8_t *const *kf_imgs, const uint8_t *const 
   }
   for (auto &th : pool) th.join();
 }
+
+
+// ---- Sim3Tracker ---------------------------------------------------------------------------------
+struct lsdo_sim3_result {
+  double frameToRef[8];  // qx qy qz qw tx ty tz scale
+  float hessian[49];
+  float lastResidual, lastDepthResidual, lastPhotometricResidual, pointUsage, affine_a, affine_b;
+  int diverged, traceLen;
+};
+
+static Sim3<double> sim3_in(const double p[8]) {
+  return Sim3<double>(Quat<double>(p[3], p[0], p[1], p[2]), Vec3<double>(p[4], p[5], p[6]), p[7]);
+}
+static void sim3_out(const Sim3<double> &s, double p[8]) {
+  p[0] = s.q.x; p[1] = s.q.y; p[2] = s.q.z; p[3] = s.q.w; p[4] = s.t.x; p[5] = s.t.y; p[6] = s.t.z; p[7] = s.s;
+}
+static void fill_sim3(const Sim3Tracker &t, const Sim3<double> &res, lsdo_sim3_result *out) {
+  sim3_out(res, out->frameToRef);
+  std::memcpy(out->hessian, t.lastSim3Hessian, sizeof(out->hessian));
+  out->lastResidual = t.lastResidual;
+  out->lastDepthResidual = t.lastDepthResidual;
+  out->lastPhotometricResidual = t.lastPhotometricResidual;
+  out->pointUsage = t.pointUsage;
+  out->affine_a = t.affineEstimation_a;
+  out->affine_b = t.affineEstimation_b;
+  out->diverged = t.diverged;
+  out->traceLen = (int)t.trace.size();
+}
+
+// Sim3Tracker::trackFrameSim3(reference, frame, frameToReference_initialEstimate, startLevel, finalLevel)
+int lsdo_sim3_track(void *refp, void *framep, const double init[8], int startLevel, int finalLevel, int mode, lsdo_sim3_result *out,
+                    lsdo_trace_entry *trace, int traceCap) {
+  auto *ref = (TrackingReference *)refp;
+  Frame *frame = (Frame *)framep;
+  Sim3Tracker t(frame->w[0], frame->h[0]);
+  t.mode = (ReduceMode)mode;
+  const Sim3<double> res = t.trackFrameSim3(ref, frame, sim3_in(init), startLevel, finalLevel);
+  fill_sim3(t, res, out);
+  if (trace)
+    for (int i = 0; i < (int)t.trace.size() && i < traceCap; i++)
+      trace[i] = {t.trace[i].level, t.trace[i].accepted, t.trace[i].error, t.trace[i].lambda, t.trace[i].bufSize};
+  return 0;
+}
+
+// n independent Sim3 tracks on `threads` host threads; returns wall seconds
+double lsdo_sim3_track_batch(int n, void **refs, void **frames, const double *inits /*n*8*/, int startLevel, int finalLevel, int mode,
+                             int threads, lsdo_sim3_result *outs) {
+  if (threads < 1) threads = 1;
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (int tid = 0; tid < threads; tid++) {
+    pool.emplace_back([=]() {
+      if (n == 0) return;
+      Frame *f0 = (Frame *)frames[0];
+      Sim3Tracker t(f0->w[0], f0->h[0]);
+      t.mode = (ReduceMode)mode;
+      for (int i = tid; i < n; i += threads) {
+        const Sim3<double> res = t.trackFrameSim3((TrackingReference *)refs[i], (Frame *)frames[i], sim3_in(inits + 8 * i), startLevel, finalLevel);
+        fill_sim3(t, res, &outs[i]);
+      }
+    });
+  }
+  for (auto &th : pool) th.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- DepthMap -----------------------------------------------------------------------------------
+static double secs_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void *lsdo_depthmap_create(int w, int h, float fx, float fy, float cx, float cy, int threads) {
+  auto *d = new DepthMap(w, h, fx, fy, cx, cy);
+  d->numThreads = threads;
+  return d;
+}
+void lsdo_depthmap_destroy(void *d) { delete (DepthMap *)d; }
+void lsdo_depthmap_set_thresholds(void *dp, int create, int keep, int unblacklist, int minBlacklist) {
+  auto *d = (DepthMap *)dp;
+  d->settings.valSumMinForCreate = create;
+  d->settings.valSumMinForKeep = keep;
+  d->settings.valSumMinForUnblacklist = unblacklist;
+  d->settings.minBlacklist = minBlacklist;
+}
+void lsdo_depthmap_init_gt(void *d, void *frame) { ((DepthMap *)d)->initializeFromGTDepth((Frame *)frame); }
+void lsdo_depthmap_init_random(void *d, void *frame, unsigned seed) {
+  srand(seed);
+  ((DepthMap *)d)->initializeRandomly((Frame *)frame);
+}
+void lsdo_depthmap_init_map(void *d, void *frame, const Hypothesis *map) { ((DepthMap *)d)->initializeFromMap((Frame *)frame, map); }
+void lsdo_depthmap_set_reactivated(void *d, int v) { ((DepthMap *)d)->activeKeyFrameIsReactivated = v != 0; }
+void lsdo_depthmap_read(void *dp, Hypothesis *out) {
+  auto *d = (DepthMap *)dp;
+  std::memcpy(out, d->currentDepthMap.data(), d->currentDepthMap.size() * sizeof(Hypothesis));
+}
+void lsdo_depthmap_write(void *dp, const Hypothesis *in) {
+  auto *d = (DepthMap *)dp;
+  std::memcpy(d->currentDepthMap.data(), in, d->currentDepthMap.size() * sizeof(Hypothesis));
+}
+float lsdo_depthmap_last_rescale(void *dp) { return ((DepthMap *)dp)->lastRescaleFactor; }
+
+// DepthMap::updateKeyframe(std::deque<std::shared_ptr<Frame>>); returns wall seconds
+double lsdo_depthmap_update_keyframe(void *dp, int n, void **frames, double *stageSecs /*4: observe, fillHoles, regularize, setDepth*/) {
+  auto *d = (DepthMap *)dp;
+  std::deque<Frame *> refs;
+  for (int i = 0; i < n; i++) refs.push_back((Frame *)frames[i]);
+  auto t0 = std::chrono::steady_clock::now();
+  d->updateKeyframe(refs);
+  (void)stageSecs;
+  return secs_since(t0);
+}
+double lsdo_depthmap_create_keyframe(void *dp, void *newKf) {
+  auto t0 = std::chrono::steady_clock::now();
+  ((DepthMap *)dp)->createKeyFrame((Frame *)newKf);
+  return secs_since(t0);
+}
+void lsdo_depthmap_finalize(void *dp) { ((DepthMap *)dp)->finalizeKeyFrame(); }
+
+// individual stages (parity + timing): 0 observeDepth (refs must have been prepared by a prior
+// lsdo_depthmap_prepare), 1 regularizeDepthMapFillHoles, 2 regularizeDepthMap(arg1 = removeOcclusions, arg2 = validityTH),
+// 3 propagateDepth(frame), 4 activeKeyFrame->setDepth + idepth pyramids
+double lsdo_depthmap_stage(void *dp, int stage, int arg1, int arg2, void *frame) {
+  auto *d = (DepthMap *)dp;
+  auto t0 = std::chrono::steady_clock::now();
+  switch (stage) {
+    case 0: d->observeDepth(); break;
+    case 1: d->regularizeDepthMapFillHoles(); break;
+    case 2: d->regularizeDepthMap(arg1 != 0, arg2); break;
+    case 3: d->propagateDepth((Frame *)frame); d->activeKeyFrame = (Frame *)frame; d->activeKeyFrameIsReactivated = false; break;
+    case 4:
+      d->activeKeyFrame->setDepth(d->currentDepthMap.data());
+      for (int l = 1; l < NL; l++) d->activeKeyFrame->requireIDepth(l);
+      break;
+    default: return -1;
+  }
+  return secs_since(t0);
+}
+// the bookkeeping part of updateKeyframe (prepareForStereoWith + referenceFrameByID) without running the stages
+void lsdo_depthmap_prepare(void *dp, int n, void **frames) {
+  auto *d = (DepthMap *)dp;
+  d->oldest_referenceFrame = (Frame *)frames[0];
+  d->newest_referenceFrame = (Frame *)frames[n - 1];
+  d->referenceFrameByID.clear();
+  d->referenceFrameByID_offset = d->oldest_referenceFrame->id;
+  for (int i = 0; i < n; i++) {
+    Frame *f = (Frame *)frames[i];
+    f->prepareForStereoWith(d->activeKeyFrame, f->thisToParent_raw, 0);
+    while ((int)d->referenceFrameByID.size() + d->referenceFrameByID_offset <= f->id) d->referenceFrameByID.push_back(f);
+  }
+}
+void lsdo_depthmap_debug_rgb(void *dp, uint8_t *rgb) { ((DepthMap *)dp)->debugPlotDepthMap(rgb); }
+
+// one doLineStereo call (unit tests against analytic disparity); out3 = {idepth, var, eplLength}; ref must be prepared
+float lsdo_line_stereo(void *dp, void *ref, float u, float v, float epxn, float epyn, float min_id, float prior_id, float max_id,
+                       float *out3) {
+  auto *d = (DepthMap *)dp;
+  Frame *r = (Frame *)ref;
+  d->activeKeyFrame->requireGradients(0);
+  float id = 0, var = 0, len = 0;
+  const float e = d->doLineStereo(u, v, epxn, epyn, min_id, prior_id, max_id, r, r->image[0].data(), id, var, len);
+  out3[0] = id; out3[1] = var; out3[2] = len;
+  return e;
+}
+int lsdo_make_epl(void *dp, void *ref, int x, int y, float *ep2) {
+  return ((DepthMap *)dp)->makeAndCheckEPL(x, y, (Frame *)ref, ep2, ep2 + 1) ? 1 : 0;
+}
+// frame state the depth map reads / writes
+void lsdo_frame_get_pose(void *fp, double out8[8]) { sim3_out(((Frame *)fp)->thisToParent_raw, out8); }
+void lsdo_frame_get_counters(void *fp, int *out3) {
+  Frame *f = (Frame *)fp;
+  out3[0] = f->numFramesTrackedOnThis; out3[1] = f->numMappedOnThis; out3[2] = f->numMappedOnThisTotal;
+}
+void lsdo_frame_set_flags(void *fp, int depthHasBeenUpdated) { ((Frame *)fp)->depthHasBeenUpdatedFlag = depthHasBeenUpdated != 0; }
+void lsdo_frame_clear_mask(void *fp) { ((Frame *)fp)->refPixelWasGood.clear(); }
 
 int lsdo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 

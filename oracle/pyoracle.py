@@ -100,21 +100,30 @@ def lib(fast: bool = False):
         ("lsdo_sim3_track_batch", dp, [ip, vp, vp, vp, ip, ip, ip, ip, vp]),
         ("lsdo_depthmap_create", vp, [ip, ip, fp, fp, fp, fp, ip]),
         ("lsdo_depthmap_destroy", None, [vp]),
+        ("lsdo_depthmap_set_thresholds", None, [vp, ip, ip, ip, ip]),
         ("lsdo_depthmap_init_gt", None, [vp, vp]),
+        ("lsdo_depthmap_init_random", None, [vp, vp, C.c_uint]),
         ("lsdo_depthmap_init_map", None, [vp, vp, vp]),
+        ("lsdo_depthmap_set_reactivated", None, [vp, ip]),
         ("lsdo_depthmap_read", None, [vp, vp]),
         ("lsdo_depthmap_write", None, [vp, vp]),
+        ("lsdo_depthmap_last_rescale", fp, [vp]),
         ("lsdo_depthmap_update_keyframe", dp, [vp, ip, vp, vp]),
         ("lsdo_depthmap_create_keyframe", dp, [vp, vp]),
         ("lsdo_depthmap_finalize", None, [vp]),
         ("lsdo_depthmap_stage", dp, [vp, ip, ip, ip, vp]),
+        ("lsdo_depthmap_prepare", None, [vp, ip, vp]),
         ("lsdo_depthmap_debug_rgb", None, [vp, vp]),
         ("lsdo_line_stereo", fp, [vp, vp, fp, fp, fp, fp, fp, fp, fp, vp]),
+        ("lsdo_make_epl", ip, [vp, vp, ip, ip, vp]),
+        ("lsdo_frame_get_pose", None, [vp, vp]),
+        ("lsdo_frame_get_counters", None, [vp, vp]),
+        ("lsdo_frame_set_flags", None, [vp, ip]),
+        ("lsdo_frame_clear_mask", None, [vp]),
     ]:
-        if hasattr(L, name):
-            f = getattr(L, name)
-            f.restype = res
-            f.argtypes = args
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
     _libs[key] = L
     return L
 
@@ -267,3 +276,123 @@ class RawBatch:
             self.L.lsdo_frame_destroy(self.kf[i])
             self.L.lsdo_frame_destroy(self.fr[i])
         self.n = 0
+
+
+def sim3_track(ref: Ref, frame: Frame, init8, start_level=4, final_level=1, mode=0, trace_cap=2048):
+    """Sim3Tracker::trackFrameSim3; init8 = frameToReference (qx,qy,qz,qw,tx,ty,tz,scale)."""
+    res = Sim3Result()
+    tr = (TraceEntry * trace_cap)()
+    init = np.ascontiguousarray(init8, np.float64)
+    ref.L.lsdo_sim3_track(ref.p, frame.p, _ptr(init), start_level, final_level, mode, C.byref(res), tr, trace_cap)
+    trace = [(tr[i].level, tr[i].accepted, tr[i].error, tr[i].lam, tr[i].bufSize) for i in range(min(res.traceLen, trace_cap))]
+    return res, trace
+
+
+def sim3_track_batch(refs, frames, inits, start_level=4, final_level=1, mode=0, threads=1):
+    n = len(refs)
+    L = refs[0].L
+    rp = (C.c_void_p * n)(*[r.p for r in refs])
+    fp = (C.c_void_p * n)(*[f.p for f in frames])
+    init = np.ascontiguousarray(inits, np.float64).reshape(n, 8)
+    outs = (Sim3Result * n)()
+    secs = L.lsdo_sim3_track_batch(n, rp, fp, _ptr(init), start_level, final_level, mode, threads, outs)
+    return secs, outs
+
+
+STAGE_OBSERVE, STAGE_FILL_HOLES, STAGE_REGULARIZE, STAGE_PROPAGATE, STAGE_SET_DEPTH = range(5)
+
+
+class DepthMap:
+    """[UP] lsd_slam::DepthMap restated on the CPU (oracle/depthmap.cpp)."""
+
+    def __init__(self, w, h, K, threads=1, fast=False):
+        self.L = lib(fast)
+        self.w, self.h = w, h
+        self.p = self.L.lsdo_depthmap_create(w, h, K[0], K[1], K[2], K[3], threads)
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.L.lsdo_depthmap_destroy(self.p)
+        except Exception:
+            pass
+
+    def set_thresholds(self, create=30, keep=24, unblacklist=100, min_blacklist=-1):
+        self.L.lsdo_depthmap_set_thresholds(self.p, create, keep, unblacklist, min_blacklist)
+
+    def init_gt(self, frame: Frame):
+        self._keep.append(frame)
+        self.L.lsdo_depthmap_init_gt(self.p, frame.p)
+
+    def init_random(self, frame: Frame, seed=1):
+        self._keep.append(frame)
+        self.L.lsdo_depthmap_init_random(self.p, frame.p, seed)
+
+    def init_map(self, frame: Frame, hyp):
+        self._keep.append(frame)
+        hyp = np.ascontiguousarray(hyp, HYP_DTYPE)
+        self.L.lsdo_depthmap_init_map(self.p, frame.p, _ptr(hyp))
+
+    def set_reactivated(self, v):
+        self.L.lsdo_depthmap_set_reactivated(self.p, int(v))
+
+    def read(self):
+        out = np.zeros((self.h, self.w), HYP_DTYPE)
+        self.L.lsdo_depthmap_read(self.p, _ptr(out))
+        return out
+
+    def write(self, hyp):
+        hyp = np.ascontiguousarray(hyp, HYP_DTYPE)
+        self.L.lsdo_depthmap_write(self.p, _ptr(hyp))
+
+    def update_keyframe(self, frames):
+        self._keep.extend(frames)
+        fp = (C.c_void_p * len(frames))(*[f.p for f in frames])
+        return self.L.lsdo_depthmap_update_keyframe(self.p, len(frames), fp, None)
+
+    def prepare(self, frames):
+        self._keep.extend(frames)
+        fp = (C.c_void_p * len(frames))(*[f.p for f in frames])
+        self.L.lsdo_depthmap_prepare(self.p, len(frames), fp)
+
+    def create_keyframe(self, new_kf: Frame):
+        self._keep.append(new_kf)
+        return self.L.lsdo_depthmap_create_keyframe(self.p, new_kf.p)
+
+    def finalize(self):
+        self.L.lsdo_depthmap_finalize(self.p)
+
+    def stage(self, stage, arg1=0, arg2=0, frame=None):
+        if frame is not None:
+            self._keep.append(frame)
+        return self.L.lsdo_depthmap_stage(self.p, stage, arg1, arg2, frame.p if frame is not None else None)
+
+    def last_rescale(self):
+        return self.L.lsdo_depthmap_last_rescale(self.p)
+
+    def debug_rgb(self):
+        out = np.zeros((self.h, self.w, 3), np.uint8)
+        self.L.lsdo_depthmap_debug_rgb(self.p, _ptr(out))
+        return out
+
+    def line_stereo(self, ref: Frame, u, v, epxn, epyn, min_id, prior_id, max_id):
+        out = np.zeros(3, np.float32)
+        e = self.L.lsdo_line_stereo(self.p, ref.p, u, v, epxn, epyn, min_id, prior_id, max_id, _ptr(out))
+        return e, out
+
+    def make_epl(self, ref: Frame, x, y):
+        out = np.zeros(2, np.float32)
+        ok = self.L.lsdo_make_epl(self.p, ref.p, x, y, _ptr(out))
+        return bool(ok), out
+
+
+def frame_pose(frame: Frame):
+    out = np.zeros(8)
+    frame.L.lsdo_frame_get_pose(frame.p, _ptr(out))
+    return out
+
+
+def frame_counters(frame: Frame):
+    out = np.zeros(3, np.int32)
+    frame.L.lsdo_frame_get_counters(frame.p, _ptr(out))
+    return out

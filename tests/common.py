@@ -31,3 +31,40 @@ def make_oracle_pair(seed, w, h, var=0.01, noise=0.0, **kw):
     kf.set_idepth(idv, vv)
     ref = O.Ref(kf)
     return dict(pr=pr, kf_img=kf_img, fr_img=fr_img, okf=kf, ofr=fr, oref=ref, idepth=idv, var=vv)
+
+
+def hyp_from_idepth(idepth, var, validity=20, smoothed=True):
+    """A DepthMapPixelHypothesis map (32-byte AoS) from idepth / var planes (var <= 0: invalid pixel)."""
+    h, w = idepth.shape
+    m = np.zeros((h, w), O.HYP_DTYPE)
+    valid = var > 0
+    m["isValid"] = valid
+    m["validity_counter"] = np.where(valid, validity, 0)
+    m["idepth"] = np.where(valid, idepth, 0)
+    m["idepth_var"] = np.where(valid, var, 0)
+    m["idepth_smoothed"] = np.where(valid, idepth if smoothed else -1, 0)
+    m["idepth_var_smoothed"] = np.where(valid, var if smoothed else -1, 0)
+    return m
+
+
+def make_oracle_depth_scene(seed, w, h, n_refs=10, noise=0.05, var=0.01, residual=1.0, with_mask=False, **kw):
+    """Keyframe + reference frames for the DepthMap tests: oracle Frames with GT relative poses installed as
+    thisToParent_raw (what SE3Tracker::trackFrame leaves behind), initialTrackedResidual = `residual`."""
+    sc = synth.make_depth_scene(seed, w, h, n_refs, **kw)
+    kf_img = sc["kf_img"].cpu().numpy()
+    okf = O.Frame(1000, kf_img, sc["K"])
+    okf.build_pyramids()
+    mg = okf.get(O.MAXGRAD, 0)
+    idv, vv = synth.semidense_idepth(sc["kf_depth"], mg, var=var, noise=noise, seed=seed)
+    refs = []
+    for i, r in enumerate(sc["refs"]):
+        img = r["img"].cpu().numpy()
+        f = O.Frame(1001 + i, img, sc["K"])
+        f.build_pyramids()
+        toParent = np.concatenate([r["toKf"], [1.0]])
+        f.set_track_meta(residual, 1000, toParent)
+        if with_mask:
+            f.set_mask(np.ones((h >> 1, w >> 1), np.uint8))
+        refs.append(dict(img=img, of=f, toParent=toParent, depth=r["depth"].cpu().numpy()))
+    gt_idepth = (1.0 / sc["kf_depth"].cpu().numpy()).astype(np.float32)
+    return dict(sc=sc, K=sc["K"], kf_img=kf_img, okf=okf, maxgrad=mg, idepth=idv, var=vv, refs=refs, gt_idepth=gt_idepth)

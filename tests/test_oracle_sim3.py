@@ -1,0 +1,64 @@
+"""CPU tests of the Sim3Tracker oracle against analytic ground truth (PARITY UNPINNED: no golden vector exists).
+
+Keyframe A (reference, true-scale depth) against keyframe B whose own inverse-depth map is expressed in a
+map scaled by c: the recovered frameToReference must have scale c, the GT rotation and translation.
+"""
+import numpy as np
+import pytest
+
+from common import make_oracle_pair, quat_angle
+from lsd_b200 import synth
+
+
+def make_sim3_pair(oracle, seed, w, h, c=1.0, var=0.01, max_t=0.05, max_r=np.radians(2.0)):
+    d = make_oracle_pair(seed, w, h, var=var, max_t=max_t, max_r=max_r)
+    # frame B gets its own semi-dense depth, in a map whose inverse depths are c times the true ones
+    mgB = d["ofr"].get(oracle.MAXGRAD, 0)
+    idB, vB = synth.semidense_idepth(d["pr"]["fr_depth"], mgB, var=var)
+    idB = np.where(vB > 0, idB * np.float32(c), idB).astype(np.float32)
+    d["ofr"].set_idepth(idB, vB)
+    gt = np.concatenate([d["pr"]["frameToRef"], [c]])  # p_ref = c * R * p_B(map) + t
+    d["gt8"] = gt
+    d["fr_idepth"], d["fr_var"] = idB, vB
+    return d
+
+
+@pytest.mark.parametrize("c", [1.0, 1.05, 0.93])
+def test_sim3_recovers_pose_and_scale(oracle, c):
+    w, h = 320, 240
+    d = make_sim3_pair(oracle, 11, w, h, c=c)
+    init = d["gt8"].copy()
+    init[4:7] += [0.01, -0.008, 0.005]
+    init[7] = 1.0
+    res, trace = oracle.sim3_track(d["oref"], d["ofr"], init, 4, 1, 0)
+    assert not res.diverged
+    got = np.array(res.frameToRef)
+    assert abs(got[7] - c) < 3e-3, (got[7], c)
+    assert np.linalg.norm(got[4:7] - d["gt8"][4:7]) < 3e-3
+    assert quat_angle(got[:4], d["gt8"][:4]) < 2e-3
+    assert res.lastResidual > 0 and res.lastDepthResidual >= 0 and res.lastPhotometricResidual > 0
+    H = np.array(res.hessian).reshape(7, 7)
+    assert np.allclose(H, H.T) and np.all(np.linalg.eigvalsh(H.astype(np.float64)) > 0)
+    lv = [t[0] for t in trace]
+    assert lv == sorted(lv, reverse=True) and lv[0] == 4 and lv[-1] == 1
+
+
+def test_sim3_reduction_modes_agree(oracle):
+    d = make_sim3_pair(oracle, 12, 320, 240, c=1.02)
+    init = d["gt8"].copy()
+    init[7] = 1.0
+    p = []
+    for mode in (0, 2):
+        res, _ = oracle.sim3_track(d["oref"], d["ofr"], init, 4, 1, mode)
+        p.append(np.array(res.frameToRef))
+    assert np.abs(p[0] - p[1]).max() < 2e-4
+
+
+def test_sim3_level_range_and_divergence(oracle):
+    d = make_sim3_pair(oracle, 13, 320, 240)
+    res, trace = oracle.sim3_track(d["oref"], d["ofr"], d["gt8"], 4, 3, 0)  # constraint search calls [4 -> 3]
+    assert {t[0] for t in trace} == {4, 3}
+    s = np.sin(np.pi / 4)
+    bad = np.array([0, s, 0, s, 0, 0, 0, 1.0])
+    res, _ = oracle.sim3_track(d["oref"], d["ofr"], bad, 4, 1, 0)
+    assert res.diverged == 1 and list(res.frameToRef) == [0, 0, 0, 1, 0, 0, 0, 1]
