@@ -157,6 +157,75 @@ int lsd_se3_eval(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refT
 /* algorithmic bytes and evaluation count of the last lsd_se3_track* call on this ctx */
 int lsd_se3_last_stats(lsd_ctx *ctx, double *algorithmic_bytes, long long *evaluations, float *kernel_ms);
 
+/* ---- frame bookkeeping the mapping side reads ---------------------------------------------------- */
+/* What SE3Tracker::trackFrame leaves on a tracked Frame ([UP] frame->pose->thisToParent_raw,
+ * trackingParent, initialTrackedResidual); settable directly for frames whose pose comes from elsewhere
+ * (ground truth, pose graph).  toParent = Sim3 double[8] {qx,qy,qz,qw,tx,ty,tz,scale}. */
+int lsd_frame_set_tracking_meta(lsd_ctx *ctx, lsd_frame *f, int parentId, const double toParent[8],
+                                float initialTrackedResidual);
+int lsd_frame_get_tracking_meta(lsd_ctx *ctx, lsd_frame *f, int *parentId, double toParent[8], float *initialTrackedResidual);
+/* refPixelWasGood(): install (mask != NULL, (h>>1)*(w>>1) bytes) or drop (NULL: refPixelWasGoodNoCreate() == 0) */
+int lsd_frame_set_mask(lsd_ctx *ctx, lsd_frame *f, const uint8_t *mask);
+/* [UP] Frame::numFramesTrackedOnThis / numMappedOnThis (feed observeDepth's skip-ahead) */
+int lsd_frame_set_counters(lsd_ctx *ctx, lsd_frame *f, int numFramesTrackedOnThis, int numMappedOnThis);
+int lsd_frame_get_counters(lsd_ctx *ctx, lsd_frame *f, int *numFramesTrackedOnThis, int *numMappedOnThis);
+int lsd_frame_set_depth_updated_flag(lsd_ctx *ctx, lsd_frame *f, int depthHasBeenUpdatedFlag);
+
+/* ---- DepthMap -------------------------------------------------------------------------------------- */
+/* [UP] DepthMapPixelHypothesis, upstream's 32-byte AoS layout; the device keeps SoA planes. */
+typedef struct lsd_hypothesis {
+  uint8_t isValid, pad_[3];
+  int32_t blacklisted;
+  float nextStereoFrameMinID;
+  int32_t validity_counter;
+  float idepth, idepth_var, idepth_smoothed, idepth_var_smoothed;
+} lsd_hypothesis;
+
+/* util/settings.h thresholds that are run-time settable here (DESIGN.md "Deviations from SURVEY") */
+typedef struct lsd_depth_settings {
+  int valSumMinForCreate;      /* VAL_SUM_MIN_FOR_CREATE      default 30  */
+  int valSumMinForKeep;        /* VAL_SUM_MIN_FOR_KEEP        default 24  */
+  int valSumMinForUnblacklist; /* VAL_SUM_MIN_FOR_UNBLACKLIST default 100 */
+  int minBlacklist;            /* MIN_BLACKLIST               default -1  */
+} lsd_depth_settings;
+
+enum lsd_depth_stage {
+  LSD_STAGE_OBSERVE = 0,    /* DepthMap::observeDepth (references from the last lsd_depth_prepare)       */
+  LSD_STAGE_FILL_HOLES = 1, /* DepthMap::regularizeDepthMapFillHoles                                      */
+  LSD_STAGE_REGULARIZE = 2, /* DepthMap::regularizeDepthMap(arg1 = removeOcclusions, arg2 = validityTH)   */
+  LSD_STAGE_PROPAGATE = 3,  /* DepthMap::propagateDepth(frame); the frame becomes the active keyframe      */
+  LSD_STAGE_SET_DEPTH = 4   /* activeKeyFrame->setDepth(currentDepthMap) + idepth pyramids                */
+};
+
+int lsd_depthmap_create(lsd_ctx *ctx, lsd_depthmap **out); /* [UP] DepthMap::DepthMap(w, h, K) */
+int lsd_depthmap_destroy(lsd_ctx *ctx, lsd_depthmap *dm);
+int lsd_default_depth_settings(lsd_depth_settings *s);
+int lsd_depthmap_set_settings(lsd_ctx *ctx, lsd_depthmap *dm, const lsd_depth_settings *s);
+/* [UP] DepthMap::initializeFromGTDepth(Frame*): the frame must carry depth (lsd_frame_set_depth_from_gt) */
+int lsd_depth_initialize_from_gt(lsd_ctx *ctx, lsd_depthmap *dm, lsd_frame *kf);
+/* [UP] DepthMap::initializeRandomly(Frame*): consumes libc rand() in raster order exactly like upstream
+ * (one draw per pixel with maxGradients > MIN_ABS_GRAD_CREATE, x in [1,w-1), y in [1,h-1)) */
+int lsd_depth_initialize_randomly(lsd_ctx *ctx, lsd_depthmap *dm, lsd_frame *kf);
+/* install an explicit hypothesis map (w*h lsd_hypothesis) for `kf` -- [UP] DepthMap::setFromExistingKF /
+ * re-activation data, and the way parity runs inject identical state into the oracle and the device */
+int lsd_depth_initialize_from_map(lsd_ctx *ctx, lsd_depthmap *dm, lsd_frame *kf, const lsd_hypothesis *map, int reactivated);
+/* [UP] DepthMap::updateKeyframe(std::deque<std::shared_ptr<Frame>> referenceFrames).  refToKf: n*8 Sim3
+ * (frame -> active keyframe) or NULL to use each frame's thisToParent_raw (frames tracked on the active keyframe). */
+int lsd_depth_update_keyframe(lsd_ctx *ctx, lsd_depthmap *dm, int n, lsd_frame *const *referenceFrames, const double *refToKf);
+/* [UP] DepthMap::createKeyFrame(Frame* new_keyframe): propagateDepth + regularize(true) + fillHoles +
+ * regularize(false) + mean-idepth normalisation + setDepth; rescaleFactor is folded into new_keyframe's
+ * thisToParent_raw exactly like upstream and also returned. */
+int lsd_depth_create_keyframe(lsd_ctx *ctx, lsd_depthmap *dm, lsd_frame *new_keyframe, float *rescaleFactor);
+int lsd_depth_finalize_keyframe(lsd_ctx *ctx, lsd_depthmap *dm); /* [UP] DepthMap::finalizeKeyFrame */
+int lsd_depth_read(lsd_ctx *ctx, lsd_depthmap *dm, lsd_hypothesis *dst); /* currentDepthMap, w*h entries */
+/* [UP] DepthMap::debugPlotDepthMap -> the w*h*3 bytes lib/GUI.cpp:104-108 (updateDepthImage) consumes */
+int lsd_depth_debug_rgb(lsd_ctx *ctx, lsd_depthmap *dm, uint8_t *rgb);
+/* stage-level entry points (parity tests, per-kernel timing: BASELINE.json configs[2]) */
+int lsd_depth_prepare(lsd_ctx *ctx, lsd_depthmap *dm, int n, lsd_frame *const *referenceFrames, const double *refToKf);
+int lsd_depth_stage(lsd_ctx *ctx, lsd_depthmap *dm, int stage, int arg1, int arg2, lsd_frame *frame);
+/* the same stage on n independent depth maps in ONE set of launches (blockIdx.z = map); frames: n or NULL */
+int lsd_depth_stage_batch(lsd_ctx *ctx, int n, lsd_depthmap *const *dms, int stage, int arg1, int arg2, lsd_frame *const *frames);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,7 +116,7 @@ static void build_planes(lsd_ctx *ctx, int n, unsigned flags, cudaStream_t st) {
   if (flags & LSD_BUILD_MAXGRAD0) launch_maxgrad0(ctx, d_slabs, n, st);
 }
 
-static int ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need) {
+int frame_ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need) {
   const unsigned missing = need & ~f->built;
   if (!missing) return LSD_OK;
   cudaStream_t st = ctx->stream;
@@ -217,6 +217,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->h_stageBytes = ctx->d_stageBytes = 0;
   ctx->h_table = ctx->d_table = nullptr;
   ctx->tableBytes = 0;
+  ctx->descSlot = 0;
   ctx->se3s = nullptr;
   ctx->lastAlgBytes = 0;
   ctx->lastEvals = 0;
@@ -353,19 +354,19 @@ int lsd_frame_read(lsd_ctx *ctx, lsd_frame *f, int field, int level, void *dst) 
   switch (field) {
     case LSD_FIELD_IMAGE: src = f->slab + L.img[level]; bytes = N * 4; break;
     case LSD_FIELD_GRADIENTS:
-      if (level == 0) rc = ensure_built(ctx, f, FB_GRAD0);
+      if (level == 0) rc = frame_ensure_built(ctx, f, FB_GRAD0);
       src = f->slab + L.grad[level]; bytes = N * 16; break;
     case LSD_FIELD_MAXGRAD:
       LSD_ARG(level == 0);
-      rc = ensure_built(ctx, f, FB_MAXGRAD0);
+      rc = frame_ensure_built(ctx, f, FB_MAXGRAD0);
       src = f->slab + L.maxgrad; bytes = N * 4; break;
     case LSD_FIELD_IDEPTH:
     case LSD_FIELD_IDEPTHVAR:
       if (!(f->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
-      if (level > 0) rc = ensure_built(ctx, f, FB_IDEPTH_PYR);
+      if (level > 0) rc = frame_ensure_built(ctx, f, FB_IDEPTH_PYR);
       src = f->slab + (field == LSD_FIELD_IDEPTH ? L.idepth[level] : L.idvar[level]); bytes = N * 4; break;
     case LSD_FIELD_MASK:
-      rc = ensure_built(ctx, f, FB_MASK);
+      rc = frame_ensure_built(ctx, f, FB_MASK);
       src = f->slab + L.mask; bytes = (size_t)ctx->K.w[1] * ctx->K.h[1]; break;
     default: LSD_ARG(!"unknown field");
   }
@@ -378,7 +379,7 @@ int lsd_frame_read(lsd_ctx *ctx, lsd_frame *f, int field, int level, void *dst) 
 int lsd_frame_num_mappable_pixels(lsd_ctx *ctx, lsd_frame *f, int *out) {
   LSD_ARG(ctx && f && out);
   LSD_CUDA(cudaSetDevice(ctx->device));
-  int rc = ensure_built(ctx, f, FB_MAXGRAD0);
+  int rc = frame_ensure_built(ctx, f, FB_MAXGRAD0);
   if (rc) return rc;
   if (f->numMappable < 0) {
     LSD_CUDA(cudaMemcpyAsync(&f->numMappable, f->slab + ctx->lay.total - 16, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -446,6 +447,59 @@ int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *nu
   std::memcpy(&f->numPoints, &h[1], 4);
   if (meanIdepth) *meanIdepth = f->meanIdepth;
   if (numPoints) *numPoints = f->numPoints;
+  return LSD_OK;
+}
+
+int lsd_frame_set_tracking_meta(lsd_ctx *ctx, lsd_frame *f, int parentId, const double toParent[8], float initialTrackedResidual) {
+  LSD_ARG(ctx && f && toParent);
+  f->trackingParentId = parentId;
+  for (int k = 0; k < 8; k++) f->thisToParent_raw[k] = toParent[k];
+  f->initialTrackedResidual = initialTrackedResidual;
+  return LSD_OK;
+}
+
+int lsd_frame_get_tracking_meta(lsd_ctx *ctx, lsd_frame *f, int *parentId, double toParent[8], float *initialTrackedResidual) {
+  LSD_ARG(ctx && f);
+  if (parentId) *parentId = f->trackingParentId;
+  if (toParent) for (int k = 0; k < 8; k++) toParent[k] = f->thisToParent_raw[k];
+  if (initialTrackedResidual) *initialTrackedResidual = f->initialTrackedResidual;
+  return LSD_OK;
+}
+
+int lsd_frame_set_mask(lsd_ctx *ctx, lsd_frame *f, const uint8_t *mask) {
+  LSD_ARG(ctx && f);
+  if (!mask) {
+    f->built &= ~FB_MASK;
+    return LSD_OK;
+  }
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->K.w[1] * ctx->K.h[1];
+  int rc = ensure_stage(ctx, bytes, 0);
+  if (rc) return rc;
+  std::memcpy(ctx->h_stage, mask, bytes);
+  LSD_CUDA(cudaMemcpyAsync(f->slab + ctx->lay.mask, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  f->built |= FB_MASK;
+  return LSD_OK;
+}
+
+int lsd_frame_set_counters(lsd_ctx *ctx, lsd_frame *f, int numFramesTrackedOnThis, int numMappedOnThis) {
+  LSD_ARG(ctx && f);
+  f->numFramesTrackedOnThis = numFramesTrackedOnThis;
+  f->numMappedOnThis = numMappedOnThis;
+  return LSD_OK;
+}
+
+int lsd_frame_get_counters(lsd_ctx *ctx, lsd_frame *f, int *numFramesTrackedOnThis, int *numMappedOnThis) {
+  LSD_ARG(ctx && f);
+  if (numFramesTrackedOnThis) *numFramesTrackedOnThis = f->numFramesTrackedOnThis;
+  if (numMappedOnThis) *numMappedOnThis = f->numMappedOnThis;
+  return LSD_OK;
+}
+
+int lsd_frame_set_depth_updated_flag(lsd_ctx *ctx, lsd_frame *f, int flag) {
+  LSD_ARG(ctx && f);
+  f->depthHasBeenUpdatedFlag = flag != 0;
   return LSD_OK;
 }
 

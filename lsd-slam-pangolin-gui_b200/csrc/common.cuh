@@ -76,7 +76,8 @@ struct lsd_frame {
   int trackingParentId;
   float meanIdepth;
   int numPoints;
-  int numFramesTrackedOnThis, numMappedOnThis;
+  int numFramesTrackedOnThis, numMappedOnThis, numMappedOnThisTotal;
+  bool depthHasBeenUpdatedFlag;
 };
 
 enum {

@@ -31,6 +31,7 @@ struct lsd_ctx {
   void *h_table;
   void *d_table;
   size_t tableBytes;
+  int descSlot;  // rotating slot of the depth-map descriptor uploads (depth.cu)
   SE3Scratch *se3s;
   // last-call stats
   double lastAlgBytes;
@@ -42,6 +43,7 @@ namespace lsd {
 
 int ensure_stage(lsd_ctx *ctx, size_t hostBytes, size_t devBytes);
 int ensure_table(lsd_ctx *ctx, size_t bytes);
+int frame_ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need);  // api.cu: lazily builds planes (blocking)
 
 // pyramid.cu
 void launch_ingest(lsd_ctx *ctx, const uint8_t *d_src, size_t srcPitch, size_t srcFrameStride, uint8_t *const *d_slabs, int n,

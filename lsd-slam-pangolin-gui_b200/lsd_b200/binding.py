@@ -82,7 +82,39 @@ SYMBOLS = {
     "lsd_se3_track_images_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _vp, _vp]),
     "lsd_se3_eval": (_ip, [_vp, _vp, _vp, _vp, _ip, _fp, _fp, _vp, _vp, _vp]),
     "lsd_se3_last_stats": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_frame_set_tracking_meta": (_ip, [_vp, _vp, _ip, _vp, _fp]),
+    "lsd_frame_get_tracking_meta": (_ip, [_vp, _vp, _vp, _vp, _vp]),
+    "lsd_frame_set_mask": (_ip, [_vp, _vp, _vp]),
+    "lsd_frame_set_counters": (_ip, [_vp, _vp, _ip, _ip]),
+    "lsd_frame_get_counters": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_frame_set_depth_updated_flag": (_ip, [_vp, _vp, _ip]),
+    "lsd_depthmap_create": (_ip, [_vp, _vp]),
+    "lsd_depthmap_destroy": (_ip, [_vp, _vp]),
+    "lsd_default_depth_settings": (_ip, [_vp]),
+    "lsd_depthmap_set_settings": (_ip, [_vp, _vp, _vp]),
+    "lsd_depth_initialize_from_gt": (_ip, [_vp, _vp, _vp]),
+    "lsd_depth_initialize_randomly": (_ip, [_vp, _vp, _vp]),
+    "lsd_depth_initialize_from_map": (_ip, [_vp, _vp, _vp, _vp, _ip]),
+    "lsd_depth_update_keyframe": (_ip, [_vp, _vp, _ip, _vp, _vp]),
+    "lsd_depth_create_keyframe": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_depth_finalize_keyframe": (_ip, [_vp, _vp]),
+    "lsd_depth_read": (_ip, [_vp, _vp, _vp]),
+    "lsd_depth_debug_rgb": (_ip, [_vp, _vp, _vp]),
+    "lsd_depth_prepare": (_ip, [_vp, _vp, _ip, _vp, _vp]),
+    "lsd_depth_stage": (_ip, [_vp, _vp, _ip, _ip, _ip, _vp]),
+    "lsd_depth_stage_batch": (_ip, [_vp, _ip, _vp, _ip, _ip, _ip, _vp]),
 }
+
+# [UP] DepthMapPixelHypothesis in upstream's 32-byte AoS layout (lsd_hypothesis)
+HYP_DTYPE = np.dtype([("isValid", np.uint8), ("_pad", np.uint8, (3,)), ("blacklisted", np.int32),
+                      ("nextStereoFrameMinID", np.float32), ("validity_counter", np.int32), ("idepth", np.float32),
+                      ("idepth_var", np.float32), ("idepth_smoothed", np.float32), ("idepth_var_smoothed", np.float32)])
+STAGE_OBSERVE, STAGE_FILL_HOLES, STAGE_REGULARIZE, STAGE_PROPAGATE, STAGE_SET_DEPTH = range(5)
+
+
+class DepthSettings(C.Structure):
+    _fields_ = [("valSumMinForCreate", C.c_int), ("valSumMinForKeep", C.c_int), ("valSumMinForUnblacklist", C.c_int),
+                ("minBlacklist", C.c_int)]
 
 
 def load():
@@ -186,6 +218,16 @@ class Context:
         n = len(frames)
         fp = (C.c_void_p * n)(*[f.p for f in frames])
         _chk(self.L.lsd_frame_set_idepth_batch_device(self.p, n, fp, C.c_void_p(d_idepth), C.c_void_p(d_var)))
+
+    def create_depthmap(self):
+        return DepthMap(self)
+
+    def depth_stage_batch(self, dms, stage, arg1=0, arg2=0, frames=None):
+        """One DepthMap stage on n independent maps in a single set of launches (blockIdx.z = map)."""
+        n = len(dms)
+        dp = (C.c_void_p * n)(*[d.p for d in dms])
+        fp = (C.c_void_p * n)(*[f.p for f in frames]) if frames is not None else None
+        _chk(self.L.lsd_depth_stage_batch(self.p, n, dp, stage, arg1, arg2, fp))
 
     # ---- SE3 tracking
     def se3_track_batch(self, refs, frames, inits, want_trace=False):
@@ -308,11 +350,110 @@ class Frame:
         b = np.ascontiguousarray(var, np.float32)
         _chk(self.ctx.L.lsd_frame_set_idepth(self.ctx.p, self.p, _ptr(a), _ptr(b)))
 
+    def set_tracking_meta(self, parent_id, toParent8, initialTrackedResidual):
+        a = np.ascontiguousarray(toParent8, np.float64)
+        _chk(self.ctx.L.lsd_frame_set_tracking_meta(self.ctx.p, self.p, int(parent_id), _ptr(a), float(initialTrackedResidual)))
+
+    def tracking_meta(self):
+        pid = C.c_int()
+        a = np.zeros(8)
+        r = C.c_float()
+        _chk(self.ctx.L.lsd_frame_get_tracking_meta(self.ctx.p, self.p, C.byref(pid), _ptr(a), C.byref(r)))
+        return pid.value, a, r.value
+
+    def set_mask(self, mask):
+        m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+        _chk(self.ctx.L.lsd_frame_set_mask(self.ctx.p, self.p, _ptr(m)))
+
+    def set_counters(self, tracked, mapped):
+        _chk(self.ctx.L.lsd_frame_set_counters(self.ctx.p, self.p, int(tracked), int(mapped)))
+
+    def counters(self):
+        a, b = C.c_int(), C.c_int()
+        _chk(self.ctx.L.lsd_frame_get_counters(self.ctx.p, self.p, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_depth_updated_flag(self, v):
+        _chk(self.ctx.L.lsd_frame_set_depth_updated_flag(self.ctx.p, self.p, int(v)))
+
     def mean_idepth(self):
         m = C.c_float()
         n = C.c_int()
         _chk(self.ctx.L.lsd_frame_mean_idepth(self.ctx.p, self.p, C.byref(m), C.byref(n)))
         return m.value, n.value
+
+
+class DepthMap:
+    """[UP] lsd_slam::DepthMap: device-resident hypothesis planes; same method names as upstream."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        p = C.c_void_p()
+        _chk(ctx.L.lsd_depthmap_create(ctx.p, C.byref(p)))
+        self.p = p
+        self._keep = []
+
+    def destroy(self):
+        if self.p:
+            self.ctx.L.lsd_depthmap_destroy(self.ctx.p, self.p)
+            self.p = None
+
+    def set_thresholds(self, create=30, keep=24, unblacklist=100, min_blacklist=-1):
+        s = DepthSettings(create, keep, unblacklist, min_blacklist)
+        _chk(self.ctx.L.lsd_depthmap_set_settings(self.ctx.p, self.p, C.byref(s)))
+
+    def initializeFromGTDepth(self, kf):
+        self._keep.append(kf)
+        _chk(self.ctx.L.lsd_depth_initialize_from_gt(self.ctx.p, self.p, kf.p))
+
+    def initializeRandomly(self, kf):
+        self._keep.append(kf)
+        _chk(self.ctx.L.lsd_depth_initialize_randomly(self.ctx.p, self.p, kf.p))
+
+    def initializeFromMap(self, kf, hyp, reactivated=False):
+        self._keep.append(kf)
+        h = np.ascontiguousarray(hyp, HYP_DTYPE)
+        assert h.shape == (self.ctx.h, self.ctx.w)
+        _chk(self.ctx.L.lsd_depth_initialize_from_map(self.ctx.p, self.p, kf.p, _ptr(h), int(reactivated)))
+
+    def _frames(self, frames, refToKf):
+        n = len(frames)
+        fp = (C.c_void_p * n)(*[f.p for f in frames])
+        poses = np.ascontiguousarray(refToKf, np.float64).reshape(n, 8) if refToKf is not None else None
+        return n, fp, poses
+
+    def updateKeyframe(self, referenceFrames, refToKf=None):
+        n, fp, poses = self._frames(referenceFrames, refToKf)
+        _chk(self.ctx.L.lsd_depth_update_keyframe(self.ctx.p, self.p, n, fp, _ptr(poses)))
+
+    def prepare(self, referenceFrames, refToKf=None):
+        n, fp, poses = self._frames(referenceFrames, refToKf)
+        self._keep.extend(referenceFrames)
+        _chk(self.ctx.L.lsd_depth_prepare(self.ctx.p, self.p, n, fp, _ptr(poses)))
+
+    def createKeyFrame(self, new_keyframe):
+        self._keep.append(new_keyframe)
+        f = C.c_float()
+        _chk(self.ctx.L.lsd_depth_create_keyframe(self.ctx.p, self.p, new_keyframe.p, C.byref(f)))
+        return f.value
+
+    def finalizeKeyFrame(self):
+        _chk(self.ctx.L.lsd_depth_finalize_keyframe(self.ctx.p, self.p))
+
+    def stage(self, stage, arg1=0, arg2=0, frame=None):
+        if frame is not None:
+            self._keep.append(frame)
+        _chk(self.ctx.L.lsd_depth_stage(self.ctx.p, self.p, stage, arg1, arg2, frame.p if frame is not None else None))
+
+    def read(self):
+        out = np.zeros((self.ctx.h, self.ctx.w), HYP_DTYPE)
+        _chk(self.ctx.L.lsd_depth_read(self.ctx.p, self.p, _ptr(out)))
+        return out
+
+    def debugPlotDepthMap(self):
+        out = np.zeros((self.ctx.h, self.ctx.w, 3), np.uint8)
+        _chk(self.ctx.L.lsd_depth_debug_rgb(self.ctx.p, self.p, _ptr(out)))
+        return out
 
 
 class Ref:

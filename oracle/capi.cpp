@@ -402,6 +402,8 @@ void lsdo_frame_get_counters(void *fp, int *out3) {
 void lsdo_frame_set_flags(void *fp, int depthHasBeenUpdated) { ((Frame *)fp)->depthHasBeenUpdatedFlag = depthHasBeenUpdated != 0; }
 void lsdo_frame_clear_mask(void *fp) { ((Frame *)fp)->refPixelWasGood.clear(); }
 
+void lsdo_set_exact_sums(int v) { g_exactSums = v != 0; }
+
 int lsdo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

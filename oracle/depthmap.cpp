@@ -648,11 +648,14 @@ void DepthMap::createKeyFrame(Frame *new_keyframe) {
 
   // make mean inverse depth be one
   float sumIdepth = 0, numIdepth = 0;
+  double sumD = 0;
   for (const Hypothesis &s : currentDepthMap) {
     if (!s.isValid) continue;
     sumIdepth += s.idepth_smoothed;
+    sumD += (double)s.idepth_smoothed;
     numIdepth++;
   }
+  if (g_exactSums) sumIdepth = (float)sumD;
   const float rescaleFactor = numIdepth / sumIdepth;
   const float rescaleFactor2 = rescaleFactor * rescaleFactor;
   for (Hypothesis &s : currentDepthMap) {

@@ -10,6 +10,8 @@
 
 namespace lsdo {
 
+bool g_exactSums = false;
+
 // Frame::Frame / Frame::initialize.  Input contract: 8-bit grey image
 // (/root/reference/lib/App/InputThread.cpp:59,65,71).
 Frame::Frame(int id_, int width, int height, float fx0, float fy0, float cx0, float cy0, const uint8_t *img) : id(id_) {
@@ -145,17 +147,20 @@ void Frame::setDepth(const Hypothesis *map) {
   idepth[0].resize(N);
   idepthVar[0].resize(N);
   float numIdepth = 0, sumIdepth = 0;
+  double sumD = 0;
   for (int i = 0; i < N; i++) {
     if (map[i].isValid && map[i].idepth_smoothed >= -0.05f) {
       idepth[0][i] = map[i].idepth_smoothed;
       idepthVar[0][i] = map[i].idepth_var_smoothed;
       numIdepth++;
       sumIdepth += map[i].idepth_smoothed;
+      sumD += (double)map[i].idepth_smoothed;
     } else {
       idepth[0][i] = -1;
       idepthVar[0][i] = -1;
     }
   }
+  if (g_exactSums) sumIdepth = (float)sumD;
   meanIdepth = sumIdepth / numIdepth;
   numPoints = (int)numIdepth;
   idepthValid[0] = true;

@@ -108,6 +108,11 @@ struct Hypothesis {
         idepth_smoothed(-1), idepth_var_smoothed(-1) {}
 };
 
+// DECISION: when set, the two whole-map sums of the depth map (createKeyFrame's sumIdepth and Frame::setDepth's
+// sumIdepth) are accumulated in fp64 and rounded once -- the order-independent definition of the same
+// quantity (upstream: sequential fp32).  Parity tests switch it on so that maps can be compared bit for bit.
+extern bool g_exactSums;
+
 // ---- Frame (DataStructures/Frame.cpp) -----------------------------------------------
 struct Frame {
   int id = 0;

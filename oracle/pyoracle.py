@@ -120,6 +120,7 @@ def lib(fast: bool = False):
         ("lsdo_frame_get_counters", None, [vp, vp]),
         ("lsdo_frame_set_flags", None, [vp, ip]),
         ("lsdo_frame_clear_mask", None, [vp]),
+        ("lsdo_set_exact_sums", None, [ip]),
     ]:
         f = getattr(L, name)
         f.restype = res
@@ -396,3 +397,8 @@ def frame_counters(frame: Frame):
     out = np.zeros(3, np.int32)
     frame.L.lsdo_frame_get_counters(frame.p, _ptr(out))
     return out
+
+
+def set_exact_sums(v, fast=False):
+    """fp64 accumulation of the depth map's two whole-map sums (see lsd_oracle.hpp g_exactSums)."""
+    lib(fast).lsdo_set_exact_sums(int(v))
