@@ -157,6 +157,27 @@ int lsd_se3_eval(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refT
 /* algorithmic bytes and evaluation count of the last lsd_se3_track* call on this ctx */
 int lsd_se3_last_stats(lsd_ctx *ctx, double *algorithmic_bytes, long long *evaluations, float *kernel_ms);
 
+/* ---- Sim3Tracker ------------------------------------------------------------------------------------ */
+/* What [UP] Sim3Tracker exposes as members after trackFrameSim3. */
+typedef struct lsd_sim3_result {
+  double frameToRef[8];      /* Sim3 {qx,qy,qz,qw,tx,ty,tz,scale}; identity when diverged (upstream returns Sim3()) */
+  float lastSim3Hessian[49]; /* 7x7, row-major: ls7.A of the last LGS (not divided by num_constraints)           */
+  float lastResidual, lastDepthResidual, lastPhotometricResidual, pointUsage, affine_a, affine_b;
+  int diverged;
+  int numResidualCalls[LSD_PYRAMID_LEVELS], numWarpUpdateCalls[LSD_PYRAMID_LEVELS];
+  int traceLen;
+} lsd_sim3_result;
+
+int lsd_ctx_set_sim3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
+/* [UP] Sim3Tracker::trackFrameSim3(TrackingReference*, Frame*, const Sim3& frameToReference_initialEstimate,
+ * int startLevel, int finalLevel).  `frame` must carry depth (it is a keyframe): its idepth pyramid is read. */
+int lsd_sim3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[8], int startLevel, int finalLevel,
+                   lsd_sim3_result *result, lsd_trace_entry *trace /* LSD_TRACE_CAP entries or NULL */);
+/* n independent tracks, one thread-block cluster each, in ONE launch (the constraint search of
+ * SlamSystem::findConstraintsForNewKeyFrames: BASELINE.json configs[3]) */
+int lsd_sim3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init_frameToRef /* n*8 */,
+                         int startLevel, int finalLevel, lsd_sim3_result *results, lsd_trace_entry *traces /* n*LSD_TRACE_CAP or NULL */);
+
 /* ---- frame bookkeeping the mapping side reads ---------------------------------------------------- */
 /* What SE3Tracker::trackFrame leaves on a tracked Frame ([UP] frame->pose->thisToParent_raw,
  * trackingParent, initialTrackedResidual); settable directly for frames whose pose comes from elsewhere

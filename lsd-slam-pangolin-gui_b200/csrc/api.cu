@@ -211,6 +211,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   for (int i = 0; i < 4; i++) LSD_CUDA(cudaEventCreateWithFlags(&ctx->evPipe[i], cudaEventDisableTiming));
   ctx->launches = 0;
   lsd_default_tracker_settings(&ctx->se3);
+  lsd_default_tracker_settings(&ctx->sim3);
   ctx->se3RecsPerItem = 0;
   ctx->refSlabBytes = 0;
   ctx->h_stage = ctx->d_stage = nullptr;

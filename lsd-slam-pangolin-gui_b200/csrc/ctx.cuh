@@ -16,7 +16,7 @@ struct lsd_ctx {
   cudaStream_t copyStream;  // second stream for the pipelined host-image path
   cudaEvent_t evA, evB, evPipe[4];
   long long launches;
-  lsd_tracker_settings se3;
+  lsd_tracker_settings se3, sim3;
   int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
   // pools
   std::vector<uint8_t *> frameSlabPool;

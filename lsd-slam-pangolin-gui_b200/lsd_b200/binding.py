@@ -42,6 +42,14 @@ class SE3Result(C.Structure):
                 ("traceLen", C.c_int)]
 
 
+class Sim3Result(C.Structure):
+    _fields_ = [("frameToRef", C.c_double * 8), ("lastSim3Hessian", C.c_float * 49),
+                ("lastResidual", C.c_float), ("lastDepthResidual", C.c_float), ("lastPhotometricResidual", C.c_float),
+                ("pointUsage", C.c_float), ("affine_a", C.c_float), ("affine_b", C.c_float),
+                ("diverged", C.c_int), ("numResidualCalls", C.c_int * NL), ("numWarpUpdateCalls", C.c_int * NL),
+                ("traceLen", C.c_int)]
+
+
 class TraceEntry(C.Structure):
     _fields_ = [("level", C.c_int), ("accepted", C.c_int), ("error", C.c_float), ("lam", C.c_float), ("bufSize", C.c_int)]
 
@@ -82,6 +90,9 @@ SYMBOLS = {
     "lsd_se3_track_images_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _vp, _vp]),
     "lsd_se3_eval": (_ip, [_vp, _vp, _vp, _vp, _ip, _fp, _fp, _vp, _vp, _vp]),
     "lsd_se3_last_stats": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_ctx_set_sim3_settings": (_ip, [_vp, _vp]),
+    "lsd_sim3_track": (_ip, [_vp, _vp, _vp, _vp, _ip, _ip, _vp, _vp]),
+    "lsd_sim3_track_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _ip, _ip, _vp, _vp]),
     "lsd_frame_set_tracking_meta": (_ip, [_vp, _vp, _ip, _vp, _fp]),
     "lsd_frame_get_tracking_meta": (_ip, [_vp, _vp, _vp, _vp, _vp]),
     "lsd_frame_set_mask": (_ip, [_vp, _vp, _vp]),
@@ -279,6 +290,33 @@ class Context:
         res = (SE3Result * n)()
         _chk(self.L.lsd_se3_track_images_batch(self.p, n, rp, ip, pitch, _ptr(init), res))
         return res
+
+    # ---- Sim3 tracking
+    def set_sim3_settings(self, s):
+        _chk(self.L.lsd_ctx_set_sim3_settings(self.p, C.byref(s)))
+
+    def sim3_track_batch(self, refs, frames, inits, start_level=4, final_level=1, want_trace=False):
+        n = len(refs)
+        rp = (C.c_void_p * n)(*[r.p for r in refs])
+        fp = (C.c_void_p * n)(*[f.p for f in frames])
+        init = np.ascontiguousarray(inits, np.float64).reshape(n, 8)
+        res = (Sim3Result * n)()
+        tr = (TraceEntry * (TRACE_CAP * n))() if want_trace else None
+        _chk(self.L.lsd_sim3_track_batch(self.p, n, rp, fp, _ptr(init), start_level, final_level, res, tr))
+        if want_trace:
+            traces = []
+            for i in range(n):
+                m = min(res[i].traceLen, TRACE_CAP)
+                traces.append([(tr[i * TRACE_CAP + k].level, tr[i * TRACE_CAP + k].accepted, tr[i * TRACE_CAP + k].error,
+                                tr[i * TRACE_CAP + k].lam, tr[i * TRACE_CAP + k].bufSize) for k in range(m)])
+            return res, traces
+        return res
+
+    def sim3_track(self, ref, frame, init8, start_level=4, final_level=1, want_trace=False):
+        out = self.sim3_track_batch([ref], [frame], [init8], start_level, final_level, want_trace)
+        if want_trace:
+            return out[0][0], out[1][0]
+        return out[0]
 
     def se3_eval(self, ref, frame, refToFrame7, level, a=1.0, b=0.0):
         A = np.zeros((6, 6), np.float32)

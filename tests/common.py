@@ -68,3 +68,16 @@ def make_oracle_depth_scene(seed, w, h, n_refs=10, noise=0.05, var=0.01, residua
         refs.append(dict(img=img, of=f, toParent=toParent, depth=r["depth"].cpu().numpy()))
     gt_idepth = (1.0 / sc["kf_depth"].cpu().numpy()).astype(np.float32)
     return dict(sc=sc, K=sc["K"], kf_img=kf_img, okf=okf, maxgrad=mg, idepth=idv, var=vv, refs=refs, gt_idepth=gt_idepth)
+
+
+def make_sim3_pair(oracle, seed, w, h, c=1.0, var=0.01, max_t=0.05, max_r=np.radians(2.0)):
+    d = make_oracle_pair(seed, w, h, var=var, max_t=max_t, max_r=max_r)
+    # frame B gets its own semi-dense depth, in a map whose inverse depths are c times the true ones
+    mgB = d["ofr"].get(oracle.MAXGRAD, 0)
+    idB, vB = synth.semidense_idepth(d["pr"]["fr_depth"], mgB, var=var)
+    idB = np.where(vB > 0, idB * np.float32(c), idB).astype(np.float32)
+    d["ofr"].set_idepth(idB, vB)
+    gt = np.concatenate([d["pr"]["frameToRef"], [c]])  # p_ref = c * R * p_B(map) + t
+    d["gt8"] = gt
+    d["fr_idepth"], d["fr_var"] = idB, vB
+    return d

@@ -6,21 +6,7 @@ map scaled by c: the recovered frameToReference must have scale c, the GT rotati
 import numpy as np
 import pytest
 
-from common import make_oracle_pair, quat_angle
-from lsd_b200 import synth
-
-
-def make_sim3_pair(oracle, seed, w, h, c=1.0, var=0.01, max_t=0.05, max_r=np.radians(2.0)):
-    d = make_oracle_pair(seed, w, h, var=var, max_t=max_t, max_r=max_r)
-    # frame B gets its own semi-dense depth, in a map whose inverse depths are c times the true ones
-    mgB = d["ofr"].get(oracle.MAXGRAD, 0)
-    idB, vB = synth.semidense_idepth(d["pr"]["fr_depth"], mgB, var=var)
-    idB = np.where(vB > 0, idB * np.float32(c), idB).astype(np.float32)
-    d["ofr"].set_idepth(idB, vB)
-    gt = np.concatenate([d["pr"]["frameToRef"], [c]])  # p_ref = c * R * p_B(map) + t
-    d["gt8"] = gt
-    d["fr_idepth"], d["fr_var"] = idB, vB
-    return d
+from common import make_sim3_pair, quat_angle
 
 
 @pytest.mark.parametrize("c", [1.0, 1.05, 0.93])
