@@ -191,6 +191,7 @@ int lsd_frame_set_mask(lsd_ctx *ctx, lsd_frame *f, const uint8_t *mask);
 int lsd_frame_set_counters(lsd_ctx *ctx, lsd_frame *f, int numFramesTrackedOnThis, int numMappedOnThis);
 int lsd_frame_get_counters(lsd_ctx *ctx, lsd_frame *f, int *numFramesTrackedOnThis, int *numMappedOnThis);
 int lsd_frame_set_depth_updated_flag(lsd_ctx *ctx, lsd_frame *f, int depthHasBeenUpdatedFlag);
+int lsd_frame_get_depth_updated_flag(lsd_ctx *ctx, lsd_frame *f, int *depthHasBeenUpdatedFlag);
 
 /* ---- DepthMap -------------------------------------------------------------------------------------- */
 /* [UP] DepthMapPixelHypothesis, upstream's 32-byte AoS layout; the device keeps SoA planes. */

@@ -504,6 +504,12 @@ int lsd_frame_set_depth_updated_flag(lsd_ctx *ctx, lsd_frame *f, int flag) {
   return LSD_OK;
 }
 
+int lsd_frame_get_depth_updated_flag(lsd_ctx *ctx, lsd_frame *f, int *flag) {
+  LSD_ARG(ctx && f && flag);
+  *flag = f->depthHasBeenUpdatedFlag ? 1 : 0;
+  return LSD_OK;
+}
+
 // ---- tracking references ----------------------------------------------------------------------
 
 int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_ref **out) {

@@ -1,0 +1,276 @@
+// lsd_b200.hpp -- header-only C++11 host adapter: the lsd-slam core classes the reference links
+// (lsd_slam::Frame, TrackingReference, SE3Tracker, Sim3Tracker, DepthMap; SURVEY.md 8b "upper face")
+// re-expressed over the C ABI of liblsd_b200.so (include/lsd_b200.h).  Method names, argument meaning and
+// result members follow upstream ([UP] = un-vendored lsd-slam core; /root/reference/fips.yml:1-4), so a
+// SlamSystem built against these classes drives the B200 kernels instead of the CPU/SSE loops:
+//   tools/LSD.cpp:102              new SlamSystem()            -> owns one lsd_b200::Context per worker thread
+//   lib/App/InputThread.cpp:71     system->nextImage(...)      -> Frame(id, w, h, K, timestamp, image)
+//   PangolinOutputIOWrapper.cpp:56-79   f->image/idepth/idepthVar(level)  -> Frame accessors (lazy D2H)
+//   TextOutputIOWrapper.cpp:104-117     kf->pose->thisToParent_raw        -> Frame::thisToParent_raw()
+//
+// Pose types: plain structs SE3 / Sim3 in Sophus' data() order.  With -DLSD_B200_WITH_SOPHUS the converting
+// constructors from / to Sophus::SE3d / Sophus::Sim3d are enabled (needs an lsd-slam checkout's SophusUtil.h).
+// Errors: upstream aborts through g3log CHECK; here every failed C call throws lsd_b200::Error.
+#pragma once
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lsd_b200.h"
+
+#ifdef LSD_B200_WITH_SOPHUS
+#include "util/SophusUtil.h"
+#endif
+
+namespace lsd_b200 {
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string &m) : std::runtime_error(m) {}
+};
+inline void check(int rc) {
+  if (rc != LSD_OK) throw Error(std::string("liblsd_b200: ") + lsd_last_error());
+}
+
+struct SE3 {  // Sophus::SE3d::data(): unit quaternion (x,y,z,w), translation
+  double d[7];
+  SE3() : d{0, 0, 0, 1, 0, 0, 0} {}
+#ifdef LSD_B200_WITH_SOPHUS
+  SE3(const Sophus::SE3d &s) { std::memcpy(d, s.data(), sizeof(d)); }
+  operator Sophus::SE3d() const {
+    return Sophus::SE3d(Eigen::Quaterniond(d[3], d[0], d[1], d[2]), Eigen::Vector3d(d[4], d[5], d[6]));
+  }
+#endif
+};
+struct Sim3 {  // quaternion (x,y,z,w), translation, scale
+  double d[8];
+  Sim3() : d{0, 0, 0, 1, 0, 0, 0, 1} {}
+#ifdef LSD_B200_WITH_SOPHUS
+  Sim3(const Sophus::Sim3d &s) {
+    const Eigen::Quaterniond q(s.rotationMatrix());
+    d[0] = q.x(); d[1] = q.y(); d[2] = q.z(); d[3] = q.w();
+    d[4] = s.translation()[0]; d[5] = s.translation()[1]; d[6] = s.translation()[2];
+    d[7] = s.scale();
+  }
+  operator Sophus::Sim3d() const {
+    Sophus::Sim3d r(Sophus::RxSO3d(d[7], Eigen::Quaterniond(d[3], d[0], d[1], d[2]).toRotationMatrix()),
+                    Eigen::Vector3d(d[4], d[5], d[6]));
+    return r;
+  }
+#endif
+};
+
+// One device + stream + scratch.  Upstream runs tracking, mapping and constraint search on separate threads:
+// give each its own Context (frames / references may be shared read-only between contexts of one device).
+class Context {
+ public:
+  Context(int width, int height, float fx, float fy, float cx, float cy, int device = 0, void *stream = nullptr) : w_(width), h_(height) {
+    const float K[4] = {fx, fy, cx, cy};
+    check(lsd_ctx_create(device, width, height, K, stream, &c_));
+  }
+  ~Context() { lsd_ctx_destroy(c_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  lsd_ctx *c() const { return c_; }
+  int width() const { return w_; }
+  int height() const { return h_; }
+
+ private:
+  lsd_ctx *c_ = nullptr;
+  int w_, h_;
+};
+
+// [UP] lsd_slam::Frame.  Pyramids live on the device; accessors copy a level to a host cache on first use.
+class Frame {
+ public:
+  typedef std::shared_ptr<Frame> SharedPtr;
+  // [UP] Frame(int id, int width, int height, const Eigen::Matrix3f& K, double timestamp, const unsigned char* image)
+  Frame(Context &ctx, int id, double timestamp, const unsigned char *image, size_t pitch = 0, bool keyframeCandidate = true)
+      : ctx_(ctx), id_(id), timestamp_(timestamp) {
+    check(lsd_frame_create(ctx.c(), id, image, pitch ? pitch : (size_t)ctx.width(), keyframeCandidate ? LSD_BUILD_MAXGRAD0 : LSD_BUILD_TRACKING, &f_));
+  }
+  ~Frame() { lsd_frame_release(ctx_.c(), f_); }
+  Frame(const Frame &) = delete;
+  Frame &operator=(const Frame &) = delete;
+
+  int id() const { return id_; }
+  double timestamp() const { return timestamp_; }
+  int width(int level = 0) const { return ctx_.width() >> level; }
+  int height(int level = 0) const { return ctx_.height() >> level; }
+  const float *image(int level = 0) { return plane(LSD_FIELD_IMAGE, level, 1); }
+  const float *gradients(int level = 0) { return plane(LSD_FIELD_GRADIENTS, level, 4); }  // Eigen::Vector4f per pixel
+  const float *maxGradients(int level = 0) { return plane(LSD_FIELD_MAXGRAD, level, 1); }
+  const float *idepth(int level = 0) { return plane(LSD_FIELD_IDEPTH, level, 1); }
+  const float *idepthVar(int level = 0) { return plane(LSD_FIELD_IDEPTHVAR, level, 1); }
+  bool hasIDepthBeenSet() {
+    float m;
+    int n;
+    return lsd_frame_mean_idepth(ctx_.c(), f_, &m, &n) == LSD_OK;
+  }
+  void setDepthFromGroundTruth(const float *depth, float cov_scale = 1.0f) {
+    check(lsd_frame_set_depth_from_gt(ctx_.c(), f_, depth, cov_scale));
+    invalidate();
+  }
+  Sim3 thisToParent_raw() const {  // [UP] pose->thisToParent_raw
+    Sim3 s;
+    int pid;
+    float r;
+    check(lsd_frame_get_tracking_meta(ctx_.c(), f_, &pid, s.d, &r));
+    return s;
+  }
+  float initialTrackedResidual() const {
+    Sim3 s;
+    int pid;
+    float r;
+    check(lsd_frame_get_tracking_meta(ctx_.c(), f_, &pid, s.d, &r));
+    return r;
+  }
+  void invalidate() { cache_.clear(); }  // device planes changed (setDepth, tracking mask)
+  lsd_frame *handle() const { return f_; }
+  Context &context() const { return ctx_; }
+
+ private:
+  const float *plane(int field, int level, int comps) {
+    const int key = field * 8 + level;
+    for (auto &e : cache_)
+      if (e.first == key) return e.second.data();
+    cache_.emplace_back(key, std::vector<float>((size_t)width(level) * height(level) * comps));
+    check(lsd_frame_read(ctx_.c(), f_, field, level, cache_.back().second.data()));
+    return cache_.back().second.data();
+  }
+  Context &ctx_;
+  lsd_frame *f_ = nullptr;
+  int id_;
+  double timestamp_;
+  std::vector<std::pair<int, std::vector<float>>> cache_;
+};
+
+// [UP] lsd_slam::TrackingReference
+class TrackingReference {
+ public:
+  explicit TrackingReference(Context &ctx) : ctx_(ctx) {}
+  ~TrackingReference() { invalidate(); }
+  void importFrame(Frame *source) {  // + makePointCloud(level) for levels 1..4, on device
+    invalidate();
+    keyframe = source;
+    frameID = source->id();
+    check(lsd_ref_create(ctx_.c(), source->handle(), &r_));
+  }
+  void invalidate() {
+    if (r_) lsd_ref_release(ctx_.c(), r_);
+    r_ = nullptr;
+    keyframe = nullptr;
+  }
+  int numData(int level) const {
+    int n = 0;
+    check(lsd_ref_num_data(ctx_.c(), r_, level, &n));
+    return n;
+  }
+  lsd_ref *handle() const { return r_; }
+  Frame *keyframe = nullptr;
+  int frameID = -1;
+
+ private:
+  Context &ctx_;
+  lsd_ref *r_ = nullptr;
+};
+
+// [UP] lsd_slam::SE3Tracker: public members keep their upstream names.
+class SE3Tracker {
+ public:
+  explicit SE3Tracker(Context &ctx) : ctx_(ctx) { lsd_default_tracker_settings(&settings); }
+  // SE3 trackFrame(TrackingReference* reference, Frame* frame, const SE3& frameToReference_initialEstimate)
+  SE3 trackFrame(TrackingReference *reference, Frame *frame, const SE3 &frameToReference_initialEstimate) {
+    check(lsd_ctx_set_se3_settings(ctx_.c(), &settings));
+    lsd_se3_result r;
+    check(lsd_se3_track(ctx_.c(), reference->handle(), frame->handle(), frameToReference_initialEstimate.d, &r, nullptr));
+    diverged = r.diverged != 0;
+    trackingWasGood = r.trackingWasGood != 0;
+    lastResidual = r.lastResidual;
+    lastMeanRes = r.lastMeanRes;
+    pointUsage = r.pointUsage;
+    lastGoodCount = r.lastGoodCount;
+    lastBadCount = r.lastBadCount;
+    affineEstimation_a = r.affine_a;
+    affineEstimation_b = r.affine_b;
+    frame->invalidate();
+    SE3 out;
+    std::memcpy(out.d, r.frameToRef, sizeof(out.d));
+    return out;
+  }
+  lsd_tracker_settings settings;  // [UP] DenseDepthTrackerSettings
+  float pointUsage = 0, lastGoodCount = 0, lastMeanRes = 0, lastBadCount = 0, lastResidual = 0;
+  float affineEstimation_a = 1, affineEstimation_b = 0;
+  bool diverged = false, trackingWasGood = false;
+
+ private:
+  Context &ctx_;
+};
+
+// [UP] lsd_slam::Sim3Tracker
+class Sim3Tracker {
+ public:
+  explicit Sim3Tracker(Context &ctx) : ctx_(ctx) { lsd_default_tracker_settings(&settings); }
+  // Sim3 trackFrameSim3(TrackingReference* reference, Frame* frame, const Sim3& frameToReference_initialEstimate, int startLevel, int finalLevel)
+  Sim3 trackFrameSim3(TrackingReference *reference, Frame *frame, const Sim3 &frameToReference_initialEstimate, int startLevel,
+                      int finalLevel) {
+    check(lsd_ctx_set_sim3_settings(ctx_.c(), &settings));
+    lsd_sim3_result r;
+    check(lsd_sim3_track(ctx_.c(), reference->handle(), frame->handle(), frameToReference_initialEstimate.d, startLevel, finalLevel, &r, nullptr));
+    diverged = r.diverged != 0;
+    lastResidual = r.lastResidual;
+    lastDepthResidual = r.lastDepthResidual;
+    lastPhotometricResidual = r.lastPhotometricResidual;
+    pointUsage = r.pointUsage;
+    affineEstimation_a = r.affine_a;
+    affineEstimation_b = r.affine_b;
+    std::memcpy(lastSim3Hessian, r.lastSim3Hessian, sizeof(lastSim3Hessian));
+    Sim3 out;
+    std::memcpy(out.d, r.frameToRef, sizeof(out.d));
+    return out;
+  }
+  lsd_tracker_settings settings;
+  float lastSim3Hessian[49] = {0};  // Matrix7x7, row-major
+  float pointUsage = 0, lastResidual = 0, lastDepthResidual = 0, lastPhotometricResidual = 0;
+  float affineEstimation_a = 1, affineEstimation_b = 0;
+  bool diverged = false;
+
+ private:
+  Context &ctx_;
+};
+
+// [UP] lsd_slam::DepthMap
+class DepthMap {
+ public:
+  explicit DepthMap(Context &ctx) : ctx_(ctx) { check(lsd_depthmap_create(ctx.c(), &d_)); }
+  ~DepthMap() { lsd_depthmap_destroy(ctx_.c(), d_); }
+  DepthMap(const DepthMap &) = delete;
+  DepthMap &operator=(const DepthMap &) = delete;
+  void initializeFromGTDepth(Frame *new_frame) { check(lsd_depth_initialize_from_gt(ctx_.c(), d_, new_frame->handle())); new_frame->invalidate(); }
+  void initializeRandomly(Frame *new_frame) { check(lsd_depth_initialize_randomly(ctx_.c(), d_, new_frame->handle())); new_frame->invalidate(); }
+  // void updateKeyframe(std::deque< std::shared_ptr<Frame> > referenceFrames)
+  void updateKeyframe(std::deque<std::shared_ptr<Frame>> referenceFrames) {
+    std::vector<lsd_frame *> h;
+    for (auto &f : referenceFrames) h.push_back(f->handle());
+    check(lsd_depth_update_keyframe(ctx_.c(), d_, (int)h.size(), h.data(), nullptr));
+  }
+  // void createKeyFrame(Frame* new_keyframe)
+  void createKeyFrame(Frame *new_keyframe) {
+    float rescale = 1;
+    check(lsd_depth_create_keyframe(ctx_.c(), d_, new_keyframe->handle(), &rescale));
+    new_keyframe->invalidate();
+  }
+  void finalizeKeyFrame() { check(lsd_depth_finalize_keyframe(ctx_.c(), d_)); }
+  // int debugPlotDepthMap(): fills the RGB image handed to OutputIOWrapper::updateDepthImage (lib/GUI.cpp:104-108)
+  void debugPlotDepthMap(unsigned char *rgb) { check(lsd_depth_debug_rgb(ctx_.c(), d_, rgb)); }
+  void readHypotheses(lsd_hypothesis *dst) { check(lsd_depth_read(ctx_.c(), d_, dst)); }
+  lsd_depthmap *handle() const { return d_; }
+
+ private:
+  Context &ctx_;
+  lsd_depthmap *d_ = nullptr;
+};
+
+}  // namespace lsd_b200

@@ -99,6 +99,7 @@ SYMBOLS = {
     "lsd_frame_set_counters": (_ip, [_vp, _vp, _ip, _ip]),
     "lsd_frame_get_counters": (_ip, [_vp, _vp, _vp, _vp]),
     "lsd_frame_set_depth_updated_flag": (_ip, [_vp, _vp, _ip]),
+    "lsd_frame_get_depth_updated_flag": (_ip, [_vp, _vp, _vp]),
     "lsd_depthmap_create": (_ip, [_vp, _vp]),
     "lsd_depthmap_destroy": (_ip, [_vp, _vp]),
     "lsd_default_depth_settings": (_ip, [_vp]),
@@ -413,6 +414,11 @@ class Frame:
 
     def set_depth_updated_flag(self, v):
         _chk(self.ctx.L.lsd_frame_set_depth_updated_flag(self.ctx.p, self.p, int(v)))
+
+    def depth_updated_flag(self):
+        v = C.c_int()
+        _chk(self.ctx.L.lsd_frame_get_depth_updated_flag(self.ctx.p, self.p, C.byref(v)))
+        return bool(v.value)
 
     def mean_idepth(self):
         m = C.c_float()

@@ -400,6 +400,7 @@ void lsdo_frame_get_counters(void *fp, int *out3) {
   out3[0] = f->numFramesTrackedOnThis; out3[1] = f->numMappedOnThis; out3[2] = f->numMappedOnThisTotal;
 }
 void lsdo_frame_set_flags(void *fp, int depthHasBeenUpdated) { ((Frame *)fp)->depthHasBeenUpdatedFlag = depthHasBeenUpdated != 0; }
+int lsdo_frame_get_flags(void *fp) { return ((Frame *)fp)->depthHasBeenUpdatedFlag ? 1 : 0; }
 void lsdo_frame_clear_mask(void *fp) { ((Frame *)fp)->refPixelWasGood.clear(); }
 
 void lsdo_set_exact_sums(int v) { g_exactSums = v != 0; }

@@ -120,6 +120,7 @@ def lib(fast: bool = False):
         ("lsdo_frame_get_counters", None, [vp, vp]),
         ("lsdo_frame_set_flags", None, [vp, ip]),
         ("lsdo_frame_clear_mask", None, [vp]),
+        ("lsdo_frame_get_flags", ip, [vp]),
         ("lsdo_set_exact_sums", None, [ip]),
     ]:
         f = getattr(L, name)

@@ -42,3 +42,13 @@ def test_product_never_touches_oracle():
             if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".py")) or f == "Makefile":
                 src = open(os.path.join(d, f), errors="ignore").read()
                 assert "pyoracle" not in src and "lsd_oracle" not in src and "oracle/" not in src.replace("the oracle", ""), f
+
+
+def test_cpp_adapter_compiles_and_links():
+    """host/lsd_b200.hpp (upstream class names over the C ABI) builds with plain g++ -std=c++11 and links the library."""
+    import subprocess
+    pkg = os.path.join(ROOT, "lsd-slam-pangolin-gui_b200")
+    subprocess.check_call(["make", "-C", pkg, "-s", "host-check"])
+    out = subprocess.run([os.path.join(pkg, "build", "adapter_check")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "no device" in out.stdout or "tracked:" in out.stdout
