@@ -246,6 +246,8 @@ int lsd_depth_debug_rgb(lsd_ctx *ctx, lsd_depthmap *dm, uint8_t *rgb);
 int lsd_depth_prepare(lsd_ctx *ctx, lsd_depthmap *dm, int n, lsd_frame *const *referenceFrames, const double *refToKf);
 int lsd_depth_stage(lsd_ctx *ctx, lsd_depthmap *dm, int stage, int arg1, int arg2, lsd_frame *frame);
 /* the same stage on n independent depth maps in ONE set of launches (blockIdx.z = map); frames: n or NULL */
+/* device time (CUDA events on the context's stream) of the kernels of the last lsd_depth_stage* call */
+int lsd_ctx_last_stage_ms(lsd_ctx *ctx, float *ms);
 int lsd_depth_stage_batch(lsd_ctx *ctx, int n, lsd_depthmap *const *dms, int stage, int arg1, int arg2, lsd_frame *const *frames);
 
 #ifdef __cplusplus

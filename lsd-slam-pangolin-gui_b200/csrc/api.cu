@@ -219,6 +219,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->h_table = ctx->d_table = nullptr;
   ctx->tableBytes = 0;
   ctx->descSlot = 0;
+  ctx->stageTimed = false;
   ctx->se3s = nullptr;
   ctx->lastAlgBytes = 0;
   ctx->lastEvals = 0;

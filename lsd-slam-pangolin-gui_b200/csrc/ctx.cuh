@@ -31,6 +31,7 @@ struct lsd_ctx {
   void *h_table;
   void *d_table;
   size_t tableBytes;
+  bool stageTimed;  // evA/evB bracket the kernels of the last depth stage
   int descSlot;  // rotating slot of the depth-map descriptor uploads (depth.cu)
   SE3Scratch *se3s;
   // last-call stats

@@ -114,6 +114,7 @@ SYMBOLS = {
     "lsd_depth_debug_rgb": (_ip, [_vp, _vp, _vp]),
     "lsd_depth_prepare": (_ip, [_vp, _vp, _ip, _vp, _vp]),
     "lsd_depth_stage": (_ip, [_vp, _vp, _ip, _ip, _ip, _vp]),
+    "lsd_ctx_last_stage_ms": (_ip, [_vp, _vp]),
     "lsd_depth_stage_batch": (_ip, [_vp, _ip, _vp, _ip, _ip, _ip, _vp]),
 }
 
@@ -240,6 +241,11 @@ class Context:
         dp = (C.c_void_p * n)(*[d.p for d in dms])
         fp = (C.c_void_p * n)(*[f.p for f in frames]) if frames is not None else None
         _chk(self.L.lsd_depth_stage_batch(self.p, n, dp, stage, arg1, arg2, fp))
+
+    def last_stage_ms(self):
+        ms = C.c_float()
+        _chk(self.L.lsd_ctx_last_stage_ms(self.p, C.byref(ms)))
+        return ms.value
 
     # ---- SE3 tracking
     def se3_track_batch(self, refs, frames, inits, want_trace=False):
