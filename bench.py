@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--pairs", type=int, default=1000, help="frame pairs per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--active", type=int, default=0, help="pairs in flight inside the tracker launch (0: library default)")
+    ap.add_argument("--recs", type=int, default=0, help="records per work item (0: library default)")
     return ap.parse_args()
 
 
@@ -238,6 +240,10 @@ def main():
     torch.cuda.set_stream(tstream)
     ctx = lsd_b200.Context(W, H, K, device=local_rank, stream=tstream.cuda_stream)
 
+    if args.active:
+        ctx.set_se3_active_pairs(args.active)
+    if args.recs:
+        ctx.set_se3_work_item_records(args.recs)
     # resident state: keyframes (with depth) -> tracking references; new frames with prebuilt pyramids
     kfs = ctx.create_frames_device(kf.data_ptr(), n)
     ctx.set_idepth_batch_device(kfs, idp.data_ptr(), var.data_ptr())

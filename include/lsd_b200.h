@@ -96,9 +96,12 @@ void *lsd_ctx_stream(lsd_ctx *ctx);
 long long lsd_ctx_launch_count(lsd_ctx *ctx);
 int lsd_default_tracker_settings(lsd_tracker_settings *s);
 int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
-/* scheduling knob of the persistent tracker: 1024-point records per work item (0 = automatic).  Never
+/* scheduling knob of the persistent tracker: 4096-point records per work item (0 = automatic).  Never
  * changes a result (the summation order is fixed by the records), only latency vs throughput. */
 int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
+/* pairs in flight inside one lsd_se3_track_batch launch (0 = default): bounds the working set to what L2 holds.
+ * Scheduling only: results are bit-identical for every value. */
+int lsd_ctx_set_se3_active_pairs(lsd_ctx *ctx, int pairs);
 
 /* ---- Frame ---------------------------------------------------------------------------------- */
 #define LSD_BUILD_TRACKING 0u /* image L0-4 + gradients L1-4: what a tracked frame needs        */

@@ -213,6 +213,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   lsd_default_tracker_settings(&ctx->se3);
   lsd_default_tracker_settings(&ctx->sim3);
   ctx->se3RecsPerItem = 0;
+  ctx->se3ActivePairs = 0;
   ctx->refSlabBytes = 0;
   ctx->h_stage = ctx->d_stage = nullptr;
   ctx->h_stageBytes = ctx->d_stageBytes = 0;
@@ -265,6 +266,12 @@ int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s) {
 int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records) {
   LSD_ARG(ctx && records >= 0 && records <= 64);
   ctx->se3RecsPerItem = records;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_se3_active_pairs(lsd_ctx *ctx, int pairs) {
+  LSD_ARG(ctx && pairs >= 0);
+  ctx->se3ActivePairs = pairs;
   return LSD_OK;
 }
 

@@ -17,6 +17,7 @@ struct lsd_ctx {
   cudaEvent_t evA, evB, evPipe[4];
   long long launches;
   lsd_tracker_settings se3, sim3;
+  int se3ActivePairs;  // 0: default; pairs in flight inside the persistent tracker (L2 residency)
   int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
   // pools
   std::vector<uint8_t *> frameSlabPool;

@@ -20,9 +20,9 @@
 //    advance independently: no host round trip and no grid-wide barrier anywhere in a track;
 //  * results are bit-reproducible run to run and independent of the batch composition.
 //
-// Compiled with -fmad=false: per-point values (warp, residual, weights, Jacobian rows) are
-// bit-identical to the oracle's (-ffp-contract=off); only summation order differs.  Accumulations use
-// explicit fmaf (an accumulation's rounding is order noise anyway).
+// Compiled with -fmad=false: everything a discrete output depends on (warp, projection, bilinear sample,
+// residual, isGood) is bit-identical to the oracle's (-ffp-contract=off); weights, Jacobian rows and the
+// accumulated terms use explicit fmaf and MUFU approximations (see accumulate_point).
 #include <cmath>
 #include <cstddef>
 #include <cstring>
@@ -32,9 +32,19 @@
 
 namespace lsd {
 
-#define SE3_THREADS 256   // threads per CTA
+#ifndef SE3_THREADS
+#define SE3_THREADS 128   // threads per CTA (small CTAs: an item's fetch / reduce barriers stall fewer warps)
+#endif
+#ifndef SE3_P
 #define SE3_P 2           // points in flight per thread (loads of a batch are issued before any math)
-#define SE3_REC 1024      // points per partial record: FIXED, it defines the summation order (see above)
+#endif
+#ifndef SE3_MINB
+#define SE3_MINB 4        // resident CTAs per SM the register budget is sized for
+#endif
+#ifndef SE3_REC
+#define SE3_REC 4096      // points per partial record: FIXED, it defines the summation order (see above)
+#endif
+#define SE3_DEFAULT_ACTIVE 1000000  // pairs in flight (lsd_ctx_set_se3_active_pairs)
 #define SE3_NRED 44       // floats per partial record: 5 doubles (affine sums) + 33 floats + pad
 #define SE3_NF 33         // fp32 sums per record
 #define SE3_ND 5          // fp64 sums per record
@@ -105,6 +115,8 @@ struct SE3Queue {
   unsigned *head;  // consumer tickets
   unsigned *tail;  // producer reservations
   int *remaining;  // pairs not finished yet
+  unsigned *nextPair;  // admission: next pair to start when an active one finishes
+  int nPairs;
   unsigned cap;    // power of two
 };
 
@@ -115,6 +127,14 @@ struct SE3Params {
   int recsPerItem;         // records per work item: scheduling granularity only, never changes a result
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
 };
+
+// gpu-scope acquire-release fetch-add: releases this CTA's record stores (ordered before it by the CTA barrier)
+// and, for the CTA that takes the last ticket, acquires every other CTA's.
+__device__ __forceinline__ unsigned atom_add_acq_rel(unsigned *p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 
 // Publish the chunks of the pair's next evaluation.  The caller has stored the pair's state already.
 __device__ void q_push(const SE3Queue &q, int pairIdx, int nch) {
@@ -338,61 +358,80 @@ __device__ __forceinline__ void warp_point(const float4 raw, const EvalConst &c,
   w.off = ix + iy * c.W;
 }
 
+// Per-point arithmetic comes in two tiers.
+//  EXACT tier (plain operators under -fmad=false, IEEE division): everything a discrete output depends on --
+//    the warp, the projection and in-image test (buf_warped_size), the bilinear sample, the residual and the
+//    isGood test (good / bad counts, refPixelWasGood).  Bit-identical to the oracle at a given pose.
+//  RELAXED tier (explicit fmaf, MUFU reciprocal / rsqrt, algebraically regrouped): Huber / variance weights,
+//    Jacobian rows and every accumulated term.  These only enter sums whose order already differs from the
+//    reference's; their 2^-22 relative error is far inside the 1e-4 residual / 1e-5 pose tolerances.
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }
+
 __device__ __forceinline__ void accumulate_point(const float4 raw, const Warped &w, const float4 p00, const float4 p10,
                                                  const float4 p01, const float4 p11, const EvalConst &c,
                                                  uint8_t *__restrict__ mask, float acc[SE3_NF], double dacc[SE3_ND]) {
-  // getInterpolatedElement43 (this exact weight form and summation order)
+  // ---- EXACT: getInterpolatedElement43 (this exact weight form and summation order), residual, isGood
   const float dxdy = w.dx * w.dy;
   const float w11 = dxdy, w01 = w.dy - dxdy, w10 = w.dx - dxdy, w00 = 1 - w.dx - w.dy + dxdy;
   const float gxI = w11 * p11.x + w01 * p01.x + w10 * p10.x + w00 * p00.x;
   const float gyI = w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y;
   const float cI = w11 * p11.z + w01 * p01.z + w10 * p10.z + w00 * p00.z;
   const float Wx = w.Wx, Wy = w.Wy, Wz = w.Wz, pz = w.pz;
-
   const float c1 = c.a * raw.z + c.b;
   const float c2 = cI;
   const float residual = c1 - c2;
-  const float weight = fabsf(residual) < 5.0f ? 1 : 5.0f / fabsf(residual);
-  dacc[D_SXX] += (double)(c1 * c1 * weight);
-  dacc[D_SYY] += (double)(c2 * c2 * weight);
-  dacc[D_SX] += (double)(c1 * weight);
-  dacc[D_SY] += (double)(c2 * weight);
-  dacc[D_SW] += (double)weight;
-  const bool isGood = residual * residual / (LSD_MAX_DIFF_CONSTANT + LSD_MAX_DIFF_GRAD_MULT * (gxI * gxI + gyI * gyI)) < 1;
+  const float r2 = residual * residual;
+  // isGood = fl(r2 / D) < 1 with D = MAX_DIFF_CONSTANT + MAX_DIFF_GRAD_MULT * |g|^2.  A correctly rounded quotient is
+  // below 1 exactly when the real quotient is below the rounding midpoint 1 - 2^-25 (the tie goes to the even 1.0),
+  // i.e. r2 < D * (1 - 2^-25); that product is exact in fp64, so the test equals upstream's division bit for bit.
+  const float D = LSD_MAX_DIFF_CONSTANT + LSD_MAX_DIFF_GRAD_MULT * (gxI * gxI + gyI * gyI);
+  const bool isGood = (double)r2 < (double)D * (1.0 - 2.9802322387695312e-08);
   if (mask) mask[w.midx] = isGood;
   if (isGood) {
-    acc[R_SUMUNW] += residual * residual;
+    acc[R_SUMUNW] += r2;
     acc[R_SUMSGN] += residual;
     acc[R_GOOD] += 1.0f;
   } else {
     acc[R_BAD] += 1.0f;
   }
-  const float depthChange = pz / Wz;
+
+  // ---- RELAXED from here on
+  const float ar = fabsf(residual);
+  const float weight = ar < 5.0f ? 1.0f : 5.0f * fast_rcp(ar);  // affine-lighting Huber weight
+  const float c1w = c1 * weight, c2w = c2 * weight;
+  dacc[D_SXX] += (double)(c1 * c1w);
+  dacc[D_SYY] += (double)(c2 * c2w);
+  dacc[D_SX] += (double)c1w;
+  dacc[D_SY] += (double)c2w;
+  dacc[D_SW] += (double)weight;
+
+  const float z = fast_rcp(Wz);
+  const float depthChange = pz * z;
   acc[R_USAGE] += depthChange < 1 ? depthChange : 1;
 
-  // calcWeightsAndResidual
+  // calcWeightsAndResidual: g0 = (tx z' - tz x') / (z'^2 d), d = 1 / p_z  =>  g0 = (tx z' - tz x') * (p_z / z'^2)
   const float gx = c.fx * gxI, gy = c.fy * gyI;
-  const float d = 1.0f / pz;
+  const float z_sqr = z * z;
+  const float kk = z_sqr * pz;
+  const float g0 = fmaf(c.t[0], Wz, -c.t[2] * Wx) * kk;
+  const float g1 = fmaf(c.t[1], Wz, -c.t[2] * Wy) * kk;
+  const float drpdd = fmaf(gx, g0, gy * g1);
   const float s = c.var_weight * raw.w;
-  const float g0 = (c.t[0] * Wz - c.t[2] * Wx) / (Wz * Wz * d);
-  const float g1 = (c.t[1] * Wz - c.t[2] * Wy) / (Wz * Wz * d);
-  const float drpdd = gx * g0 + gy * g1;
-  const float w_p = 1.0f / (LSD_CAMERA_PIXEL_NOISE2 + s * drpdd * drpdd);
-  const float weighted_rp = fabsf(residual * sqrtf(w_p));
-  const float wh = fabsf(weighted_rp < c.huber_half ? 1 : c.huber_half / weighted_rp);
-  acc[R_SUMRES] += wh * w_p * residual * residual;
+  const float rs = rsqrtf(fmaf(s * drpdd, drpdd, LSD_CAMERA_PIXEL_NOISE2));  // sqrt(w_p)
+  const float w_p = rs * rs;
+  const float weighted_rp = ar * rs;
+  const float wh = weighted_rp < c.huber_half ? 1.0f : c.huber_half * fast_rcp(weighted_rp);
   const float wgt = wh * w_p;
+  acc[R_SUMRES] = fmaf(wgt, r2, acc[R_SUMRES]);
 
-  // calculateWarpUpdate (the two rows with upstream's `1.0 +` double literals are evaluated in fp64)
-  const float z = 1.0f / Wz;
-  const float z_sqr = 1.0f / (Wz * Wz);
+  // calculateWarpUpdate, regrouped:  v2 = -z (x' v0 + y' v1),  v3 = y' v2 - gy,  v4 = gx - x' v2,  v5 = x' v1 - y' v0
   float v[6];
-  v[0] = z * gx + 0;
-  v[1] = 0 + z * gy;
-  v[2] = (-Wx * z_sqr) * gx + (-Wy * z_sqr) * gy;
-  v[3] = (float)((double)((-Wx * Wy * z_sqr) * gx) + (-(1.0 + (double)(Wy * Wy * z_sqr))) * (double)gy);
-  v[4] = (float)((1.0 + (double)(Wx * Wx * z_sqr)) * (double)gx + (double)((Wx * Wy * z_sqr) * gy));
-  v[5] = (-Wy * z) * gx + (Wx * z) * gy;
+  v[0] = z * gx;
+  v[1] = z * gy;
+  v[2] = -z * fmaf(Wx, v[0], Wy * v[1]);
+  v[3] = fmaf(Wy, v[2], -gy);
+  v[4] = fmaf(-Wx, v[2], gx);
+  v[5] = fmaf(Wx, v[1], -Wy * v[0]);
   int k = 0;
 #pragma unroll
   for (int a = 0; a < 6; a++) {
@@ -480,7 +519,9 @@ __device__ __forceinline__ void block_reduce_store(const float acc[SE3_NF], cons
       if (lane == 0) reinterpret_cast<double *>(dst)[r] = v;
     }
   }
-  __threadfence();  // partial record visible device-wide before this CTA's completion ticket
+  // No fence here: the record is published by the release-ordered completion ticket below (the CTA barrier
+  // orders these stores before thread 0's gpu-scope release; a per-thread __threadfence would also flush L1
+  // -- CCTL.IVALL -- after every record and throw away the tap locality of the next one).
   __syncthreads();
 }
 
@@ -499,7 +540,7 @@ __device__ __forceinline__ void load_eval_const(const SE3Params &prm, int level,
   c.H = prm.K.h[level];
 }
 
-__global__ void __launch_bounds__(SE3_THREADS, 2)
+__global__ void __launch_bounds__(SE3_THREADS, SE3_MINB)
 k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials, const SE3Queue q,
             const __grid_constant__ SE3Params prm, lsd_trace_entry *traces) {
   __shared__ SE3Smem sm;
@@ -563,10 +604,9 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
       float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
       block_reduce_store(acc, dacc, dst, sm);
     }
-    if (threadIdx.x == 0) sIsLast = (atomicAdd(&S->done, 1u) == (unsigned)(nch - 1));
+    if (threadIdx.x == 0) sIsLast = (atom_add_acq_rel(&S->done, 1u) == (unsigned)(nch - 1));
     __syncthreads();
     if (sIsLast) {
-      __threadfence();
       const float *recBase = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED;
       if (threadIdx.x < SE3_ND) {
         const double *src = reinterpret_cast<const double *>(recBase) + threadIdx.x;
@@ -589,6 +629,19 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
         if (next > 0) {
           q_push(q, pairIdx, next);
         } else {
+          // Admission control: the number of pairs in flight is bounded so that their level data stays in L2
+          // between consecutive LM evaluations; a finished pair hands its slot to the next waiting one.
+          for (;;) {
+            const unsigned cand = atomicAdd(q.nextPair, 1u);
+            if (cand >= (unsigned)q.nPairs) break;
+            SE3State *S2 = states + cand;
+            const int nch2 = __ldcg(&S2->nChunks);
+            if (nch2 > 0 && !__ldcg(&S2->finished)) {  // initialised by k_se3_init, not started yet
+              q_push(q, (int)cand, nch2);
+              break;
+            }
+            atomicSub(q.remaining, 1);  // a pair that diverged at initialisation: nothing to run
+          }
           __threadfence();
           atomicSub(q.remaining, 1);
         }
@@ -599,7 +652,8 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
 }
 
 // Build the initial state of every pair and publish the first evaluations (level maxLevel).
-__global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, const SE3Queue q, SE3Params prm) {
+__global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, const SE3Queue q, SE3Params prm,
+                           int active) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   SE3Pair *P = pairs + i;
@@ -616,8 +670,10 @@ __global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ s
   L.trackingWasGood = 1;
   const int next = start_level(P, &L, prm.maxLevel, prm);
   state_store(states + i, &L);
-  if (next > 0) q_push(q, i, next);
-  else atomicSub(q.remaining, 1);
+  if (i < active) {  // the rest is admitted by finishing pairs (k_se3_track)
+    if (next > 0) q_push(q, i, next);
+    else atomicSub(q.remaining, 1);
+  }
 }
 
 struct SE3ScratchImpl {
@@ -709,9 +765,9 @@ static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   prm.K = ctx->K;
   prm.s = ctx->se3;
   prm.maxChunks = ctx->se3s->maxChunks;
-  // Work-item size: single-record items spread ONE pair over many SMs (latency of a live sequence);
-  // longer items amortise the queue round trip when the batch alone fills the machine.
-  prm.recsPerItem = ctx->se3RecsPerItem > 0 ? ctx->se3RecsPerItem : (nPairs >= 256 ? 4 : (nPairs >= 32 ? 2 : 1));
+  // Work-item size: one 4096-point record per item measured best at every batch size on B200 (profiles/);
+  // the knob stays for experiments.
+  prm.recsPerItem = ctx->se3RecsPerItem > 0 ? ctx->se3RecsPerItem : 1;
   prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
   prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
   return prm;
@@ -781,14 +837,18 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
   q.head = s->d_ctrs;
   q.tail = s->d_ctrs + 1;
   q.remaining = reinterpret_cast<int *>(s->d_ctrs + 2);
+  q.nextPair = s->d_ctrs + 3;
+  q.nPairs = n;
   q.cap = s->qcap;
+  int active = ctx->se3ActivePairs > 0 ? ctx->se3ActivePairs : SE3_DEFAULT_ACTIVE;
+  if (active > n) active = n;
   unsigned *ctr0 = reinterpret_cast<unsigned *>(s->h_states);  // pinned scratch, rewritten by the D2H below
-  ctr0[0] = 0u; ctr0[1] = 0u; ctr0[2] = (unsigned)n; ctr0[3] = 0u;
+  ctr0[0] = 0u; ctr0[1] = 0u; ctr0[2] = (unsigned)n; ctr0[3] = (unsigned)active;
   LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
   LSD_CUDA(cudaMemcpyAsync(s->d_ctrs, ctr0, sizeof(unsigned) * 4, cudaMemcpyHostToDevice, st));
   LSD_CUDA(cudaMemsetAsync(s->d_slots, 0, sizeof(unsigned long long) * q.cap, st));
   LSD_CUDA(cudaEventRecord(ctx->evA, st));
-  k_se3_init<<<(n + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, n, q, prm);
+  k_se3_init<<<(n + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, n, q, prm, active);
   lsd_trace_entry *d_tr = traces ? s->d_traces : nullptr;
   k_se3_track<<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs, s->d_states, s->d_partials, q, prm, d_tr);
   LSD_CUDA(cudaGetLastError());

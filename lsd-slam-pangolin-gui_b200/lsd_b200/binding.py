@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "liblsd_b200.so")
+LIB_PATH = os.environ.get("LSD_B200_LIB") or os.path.join(PKG_DIR, "liblsd_b200.so")  # override: kernel-variant experiments
 
 NL = 5
 TRACE_CAP = 512
@@ -69,6 +69,7 @@ SYMBOLS = {
     "lsd_default_tracker_settings": (_ip, [_vp]),
     "lsd_ctx_set_se3_settings": (_ip, [_vp, _vp]),
     "lsd_ctx_set_se3_work_item_records": (_ip, [_vp, _ip]),
+    "lsd_ctx_set_se3_active_pairs": (_ip, [_vp, _ip]),
     "lsd_frame_create": (_ip, [_vp, _ip, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch_device": (_ip, [_vp, _ip, _vp, _vp, _u, _vp]),
@@ -192,6 +193,9 @@ class Context:
 
     def set_se3_settings(self, s):
         _chk(self.L.lsd_ctx_set_se3_settings(self.p, C.byref(s)))
+
+    def set_se3_active_pairs(self, n):
+        _chk(self.L.lsd_ctx_set_se3_active_pairs(self.p, int(n)))
 
     def set_se3_work_item_records(self, n):
         _chk(self.L.lsd_ctx_set_se3_work_item_records(self.p, int(n)))
