@@ -1,6 +1,9 @@
 // api.cu -- extern "C" surface of liblsd_b200.so (include/lsd_b200.h): contexts, device-resident
 // frames, tracking references and the SE3 tracker entry points.  No CPU fallback exists: every
 // entry point either runs the sm_100a kernels or returns an error.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.cuh"
@@ -643,7 +646,7 @@ int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *co
                         lsd_se3_result *results, lsd_trace_entry *traces) {
   LSD_ARG(ctx && refs && frames && init_frameToRef && results && n >= 0);
   LSD_CUDA(cudaSetDevice(ctx->device));
-  return se3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, results, traces, ctx->stream, false);
+  return se3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, results, traces, ctx->stream);
 }
 
 int lsd_se3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[7], lsd_se3_result *result,
@@ -666,8 +669,13 @@ int lsd_se3_last_stats(lsd_ctx *ctx, double *algorithmic_bytes, long long *evalu
   return LSD_OK;
 }
 
-// Host images in, poses out.  Chunks of frames are uploaded on the copy stream while the previous
-// chunk is ingested and tracked on the compute stream (two staging halves, event-ordered).
+// Host images in, poses out: SE3Tracker::trackFrame for n freshly captured frames.  A fully asynchronous pipeline:
+//   * every small host->device table (frame slab pointers, the tracker's pair table) is uploaded ONCE, before any
+//     image copy is queued, so that no kernel launch ever waits behind a bulk transfer on the copy engine;
+//   * images go up chunk by chunk on the copy stream (frames that are contiguous in host memory in one
+//     cudaMemcpyAsync), double-buffered staging, event-ordered against the ingest that consumes them;
+//   * per chunk the compute stream runs ingest -> gradients -> mask init -> tracker launch back to back;
+//   * the host synchronises once, at the end, and reads all results in one device->host copy.
 int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const uint8_t *const *images, size_t pitch,
                                const double *init_frameToRef, lsd_se3_result *results) {
   LSD_ARG(ctx && refs && images && init_frameToRef && results && n >= 0);
@@ -675,57 +683,75 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
   if (n == 0) return LSD_OK;
   LSD_CUDA(cudaSetDevice(ctx->device));
   const size_t fbytes = (size_t)ctx->w * ctx->h;
-  const int CH = n < 256 ? n : 256;
+  static const int envChunk = getenv("LSD_B200_E2E_CHUNK") ? atoi(getenv("LSD_B200_E2E_CHUNK")) : 0;
+  const int chunk = envChunk > 0 ? envChunk : 250;
+  const int CH = n < chunk ? n : chunk;
   int rc = ensure_stage(ctx, 0, 2 * fbytes * CH);
   if (rc) return rc;
-  std::vector<lsd_frame *> fr(n, nullptr);
-  std::vector<void *> slabs;
   const int nChunks = (n + CH - 1) / CH;
-  ctx->lastAlgBytes = 0;
-  ctx->lastEvals = 0;
-  ctx->lastKernelMs = 0;
+  cudaStream_t st = ctx->stream;
+  // frames + all tables first
+  std::vector<lsd_frame *> fr(n, nullptr);
+  std::vector<void *> slabs(n);
+  for (int i = 0; i < n; i++) {
+    uint8_t *s = nullptr;
+    rc = alloc_frame_slab(ctx, &s);
+    if (rc) return rc;
+    slabs[i] = s;
+    fr[i] = new_frame(i, s);
+    fr[i]->built = FB_TRACKING | FB_MASK;  // mask initialised below, in stream order
+  }
+  rc = upload_ptrs(ctx, slabs, st);
+  if (rc) return rc;
+  rc = se3_prepare(ctx, n, refs, fr.data(), init_frameToRef, false, st);
+  if (rc) return rc;
+  LSD_CUDA(cudaEventRecord(ctx->evPipe[0], st));
+  LSD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evPipe[0], 0));  // tables precede the bulk copies on the copy engine
+  std::vector<cudaEvent_t> copied(nChunks), consumed(nChunks);
+  for (int c = 0; c < nChunks; c++) {
+    LSD_CUDA(cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming));
+    LSD_CUDA(cudaEventCreateWithFlags(&consumed[c], cudaEventDisableTiming));
+  }
+  uint8_t *const *d_slabs = reinterpret_cast<uint8_t *const *>(ctx->d_table);
   auto issue_copy = [&](int c) -> int {
     const int i0 = c * CH, m = (n - i0) < CH ? (n - i0) : CH;
     uint8_t *dst = ctx->d_stage + (size_t)(c & 1) * fbytes * CH;
-    // the half must have been consumed by the ingest of chunk c-2
-    if (c >= 2) LSD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evPipe[2 + (c & 1)], 0));
-    for (int i = 0; i < m; i++)
-      LSD_CUDA(cudaMemcpy2DAsync(dst + fbytes * i, ctx->w, images[i0 + i], pitch, ctx->w, ctx->h, cudaMemcpyHostToDevice,
-                                 ctx->copyStream));
-    LSD_CUDA(cudaEventRecord(ctx->evPipe[c & 1], ctx->copyStream));
+    if (c >= 2) LSD_CUDA(cudaStreamWaitEvent(ctx->copyStream, consumed[c - 2], 0));  // staging half free again
+    int i = 0;
+    while (i < m) {  // runs of frames that are back to back in host memory
+      int j = i + 1;
+      if (pitch == (size_t)ctx->w) {
+        while (j < m && images[i0 + j] == images[i0 + j - 1] + fbytes) j++;
+        LSD_CUDA(cudaMemcpyAsync(dst + fbytes * i, images[i0 + i], fbytes * (size_t)(j - i), cudaMemcpyHostToDevice, ctx->copyStream));
+      } else {
+        LSD_CUDA(cudaMemcpy2DAsync(dst + fbytes * i, ctx->w, images[i0 + i], pitch, ctx->w, ctx->h, cudaMemcpyHostToDevice,
+                                   ctx->copyStream));
+      }
+      i = j;
+    }
+    LSD_CUDA(cudaEventRecord(copied[c], ctx->copyStream));
     return LSD_OK;
   };
-  rc = issue_copy(0);
-  if (rc) return rc;
   for (int c = 0; c < nChunks; c++) {
     const int i0 = c * CH, m = (n - i0) < CH ? (n - i0) : CH;
-    if (c + 1 < nChunks) {
-      rc = issue_copy(c + 1);
-      if (rc) return rc;
-    }
-    slabs.assign(m, nullptr);
-    for (int i = 0; i < m; i++) {
-      uint8_t *s = nullptr;
-      rc = alloc_frame_slab(ctx, &s);
-      if (rc) return rc;
-      slabs[i] = s;
-      fr[i0 + i] = new_frame(i0 + i, s);
-      fr[i0 + i]->built = FB_TRACKING;
-    }
-    rc = upload_ptrs(ctx, slabs, ctx->stream);
+    rc = issue_copy(c);
     if (rc) return rc;
-    LSD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evPipe[c & 1], 0));
+    LSD_CUDA(cudaStreamWaitEvent(st, copied[c], 0));
     const uint8_t *src = ctx->d_stage + (size_t)(c & 1) * fbytes * CH;
-    launch_ingest(ctx, src, ctx->w, fbytes, reinterpret_cast<uint8_t *const *>(ctx->d_table), m, ctx->stream);
-    LSD_CUDA(cudaEventRecord(ctx->evPipe[2 + (c & 1)], ctx->stream));
-    launch_gradients(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), m, 1, NL - 1, ctx->stream);
-    LSD_CUDA(cudaStreamSynchronize(ctx->stream));  // d_table is reused by the tracker below
-    rc = se3_track_batch_impl(ctx, m, refs + i0, fr.data() + i0, init_frameToRef + 7 * (size_t)i0, results + i0, nullptr,
-                              ctx->stream, true);
+    launch_ingest(ctx, src, ctx->w, fbytes, d_slabs + i0, m, st);
+    LSD_CUDA(cudaEventRecord(consumed[c], st));
+    launch_gradients(ctx, d_slabs + i0, m, 1, NL - 1, st);
+    launch_mask_init(ctx, d_slabs + i0, m, st);
+    rc = se3_launch(ctx, i0, m, false, st);
     if (rc) return rc;
   }
+  rc = se3_collect(ctx, n, refs, fr.data(), results, nullptr, st, 0.0f);
+  for (int c = 0; c < nChunks; c++) {
+    cudaEventDestroy(copied[c]);
+    cudaEventDestroy(consumed[c]);
+  }
   for (int i = 0; i < n; i++) lsd_frame_release(ctx, fr[i]);
-  return LSD_OK;
+  return rc;
 }
 
 }  // extern "C"

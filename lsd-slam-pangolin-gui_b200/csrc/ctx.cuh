@@ -63,7 +63,12 @@ void launch_make_pointcloud(lsd_ctx *ctx, uint8_t *const *d_kfSlabs, uint8_t *co
 
 // se3_track.cu
 int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
-                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st, bool accumulateStats);
+                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st);
+int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init, bool wantTrace,
+                cudaStream_t st);
+int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st);
+int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, lsd_se3_result *results, lsd_trace_entry *traces,
+                cudaStream_t st, float kernelMs);
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
                   float *A36, float *b6, float *scalars);
 void se3_scratch_free(lsd_ctx *ctx);

@@ -808,11 +808,20 @@ static int init_masks(lsd_ctx *ctx, int n, lsd_frame *const *frames, cudaStream_
   return LSD_OK;
 }
 
-int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
-                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st, bool accumulateStats) {
-  if (n == 0) return LSD_OK;
+// resets the queue counters of one launch (head, tail, remaining, nextPair)
+__global__ void k_se3_reset(unsigned *ctrs, unsigned n, unsigned active) {
+  ctrs[0] = 0u;
+  ctrs[1] = 0u;
+  ctrs[2] = n;
+  ctrs[3] = active;
+}
+
+// ---- the batch API in three steps, so that the host-image pipeline can queue several launches without a host
+// ---- synchronisation in between:  prepare (pair table for ALL n pairs, one upload)  ->  launch(i0, m) ...  ->  collect
+int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init, bool wantTrace,
+                cudaStream_t st) {
   LSD_ARG(n < (1 << 19));
-  int rc = se3_scratch_ensure(ctx, n, traces != nullptr);
+  int rc = se3_scratch_ensure(ctx, n, wantTrace);
   if (rc) return rc;
   SE3Scratch *s = ctx->se3s;
   const FrameLayout &lay = ctx->lay;
@@ -829,37 +838,43 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
     P.mask = frames[i]->slab + lay.mask;
     invert_pose_to_float(init + 7 * i, P.q0, P.t0);
   }
-  rc = init_masks(ctx, n, frames, st);
-  if (rc) return rc;
-  SE3Params prm = make_params(ctx, n);
+  LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
+  return LSD_OK;
+}
+
+// tracks pairs [i0, i0 + m) of the prepared table; everything it touches (queue, counters, partial records, states) is
+// private to the launch or indexed by pair, and all of it is ordered on `st`
+int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
+  SE3Scratch *s = ctx->se3s;
+  SE3Params prm = make_params(ctx, m);
   SE3Queue q;
   q.slots = s->d_slots;
   q.head = s->d_ctrs;
   q.tail = s->d_ctrs + 1;
   q.remaining = reinterpret_cast<int *>(s->d_ctrs + 2);
   q.nextPair = s->d_ctrs + 3;
-  q.nPairs = n;
+  q.nPairs = m;
   q.cap = s->qcap;
   int active = ctx->se3ActivePairs > 0 ? ctx->se3ActivePairs : SE3_DEFAULT_ACTIVE;
-  if (active > n) active = n;
-  unsigned *ctr0 = reinterpret_cast<unsigned *>(s->h_states);  // pinned scratch, rewritten by the D2H below
-  ctr0[0] = 0u; ctr0[1] = 0u; ctr0[2] = (unsigned)n; ctr0[3] = (unsigned)active;
-  LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
-  LSD_CUDA(cudaMemcpyAsync(s->d_ctrs, ctr0, sizeof(unsigned) * 4, cudaMemcpyHostToDevice, st));
+  if (active > m) active = m;
   LSD_CUDA(cudaMemsetAsync(s->d_slots, 0, sizeof(unsigned long long) * q.cap, st));
-  LSD_CUDA(cudaEventRecord(ctx->evA, st));
-  k_se3_init<<<(n + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, n, q, prm, active);
-  lsd_trace_entry *d_tr = traces ? s->d_traces : nullptr;
-  k_se3_track<<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs, s->d_states, s->d_partials, q, prm, d_tr);
+  k_se3_reset<<<1, 1, 0, st>>>(s->d_ctrs, (unsigned)m, (unsigned)active);
+  k_se3_init<<<(m + 127) / 128, 128, 0, st>>>(s->d_pairs + i0, s->d_states + i0, m, q, prm, active);
+  lsd_trace_entry *d_tr = wantTrace ? s->d_traces + (size_t)i0 * LSD_TRACE_CAP : nullptr;
+  k_se3_track<<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs + i0, s->d_states + i0, s->d_partials + (size_t)i0 * prm.maxChunks * SE3_NRED,
+                                                    q, prm, d_tr);
   LSD_CUDA(cudaGetLastError());
-  ctx->launches += 2;
-  LSD_CUDA(cudaEventRecord(ctx->evB, st));
+  ctx->launches += 3;
+  return LSD_OK;
+}
+
+int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, lsd_se3_result *results, lsd_trace_entry *traces,
+                cudaStream_t st, float kernelMs) {
+  SE3Scratch *s = ctx->se3s;
   LSD_CUDA(cudaMemcpyAsync(s->h_states, s->d_states, sizeof(SE3State) * n, cudaMemcpyDeviceToHost, st));
   if (traces)
     LSD_CUDA(cudaMemcpyAsync(traces, s->d_traces, sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)n, cudaMemcpyDeviceToHost, st));
   LSD_CUDA(cudaStreamSynchronize(st));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
   double bytes = 0;
   long long evals = 0;
   for (int i = 0; i < n; i++) {
@@ -896,16 +911,27 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
     }
     if (P.trackingWasGood) refs[i]->keyframe->numFramesTrackedOnThis++;
   }
-  if (accumulateStats) {
-    ctx->lastAlgBytes += bytes;
-    ctx->lastEvals += evals;
-    ctx->lastKernelMs += ms;
-  } else {
-    ctx->lastAlgBytes = bytes;
-    ctx->lastEvals = evals;
-    ctx->lastKernelMs = ms;
-  }
+  ctx->lastAlgBytes = bytes;
+  ctx->lastEvals = evals;
+  ctx->lastKernelMs = kernelMs;
   return LSD_OK;
+}
+
+int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
+                         lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st) {
+  if (n == 0) return LSD_OK;
+  int rc = se3_prepare(ctx, n, refs, frames, init, traces != nullptr, st);
+  if (rc) return rc;
+  rc = init_masks(ctx, n, frames, st);
+  if (rc) return rc;
+  LSD_CUDA(cudaEventRecord(ctx->evA, st));
+  rc = se3_launch(ctx, 0, n, traces != nullptr, st);
+  if (rc) return rc;
+  LSD_CUDA(cudaEventRecord(ctx->evB, st));
+  LSD_CUDA(cudaEventSynchronize(ctx->evB));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
+  return se3_collect(ctx, n, refs, frames, results, traces, st, ms);
 }
 
 // ---------------------------------------------------------------------------------------
