@@ -626,7 +626,7 @@ int lsd_ref_read(lsd_ctx *ctx, lsd_ref *r, int level, float *pos, float *grad, f
   for (int i = 0; i < n; i++) {
     const int x = pts[i].xy & 0xffff, y = pts[i].xy >> 16;
     if (pos) {  // same operations as the kernel (and upstream makePointCloud)
-      volatile float inv = 1.0f / pts[i].idepth;
+      volatile float inv = pts[i].invDepth;
       volatile float ax = fxi * x, ay = fyi * y;
       volatile float bx = ax + cxi, by = ay + cyi;
       pos[3 * i] = inv * bx;

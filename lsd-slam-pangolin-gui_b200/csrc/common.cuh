@@ -90,10 +90,12 @@ enum {
 };
 
 // One tracking-reference point (16 B, one LDG.128): what TrackingReference::makePointCloud emits,
-// with pos recomputed on the fly from (x, y, idepth) -- bit-identical to the stored posData.
+// with pos = invDepth * (fxi*x+cxi, fyi*y+cyi, 1) recomputed on the fly.  invDepth is upstream's own
+// intermediate 1.0f / idepth (IEEE division, done once in k_make_pointcloud), so the position is
+// bit-identical to the stored posData and the trackers save one division per point per evaluation.
 struct __align__(16) RefPoint {
   uint32_t xy;  // x | y << 16
-  float idepth;
+  float invDepth;
   float color;
   float var;
 };

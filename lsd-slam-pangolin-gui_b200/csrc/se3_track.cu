@@ -35,8 +35,8 @@ namespace lsd {
 #ifndef SE3_THREADS
 #define SE3_THREADS 128   // threads per CTA (small CTAs: an item's fetch / reduce barriers stall fewer warps)
 #endif
-#ifndef SE3_P
-#define SE3_P 2           // points in flight per thread (loads of a batch are issued before any math)
+#ifndef SE3_D
+#define SE3_D 2           // per-thread software-pipeline depth of eval_range (points whose taps are in flight + 1)
 #endif
 #ifndef SE3_MINB
 #define SE3_MINB 4        // resident CTAs per SM the register budget is sized for
@@ -316,8 +316,8 @@ __device__ int lm_step(const SE3Pair *P, SE3State *S, const float *tot, const do
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate, split in two phases so
-// that the bilinear taps of SE3_P points are in flight before any dependent math starts.
+// Fused calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate, split in a warp stage and an
+// accumulate stage that are software-pipelined per thread (eval_range).
 // ---------------------------------------------------------------------------------------------
 struct EvalConst {
   float R[9], t[3];
@@ -327,16 +327,31 @@ struct EvalConst {
   int W, H;
 };
 
-struct Warped {  // phase-A result of one point
-  float Wx, Wy, Wz, pz, dx, dy;
-  int off;   // tap base offset (float4 units); -1 when the point projects outside; -2 past the end
+// What the warp stage of one point hands to its accumulate stage (kept in registers while the taps fly).
+struct Pending {
+  float Wx, Wy, Wz, pz, dx, dy, color, var;
   int midx;  // x + y*W (mask index)
+  int st;    // 1: taps in flight, 0: projects outside the image, -1: no point (past the end)
 };
 
-__device__ __forceinline__ void warp_point(const float4 raw, const EvalConst &c, Warped &w) {
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Warp stage: TrackingReference position -> warp -> projection -> in-image test; when the point is inside, its four
+// bilinear taps (16 B each) are sent straight from global memory into this thread's shared-memory slot
+// (cp.async: no register is held while they are in flight).  EXACT tier (see below).
+__device__ __forceinline__ void warp_point(const float4 raw, const EvalConst &c, const float4 *__restrict__ G, float4 *slot,
+                                           Pending &w) {
   const uint32_t xy = __float_as_uint(raw.x);
   const int x = xy & 0xffff, y = xy >> 16;
-  const float inv = 1.0f / raw.y;  // pos = (1/idepth) * (fxi*x+cxi, fyi*y+cyi, 1): TrackingReference::makePointCloud
+  const float inv = raw.y;  // RefPoint::invDepth; pos = (1/idepth) * (fxi*x+cxi, fyi*y+cyi, 1): TrackingReference::makePointCloud
   const float px = inv * (c.fxi * x + c.cxi);
   const float py = inv * (c.fyi * y + c.cyi);
   const float pz = inv * 1.0f;
@@ -344,18 +359,24 @@ __device__ __forceinline__ void warp_point(const float4 raw, const EvalConst &c,
   w.Wy = (c.R[3] * px + c.R[4] * py + c.R[5] * pz) + c.t[1];
   w.Wz = (c.R[6] * px + c.R[7] * py + c.R[8] * pz) + c.t[2];
   w.pz = pz;
+  w.color = raw.z;
+  w.var = raw.w;
   const float u_new = (w.Wx / w.Wz) * c.fx + c.cx;
   const float v_new = (w.Wy / w.Wz) * c.fy + c.cy;
   w.midx = x + y * c.W;
   if (!(u_new > 1 && v_new > 1 && u_new < c.W - 2 && v_new < c.H - 2)) {  // inverse test excludes NaN
-    w.off = -1;
-    w.dx = w.dy = 0;
+    w.st = 0;
     return;
   }
   const int ix = (int)u_new, iy = (int)v_new;
   w.dx = u_new - ix;
   w.dy = v_new - iy;
-  w.off = ix + iy * c.W;
+  w.st = 1;
+  const float4 *bp = G + (ix + iy * c.W);
+  cp_async16(slot, bp);
+  cp_async16(slot + SE3_THREADS, bp + 1);
+  cp_async16(slot + 2 * SE3_THREADS, bp + c.W);
+  cp_async16(slot + 3 * SE3_THREADS, bp + c.W + 1);
 }
 
 // Per-point arithmetic comes in two tiers.
@@ -367,9 +388,9 @@ __device__ __forceinline__ void warp_point(const float4 raw, const EvalConst &c,
 //    reference's; their 2^-22 relative error is far inside the 1e-4 residual / 1e-5 pose tolerances.
 __device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }
 
-__device__ __forceinline__ void accumulate_point(const float4 raw, const Warped &w, const float4 p00, const float4 p10,
-                                                 const float4 p01, const float4 p11, const EvalConst &c,
-                                                 uint8_t *__restrict__ mask, float acc[SE3_NF], double dacc[SE3_ND]) {
+__device__ __forceinline__ void accumulate_point(const Pending &w, const float4 p00, const float4 p10, const float4 p01,
+                                                 const float4 p11, const EvalConst &c, uint8_t *__restrict__ mask,
+                                                 float acc[SE3_NF], double dacc[SE3_ND]) {
   // ---- EXACT: getInterpolatedElement43 (this exact weight form and summation order), residual, isGood
   const float dxdy = w.dx * w.dy;
   const float w11 = dxdy, w01 = w.dy - dxdy, w10 = w.dx - dxdy, w00 = 1 - w.dx - w.dy + dxdy;
@@ -377,15 +398,16 @@ __device__ __forceinline__ void accumulate_point(const float4 raw, const Warped 
   const float gyI = w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y;
   const float cI = w11 * p11.z + w01 * p01.z + w10 * p10.z + w00 * p00.z;
   const float Wx = w.Wx, Wy = w.Wy, Wz = w.Wz, pz = w.pz;
-  const float c1 = c.a * raw.z + c.b;
+  const float c1 = c.a * w.color + c.b;
   const float c2 = cI;
   const float residual = c1 - c2;
   const float r2 = residual * residual;
-  // isGood = fl(r2 / D) < 1 with D = MAX_DIFF_CONSTANT + MAX_DIFF_GRAD_MULT * |g|^2.  A correctly rounded quotient is
-  // below 1 exactly when the real quotient is below the rounding midpoint 1 - 2^-25 (the tie goes to the even 1.0),
-  // i.e. r2 < D * (1 - 2^-25); that product is exact in fp64, so the test equals upstream's division bit for bit.
+  // isGood = fl(r2 / D) < 1 with D = MAX_DIFF_CONSTANT + MAX_DIFF_GRAD_MULT * |g|^2 >= 1600.  The correctly rounded
+  // quotient of two floats is below 1 exactly when r2 < D: r2 >= D gives a quotient >= 1, and r2 < D means
+  // r2 <= pred(D) <= D (1 - 2^-24), strictly below the rounding midpoint D (1 - 2^-25) of [pred(1), 1].
+  // So the comparison equals upstream's division bit for bit (NaN: both false).
   const float D = LSD_MAX_DIFF_CONSTANT + LSD_MAX_DIFF_GRAD_MULT * (gxI * gxI + gyI * gyI);
-  const bool isGood = (double)r2 < (double)D * (1.0 - 2.9802322387695312e-08);
+  const bool isGood = r2 < D;
   if (mask) mask[w.midx] = isGood;
   if (isGood) {
     acc[R_SUMUNW] += r2;
@@ -416,7 +438,7 @@ __device__ __forceinline__ void accumulate_point(const float4 raw, const Warped 
   const float g0 = fmaf(c.t[0], Wz, -c.t[2] * Wx) * kk;
   const float g1 = fmaf(c.t[1], Wz, -c.t[2] * Wy) * kk;
   const float drpdd = fmaf(gx, g0, gy * g1);
-  const float s = c.var_weight * raw.w;
+  const float s = c.var_weight * w.var;
   const float rs = rsqrtf(fmaf(s * drpdd, drpdd, LSD_CAMERA_PIXEL_NOISE2));  // sqrt(w_p)
   const float w_p = rs * rs;
   const float weighted_rp = ar * rs;
@@ -447,55 +469,66 @@ __device__ __forceinline__ void accumulate_point(const float4 raw, const Warped 
   for (int a = 0; a < 6; a++) acc[R_B + a] = fmaf(v[a], rw, acc[R_B + a]);
 }
 
-// All points [begin, end) of one evaluation handled by this CTA: SE3_P points per thread per step.
+// All points [begin, end) of one evaluation handled by this CTA.  Thread t takes points begin + t + m * SE3_THREADS
+// in order of m (this order is part of the summation order).  Software pipeline, SE3_D stages deep, per thread:
+//   point m + SE3_D       : its 16-byte record is loaded into a register (one stage ahead of its warp stage)
+//   point m + SE3_D - 1   : warp stage -> four cp.async taps into this thread's slot (m + SE3_D - 1) % SE3_D
+//   point m               : cp.async.wait_group(SE3_D - 1), then the accumulate stage reads its slot
+// so both global-memory latencies of a point (record, taps) overlap the arithmetic of the SE3_D - 1 points
+// before it.  A thread only ever reads slots it filled itself: no CTA barrier inside the loop.
 __device__ __forceinline__ void eval_range(const RefPoint *__restrict__ pts, int begin, int end, const float4 *__restrict__ G,
                                            uint8_t *__restrict__ mask, const EvalConst &c, float acc[SE3_NF],
-                                           double dacc[SE3_ND]) {
+                                           double dacc[SE3_ND], float4 *tapbuf) {
   const float4 *pts4 = reinterpret_cast<const float4 *>(pts);
-  for (int i0 = begin + threadIdx.x; i0 < end; i0 += SE3_THREADS * SE3_P) {
-    float4 raw[SE3_P];
-    Warped w[SE3_P];
-    float4 tap[SE3_P][4];
+  float4 *mySlot = tapbuf + threadIdx.x;
+  Pending pd[SE3_D];
+  int iLoad = begin + threadIdx.x;
+  float4 rawNext = (iLoad < end) ? __ldg(pts4 + iLoad) : make_float4(0, 0, 0, 0);
+  auto issue = [&](const int s) {
+    const float4 raw = rawNext;
+    const bool have = iLoad < end;
+    iLoad += SE3_THREADS;
+    if (iLoad < end) rawNext = __ldg(pts4 + iLoad);
+    if (have) warp_point(raw, c, G, mySlot + s * 4 * SE3_THREADS, pd[s]);
+    else pd[s].st = -1;
+    cp_async_commit();
+  };
 #pragma unroll
-    for (int k = 0; k < SE3_P; k++) {
-      const int i = i0 + k * SE3_THREADS;
-      raw[k] = (i < end) ? __ldg(pts4 + i) : make_float4(0, 0, 0, 0);
-    }
+  for (int s = 0; s < SE3_D - 1; s++) issue(s);
+  const int steps = (end - begin + SE3_THREADS - 1) / SE3_THREADS;  // CTA-uniform
+  for (int m0 = 0; m0 < steps; m0 += SE3_D) {
 #pragma unroll
-    for (int k = 0; k < SE3_P; k++) {
-      const int i = i0 + k * SE3_THREADS;
-      if (i < end) {
-        warp_point(raw[k], c, w[k]);
-      } else {
-        w[k].off = -2;
-        w[k].midx = 0;
+    for (int s = 0; s < SE3_D; s++) {
+      issue((s + SE3_D - 1) % SE3_D);
+      cp_async_wait<SE3_D - 1>();
+      if (pd[s].st > 0) {
+        const float4 *sl = mySlot + s * 4 * SE3_THREADS;
+        accumulate_point(pd[s], sl[0], sl[SE3_THREADS], sl[2 * SE3_THREADS], sl[3 * SE3_THREADS], c, mask, acc, dacc);
+      } else if (pd[s].st == 0 && mask) {
+        mask[pd[s].midx] = 0;
       }
-      if (w[k].off >= 0) {
-        const float4 *bp = G + w[k].off;
-        tap[k][0] = __ldg(bp);
-        tap[k][1] = __ldg(bp + 1);
-        tap[k][2] = __ldg(bp + c.W);
-        tap[k][3] = __ldg(bp + 1 + c.W);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < SE3_P; k++) {
-      if (w[k].off >= 0) accumulate_point(raw[k], w[k], tap[k][0], tap[k][1], tap[k][2], tap[k][3], c, mask, acc, dacc);
-      else if (w[k].off == -1 && mask) mask[w[k].midx] = 0;
     }
   }
+  cp_async_wait<0>();
 }
 
 // Block reduction through shared memory: every thread parks its 38 sums (column = thread), then warp w
 // reduces rows w, w+8, ...: 8 conflict-free LDS + one shuffle tree per row.  Fixed order => deterministic.
-struct SE3Smem {
+struct SE3Red {
   float f[SE3_NF][SE3_THREADS];
   double d[SE3_ND][SE3_THREADS];
 };
+// The tap slots of eval_range and the reduction scratch are never live at the same time (one CTA barrier separates them).
+union SE3Smem {
+  float4 taps[SE3_D * 4 * SE3_THREADS];  // [stage][tap][thread]: a warp's LDS.128 / cp.async rows are conflict-free
+  SE3Red red;
+};
 
 __device__ __forceinline__ void block_reduce_store(const float acc[SE3_NF], const double dacc[SE3_ND], float *__restrict__ dst,
-                                                   SE3Smem &sm) {
+                                                   SE3Smem &smu) {
+  SE3Red &sm = smu.red;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();  // every thread has left eval_range: the tap slots may be overwritten
 #pragma unroll
   for (int j = 0; j < SE3_NF; j++) sm.f[j][threadIdx.x] = acc[j];
 #pragma unroll
@@ -543,7 +576,7 @@ __device__ __forceinline__ void load_eval_const(const SE3Params &prm, int level,
 __global__ void __launch_bounds__(SE3_THREADS, SE3_MINB)
 k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials, const SE3Queue q,
             const __grid_constant__ SE3Params prm, lsd_trace_entry *traces) {
-  __shared__ SE3Smem sm;
+  __shared__ __align__(16) SE3Smem sm;
   __shared__ float stot[SE3_NF];
   __shared__ double sdtot[SE3_ND];
   __shared__ int sCode, sIsLast;
@@ -600,7 +633,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
       }
       const int begin = rec * SE3_REC;
       const int end = min(n, begin + SE3_REC);
-      eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc);
+      eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
       float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
       block_reduce_store(acc, dacc, dst, sm);
     }
@@ -940,7 +973,7 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
 __global__ void __launch_bounds__(SE3_THREADS)
 k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, float *__restrict__ partials, int level,
                 const __grid_constant__ SE3Params prm) {
-  __shared__ SE3Smem sm;
+  __shared__ __align__(16) SE3Smem sm;
   const int4 *hp = reinterpret_cast<const int4 *>(S);
   const int4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1), h2 = __ldcg(hp + 2), h3 = __ldcg(hp + 3);
   EvalConst c;
@@ -955,7 +988,7 @@ k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, f
   for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
   const int begin = blockIdx.x * SE3_REC;
   const int end = min(n, begin + SE3_REC);
-  eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc);
+  eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
   block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sm);
 }
 

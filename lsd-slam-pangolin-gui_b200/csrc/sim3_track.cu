@@ -138,7 +138,7 @@ __device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, cons
   const float fx_l = prm.K.fx[lvl], fy_l = prm.K.fy[lvl], cx_l = prm.K.cx[lvl], cy_l = prm.K.cy[lvl];
   const uint32_t xy = __float_as_uint(raw.x);
   const int x = xy & 0xffff, y = xy >> 16;
-  const float inv = 1.0f / raw.y;
+  const float inv = raw.y;  // RefPoint::invDepth
   const float px = inv * (prm.K.fxi[lvl] * x + prm.K.cxi[lvl]);
   const float py = inv * (prm.K.fyi[lvl] * y + prm.K.cyi[lvl]);
   const float pz = inv * 1.0f;

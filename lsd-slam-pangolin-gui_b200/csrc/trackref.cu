@@ -6,7 +6,7 @@
 // x, so the 16-byte bilinear taps of a warp in the tracker fall into the same 128-byte lines.
 // Order only affects fp32 summation order (hard part 6).
 //
-// One point = 16 B {x|y<<16, idepth, colour, var}; the 3-D position
+// One point = 16 B {x|y<<16, 1/idepth, colour, var}; the 3-D position
 // (1/idepth)*(fxi*x+cxi, fyi*y+cyi, 1) is recomputed by the tracker with the same operations,
 // so it is bit-identical to upstream's stored posData.  grad (Sim3 only) is a separate float2 plane.
 #include "ctx.cuh"
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(1024) k_make_pointcloud(uint8_t *const *__rest
       const float4 g = G[i];
       RefPoint p;
       p.xy = (uint32_t)x | ((uint32_t)y << 16);
-      p.idepth = id;
+      p.invDepth = 1.0f / id;  // == posData z (upstream: pos = (1/idepth) * (...))
       p.color = g.z;  // gradients.z == image(level)
       p.var = var;
       pts[o] = p;
