@@ -215,7 +215,9 @@ def main():
     torch.cuda.set_device(dev)
     from lsd_b200 import synth
     ctx = lsd_b200.Context(W, H, synth.default_K(W, H), device=0)
-    out = {"depthmap": depth_bench(ctx, lsd_b200), "sim3": sim3_bench(ctx, lsd_b200)}
+    reps = int(os.environ.get("EXTRA_REPS", "5"))
+    cpu = os.environ.get("EXTRA_NO_CPU", "") == ""
+    out = {"depthmap": depth_bench(ctx, lsd_b200, reps=reps, cpu=cpu), "sim3": sim3_bench(ctx, lsd_b200, reps=min(reps, 3), cpu=cpu)}
     ctx.close()
     print(json.dumps(out), flush=True)
 
