@@ -253,6 +253,38 @@ int lsd_depth_stage(lsd_ctx *ctx, lsd_depthmap *dm, int stage, int arg1, int arg
 int lsd_ctx_last_stage_ms(lsd_ctx *ctx, float *ms);
 int lsd_depth_stage_batch(lsd_ctx *ctx, int n, lsd_depthmap *const *dms, int stage, int arg1, int arg2, lsd_frame *const *frames);
 
+/* ---- keyframe publish / point-cloud extraction ---------------------------------------- */
+/* InputPointDense, /root/reference/lib/Pangolin_IOWrapper/Keyframe.h:16-21 */
+typedef struct lsd_input_point_dense {
+  float idepth, idepth_var;
+  unsigned char color[4];
+} lsd_input_point_dense;
+/* Keyframe::MyVertex, Keyframe.h:47-51 */
+typedef struct lsd_vertex {
+  float point[3];
+  unsigned char color[4];
+} lsd_vertex;
+/* the locals of Keyframe::computeVbo (Keyframe.h:79-84).  contractFma = 1 evaluates x*fxi+cxi as one FMA, which is
+ * what gcc emits for the reference's Release flags (-march=native, CMakeLists.txt:59) on an FMA host; 0 = IEEE. */
+typedef struct lsd_vbo_params {
+  float scaledTH, absTH; /* my_scaledTH 1e-3, my_absTH 1e-1 */
+  int minNearSupport;    /* 9 */
+  int sparsifyFactor;    /* 1 (the reference's constant; anything else is rejected) */
+  int contractFma;
+} lsd_vbo_params;
+int lsd_default_vbo_params(lsd_vbo_params *p);
+/* PangolinOutputIOWrapper::publishKeyframe's pack loop (PangolinOutputIOWrapper.cpp:69-89): writes w_l*h_l records
+ * into dst (what the reference stores in Keyframe::pointData).  A frame without depth yields zeros. */
+int lsd_frame_publish_keyframe(lsd_ctx *ctx, lsd_frame *f, int level, lsd_input_point_dense *dst);
+/* Keyframe::computeVbo (Keyframe.h:66-158) straight from the frame's planes: dst receives `*points` vertices in the
+ * reference's raster order (capacity w_l*h_l).  camToWorldScale = Keyframe::camToWorld.scale(). */
+int lsd_keyframe_compute_vbo(lsd_ctx *ctx, lsd_frame *f, int level, float camToWorldScale, const lsd_vbo_params *params,
+                             lsd_vertex *dst, int *points);
+/* n keyframes in ONE launch.  d_vertices: device memory for n * w_l*h_l vertices (e.g. a mapped GL buffer; keyframe i
+ * starts at i*w_l*h_l) or NULL to use context scratch; dst: n host pointers (entries may be NULL) or NULL. */
+int lsd_keyframe_compute_vbo_batch(lsd_ctx *ctx, int n, lsd_frame *const *frames, int level, const float *camToWorldScale,
+                                   const lsd_vbo_params *params, void *d_vertices, lsd_vertex *const *dst, int *points);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,7 +117,20 @@ SYMBOLS = {
     "lsd_depth_stage": (_ip, [_vp, _vp, _ip, _ip, _ip, _vp]),
     "lsd_ctx_last_stage_ms": (_ip, [_vp, _vp]),
     "lsd_depth_stage_batch": (_ip, [_vp, _ip, _vp, _ip, _ip, _ip, _vp]),
+    "lsd_default_vbo_params": (_ip, [_vp]),
+    "lsd_frame_publish_keyframe": (_ip, [_vp, _vp, _ip, _vp]),
+    "lsd_keyframe_compute_vbo": (_ip, [_vp, _vp, _ip, _fp, _vp, _vp, _vp]),
+    "lsd_keyframe_compute_vbo_batch": (_ip, [_vp, _ip, _vp, _ip, _vp, _vp, _vp, _vp, _vp]),
 }
+
+# InputPointDense / Keyframe::MyVertex (/root/reference/lib/Pangolin_IOWrapper/Keyframe.h:16-21,47-51)
+POINT_DTYPE = np.dtype([("idepth", np.float32), ("idepth_var", np.float32), ("color", np.uint8, (4,))])
+VERTEX_DTYPE = np.dtype([("point", np.float32, (3,)), ("color", np.uint8, (4,))])
+
+
+class VboParams(C.Structure):
+    _fields_ = [("scaledTH", C.c_float), ("absTH", C.c_float), ("minNearSupport", C.c_int), ("sparsifyFactor", C.c_int),
+                ("contractFma", C.c_int)]
 
 # [UP] DepthMapPixelHypothesis in upstream's 32-byte AoS layout (lsd_hypothesis)
 HYP_DTYPE = np.dtype([("isValid", np.uint8), ("_pad", np.uint8, (3,)), ("blacklisted", np.int32),
@@ -250,6 +263,29 @@ class Context:
         ms = C.c_float()
         _chk(self.L.lsd_ctx_last_stage_ms(self.p, C.byref(ms)))
         return ms.value
+
+    # ---- keyframe publish (PangolinOutputIOWrapper::publishKeyframe + Keyframe::computeVbo)
+    def default_vbo_params(self):
+        p = VboParams()
+        _chk(self.L.lsd_default_vbo_params(C.byref(p)))
+        return p
+
+    def compute_vbo_batch(self, frames, scales, level=0, params=None, read=True):
+        """Keyframe::computeVbo for n keyframes in one launch.  Returns (points[n], [vertex arrays] or None)."""
+        n = len(frames)
+        fp = (C.c_void_p * n)(*[f.p for f in frames])
+        sc = np.ascontiguousarray(scales, np.float32).reshape(n)
+        pts = np.zeros(n, np.int32)
+        cap = (self.w >> level) * (self.h >> level)
+        outs, dp = None, None
+        if read:
+            outs = [np.zeros(cap, VERTEX_DTYPE) for _ in range(n)]
+            dp = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        _chk(self.L.lsd_keyframe_compute_vbo_batch(self.p, n, fp, level, _ptr(sc), C.byref(params) if params is not None else None,
+                                                   None, dp, _ptr(pts)))
+        if read:
+            outs = [o[:k] for o, k in zip(outs, pts)]
+        return pts, outs
 
     # ---- SE3 tracking
     def se3_track_batch(self, refs, frames, inits, want_trace=False):
@@ -384,6 +420,20 @@ class Frame:
 
     def refPixelWasGood(self):
         return self.read(FIELD_MASK, 1)
+
+    def publish_keyframe(self, level=0):
+        """InputPointDense records of PangolinOutputIOWrapper::publishKeyframe (what Keyframe::pointData holds)."""
+        out = np.zeros((self.ctx.h >> level, self.ctx.w >> level), POINT_DTYPE)
+        _chk(self.ctx.L.lsd_frame_publish_keyframe(self.ctx.p, self.p, level, _ptr(out)))
+        return out
+
+    def compute_vbo(self, scale=1.0, level=0, params=None):
+        """Keyframe::computeVbo: the MyVertex array the reference uploads with glBufferData."""
+        out = np.zeros((self.ctx.h >> level) * (self.ctx.w >> level), VERTEX_DTYPE)
+        n = C.c_int()
+        _chk(self.ctx.L.lsd_keyframe_compute_vbo(self.ctx.p, self.p, level, float(scale),
+                                                 C.byref(params) if params is not None else None, _ptr(out), C.byref(n)))
+        return out[:n.value].copy()
 
     def num_mappable_pixels(self):
         v = C.c_int()

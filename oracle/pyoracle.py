@@ -122,6 +122,8 @@ def lib(fast: bool = False):
         ("lsdo_frame_clear_mask", None, [vp]),
         ("lsdo_frame_get_flags", ip, [vp]),
         ("lsdo_set_exact_sums", None, [ip]),
+        ("lsdo_publish_keyframe_pack", None, [vp, vp, vp, ip, ip, vp]),
+        ("lsdo_compute_vbo", ip, [vp, ip, ip, fp, fp, fp, fp, fp, fp, fp, ip, ip, vp]),
     ]:
         f = getattr(L, name)
         f.restype = res
@@ -403,3 +405,71 @@ def frame_counters(frame: Frame):
 def set_exact_sums(v, fast=False):
     """fp64 accumulation of the depth map's two whole-map sums (see lsd_oracle.hpp g_exactSums)."""
     lib(fast).lsdo_set_exact_sums(int(v))
+
+
+# ---- keyframe publish / VBO extraction (oracle/keyframe.cpp; the only PINNED part of the oracle) ----------------
+POINT_DTYPE = np.dtype([("idepth", np.float32), ("idepth_var", np.float32), ("color", np.uint8, (4,))])  # InputPointDense
+VERTEX_DTYPE = np.dtype([("point", np.float32, (3,)), ("color", np.uint8, (4,))])  # Keyframe::MyVertex
+assert POINT_DTYPE.itemsize == 12 and VERTEX_DTYPE.itemsize == 16
+VBO_SCALED_TH, VBO_ABS_TH, VBO_MIN_NEAR_SUPPORT = 1e-3, 1e-1, 9  # Keyframe.h:79-83
+
+
+def publish_keyframe_pack(idepth, idepth_var, image, has_idepth=True, fast=False):
+    """PangolinOutputIOWrapper::publishKeyframe's pack loop (PangolinOutputIOWrapper.cpp:69-89), restated."""
+    idepth = np.ascontiguousarray(idepth, np.float32)
+    idepth_var = np.ascontiguousarray(idepth_var, np.float32)
+    image = np.ascontiguousarray(image, np.float32)
+    out = np.zeros(idepth.shape, POINT_DTYPE)
+    lib(fast).lsdo_publish_keyframe_pack(_ptr(idepth), _ptr(idepth_var), _ptr(image), idepth.size, int(has_idepth), _ptr(out))
+    return out
+
+
+def compute_vbo(points, K, scale=1.0, scaled_th=VBO_SCALED_TH, abs_th=VBO_ABS_TH, min_near_support=VBO_MIN_NEAR_SUPPORT,
+                contract_fma=False, fast=False):
+    """Keyframe::computeVbo (Keyframe.h:66-158), restated.  points: (h, w) POINT_DTYPE.  Returns the vertex array."""
+    points = np.ascontiguousarray(points, POINT_DTYPE)
+    h, w = points.shape
+    out = np.zeros(h * w, VERTEX_DTYPE)
+    n = lib(fast).lsdo_compute_vbo(_ptr(points), w, h, K[0], K[1], K[2], K[3], scale, scaled_th, abs_th, min_near_support,
+                                   int(contract_fma), _ptr(out))
+    return out[:n].copy()
+
+
+_ref_kf = None
+
+
+def ref_keyframe_lib():
+    """oracle/_ref/libref_keyframe.so: the reference's own Keyframe.h compiled by oracle/Makefile (None when neither
+    /root/reference nor a prebuilt library is present)."""
+    global _ref_kf
+    if _ref_kf is None:
+        path = os.path.join(HERE, "_ref", "libref_keyframe.so")
+        if not os.path.exists(path):
+            build(force=True)
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        vp, ip, fp = C.c_void_p, C.c_int, C.c_float
+        L.ref_keyframe_compute_vbo.restype = ip
+        L.ref_keyframe_compute_vbo.argtypes = [vp, ip, ip, fp, fp, fp, fp, fp, vp]
+        L.ref_keyframe_update_and_compute_vbo.restype = ip
+        L.ref_keyframe_update_and_compute_vbo.argtypes = [vp, vp, ip, ip, fp, fp, fp, fp, fp, vp]
+        _ref_kf = L
+    return _ref_kf
+
+
+def ref_compute_vbo(points, K, scale=1.0, republish=None):
+    """The REFERENCE's Keyframe::computeVbo itself (republish: a second point set pushed through
+    Keyframe::updatePoints first, the path of GUI::addKeyframe for a known id, lib/GUI.cpp:126-131)."""
+    L = ref_keyframe_lib()
+    assert L is not None, "oracle/_ref/libref_keyframe.so unavailable"
+    points = np.ascontiguousarray(points, POINT_DTYPE)
+    h, w = points.shape
+    out = np.zeros(h * w, VERTEX_DTYPE)
+    if republish is None:
+        n = L.ref_keyframe_compute_vbo(_ptr(points), w, h, K[0], K[1], K[2], K[3], scale, _ptr(out))
+    else:
+        second = np.ascontiguousarray(republish, POINT_DTYPE)
+        n = L.ref_keyframe_update_and_compute_vbo(_ptr(points), _ptr(second), w, h, K[0], K[1], K[2], K[3], scale, _ptr(out))
+    assert n >= 0
+    return out[:n].copy()
