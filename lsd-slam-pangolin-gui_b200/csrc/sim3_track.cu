@@ -28,6 +28,11 @@ namespace lsd {
 
 #define S3_THREADS 256
 #define S3_CL 8
+// resident CTAs per SM the register allocation is capped for (221 registers uncapped = ONE 256-thread CTA per SM, i.e.
+// 18 clusters on the whole GPU; the cap trades a few spills in the single-thread LM step for 2-4x the clusters in flight)
+#ifndef S3_MINB
+#define S3_MINB 2
+#endif
 // fp32 sums
 enum { Q_A6 = 0, Q_B6 = 21, Q_A4 = 27, Q_B4 = 37, Q_RD = 41, Q_RP = 42, Q_USAGE = 43, Q_ND = 44, Q_CNT = 45, S3_NF = 46 };
 #define S3_ND 5  // fp64 affine-lighting sums (sxx, syy, sx, sy, sw), see se3_track.cu
@@ -455,7 +460,7 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
   return true;
 }
 
-__global__ void __cluster_dims__(S3_CL, 1, 1) __launch_bounds__(S3_THREADS, 1)
+__global__ void __cluster_dims__(S3_CL, 1, 1) __launch_bounds__(S3_THREADS, S3_MINB)
 k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const __grid_constant__ Sim3Params prm,
              lsd_trace_entry *__restrict__ traces) {
   cg::cluster_group cluster = cg::this_cluster();

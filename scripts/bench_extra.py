@@ -34,7 +34,7 @@ def peak():
     return PEAK_FALLBACK, "fallback"
 
 
-def depth_bench(ctx, lsd, B=16, n_refs=10, reps=5, device="cuda", cpu=True):
+def depth_bench(ctx, lsd, B=64, n_refs=10, reps=5, device="cuda", cpu=True):
     import torch
 
     from lsd_b200 import synth
@@ -207,6 +207,51 @@ def sim3_bench(ctx, lsd, n_cand=64, reps=3, device="cuda", cpu=True):
     return out
 
 
+def vbo_bench(ctx, lsd, B=64, reps=5, device="cuda", cpu=True):
+    """Keyframe::computeVbo (SURVEY.md 8f N2) on B keyframes in one launch; algorithmic bytes = 12 B/px read (idepth, var,
+    image) + 16 B per emitted vertex.  CPU leg: the reference's OWN Keyframe.h (oracle/_ref) when present, else the port."""
+    from lsd_b200 import synth
+    K = synth.default_K(W, H)
+    frames, host = [], []
+    for i in range(B):
+        pr = synth.make_pair(700 + i, W, H, K, device=device)
+        f = ctx.create_frame(pr["kf_img"].cpu().numpy(), i, flags=lsd.BUILD_MAXGRAD0)
+        idv, vv = synth.semidense_idepth(pr["kf_depth"], f.maxGradients(0), var=1e-4, noise=0.002, seed=i)
+        idv = np.where(vv > 0, idv, -1).astype(np.float32)  # what Frame::setDepth leaves on invalid pixels
+        vv = np.where(vv > 0, vv, -1).astype(np.float32)
+        f.set_idepth(idv, vv)
+        frames.append(f)
+        if i == 0:
+            host = (idv, vv, pr["kf_img"].cpu().numpy().astype(np.float32))
+    scales = np.ones(B, np.float32)
+    ts = []
+    for _ in range(reps + 1):
+        pts, _ = ctx.compute_vbo_batch(frames, scales, read=False)
+        ts.append(ctx.last_stage_ms())
+    ms = float(np.median(ts[1:]))
+    byts = 12.0 * N * B + 16.0 * float(pts.sum())
+    pk, src = peak()
+    out = {"B": B, "vertices_per_keyframe": float(pts.mean()), "ms_batch": ms, "us_per_keyframe": 1e3 * ms / B, "alg_bytes": byts,
+           "achieved_GBs": byts / (ms * 1e-3) / 1e9, "frac_of_" + src + "_peak": byts / (ms * 1e-3) / 1e9 / pk}
+    t0 = time.perf_counter(); one = frames[0].compute_vbo(1.0); out["latency_ms_one_keyframe_incl_d2h"] = 1e3 * (time.perf_counter() - t0)
+    if cpu:
+        from oracle import pyoracle as O
+        O.build()
+        pk_pts = O.publish_keyframe_pack(*host)
+        Kf = np.array(K, np.float32)
+        kind = "reference" if O.ref_keyframe_lib() is not None else "port"
+        fn = (lambda: O.ref_compute_vbo(pk_pts, Kf, 1.0)) if kind == "reference" else (lambda: O.compute_vbo(pk_pts, Kf, 1.0, fast=True))
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            v = fn()
+        out["cpu"] = {"ms_per_keyframe": 1e2 * (time.perf_counter() - t0), "threads": 1, "kind": kind,
+                      "bit_exact_vs_gpu": bool(v.tobytes() == one.tobytes())}
+    for f in frames:
+        f.release()
+    return out
+
+
 def main():
     import torch
 
@@ -217,7 +262,15 @@ def main():
     ctx = lsd_b200.Context(W, H, synth.default_K(W, H), device=0)
     reps = int(os.environ.get("EXTRA_REPS", "5"))
     cpu = os.environ.get("EXTRA_NO_CPU", "") == ""
-    out = {"depthmap": depth_bench(ctx, lsd_b200, reps=reps, cpu=cpu), "sim3": sim3_bench(ctx, lsd_b200, reps=min(reps, 3), cpu=cpu)}
+    parts = os.environ.get("EXTRA_PARTS", "depthmap,sim3,vbo").split(",")
+    B = int(os.environ.get("EXTRA_B", "64"))
+    out = {}
+    if "depthmap" in parts:
+        out["depthmap"] = depth_bench(ctx, lsd_b200, B=B, reps=reps, cpu=cpu)
+    if "sim3" in parts:
+        out["sim3"] = sim3_bench(ctx, lsd_b200, reps=min(reps, 3), cpu=cpu)
+    if "vbo" in parts:
+        out["vbo"] = vbo_bench(ctx, lsd_b200, B=B, reps=reps, cpu=cpu)
     ctx.close()
     print(json.dumps(out), flush=True)
 

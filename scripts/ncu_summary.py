@@ -58,8 +58,13 @@ def full(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
+    seen = collections.Counter()
     for r in rows[2:]:
         d = dict(zip(hdr, r))
+        name = d['Kernel Name'].split('(')[0]
+        seen[name] += 1
+        if seen[name] > 2:
+            continue
         u = dict(zip(hdr, units))
         print(f"## {d['Kernel Name'].split('(')[0]}  grid {d.get('Grid Size')} block {d.get('Block Size')}")
         for k in KEYS:
