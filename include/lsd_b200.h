@@ -285,6 +285,37 @@ int lsd_keyframe_compute_vbo(lsd_ctx *ctx, lsd_frame *f, int level, float camToW
 int lsd_keyframe_compute_vbo_batch(lsd_ctx *ctx, int n, lsd_frame *const *frames, int level, const float *camToWorldScale,
                                    const lsd_vbo_params *params, void *d_vertices, lsd_vertex *const *dst, int *points);
 
+/* ---- lock-step SlamSystem driver -------------------------------------------------------- */
+/* The part of [UP] lsd_slam::SlamSystem the reference application drives (new SlamSystem() tools/LSD.cpp:102,
+ * system->nextImage(idx, image, camera) lib/App/InputThread.cpp:71) with its `runRealTime == false` semantics:
+ * nextImage returns once the frame is tracked AND mapped.  Tracking, mapping and keyframe selection run through the
+ * entry points above; pose graph, loop closure and relocalisation stay on the reference's CPU code. */
+typedef struct lsd_slam lsd_slam;
+typedef struct lsd_slam_status {
+  int frameId;
+  int tracked;            /* 0: tracking lost on this frame (upstream would start the Relocalizer) */
+  int isKeyframe;         /* this frame became the current keyframe */
+  int numKeyframes, currentKeyframeId;
+  int trackingWasGood, diverged;
+  float pointUsage, lastResidual, keyframeScore;
+  double camToWorld[8];       /* Frame::getCamToWorld(): what publishPose / pose.txt columns 2-4 carry */
+  double thisToParent_raw[8]; /* frame -> keyframe (pose.txt columns 5-7)                              */
+} lsd_slam_status;
+int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out); /* SlamSystem::SlamSystem() */
+int lsd_slam_destroy(lsd_slam *s);                 /* fullReset() = destroy + create */
+/* keep finished keyframes alive (upstream: KeyFrameGraph::keyframesAll) -- default 1; 0 frees them for long benches */
+int lsd_slam_set_keep_keyframes(lsd_slam *s, int keep);
+/* SlamSystem::gtDepthInit / randomInit on the first image (nextImage on an empty system = randomInit) */
+int lsd_slam_gt_depth_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st);
+int lsd_slam_random_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
+/* SlamSystem::nextImage: 8-bit grey image as handed over at lib/App/InputThread.cpp:71 */
+int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
+int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm);
+int lsd_slam_counters(lsd_slam *s, int *tracked, int *lost, int *keyframes);
+/* "id,tx,ty,tz,rawtx,rawty,rawtz\n" as written by TextOutputIOWrapper::publishTrackedFrame
+ * (lib/Pangolin_IOWrapper/TextOutputIOWrapper.cpp:100-120) */
+int lsd_slam_pose_line(const lsd_slam_status *st, char *buf, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

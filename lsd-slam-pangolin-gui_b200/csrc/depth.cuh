@@ -54,6 +54,7 @@ struct DepthDesc {
   float R[9], t[3];        // oldToNew
   unsigned *cnt, *offs, *srcPack, *bucket, *cursor;
   float2 *rec;
+  float4 *tgt;  // per TARGET pixel: (new_idepth, new_var, validity) of its rank-0 source
   // setDepth target
   float *frIdepth, *frVar;
   double *sums;  // [4]: sum ids (valid), n valid, sum ids (valid && ids >= -0.05), n
@@ -72,6 +73,7 @@ struct lsd_depthmap {
   int mi, di;  // current copies
   unsigned *cnt, *offs, *srcPack, *bucket, *cursor;
   float2 *rec;
+  float4 *tgt;
   double *sums;
   lsd_frame *activeKeyFrame;
   bool reactivated;

@@ -1,0 +1,255 @@
+// slam.cu -- lock-step tracking + mapping driver over the hot path: the part of [UP]
+// lsd_slam::SlamSystem that the reference application drives, with the semantics it uses when
+// Conf().runRealTime == false -- `system->nextImage(idx, image, camera)` blocks until the frame has been tracked
+// AND mapped (/root/reference/lib/App/InputThread.cpp:70-71).  Host code only: every piece of arithmetic is a call
+// into the C ABI of this library (lsd_frame_create, lsd_se3_track, lsd_depth_update_keyframe, ...).
+//
+//   nextImage      -> first frame: randomInit (or gtDepthInit when depth is supplied);
+//                     otherwise SlamSystem::trackFrame (TrackingReference::importFrame when the keyframe or its depth
+//                     changed, SE3Tracker::trackFrame from the last frame-to-keyframe pose) followed by one
+//                     doMappingIteration: updateKeyframe, or finishCurrentKeyframe + createNewCurrentKeyframe when the
+//                     keyframe-selection score asks for a new one.
+//   status         -> what the reference's output wrappers read per frame: camToWorld (publishPose,
+//                     PangolinOutputIOWrapper / TextOutputIOWrapper.cpp:104-117), thisToParent_raw, keyframe flag.
+// Pose-graph optimisation, loop closure and relocalisation are not here: they stay on the reference's CPU code
+// (BASELINE.json north_star); a lost frame is reported and dropped.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "ctx.cuh"
+#include "lie_dev.cuh"
+
+namespace lsd {
+
+// util/settings.h
+static const float KF_DIST_WEIGHT = 4.0f, KF_USAGE_WEIGHT = 3.0f;
+static const int INITIALIZATION_PHASE_COUNT = 5, MIN_NUM_MAPPED = 5;
+
+static void sim3_identity(double p[8]) {
+  p[0] = p[1] = p[2] = 0; p[3] = 1;
+  p[4] = p[5] = p[6] = 0; p[7] = 1;
+}
+
+// a * b for Sim3 {qx,qy,qz,qw,tx,ty,tz,s}
+static void sim3_mul(const double a[8], const double b[8], double o[8]) {
+  QuatT<double> qa = {a[0], a[1], a[2], a[3]}, qb = {b[0], b[1], b[2], b[3]};
+  QuatT<double> q = qmul(qa, qb);
+  qnormalize(q);
+  double R[9], rt[3];
+  qtoR(qa, R);
+  mat3vec(R, b + 4, rt);
+  o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+  for (int i = 0; i < 3; i++) o[4 + i] = a[4 + i] + a[7] * rt[i];
+  o[7] = a[7] * b[7];
+}
+
+}  // namespace lsd
+
+using namespace lsd;
+
+struct lsd_slam {
+  lsd_ctx *ctx;
+  lsd_depthmap *dm;
+  lsd_frame *kf;       // current keyframe
+  lsd_ref *ref;        // tracking reference of `kf`
+  int refKfId;
+  std::vector<lsd_frame *> keyframes;  // finished keyframes stay alive (upstream keeps them in the KeyFrameGraph)
+  double kfWorld[8];   // camToWorld of the current keyframe
+  double lastToKf[8];  // last tracked frame -> current keyframe
+  int nKeyframes, tracked, lost;
+  float kfMeanIdepth;
+  bool kfMeanValid;
+  int keepFinishedKeyframes;
+};
+
+extern "C" {
+
+int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out) {
+  LSD_ARG(ctx && out);
+  lsd_slam *s = new lsd_slam();
+  s->ctx = ctx;
+  s->dm = nullptr;
+  s->kf = nullptr;
+  s->ref = nullptr;
+  s->refKfId = -1;
+  sim3_identity(s->kfWorld);
+  sim3_identity(s->lastToKf);
+  s->nKeyframes = s->tracked = s->lost = 0;
+  s->kfMeanIdepth = 0;
+  s->kfMeanValid = false;
+  s->keepFinishedKeyframes = 1;
+  int rc = lsd_depthmap_create(ctx, &s->dm);
+  if (rc) { delete s; return rc; }
+  *out = s;
+  return LSD_OK;
+}
+
+int lsd_slam_destroy(lsd_slam *s) {
+  if (!s) return LSD_OK;
+  if (s->ref) lsd_ref_release(s->ctx, s->ref);
+  for (lsd_frame *f : s->keyframes) lsd_frame_release(s->ctx, f);
+  if (s->kf) lsd_frame_release(s->ctx, s->kf);
+  if (s->dm) lsd_depthmap_destroy(s->ctx, s->dm);
+  delete s;
+  return LSD_OK;
+}
+
+int lsd_slam_set_keep_keyframes(lsd_slam *s, int keep) {
+  LSD_ARG(s);
+  s->keepFinishedKeyframes = keep;
+  return LSD_OK;
+}
+
+static void fill_status(lsd_slam *s, int id, int tracked, int isKeyframe, const double toKf[8], const lsd_se3_result *r, float score,
+                        lsd_slam_status *st) {
+  if (!st) return;
+  std::memset(st, 0, sizeof(*st));
+  st->frameId = id;
+  st->tracked = tracked;
+  st->isKeyframe = isKeyframe;
+  st->numKeyframes = s->nKeyframes;
+  st->currentKeyframeId = s->kf ? s->kf->id : -1;
+  st->keyframeScore = score;
+  std::memcpy(st->thisToParent_raw, toKf, sizeof(double) * 8);
+  if (isKeyframe) std::memcpy(st->camToWorld, s->kfWorld, sizeof(double) * 8);
+  else sim3_mul(s->kfWorld, toKf, st->camToWorld);
+  if (r) {
+    st->pointUsage = r->pointUsage;
+    st->lastResidual = r->lastResidual;
+    st->trackingWasGood = r->trackingWasGood;
+    st->diverged = r->diverged;
+  }
+}
+
+static int first_keyframe(lsd_slam *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st) {
+  LSD_ARG(s && image);
+  if (s->kf) { set_error("SlamSystem already initialised (fullReset = destroy + create)"); return LSD_ERR_STATE; }
+  lsd_frame *kf = nullptr;
+  int rc = lsd_frame_create(s->ctx, id, image, pitch, LSD_BUILD_MAXGRAD0 | LSD_BUILD_GRAD0, &kf);
+  if (rc) return rc;
+  if (depth) {  // SlamSystem::gtDepthInit: Frame::setDepthFromGroundTruth + DepthMap::initializeFromGTDepth
+    if ((rc = lsd_frame_set_depth_from_gt(s->ctx, kf, depth, 1.0f))) return rc;
+    if ((rc = lsd_depth_initialize_from_gt(s->ctx, s->dm, kf))) return rc;
+  } else {  // SlamSystem::randomInit
+    if ((rc = lsd_depth_initialize_randomly(s->ctx, s->dm, kf))) return rc;
+  }
+  s->kf = kf;
+  s->nKeyframes = 1;
+  s->kfMeanValid = false;
+  sim3_identity(s->kfWorld);
+  sim3_identity(s->lastToKf);
+  double id8[8];
+  sim3_identity(id8);
+  fill_status(s, id, 1, 1, id8, nullptr, 0.0f, st);
+  return LSD_OK;
+}
+
+int lsd_slam_gt_depth_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st) {
+  LSD_ARG(depth);
+  return first_keyframe(s, id, image, pitch, depth, st);
+}
+
+int lsd_slam_random_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st) {
+  return first_keyframe(s, id, image, pitch, nullptr, st);
+}
+
+int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st) {
+  LSD_ARG(s && image);
+  if (!s->kf) return first_keyframe(s, id, image, pitch, nullptr, st);  // SlamSystem::nextImage: randomInit on the first image
+  lsd_ctx *ctx = s->ctx;
+  int rc;
+  lsd_frame *f = nullptr;
+  if ((rc = lsd_frame_create(ctx, id, image, pitch, LSD_BUILD_MAXGRAD0, &f))) return rc;
+
+  // ---- SlamSystem::trackFrame
+  if (!s->ref || s->refKfId != s->kf->id || s->kf->depthHasBeenUpdatedFlag) {
+    if (s->ref) lsd_ref_release(ctx, s->ref);
+    s->ref = nullptr;
+    if ((rc = lsd_ref_create(ctx, s->kf, &s->ref))) return rc;
+    s->refKfId = s->kf->id;
+    s->kf->depthHasBeenUpdatedFlag = false;
+  }
+  lsd_se3_result res;
+  if ((rc = lsd_se3_track(ctx, s->ref, f, s->lastToKf, &res, nullptr))) return rc;
+  if (res.diverged || !res.trackingWasGood) {  // upstream hands over to the Relocalizer (out of scope): drop the frame
+    s->lost++;
+    lsd_frame_release(ctx, f);
+    fill_status(s, id, 0, 0, s->lastToKf, &res, 0.0f, st);
+    return LSD_OK;
+  }
+  s->tracked++;
+  double toKf[8];
+  std::memcpy(toKf, res.frameToRef, sizeof(double) * 7);
+  toKf[7] = 1.0;
+  std::memcpy(s->lastToKf, toKf, sizeof(toKf));
+
+  // ---- keyframe selection (A.10): distance weighted by the keyframe's mean inverse depth + point usage
+  bool create = false;
+  float score = 0.0f;
+  if (s->kf->numMappedOnThis > MIN_NUM_MAPPED) {
+    if (!s->kfMeanValid) {
+      if ((rc = lsd_frame_mean_idepth(ctx, s->kf, &s->kfMeanIdepth, nullptr))) return rc;
+      s->kfMeanValid = true;
+    }
+    const double m = (double)s->kfMeanIdepth;
+    const double d[3] = {toKf[4] * m, toKf[5] * m, toKf[6] * m};
+    float minVal = std::fmin(0.2f + s->nKeyframes * 0.8f / INITIALIZATION_PHASE_COUNT, 1.0f);
+    if (s->nKeyframes < INITIALIZATION_PHASE_COUNT) minVal *= 0.7f;
+    const double usage = 1.0 - (double)res.pointUsage;
+    score = (float)(KF_DIST_WEIGHT * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) + KF_USAGE_WEIGHT * usage * usage);
+    create = score > minVal;
+  }
+
+  // ---- one blocking mapping iteration
+  if (create) {
+    if ((rc = lsd_depth_finalize_keyframe(ctx, s->dm))) return rc;          // finishCurrentKeyframe
+    if ((rc = lsd_depth_create_keyframe(ctx, s->dm, f, nullptr))) return rc;  // createNewCurrentKeyframe
+    double world[8];
+    sim3_mul(s->kfWorld, f->thisToParent_raw, world);  // thisToParent_raw now carries the rescale factor
+    std::memcpy(s->kfWorld, world, sizeof(world));
+    lsd_ref_release(ctx, s->ref);  // the tracking reference belongs to the finished keyframe
+    s->ref = nullptr;
+    if (s->keepFinishedKeyframes) s->keyframes.push_back(s->kf);
+    else lsd_frame_release(ctx, s->kf);
+    s->kf = f;
+    s->nKeyframes++;
+    s->kfMeanValid = false;
+    sim3_identity(s->lastToKf);
+    fill_status(s, id, 1, 1, f->thisToParent_raw, &res, score, st);
+  } else {
+    const bool setsDepth = !s->kf->depthHasBeenUpdatedFlag;  // updateKeyframe runs setDepth only when the flag is clear
+    if ((rc = lsd_depth_update_keyframe(ctx, s->dm, 1, &f, nullptr))) return rc;
+    if (setsDepth) s->kfMeanValid = false;
+    fill_status(s, id, 1, 0, toKf, &res, score, st);
+    lsd_frame_release(ctx, f);
+  }
+  return LSD_OK;
+}
+
+int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm) {
+  LSD_ARG(s);
+  if (kf) *kf = s->kf;
+  if (dm) *dm = s->dm;
+  return LSD_OK;
+}
+
+int lsd_slam_counters(lsd_slam *s, int *tracked, int *lost, int *keyframes) {
+  LSD_ARG(s);
+  if (tracked) *tracked = s->tracked;
+  if (lost) *lost = s->lost;
+  if (keyframes) *keyframes = s->nKeyframes;
+  return LSD_OK;
+}
+
+// one line of the reference's pose.txt: "id,tx,ty,tz,rawtx,rawty,rawtz\n" with ostream's default float formatting
+// (/root/reference/lib/Pangolin_IOWrapper/TextOutputIOWrapper.cpp:100-120)
+int lsd_slam_pose_line(const lsd_slam_status *st, char *buf, size_t n) {
+  LSD_ARG(st && buf && n > 0);
+  const int k = std::snprintf(buf, n, "%d,%g,%g,%g,%g,%g,%g\n", st->frameId, st->camToWorld[4], st->camToWorld[5], st->camToWorld[6],
+                              st->thisToParent_raw[4], st->thisToParent_raw[5], st->thisToParent_raw[6]);
+  LSD_ARG(k > 0 && (size_t)k < n);
+  return LSD_OK;
+}
+
+}  // extern "C"

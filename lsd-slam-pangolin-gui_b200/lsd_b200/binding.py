@@ -117,6 +117,15 @@ SYMBOLS = {
     "lsd_depth_stage": (_ip, [_vp, _vp, _ip, _ip, _ip, _vp]),
     "lsd_ctx_last_stage_ms": (_ip, [_vp, _vp]),
     "lsd_depth_stage_batch": (_ip, [_vp, _ip, _vp, _ip, _ip, _ip, _vp]),
+    "lsd_slam_create": (_ip, [_vp, _vp]),
+    "lsd_slam_destroy": (_ip, [_vp]),
+    "lsd_slam_set_keep_keyframes": (_ip, [_vp, _ip]),
+    "lsd_slam_gt_depth_init": (_ip, [_vp, _ip, _vp, _sz, _vp, _vp]),
+    "lsd_slam_random_init": (_ip, [_vp, _ip, _vp, _sz, _vp]),
+    "lsd_slam_next_image": (_ip, [_vp, _ip, _vp, _sz, _vp]),
+    "lsd_slam_current_keyframe": (_ip, [_vp, _vp, _vp]),
+    "lsd_slam_counters": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_slam_pose_line": (_ip, [_vp, _vp, _sz]),
     "lsd_default_vbo_params": (_ip, [_vp]),
     "lsd_frame_publish_keyframe": (_ip, [_vp, _vp, _ip, _vp]),
     "lsd_keyframe_compute_vbo": (_ip, [_vp, _vp, _ip, _fp, _vp, _vp, _vp]),
@@ -126,6 +135,13 @@ SYMBOLS = {
 # InputPointDense / Keyframe::MyVertex (/root/reference/lib/Pangolin_IOWrapper/Keyframe.h:16-21,47-51)
 POINT_DTYPE = np.dtype([("idepth", np.float32), ("idepth_var", np.float32), ("color", np.uint8, (4,))])
 VERTEX_DTYPE = np.dtype([("point", np.float32, (3,)), ("color", np.uint8, (4,))])
+
+
+class SlamStatus(C.Structure):
+    _fields_ = [("frameId", C.c_int), ("tracked", C.c_int), ("isKeyframe", C.c_int), ("numKeyframes", C.c_int),
+                ("currentKeyframeId", C.c_int), ("trackingWasGood", C.c_int), ("diverged", C.c_int),
+                ("pointUsage", C.c_float), ("lastResidual", C.c_float), ("keyframeScore", C.c_float),
+                ("camToWorld", C.c_double * 8), ("thisToParent_raw", C.c_double * 8)]
 
 
 class VboParams(C.Structure):
@@ -584,3 +600,50 @@ class Ref:
         idx = np.empty((n,), np.int32)
         _chk(self.ctx.L.lsd_ref_read(self.ctx.p, self.p, level, _ptr(pos), _ptr(grad), _ptr(cv), _ptr(idx)))
         return pos, grad, cv, idx
+
+
+class SlamSystem:
+    """[UP] lsd_slam::SlamSystem, lock-step (runRealTime == false): the native driver in csrc/slam.cu."""
+
+    def __init__(self, ctx: Context, keep_keyframes=True):
+        self.ctx = ctx
+        p = C.c_void_p()
+        _chk(ctx.L.lsd_slam_create(ctx.p, C.byref(p)))
+        self.p = p
+        _chk(ctx.L.lsd_slam_set_keep_keyframes(self.p, int(keep_keyframes)))
+        self.lines = []
+
+    def close(self):
+        if self.p:
+            self.ctx.L.lsd_slam_destroy(self.p)
+            self.p = None
+
+    def _done(self, st):
+        if st.tracked:
+            buf = C.create_string_buffer(256)
+            _chk(self.ctx.L.lsd_slam_pose_line(C.byref(st), buf, 256))
+            self.lines.append(buf.value.decode().rstrip("\n"))
+        return st
+
+    def gtDepthInit(self, image, fid, depth):
+        im = np.ascontiguousarray(image, np.uint8)
+        d = np.ascontiguousarray(depth, np.float32)
+        st = SlamStatus()
+        _chk(self.ctx.L.lsd_slam_gt_depth_init(self.p, int(fid), _ptr(im), im.shape[1], _ptr(d), C.byref(st)))
+        return self._done(st)
+
+    def nextImage(self, image, fid):
+        im = np.ascontiguousarray(image, np.uint8)
+        st = SlamStatus()
+        _chk(self.ctx.L.lsd_slam_next_image(self.p, int(fid), _ptr(im), im.shape[1], C.byref(st)))
+        return self._done(st)
+
+    def counters(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _chk(self.ctx.L.lsd_slam_counters(self.p, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(tracked=a.value, lost=b.value, keyframes=c.value - 1)
+
+    def current_keyframe(self):
+        kf = C.c_void_p()
+        _chk(self.ctx.L.lsd_slam_current_keyframe(self.p, C.byref(kf), None))
+        return Frame(self.ctx, kf, -1)

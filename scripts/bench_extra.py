@@ -252,6 +252,100 @@ def vbo_bench(ctx, lsd, B=64, reps=5, device="cuda", cpu=True):
     return out
 
 
+def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda", cpu=True, K=None):
+    """BASELINE configs[0] / configs[4] shape: lock-step tracking + mapping (lsd_b200/pipeline.py: track every frame, map
+    every frame, keyframe switch by the upstream score) over a synthetic rendered sequence with known trajectory, through
+    the blocking C ABI with HOST images (H2D inside the timed loop).  The CPU leg runs the SAME driver on the oracle port
+    (1 tracking thread + 4 mapping threads = upstream MAPPING_THREADS) over the first `cpu_frames` frames."""
+    from lsd_b200 import synth
+    from lsd_b200.pipeline import DeviceBackend, LockStepSlam
+    K = K or synth.default_K(w, h)
+    room = synth.make_room(0, device=device)
+    traj = synth.trajectory(n_frames, seed=0)
+    frames = []
+    for i, (R, t) in enumerate(traj):
+        img, depth = synth.render(room, w, h, K, R, t, noise_seed=i)
+        frames.append((img.cpu().numpy(), depth.cpu().numpy() if i == 0 else None))
+
+    def run(backend, n):
+        slam = LockStepSlam(backend)
+        slam.first_frame(frames[0][0], 0, frames[0][1])
+        t_kf, n_kf0 = 0.0, 0
+        t0 = time.perf_counter()
+        for i in range(1, n):
+            k0 = slam.stats["keyframes"]
+            t1 = time.perf_counter()
+            slam.next_image(frames[i][0], i)
+            if slam.stats["keyframes"] != k0:
+                t_kf += time.perf_counter() - t1
+        dt = time.perf_counter() - t0
+        return slam, dt, t_kf
+
+    class Native:  # csrc/slam.cu through the LockStepSlam-shaped surface run() needs
+        def __init__(self, ctx):
+            self.s = lsd.SlamSystem(ctx, keep_keyframes=False)
+            self.stats = dict(tracked=0, lost=0, keyframes=0)
+            self.world_poses = []
+
+        def first_frame(self, img, fid, depth):
+            st = self.s.gtDepthInit(img, fid, depth)
+            self.world_poses.append((fid, np.array(st.camToWorld)))
+
+        def next_image(self, img, fid):
+            st = self.s.nextImage(img, fid)
+            if st.tracked:
+                self.world_poses.append((fid, np.array(st.camToWorld)))
+                self.stats["tracked"] += 1
+                self.stats["keyframes"] += st.isKeyframe
+            else:
+                self.stats["lost"] += 1
+
+    def run_native(ctx, n):
+        slam = Native(ctx)
+        slam.first_frame(frames[0][0], 0, frames[0][1])
+        t_kf = 0.0
+        t0 = time.perf_counter()
+        for i in range(1, n):
+            k0 = slam.stats["keyframes"]
+            t1 = time.perf_counter()
+            slam.next_image(frames[i][0], i)
+            if slam.stats["keyframes"] != k0:
+                t_kf += time.perf_counter() - t1
+        dt = time.perf_counter() - t0
+        slam.s.close()
+        return slam, dt, t_kf
+
+    ctx = lsd.Context(w, h, K, device=0)
+    run_native(ctx, min(20, n_frames))  # warm-up (allocations, pools, lazy init)
+    slam, dt, t_kf = run_native(ctx, n_frames)
+    pslam, pdt, _ = run(DeviceBackend(ctx), min(n_frames, 100))  # the Python driver over the same ABI, for reference
+    R0, t0_ = traj[0]
+    gt = np.array([R0.T @ (t - t0_) for _, t in traj])
+    ids = [i for i, _ in slam.world_poses]
+    est = np.array([p[4:7] for _, p in slam.world_poses])
+    ate = float(np.sqrt(np.mean(np.sum((est - gt[ids]) ** 2, axis=1))))
+    out = {"width": w, "height": h, "frames": n_frames, "fps": (n_frames - 1) / dt, "ms_per_frame": 1e3 * dt / (n_frames - 1),
+           "keyframes": slam.stats["keyframes"], "lost": slam.stats["lost"],
+           "ms_per_keyframe_switch_frame": 1e3 * t_kf / max(1, slam.stats["keyframes"]),
+           "ate_rmse_m": ate, "path_m": float(np.linalg.norm(np.diff(gt, axis=0), axis=1).sum()),
+           "h2d_bytes_per_frame": w * h, "driver": "native lock-step driver (csrc/slam.cu: lsd_slam_next_image), blocking, host images",
+           "python_driver_fps": (min(n_frames, 100) - 1) / pdt}
+    ctx.close()
+    if cpu:
+        from oracle import pyoracle as O
+        from oracle_backend import OracleBackend
+        O.build()
+        m = min(cpu_frames, n_frames)
+        oslam, odt, okf = run(OracleBackend(w, h, K, mode=0, threads=4, fast=True), m)
+        both = min(len(oslam.world_poses), len(slam.world_poses), m)
+        dev = float(np.abs(np.array([p[4:7] for _, p in oslam.world_poses[:both]]) - est[:both]).max())
+        out["cpu_port"] = {"fps": (m - 1) / odt, "ms_per_frame": 1e3 * odt / (m - 1), "frames": m, "kind": "port",
+                           "threads": "1 tracking + 4 mapping (upstream MAPPING_THREADS)", "keyframes": oslam.stats["keyframes"],
+                           "max_translation_diff_vs_gpu_m": dev}
+        out["speedup_vs_cpu_port"] = out["fps"] / out["cpu_port"]["fps"]
+    return out
+
+
 def main():
     import torch
 
@@ -271,6 +365,11 @@ def main():
         out["sim3"] = sim3_bench(ctx, lsd_b200, reps=min(reps, 3), cpu=cpu)
     if "vbo" in parts:
         out["vbo"] = vbo_bench(ctx, lsd_b200, B=B, reps=reps, cpu=cpu)
+    nf = int(os.environ.get("EXTRA_FRAMES", "500"))
+    if "pipeline" in parts:
+        out["pipeline_640x480"] = pipeline_bench(lsd_b200, 640, 480, nf, cpu=cpu)
+    if "pipeline_d2" in parts:
+        out["pipeline_1280x960"] = pipeline_bench(lsd_b200, 1280, 960, nf, cpu_frames=20, cpu=cpu, K=synth.d2_K())
     ctx.close()
     print(json.dumps(out), flush=True)
 

@@ -40,7 +40,7 @@ def main():
     specs = [  # name, seed, w, h, K(fx, fy, cx, cy), camToWorld scale
         ("a64x48", 1, 64, 48, (52.5, 52.5, 31.5, 23.5), 1.0),
         ("b64x48_scale7", 2, 64, 48, (52.5, 50.0, 30.0, 25.0), 7.0),   # absTH active: var*depth^4*49 > 0.1
-        ("c160x120", 3, 160, 120, (131.25, 131.25, 79.5, 59.5), 0.5),
+        ("c160x112", 3, 160, 112, (131.25, 131.25, 79.5, 55.5), 0.5),
         ("d48x32_dense", 4, 48, 32, (39.0, 39.0, 23.5, 15.5), 1.3),
     ]
     for name, seed, w, h, K, scale in specs:

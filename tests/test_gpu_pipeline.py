@@ -52,3 +52,35 @@ def test_lockstep_sequence_matches_oracle(lsd, oracle):
     assert err.max() < 0.1 * path, (err.max(), path)  # monocular scale drift over keyframe changes, no pose graph
     assert len(g.lines) == len(ids) and g.lines[5].count(",") == 6  # pose.txt: id,tx,ty,tz,rawtx,rawty,rawtz
     ctx.close()
+
+
+def test_native_slam_driver_equals_python_driver(lsd):
+    """csrc/slam.cu (lsd_slam_next_image = SlamSystem::nextImage, lock-step) issues the same C-ABI calls as the Python
+    driver: same keyframe switches, bit-identical poses, and the reference's pose.txt line format."""
+    w, h = 320, 240
+    K = synth.default_K(w, h)
+    room = synth.make_room(0)
+    traj = synth.trajectory(160, seed=0)[::4]
+    frames = [synth.render(room, w, h, K, R, t, noise_seed=i) for i, (R, t) in enumerate(traj)]
+    ctx = lsd.Context(w, h, K)
+    py = LockStepSlam(DeviceBackend(ctx))
+    py.first_frame(frames[0][0].numpy(), 0, frames[0][1].numpy())
+    for i in range(1, len(frames)):
+        py.next_image(frames[i][0].numpy(), i)
+    nat = lsd.SlamSystem(ctx)
+    sts = [nat.gtDepthInit(frames[0][0].numpy(), 0, frames[0][1].numpy())]
+    for i in range(1, len(frames)):
+        sts.append(nat.nextImage(frames[i][0].numpy(), i))
+    assert nat.counters() == py.stats and py.stats["keyframes"] >= 2
+    assert [s.frameId for s in sts if s.isKeyframe] == py.keyframe_ids
+    got = np.array([list(s.camToWorld) for s in sts if s.tracked])
+    want = np.array([p for _, p in py.world_poses])
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12  # same device results, double-precision pose chaining on both sides
+    assert nat.lines == py.lines
+    assert nat.lines[3].count(",") == 6 and nat.lines[3].split(",")[0] == "3"
+    # the current keyframe is publishable (N2) straight from the driver
+    kf = nat.current_keyframe()
+    assert len(kf.compute_vbo(float(sts[-1].camToWorld[7]))) > 0
+    nat.close()
+    ctx.close()
