@@ -34,6 +34,7 @@ typedef struct lsd_ctx lsd_ctx;           /* one device, one stream, one set of 
 typedef struct lsd_frame lsd_frame;       /* [UP] lsd_slam::Frame -- device-resident pyramids       */
 typedef struct lsd_ref lsd_ref;           /* [UP] lsd_slam::TrackingReference -- per-level points   */
 typedef struct lsd_depthmap lsd_depthmap; /* [UP] lsd_slam::DepthMap -- SoA hypothesis planes       */
+typedef struct lsd_undistorter lsd_undistorter; /* libvideoio::Undistorter -- OpenCV fixed-point remap maps */
 
 enum lsd_status {
   LSD_OK = 0,
@@ -305,6 +306,9 @@ int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out); /* SlamSystem::SlamSystem() *
 int lsd_slam_destroy(lsd_slam *s);                 /* fullReset() = destroy + create */
 /* keep finished keyframes alive (upstream: KeyFrameGraph::keyframesAll) -- default 1; 0 frees them for long benches */
 int lsd_slam_set_keep_keyframes(lsd_slam *s, int keep);
+/* optional: images handed to nextImage are still distorted and go through `und` first (undistort + ingest fused:
+ * lib/App/InputThread.cpp:59-71 in one call); NULL = images are already undistorted */
+int lsd_slam_set_undistorter(lsd_slam *s, lsd_undistorter *und);
 /* SlamSystem::gtDepthInit / randomInit on the first image (nextImage on an empty system = randomInit) */
 int lsd_slam_gt_depth_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st);
 int lsd_slam_random_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
@@ -315,6 +319,28 @@ int lsd_slam_counters(lsd_slam *s, int *tracked, int *lost, int *keyframes);
 /* "id,tx,ty,tz,rawtx,rawty,rawtz\n" as written by TextOutputIOWrapper::publishTrackedFrame
  * (lib/Pangolin_IOWrapper/TextOutputIOWrapper.cpp:100-120) */
 int lsd_slam_pose_line(const lsd_slam_status *st, char *buf, size_t n);
+
+/* ---- undistortion in front of the ingest ------------------------------------------------ */
+/* libvideoio::Undistorter as the reference uses it: created from the calibration file (tools/LSD.cpp:88),
+ * undistorter->undistort(image, imageUndist) per frame (lib/App/InputThread.cpp:61-65).  Its arithmetic is OpenCV's
+ * fixed-point remap: map1 = int16 (x, y) pairs, map2 = uint16 sub-pixel index (fy*32 + fx), as produced by
+ * cv::initUndistortRectifyMap(..., CV_16SC2); output size = the context's width x height. */
+int lsd_undistorter_create_from_maps(lsd_ctx *ctx, int inWidth, int inHeight, const int16_t *map1, const uint16_t *map2,
+                                     lsd_undistorter **out);
+/* builds the maps itself: K = {fx, fy, cx, cy} of the distorted camera, dist = {k1, k2, p1, p2, k3}, Kout = the
+ * undistorted camera (what undistorter->getCamera() returns and the context was created with) */
+int lsd_undistorter_create_opencv(lsd_ctx *ctx, int inWidth, int inHeight, const double K[4], const double dist[5],
+                                  const double Kout[4], lsd_undistorter **out);
+int lsd_undistorter_destroy(lsd_ctx *ctx, lsd_undistorter *u);
+int lsd_undistorter_maps(lsd_ctx *ctx, lsd_undistorter *u, int16_t *map1, uint16_t *map2);
+/* Undistorter::undistort: 8-bit grey in (inWidth x inHeight, pitch in bytes), 8-bit grey out (width x height) */
+int lsd_undistort(lsd_ctx *ctx, lsd_undistorter *u, const uint8_t *image, size_t pitch, uint8_t *undistorted);
+/* undistort + Frame construction without the host round trip; `undistorted` (optional) receives the image the GUI
+ * shows (output->updateLiveImage(imageUndist), InputThread.cpp:78) */
+int lsd_frame_create_undistorted(lsd_ctx *ctx, lsd_undistorter *u, int id, const uint8_t *image, size_t pitch, unsigned flags,
+                                 uint8_t *undistorted, lsd_frame **out);
+int lsd_frame_create_undistorted_batch(lsd_ctx *ctx, lsd_undistorter *u, int n, const int *ids, const uint8_t *const *images,
+                                       size_t pitch, unsigned flags, uint8_t *const *undistorted, lsd_frame **out);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,7 @@ struct lsd_slam {
   float kfMeanIdepth;
   bool kfMeanValid;
   int keepFinishedKeyframes;
+  lsd_undistorter *und;  // optional: images arrive distorted, as at InputThread.cpp:59-62
 };
 
 extern "C" {
@@ -79,6 +80,7 @@ int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out) {
   s->kfMeanIdepth = 0;
   s->kfMeanValid = false;
   s->keepFinishedKeyframes = 1;
+  s->und = nullptr;
   int rc = lsd_depthmap_create(ctx, &s->dm);
   if (rc) { delete s; return rc; }
   *out = s;
@@ -99,6 +101,17 @@ int lsd_slam_set_keep_keyframes(lsd_slam *s, int keep) {
   LSD_ARG(s);
   s->keepFinishedKeyframes = keep;
   return LSD_OK;
+}
+
+int lsd_slam_set_undistorter(lsd_slam *s, lsd_undistorter *und) {
+  LSD_ARG(s);
+  s->und = und;
+  return LSD_OK;
+}
+
+static int slam_new_frame(lsd_slam *s, int id, const uint8_t *image, size_t pitch, unsigned flags, lsd_frame **f) {
+  if (s->und) return lsd_frame_create_undistorted(s->ctx, s->und, id, image, pitch, flags, nullptr, f);
+  return lsd_frame_create(s->ctx, id, image, pitch, flags, f);
 }
 
 static void fill_status(lsd_slam *s, int id, int tracked, int isKeyframe, const double toKf[8], const lsd_se3_result *r, float score,
@@ -126,7 +139,7 @@ static int first_keyframe(lsd_slam *s, int id, const uint8_t *image, size_t pitc
   LSD_ARG(s && image);
   if (s->kf) { set_error("SlamSystem already initialised (fullReset = destroy + create)"); return LSD_ERR_STATE; }
   lsd_frame *kf = nullptr;
-  int rc = lsd_frame_create(s->ctx, id, image, pitch, LSD_BUILD_MAXGRAD0 | LSD_BUILD_GRAD0, &kf);
+  int rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_MAXGRAD0 | LSD_BUILD_GRAD0, &kf);
   if (rc) return rc;
   if (depth) {  // SlamSystem::gtDepthInit: Frame::setDepthFromGroundTruth + DepthMap::initializeFromGTDepth
     if ((rc = lsd_frame_set_depth_from_gt(s->ctx, kf, depth, 1.0f))) return rc;
@@ -160,7 +173,7 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
   lsd_ctx *ctx = s->ctx;
   int rc;
   lsd_frame *f = nullptr;
-  if ((rc = lsd_frame_create(ctx, id, image, pitch, LSD_BUILD_MAXGRAD0, &f))) return rc;
+  if ((rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_MAXGRAD0, &f))) return rc;
 
   // ---- SlamSystem::trackFrame
   if (!s->ref || s->refKfId != s->kf->id || s->kf->depthHasBeenUpdatedFlag) {

@@ -6,9 +6,9 @@ every compute call does (there is no CPU fallback).
 """
 from .binding import (BUILD_GRAD0, BUILD_MAXGRAD0, BUILD_TRACKING, FIELD_GRADIENTS, FIELD_IDEPTH, FIELD_IDEPTHVAR,
                       FIELD_IMAGE, FIELD_MASK, FIELD_MAXGRAD, HYP_DTYPE, LIB_PATH, STAGE_FILL_HOLES, STAGE_OBSERVE, STAGE_PROPAGATE,
-                      STAGE_REGULARIZE, STAGE_SET_DEPTH, SYMBOLS, POINT_DTYPE, VERTEX_DTYPE, VboParams, SlamStatus, SlamSystem, Context, DepthMap, Frame, LsdError, Ref, load)
+                      STAGE_REGULARIZE, STAGE_SET_DEPTH, SYMBOLS, POINT_DTYPE, VERTEX_DTYPE, VboParams, SlamStatus, SlamSystem, Undistorter, Context, DepthMap, Frame, LsdError, Ref, load)
 
 __all__ = ["Context", "Frame", "Ref", "DepthMap", "HYP_DTYPE", "STAGE_OBSERVE", "STAGE_FILL_HOLES", "STAGE_REGULARIZE",
            "STAGE_PROPAGATE", "STAGE_SET_DEPTH", "LsdError", "load", "LIB_PATH", "SYMBOLS", "FIELD_IMAGE", "FIELD_GRADIENTS",
            "FIELD_MAXGRAD", "FIELD_IDEPTH", "FIELD_IDEPTHVAR", "FIELD_MASK", "BUILD_TRACKING", "BUILD_MAXGRAD0",
-           "BUILD_GRAD0", "POINT_DTYPE", "VERTEX_DTYPE", "VboParams", "SlamSystem", "SlamStatus"]
+           "BUILD_GRAD0", "POINT_DTYPE", "VERTEX_DTYPE", "VboParams", "SlamSystem", "SlamStatus", "Undistorter"]

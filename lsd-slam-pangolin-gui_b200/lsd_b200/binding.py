@@ -120,12 +120,20 @@ SYMBOLS = {
     "lsd_slam_create": (_ip, [_vp, _vp]),
     "lsd_slam_destroy": (_ip, [_vp]),
     "lsd_slam_set_keep_keyframes": (_ip, [_vp, _ip]),
+    "lsd_slam_set_undistorter": (_ip, [_vp, _vp]),
     "lsd_slam_gt_depth_init": (_ip, [_vp, _ip, _vp, _sz, _vp, _vp]),
     "lsd_slam_random_init": (_ip, [_vp, _ip, _vp, _sz, _vp]),
     "lsd_slam_next_image": (_ip, [_vp, _ip, _vp, _sz, _vp]),
     "lsd_slam_current_keyframe": (_ip, [_vp, _vp, _vp]),
     "lsd_slam_counters": (_ip, [_vp, _vp, _vp, _vp]),
     "lsd_slam_pose_line": (_ip, [_vp, _vp, _sz]),
+    "lsd_undistorter_create_from_maps": (_ip, [_vp, _ip, _ip, _vp, _vp, _vp]),
+    "lsd_undistorter_create_opencv": (_ip, [_vp, _ip, _ip, _vp, _vp, _vp, _vp]),
+    "lsd_undistorter_destroy": (_ip, [_vp, _vp]),
+    "lsd_undistorter_maps": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_undistort": (_ip, [_vp, _vp, _vp, _sz, _vp]),
+    "lsd_frame_create_undistorted": (_ip, [_vp, _vp, _ip, _vp, _sz, _u, _vp, _vp]),
+    "lsd_frame_create_undistorted_batch": (_ip, [_vp, _vp, _ip, _vp, _vp, _sz, _u, _vp, _vp]),
     "lsd_default_vbo_params": (_ip, [_vp]),
     "lsd_frame_publish_keyframe": (_ip, [_vp, _vp, _ip, _vp]),
     "lsd_keyframe_compute_vbo": (_ip, [_vp, _vp, _ip, _fp, _vp, _vp, _vp]),
@@ -602,6 +610,58 @@ class Ref:
         return pos, grad, cv, idx
 
 
+class Undistorter:
+    """libvideoio::Undistorter (OpenCV fixed-point remap) on the device; output size = the context's size."""
+
+    def __init__(self, ctx: Context, in_w, in_h, maps=None, K=None, dist=None, K_out=None):
+        self.ctx, self.in_w, self.in_h = ctx, in_w, in_h
+        p = C.c_void_p()
+        if maps is not None:
+            m1 = np.ascontiguousarray(maps[0], np.int16)
+            m2 = np.ascontiguousarray(maps[1], np.uint16)
+            assert m1.shape == (ctx.h, ctx.w, 2) and m2.shape == (ctx.h, ctx.w)
+            _chk(ctx.L.lsd_undistorter_create_from_maps(ctx.p, in_w, in_h, _ptr(m1), _ptr(m2), C.byref(p)))
+        else:
+            Kd = np.ascontiguousarray(K, np.float64)
+            dd = np.zeros(5)
+            dd[:len(dist)] = dist
+            Ko = np.ascontiguousarray(K_out if K_out is not None else ctx.K, np.float64)
+            _chk(ctx.L.lsd_undistorter_create_opencv(ctx.p, in_w, in_h, _ptr(Kd), _ptr(dd), _ptr(Ko), C.byref(p)))
+        self.p = p
+
+    def close(self):
+        if self.p:
+            self.ctx.L.lsd_undistorter_destroy(self.ctx.p, self.p)
+            self.p = None
+
+    def maps(self):
+        m1 = np.zeros((self.ctx.h, self.ctx.w, 2), np.int16)
+        m2 = np.zeros((self.ctx.h, self.ctx.w), np.uint16)
+        _chk(self.ctx.L.lsd_undistorter_maps(self.ctx.p, self.p, _ptr(m1), _ptr(m2)))
+        return m1, m2
+
+    def undistort(self, image):
+        im = np.ascontiguousarray(image, np.uint8)
+        assert im.shape == (self.in_h, self.in_w)
+        out = np.zeros((self.ctx.h, self.ctx.w), np.uint8)
+        _chk(self.ctx.L.lsd_undistort(self.ctx.p, self.p, _ptr(im), self.in_w, _ptr(out)))
+        return out
+
+    def create_frames(self, images, ids=None, flags=BUILD_TRACKING, want_undistorted=False):
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        idarr = (C.c_int * n)(*ids) if ids is not None else None
+        outs, up = None, None
+        if want_undistorted:
+            outs = [np.zeros((self.ctx.h, self.ctx.w), np.uint8) for _ in range(n)]
+            up = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        fr = (C.c_void_p * n)()
+        _chk(self.ctx.L.lsd_frame_create_undistorted_batch(self.ctx.p, self.p, n, idarr, ptrs, self.in_w, flags, up, fr))
+        frames = [Frame(self.ctx, fr[i], ids[i] if ids is not None else i) for i in range(n)]
+        return (frames, outs) if want_undistorted else frames
+
+
 class SlamSystem:
     """[UP] lsd_slam::SlamSystem, lock-step (runRealTime == false): the native driver in csrc/slam.cu."""
 
@@ -617,6 +677,9 @@ class SlamSystem:
         if self.p:
             self.ctx.L.lsd_slam_destroy(self.p)
             self.p = None
+
+    def set_undistorter(self, und):
+        _chk(self.ctx.L.lsd_slam_set_undistorter(self.p, und.p if und is not None else None))
 
     def _done(self, st):
         if st.tracked:

@@ -122,6 +122,8 @@ def lib(fast: bool = False):
         ("lsdo_frame_clear_mask", None, [vp]),
         ("lsdo_frame_get_flags", ip, [vp]),
         ("lsdo_set_exact_sums", None, [ip]),
+        ("lsdo_init_undistort_rectify_map", None, [vp, vp, vp, ip, ip, vp, vp]),
+        ("lsdo_remap_u8", None, [vp, ip, ip, C.c_size_t, vp, vp, ip, ip, vp]),
         ("lsdo_publish_keyframe_pack", None, [vp, vp, vp, ip, ip, vp]),
         ("lsdo_compute_vbo", ip, [vp, ip, ip, fp, fp, fp, fp, fp, fp, fp, ip, ip, vp]),
     ]:
@@ -473,3 +475,27 @@ def ref_compute_vbo(points, K, scale=1.0, republish=None):
         n = L.ref_keyframe_update_and_compute_vbo(_ptr(points), _ptr(second), w, h, K[0], K[1], K[2], K[3], scale, _ptr(out))
     assert n >= 0
     return out[:n].copy()
+
+
+# ---- undistortion (oracle/undistort.cpp; pinned on cv2's own output, tests/golden/undistort.npz) ------------------
+def init_undistort_rectify_map(K, dist, K_out, w, h, fast=False):
+    """cv::initUndistortRectifyMap(K, dist, I, K_out, (w, h), CV_16SC2), restated.  K = (fx, fy, cx, cy); dist = (k1, k2, p1, p2[, k3])."""
+    Kd = np.ascontiguousarray(K, np.float64)
+    dd = np.zeros(5)
+    dd[:len(dist)] = dist
+    Ko = np.ascontiguousarray(K_out, np.float64)
+    m1 = np.zeros((h, w, 2), np.int16)
+    m2 = np.zeros((h, w), np.uint16)
+    lib(fast).lsdo_init_undistort_rectify_map(_ptr(Kd), _ptr(dd), _ptr(Ko), w, h, _ptr(m1), _ptr(m2))
+    return m1, m2
+
+
+def remap_u8(src, map1, map2, fast=False):
+    """cv::remap(src, map1, map2, INTER_LINEAR) for 8-bit single-channel images, BORDER_CONSTANT 0, restated."""
+    src = np.ascontiguousarray(src, np.uint8)
+    map1 = np.ascontiguousarray(map1, np.int16)
+    map2 = np.ascontiguousarray(map2, np.uint16)
+    h, w = map2.shape
+    dst = np.zeros((h, w), np.uint8)
+    lib(fast).lsdo_remap_u8(_ptr(src), src.shape[1], src.shape[0], src.shape[1], _ptr(map1), _ptr(map2), w, h, _ptr(dst))
+    return dst

@@ -96,7 +96,7 @@ def test_pipeline_keyframe_publishes(lsd, oracle, synth):
     """End of the hot path: a keyframe whose depth came from DepthMap (setDepth) publishes the same cloud as the oracle's."""
     from common import make_oracle_depth_scene, hyp_from_idepth
     w, h = 320, 240
-    d = make_oracle_depth_scene(3, w, h, n_refs=3)
+    d = make_oracle_depth_scene(3, w, h, n_refs=3, var=1e-4, noise=0.002)  # converged map: passes computeVbo's variance gates
     ctx = lsd.Context(w, h, d["K"])
     kf = ctx.create_frame(d["kf_img"], 1000, flags=lsd.BUILD_MAXGRAD0 | lsd.BUILD_GRAD0)
     dm = ctx.create_depthmap()
@@ -109,7 +109,7 @@ def test_pipeline_keyframe_publishes(lsd, oracle, synth):
     want = oracle.compute_vbo(oracle.publish_keyframe_pack(d["okf"].get(oracle.IDEPTH, 0), d["okf"].get(oracle.IDEPTHVAR, 0),
                                                            d["okf"].get(oracle.IMAGE, 0)), np.array(d["K"], np.float32), 1.0)
     got = kf.compute_vbo(1.0)
-    assert len(want) > 500
+    assert len(want) > 100
     assert got.tobytes() == want.tobytes()
     dm.destroy()
     ctx.close()
