@@ -316,6 +316,9 @@ int lsd_slam_random_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch
 int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
 int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm);
 int lsd_slam_counters(lsd_slam *s, int *tracked, int *lost, int *keyframes);
+/* host wall time accumulated inside nextImage, by stage: {frame ingest, reference import, tracking, updateKeyframe
+ * (incl. keyframe selection), keyframe switch (finalize + createKeyFrame)} */
+int lsd_slam_stage_seconds(lsd_slam *s, double out[5]);
 /* "id,tx,ty,tz,rawtx,rawty,rawtz\n" as written by TextOutputIOWrapper::publishTrackedFrame
  * (lib/Pangolin_IOWrapper/TextOutputIOWrapper.cpp:100-120) */
 int lsd_slam_pose_line(const lsd_slam_status *st, char *buf, size_t n);

@@ -536,7 +536,8 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
     offGrad[l] = off; off = align_up(off + N * sizeof(float2), 256);
   }
   const size_t offNum = off;
-  off += 256;
+  const size_t numBytes = sizeof(int) * (size_t)pointcloud_state_words(ctx);  // numData + look-back state of k_make_pointcloud
+  off += align_up(numBytes, 256);
   ctx->refSlabBytes = off;
   // frames that still need their idepth pyramid
   std::vector<void *> needPyr;
@@ -576,7 +577,7 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
   int rc = upload_ptrs(ctx, tab, st);
   if (rc) return rc;
   void **d = reinterpret_cast<void **>(ctx->d_table);
-  for (int i = 0; i < n; i++) LSD_CUDA(cudaMemsetAsync(out[i]->d_num, 0, sizeof(int) * NL, st));
+  for (int i = 0; i < n; i++) LSD_CUDA(cudaMemsetAsync(out[i]->d_num, 0, numBytes, st));
   launch_make_pointcloud(ctx, reinterpret_cast<uint8_t *const *>(d), reinterpret_cast<uint8_t *const *>(d + n),
                          reinterpret_cast<int *const *>(d + 2 * (size_t)n), n, offPts, offGrad, st);
   LSD_CUDA(cudaStreamSynchronize(st));

@@ -65,6 +65,38 @@ struct FrameLayout {
 
 }  // namespace lsd
 
+
+#ifdef __CUDACC__
+// Decoupled look-back over raster-ordered chunks (single-pass ordered compaction; used by k_make_pointcloud and
+// k_vbo_extract).  state[c] = flag << 30 | count, flag 1 = the chunk's own count, 2 = inclusive prefix; all zero before
+// the launch.  Chunk ids must be handed out by an atomic ticket so that every predecessor is resident.  Called by ALL
+// 32 lanes of one warp with the chunk's own `total`; returns the number of items in the chunks before `chunk`.
+#define LSD_LB_SHIFT 30
+#define LSD_LB_MASK ((1u << LSD_LB_SHIFT) - 1u)
+__device__ __forceinline__ unsigned lookback_exclusive(unsigned *state, unsigned chunk, unsigned total, int lane) {
+  volatile unsigned *vs = state;
+  unsigned excl = 0;
+  if (chunk > 0) {
+    if (lane == 0) vs[chunk] = (1u << LSD_LB_SHIFT) | total;
+    int idx = (int)chunk - 1 - lane;
+    while (true) {
+      unsigned v = idx >= 0 ? vs[idx] : (2u << LSD_LB_SHIFT);
+      while (__any_sync(0xffffffffu, (v >> LSD_LB_SHIFT) == 0u)) v = idx >= 0 ? vs[idx] : (2u << LSD_LB_SHIFT);
+      const unsigned inclMask = __ballot_sync(0xffffffffu, (v >> LSD_LB_SHIFT) == 2u);
+      const int first = inclMask ? __ffs(inclMask) - 1 : 32;  // nearest predecessor that holds an inclusive prefix
+      unsigned c = lane <= first ? (v & LSD_LB_MASK) : 0u;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      excl += c;
+      if (inclMask) break;
+      idx -= 32;
+    }
+  }
+  if (lane == 0) vs[chunk] = (2u << LSD_LB_SHIFT) | (excl + total);
+  return excl;
+}
+#endif
+
 struct lsd_frame {
   int id;
   uint8_t *slab;       // device

@@ -58,6 +58,7 @@ void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t
 void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st);
 
 // trackref.cu
+int pointcloud_state_words(const lsd_ctx *ctx);  // ints behind a reference's counters: numData[NL], pad, look-back state
 void launch_make_pointcloud(lsd_ctx *ctx, uint8_t *const *d_kfSlabs, uint8_t *const *d_refSlabs, int *const *d_nums, int n,
                             const size_t *offPts, const size_t *offGrad, cudaStream_t st);
 

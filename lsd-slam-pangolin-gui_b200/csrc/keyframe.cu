@@ -26,10 +26,7 @@ namespace lsd {
 #define VBO_THREADS 256
 #define VBO_PX_PER_THREAD 4
 #define VBO_CHUNK (VBO_THREADS * VBO_PX_PER_THREAD)
-#define VBO_FLAG_SHIFT 30
-#define VBO_VALUE_MASK ((1u << VBO_FLAG_SHIFT) - 1u)
-#define VBO_AGGREGATE (1u << VBO_FLAG_SHIFT)
-#define VBO_INCLUSIVE (2u << VBO_FLAG_SHIFT)
+#define VBO_VALUE_MASK LSD_LB_MASK
 
 struct VboJob {
   const float *idepth, *var, *img;
@@ -46,9 +43,6 @@ struct VboK {
   int minNearSupport, contractFma;
 };
 
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
-__device__ __forceinline__ void st_volatile_u32(unsigned *p, unsigned v) { *reinterpret_cast<volatile unsigned *>(p) = v; }
-
 __global__ void __launch_bounds__(VBO_THREADS) k_vbo_extract(const VboJob *__restrict__ jobs, const VboK P) {
   __shared__ unsigned s_chunk, s_base;
   __shared__ unsigned s_warp[VBO_THREADS / 32];
@@ -60,63 +54,57 @@ __global__ void __launch_bounds__(VBO_THREADS) k_vbo_extract(const VboJob *__res
   const int N = P.W * P.H;
   const int p0 = (int)chunk * VBO_CHUNK + tid * VBO_PX_PER_THREAD;
 
-  // ---- per-pixel filter (Keyframe.h:95-134) on 4 consecutive pixels of one row
+  // ---- per-pixel filter (Keyframe.h:95-134) on 4 consecutive pixels of one row.  Every load of the thread is issued
+  // up front and unconditionally (one memory round trip per CTA instead of three dependent ones; the kernel is bound by
+  // per-CTA latency, not by bytes): 3 rows of idepth, var, image.
   float depthK[4];
+  float col[4] = {0, 0, 0, 0};
   unsigned keep = 0;
   int y = 0, x0 = 0;
   if (p0 < N) {
     y = p0 / P.W;
     x0 = p0 - y * P.W;
     if (y >= 1 && y < P.H - 1) {
-      const float4 id4 = __ldg(reinterpret_cast<const float4 *>(J.idepth + p0));
-      const float idc[4] = {id4.x, id4.y, id4.z, id4.w};
-      bool any = false;
+      float nb[3][6];  // rows y-1, y, y+1 x columns x0-1 .. x0+4 of idepth
 #pragma unroll
-      for (int j = 0; j < 4; j++) any |= !(idc[j] <= 0) && (x0 + j >= 1) && (x0 + j < P.W - 1);
-      if (any) {
-        const float4 v4 = __ldg(reinterpret_cast<const float4 *>(J.var + p0));
-        const float vc[4] = {v4.x, v4.y, v4.z, v4.w};
-        // rows y-1, y, y+1 x columns x0-1 .. x0+4 of idepth
-        float nb[3][6];
+      for (int r = 0; r < 3; r++) {
+        const float *row = J.idepth + p0 + (r - 1) * P.W;
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(row));
+        nb[r][1] = q.x; nb[r][2] = q.y; nb[r][3] = q.z; nb[r][4] = q.w;
+        nb[r][0] = x0 > 0 ? __ldg(row - 1) : 0.0f;          // unused when x0 == 0 (pixel x = 0 is never emitted)
+        nb[r][5] = x0 + 4 < P.W ? __ldg(row + 4) : 0.0f;    // unused when x0 + 3 == W - 1
+      }
+      const float4 v4 = __ldg(reinterpret_cast<const float4 *>(J.var + p0));
+      const float4 c4 = __ldg(reinterpret_cast<const float4 *>(J.img + p0));
+      const float vc[4] = {v4.x, v4.y, v4.z, v4.w};
+      col[0] = c4.x; col[1] = c4.y; col[2] = c4.z; col[3] = c4.w;
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-          const float *row = J.idepth + p0 + (r - 1) * P.W;
-          if (r != 1) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(row));
-            nb[r][1] = q.x; nb[r][2] = q.y; nb[r][3] = q.z; nb[r][4] = q.w;
-          } else {
-            nb[r][1] = id4.x; nb[r][2] = id4.y; nb[r][3] = id4.z; nb[r][4] = id4.w;
-          }
-          nb[r][0] = x0 > 0 ? __ldg(row - 1) : 0.0f;          // unused when x0 == 0 (pixel x = 0 is never emitted)
-          nb[r][5] = x0 + 4 < P.W ? __ldg(row + 4) : 0.0f;    // unused when x0 + 3 == W - 1
-        }
+      for (int j = 0; j < 4; j++) {
+        const int x = x0 + j;
+        const float idc = nb[1][j + 1];
+        if (x < 1 || x >= P.W - 1) continue;
+        if (idc <= 0) continue;
+        const float depth = 1 / idc;
+        float depth4 = depth * depth;
+        depth4 *= depth4;
+        if (vc[j] * depth4 > P.scaledTH) continue;
+        if (vc[j] * depth4 * J.scale * J.scale > P.absTH) continue;
+        if (P.minNearSupport > 1) {
+          int nearSupport = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int x = x0 + j;
-          if (x < 1 || x >= P.W - 1) continue;
-          if (idc[j] <= 0) continue;
-          const float depth = 1 / idc[j];
-          float depth4 = depth * depth;
-          depth4 *= depth4;
-          if (vc[j] * depth4 > P.scaledTH) continue;
-          if (vc[j] * depth4 * J.scale * J.scale > P.absTH) continue;
-          if (P.minNearSupport > 1) {
-            int nearSupport = 0;
+          for (int dx = 0; dx < 3; dx++)
 #pragma unroll
-            for (int dx = 0; dx < 3; dx++)
-#pragma unroll
-              for (int dy = 0; dy < 3; dy++) {
-                const float nid = nb[dy][j + dx];
-                if (nid > 0) {
-                  const float diff = nid - 1.0f / depth;
-                  if (diff * diff < 2 * vc[j]) nearSupport++;
-                }
+            for (int dy = 0; dy < 3; dy++) {
+              const float nid = nb[dy][j + dx];
+              if (nid > 0) {
+                const float diff = nid - 1.0f / depth;
+                if (diff * diff < 2 * vc[j]) nearSupport++;
               }
-            if (nearSupport < P.minNearSupport) continue;
-          }
-          keep |= 1u << j;
-          depthK[j] = depth;
+            }
+          if (nearSupport < P.minNearSupport) continue;
         }
+        keep |= 1u << j;
+        depthK[j] = depth;
       }
     }
   }
@@ -137,25 +125,8 @@ __global__ void __launch_bounds__(VBO_THREADS) k_vbo_extract(const VboJob *__res
     unsigned total = 0;
 #pragma unroll
     for (int k = 0; k < VBO_THREADS / 32; k++) total += s_warp[k];
-    unsigned excl = 0;
-    if (chunk > 0) {
-      if (lane == 0) st_volatile_u32(J.state + chunk, VBO_AGGREGATE | total);
-      int idx = (int)chunk - 1 - lane;
-      while (true) {
-        unsigned v = idx >= 0 ? ld_volatile_u32(J.state + idx) : VBO_INCLUSIVE;
-        while (__any_sync(0xffffffffu, (v >> VBO_FLAG_SHIFT) == 0u)) v = idx >= 0 ? ld_volatile_u32(J.state + idx) : VBO_INCLUSIVE;
-        const unsigned inclMask = __ballot_sync(0xffffffffu, (v >> VBO_FLAG_SHIFT) == 2u);
-        const int first = inclMask ? __ffs(inclMask) - 1 : 32;  // nearest predecessor holding an inclusive prefix
-        unsigned c = lane <= first ? (v & VBO_VALUE_MASK) : 0u;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        excl += c;
-        if (inclMask) break;
-        idx -= 32;
-      }
-    }
+    const unsigned excl = lookback_exclusive(J.state, chunk, total, lane);
     if (lane == 0) {
-      st_volatile_u32(J.state + chunk, VBO_INCLUSIVE | (excl + total));
       s_base = excl;
       if ((int)chunk == P.nChunks - 1) *J.points = (int)(excl + total);
     }
@@ -166,8 +137,6 @@ __global__ void __launch_bounds__(VBO_THREADS) k_vbo_extract(const VboJob *__res
   if (keep) {
     unsigned o = s_base + (incl - cnt);
     for (int k = 0; k < warp; k++) o += s_warp[k];
-    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(J.img + p0));
-    const float col[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       if (!(keep >> j & 1u)) continue;

@@ -13,6 +13,7 @@
 //                     PangolinOutputIOWrapper / TextOutputIOWrapper.cpp:104-117), thisToParent_raw, keyframe flag.
 // Pose-graph optimisation, loop closure and relocalisation are not here: they stay on the reference's CPU code
 // (BASELINE.json north_star); a lost frame is reported and dropped.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -62,6 +63,7 @@ struct lsd_slam {
   bool kfMeanValid;
   int keepFinishedKeyframes;
   lsd_undistorter *und;  // optional: images arrive distorted, as at InputThread.cpp:59-62
+  double stageSec[5];    // wall time spent in: frame ingest, reference import, tracking, updateKeyframe, keyframe switch
 };
 
 extern "C" {
@@ -81,6 +83,7 @@ int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out) {
   s->kfMeanValid = false;
   s->keepFinishedKeyframes = 1;
   s->und = nullptr;
+  for (double &v : s->stageSec) v = 0;
   int rc = lsd_depthmap_create(ctx, &s->dm);
   if (rc) { delete s; return rc; }
   *out = s;
@@ -173,7 +176,15 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
   lsd_ctx *ctx = s->ctx;
   int rc;
   lsd_frame *f = nullptr;
+  typedef std::chrono::steady_clock clk;
+  clk::time_point t0 = clk::now();
+  auto lap = [&](int k) {
+    const clk::time_point t1 = clk::now();
+    s->stageSec[k] += std::chrono::duration<double>(t1 - t0).count();
+    t0 = t1;
+  };
   if ((rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_MAXGRAD0, &f))) return rc;
+  lap(0);
 
   // ---- SlamSystem::trackFrame
   if (!s->ref || s->refKfId != s->kf->id || s->kf->depthHasBeenUpdatedFlag) {
@@ -183,8 +194,10 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     s->refKfId = s->kf->id;
     s->kf->depthHasBeenUpdatedFlag = false;
   }
+  lap(1);
   lsd_se3_result res;
   if ((rc = lsd_se3_track(ctx, s->ref, f, s->lastToKf, &res, nullptr))) return rc;
+  lap(2);
   if (res.diverged || !res.trackingWasGood) {  // upstream hands over to the Relocalizer (out of scope): drop the frame
     s->lost++;
     lsd_frame_release(ctx, f);
@@ -230,12 +243,14 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     s->kfMeanValid = false;
     sim3_identity(s->lastToKf);
     fill_status(s, id, 1, 1, f->thisToParent_raw, &res, score, st);
+    lap(4);
   } else {
     const bool setsDepth = !s->kf->depthHasBeenUpdatedFlag;  // updateKeyframe runs setDepth only when the flag is clear
     if ((rc = lsd_depth_update_keyframe(ctx, s->dm, 1, &f, nullptr))) return rc;
     if (setsDepth) s->kfMeanValid = false;
     fill_status(s, id, 1, 0, toKf, &res, score, st);
     lsd_frame_release(ctx, f);
+    lap(3);
   }
   return LSD_OK;
 }
@@ -244,6 +259,12 @@ int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm) {
   LSD_ARG(s);
   if (kf) *kf = s->kf;
   if (dm) *dm = s->dm;
+  return LSD_OK;
+}
+
+int lsd_slam_stage_seconds(lsd_slam *s, double out[5]) {
+  LSD_ARG(s && out);
+  for (int i = 0; i < 5; i++) out[i] = s->stageSec[i];
   return LSD_OK;
 }
 

@@ -126,6 +126,7 @@ SYMBOLS = {
     "lsd_slam_next_image": (_ip, [_vp, _ip, _vp, _sz, _vp]),
     "lsd_slam_current_keyframe": (_ip, [_vp, _vp, _vp]),
     "lsd_slam_counters": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_slam_stage_seconds": (_ip, [_vp, _vp]),
     "lsd_slam_pose_line": (_ip, [_vp, _vp, _sz]),
     "lsd_undistorter_create_from_maps": (_ip, [_vp, _ip, _ip, _vp, _vp, _vp]),
     "lsd_undistorter_create_opencv": (_ip, [_vp, _ip, _ip, _vp, _vp, _vp, _vp]),
@@ -705,6 +706,11 @@ class SlamSystem:
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         _chk(self.ctx.L.lsd_slam_counters(self.p, C.byref(a), C.byref(b), C.byref(c)))
         return dict(tracked=a.value, lost=b.value, keyframes=c.value - 1)
+
+    def stage_seconds(self):
+        out = np.zeros(5)
+        _chk(self.ctx.L.lsd_slam_stage_seconds(self.p, _ptr(out)))
+        return dict(zip(("ingest", "import_reference", "track", "update_keyframe", "keyframe_switch"), out.tolist()))
 
     def current_keyframe(self):
         kf = C.c_void_p()

@@ -312,6 +312,7 @@ def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda"
             if slam.stats["keyframes"] != k0:
                 t_kf += time.perf_counter() - t1
         dt = time.perf_counter() - t0
+        slam.stage_seconds = slam.s.stage_seconds()
         slam.s.close()
         return slam, dt, t_kf
 
@@ -329,7 +330,8 @@ def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda"
            "ms_per_keyframe_switch_frame": 1e3 * t_kf / max(1, slam.stats["keyframes"]),
            "ate_rmse_m": ate, "path_m": float(np.linalg.norm(np.diff(gt, axis=0), axis=1).sum()),
            "h2d_bytes_per_frame": w * h, "driver": "native lock-step driver (csrc/slam.cu: lsd_slam_next_image), blocking, host images",
-           "python_driver_fps": (min(n_frames, 100) - 1) / pdt}
+           "python_driver_fps": (min(n_frames, 100) - 1) / pdt,
+           "stage_ms_per_frame": {k: 1e3 * v / (n_frames - 1) for k, v in slam.stage_seconds.items()}}
     ctx.close()
     if cpu:
         from oracle import pyoracle as O
