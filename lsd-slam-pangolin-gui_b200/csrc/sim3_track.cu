@@ -6,10 +6,10 @@
 // calcSim3Buffers (12 SoA buffers) -> calcSim3WeightsAndResidual -> calcSim3LGS (LGS6 + LGS4 -> LGS7), with
 // the 7x7 LDLT and the fp64 Sim3 exponential on the host in between.
 //
-// B200 structure: ONE THREAD-BLOCK CLUSTER (8 CTAs x 256 threads) PER TRACK, the whole coarse-to-fine LM
-// loop on device.  Every evaluation is cut into 8 contiguous parts, one per CTA of the cluster; each CTA
+// B200 structure: ONE THREAD-BLOCK CLUSTER (S3_CL = 4 CTAs x 256 threads) PER TRACK, the whole coarse-to-fine LM
+// loop on device.  Every evaluation is cut into S3_CL contiguous parts, one per CTA of the cluster; each CTA
 // fuses the three reference passes per point (no buffers are materialised), reduces its 41 normal-equation
-// terms + residual sums in a fixed order, and CTA 0 gathers the 8 partials over distributed shared memory
+// terms + residual sums in a fixed order, and CTA 0 gathers the S3_CL partials over distributed shared memory
 // in rank order, runs accept / reject, the 7x7 LDL^T solve and the fp64 Sim3 exponential, and broadcasts the
 // next pose into every CTA's shared memory.  Two cluster barriers per evaluation, no global-memory round
 // trip, no host involvement, bit-reproducible (the decomposition never depends on the batch).
@@ -27,7 +27,11 @@ namespace cg = cooperative_groups;
 namespace lsd {
 
 #define S3_THREADS 256
-#define S3_CL 8
+// CTAs per cluster = per track.  Measured on B200 (64 candidates x 2 directions, levels 4->1): 8 CTAs 2.96 ms, 4 CTAs
+// 2.70 ms, 2 CTAs 3.22 ms, 1 CTA 6.2 ms (profiles/r01j_sim3_cluster_sweep.txt)
+#ifndef S3_CL
+#define S3_CL 4
+#endif
 // resident CTAs per SM the register allocation is capped for (221 registers uncapped = ONE 256-thread CTA per SM, i.e.
 // 18 clusters on the whole GPU; the cap trades a few spills in the single-thread LM step for 2-4x the clusters in flight)
 #ifndef S3_MINB

@@ -25,6 +25,12 @@ int main() {
     ref.importFrame(&kf);
     SE3Tracker tracker(ctx);
     const SE3 pose = tracker.trackFrame(&ref, &fr, SE3());
+    std::vector<lsd_vertex> vbo(w * h);
+    const int points = KeyframePublisher::computeVbo(ctx, kf, 0, 1.0f, vbo.data());
+    SlamSystem slam(ctx);
+    slam.gtDepthInit(0, a.data(), w, depth.data());
+    slam.nextImage(1, b.data(), w);
+    std::printf("vbo points = %d  pose line: %s", points, slam.poseLine().c_str());
     std::printf("tracked: t = %g %g %g  good = %g  diverged = %d\n", pose.d[4], pose.d[5], pose.d[6], tracker.lastGoodCount, (int)tracker.diverged);
   } catch (const Error &e) {
     std::printf("no device (%s)\n", e.what());

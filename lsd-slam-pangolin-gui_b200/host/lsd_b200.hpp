@@ -273,4 +273,67 @@ class DepthMap {
   lsd_depthmap *d_ = nullptr;
 };
 
+// libvideoio::Undistorter as used at tools/LSD.cpp:88 / lib/App/InputThread.cpp:62 (OpenCV fixed-point remap maps)
+class Undistorter {
+ public:
+  // maps as an OpenCV undistorter holds them: map1 CV_16SC2 (x, y), map2 CV_16UC1 (sub-pixel table index)
+  Undistorter(Context &ctx, int inWidth, int inHeight, const int16_t *map1, const uint16_t *map2) : ctx_(ctx) {
+    check(lsd_undistorter_create_from_maps(ctx.c(), inWidth, inHeight, map1, map2, &u_));
+  }
+  // K = {fx, fy, cx, cy} of the distorted camera, dist = {k1, k2, p1, p2, k3}, Kout = getCamera() of the output
+  Undistorter(Context &ctx, int inWidth, int inHeight, const double K[4], const double dist[5], const double Kout[4]) : ctx_(ctx) {
+    check(lsd_undistorter_create_opencv(ctx.c(), inWidth, inHeight, K, dist, Kout, &u_));
+  }
+  ~Undistorter() { lsd_undistorter_destroy(ctx_.c(), u_); }
+  Undistorter(const Undistorter &) = delete;
+  Undistorter &operator=(const Undistorter &) = delete;
+  // void undistort(const cv::Mat &image, cv::OutputArray result): 8-bit grey in / out
+  void undistort(const unsigned char *image, size_t pitch, unsigned char *result) { check(lsd_undistort(ctx_.c(), u_, image, pitch, result)); }
+  lsd_undistorter *handle() const { return u_; }
+
+ private:
+  Context &ctx_;
+  lsd_undistorter *u_ = nullptr;
+};
+
+// lib/Pangolin_IOWrapper/Keyframe.h: the two loops that touch every pixel of a published keyframe
+struct KeyframePublisher {
+  // PangolinOutputIOWrapper::publishKeyframe (PangolinOutputIOWrapper.cpp:69-89): fills Keyframe::pointData
+  static void pack(Context &ctx, Frame &f, int publishLvl, unsigned char *pointData) {
+    check(lsd_frame_publish_keyframe(ctx.c(), f.handle(), publishLvl, reinterpret_cast<lsd_input_point_dense *>(pointData)));
+  }
+  // Keyframe::computeVbo (Keyframe.h:66-158): fills the MyVertex buffer handed to glBufferData; returns `points`
+  static int computeVbo(Context &ctx, Frame &f, int publishLvl, float camToWorldScale, lsd_vertex *vertices) {
+    int points = 0;
+    check(lsd_keyframe_compute_vbo(ctx.c(), f.handle(), publishLvl, camToWorldScale, nullptr, vertices, &points));
+    return points;
+  }
+};
+
+// [UP] lsd_slam::SlamSystem, lock-step (Conf().runRealTime == false): tools/LSD.cpp:102, lib/App/InputThread.cpp:71
+class SlamSystem {
+ public:
+  explicit SlamSystem(Context &ctx) : ctx_(ctx) { check(lsd_slam_create(ctx.c(), &s_)); }
+  ~SlamSystem() { lsd_slam_destroy(s_); }
+  SlamSystem(const SlamSystem &) = delete;
+  SlamSystem &operator=(const SlamSystem &) = delete;
+  void setUndistorter(Undistorter *u) { check(lsd_slam_set_undistorter(s_, u ? u->handle() : nullptr)); }
+  void gtDepthInit(int id, const unsigned char *image, size_t pitch, const float *depth) { check(lsd_slam_gt_depth_init(s_, id, image, pitch, depth, &last)); }
+  void randomInit(int id, const unsigned char *image, size_t pitch) { check(lsd_slam_random_init(s_, id, image, pitch, &last)); }
+  // void nextImage(unsigned int id, const cv::Mat &img, const Camera &cam): returns after tracking AND mapping
+  void nextImage(int id, const unsigned char *image, size_t pitch) { check(lsd_slam_next_image(s_, id, image, pitch, &last)); }
+  // SlamSystem* fullReset(): a fresh system on the same context (lib/App/InputThread.cpp:86)
+  SlamSystem *fullReset() { return new SlamSystem(ctx_); }
+  std::string poseLine() const {  // TextOutputIOWrapper::publishTrackedFrame's line
+    char buf[256];
+    check(lsd_slam_pose_line(&last, buf, sizeof(buf)));
+    return buf;
+  }
+  lsd_slam_status last = lsd_slam_status();
+
+ private:
+  Context &ctx_;
+  lsd_slam *s_ = nullptr;
+};
+
 }  // namespace lsd_b200
