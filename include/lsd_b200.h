@@ -301,6 +301,7 @@ typedef struct lsd_slam_status {
   float pointUsage, lastResidual, keyframeScore;
   double camToWorld[8];       /* Frame::getCamToWorld(): what publishPose / pose.txt columns 2-4 carry */
   double thisToParent_raw[8]; /* frame -> keyframe (pose.txt columns 5-7)                              */
+  double keyframeRescale;     /* isKeyframe: the mean-idepth rescale createKeyFrame folded into the new keyframe's pose */
 } lsd_slam_status;
 int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out); /* SlamSystem::SlamSystem() */
 int lsd_slam_destroy(lsd_slam *s);                 /* fullReset() = destroy + create */

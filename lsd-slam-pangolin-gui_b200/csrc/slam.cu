@@ -128,8 +128,8 @@ static void fill_status(lsd_slam *s, int id, int tracked, int isKeyframe, const 
   st->currentKeyframeId = s->kf ? s->kf->id : -1;
   st->keyframeScore = score;
   std::memcpy(st->thisToParent_raw, toKf, sizeof(double) * 8);
-  if (isKeyframe) std::memcpy(st->camToWorld, s->kfWorld, sizeof(double) * 8);
-  else sim3_mul(s->kfWorld, toKf, st->camToWorld);
+  sim3_mul(s->kfWorld, toKf, st->camToWorld);
+  st->keyframeRescale = 1.0;
   if (r) {
     st->pointUsage = r->pointUsage;
     st->lastResidual = r->lastResidual;
@@ -229,6 +229,9 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
 
   // ---- one blocking mapping iteration
   if (create) {
+    // the frame is published with the pose it was tracked at (keyframe pose * frame-to-keyframe, scale 1): upstream's
+    // publishTrackedFrame runs before the mapping thread promotes the frame and folds the rescale factor in
+    fill_status(s, id, 1, 1, toKf, &res, score, st);
     if ((rc = lsd_depth_finalize_keyframe(ctx, s->dm))) return rc;          // finishCurrentKeyframe
     if ((rc = lsd_depth_create_keyframe(ctx, s->dm, f, nullptr))) return rc;  // createNewCurrentKeyframe
     double world[8];
@@ -242,7 +245,11 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     s->nKeyframes++;
     s->kfMeanValid = false;
     sim3_identity(s->lastToKf);
-    fill_status(s, id, 1, 1, f->thisToParent_raw, &res, score, st);
+    if (st) {
+      st->numKeyframes = s->nKeyframes;
+      st->currentKeyframeId = s->kf->id;
+      st->keyframeRescale = f->thisToParent_raw[7];
+    }
     lap(4);
   } else {
     const bool setsDepth = !s->kf->depthHasBeenUpdatedFlag;  // updateKeyframe runs setDepth only when the flag is clear

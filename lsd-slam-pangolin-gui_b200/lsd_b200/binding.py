@@ -150,7 +150,7 @@ class SlamStatus(C.Structure):
     _fields_ = [("frameId", C.c_int), ("tracked", C.c_int), ("isKeyframe", C.c_int), ("numKeyframes", C.c_int),
                 ("currentKeyframeId", C.c_int), ("trackingWasGood", C.c_int), ("diverged", C.c_int),
                 ("pointUsage", C.c_float), ("lastResidual", C.c_float), ("keyframeScore", C.c_float),
-                ("camToWorld", C.c_double * 8), ("thisToParent_raw", C.c_double * 8)]
+                ("camToWorld", C.c_double * 8), ("thisToParent_raw", C.c_double * 8), ("keyframeRescale", C.c_double)]
 
 
 class VboParams(C.Structure):

@@ -252,7 +252,7 @@ def vbo_bench(ctx, lsd, B=64, reps=5, device="cuda", cpu=True):
     return out
 
 
-def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda", cpu=True, K=None):
+def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda", cpu=True, K=None, contrast=60.0):
     """BASELINE configs[0] / configs[4] shape: lock-step tracking + mapping (lsd_b200/pipeline.py: track every frame, map
     every frame, keyframe switch by the upstream score) over a synthetic rendered sequence with known trajectory, through
     the blocking C ABI with HOST images (H2D inside the timed loop).  The CPU leg runs the SAME driver on the oracle port
@@ -260,7 +260,7 @@ def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda"
     from lsd_b200 import synth
     from lsd_b200.pipeline import DeviceBackend, LockStepSlam
     K = K or synth.default_K(w, h)
-    room = synth.make_room(0, device=device)
+    room = synth.make_room(0, device=device, contrast=contrast)
     traj = synth.trajectory(n_frames, seed=0)
     frames = []
     for i, (R, t) in enumerate(traj):
@@ -325,7 +325,7 @@ def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda"
     ids = [i for i, _ in slam.world_poses]
     est = np.array([p[4:7] for _, p in slam.world_poses])
     ate = float(np.sqrt(np.mean(np.sum((est - gt[ids]) ** 2, axis=1))))
-    out = {"width": w, "height": h, "frames": n_frames, "fps": (n_frames - 1) / dt, "ms_per_frame": 1e3 * dt / (n_frames - 1),
+    out = {"width": w, "height": h, "texture_contrast": contrast, "frames": n_frames, "fps": (n_frames - 1) / dt, "ms_per_frame": 1e3 * dt / (n_frames - 1),
            "keyframes": slam.stats["keyframes"], "lost": slam.stats["lost"],
            "ms_per_keyframe_switch_frame": 1e3 * t_kf / max(1, slam.stats["keyframes"]),
            "ate_rmse_m": ate, "path_m": float(np.linalg.norm(np.diff(gt, axis=0), axis=1).sum()),
@@ -367,11 +367,13 @@ def main():
         out["sim3"] = sim3_bench(ctx, lsd_b200, reps=min(reps, 3), cpu=cpu)
     if "vbo" in parts:
         out["vbo"] = vbo_bench(ctx, lsd_b200, B=B, reps=reps, cpu=cpu)
+    from lsd_b200 import synth
     nf = int(os.environ.get("EXTRA_FRAMES", "500"))
     if "pipeline" in parts:
         out["pipeline_640x480"] = pipeline_bench(lsd_b200, 640, 480, nf, cpu=cpu)
     if "pipeline_d2" in parts:
-        out["pipeline_1280x960"] = pipeline_bench(lsd_b200, 1280, 960, nf, cpu_frames=20, cpu=cpu, K=synth.d2_K())
+        out["pipeline_1280x960"] = pipeline_bench(lsd_b200, 1280, 960, nf, cpu_frames=20, cpu=cpu, K=synth.d2_K(),
+                                                   contrast=130.0)  # same wall texture seen at twice the resolution: per-pixel gradients halve, so the contrast is raised to keep ~the same semi-dense density
     ctx.close()
     print(json.dumps(out), flush=True)
 
