@@ -100,6 +100,12 @@ int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
 /* scheduling knob of the persistent tracker: 4096-point records per work item (0 = automatic).  Never
  * changes a result (the summation order is fixed by the records), only latency vs throughput. */
 int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
+/* Points per partial record of the SE3 tracker (0 = default 4096; multiple of 128).  A record is reduced by one CTA and
+ * records are summed in order, so this value DEFINES the fp32 summation order: for a given value results are
+ * bit-identical for every batch size and scheduling; between values they differ by reassociation only.  Large records
+ * maximise batch throughput; a context that tracks ONE live sequence (SlamSystem's tracking thread) wants small records
+ * (1024): an evaluation then spreads over 4x the CTAs (measured: 0.51 -> 0.38 ms per tracked frame, batch 4.2 -> 6.1 ms). */
+int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points);
 /* pairs in flight inside one lsd_se3_track_batch launch (0 = default): bounds the working set to what L2 holds.
  * Scheduling only: results are bit-identical for every value. */
 int lsd_ctx_set_se3_active_pairs(lsd_ctx *ctx, int pairs);

@@ -216,6 +216,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   lsd_default_tracker_settings(&ctx->se3);
   lsd_default_tracker_settings(&ctx->sim3);
   ctx->se3RecsPerItem = 0;
+  ctx->se3RecordPoints = 0;
   ctx->se3ActivePairs = 0;
   ctx->refSlabBytes = 0;
   ctx->h_stage = ctx->d_stage = nullptr;
@@ -269,6 +270,14 @@ int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s) {
 int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records) {
   LSD_ARG(ctx && records >= 0 && records <= 64);
   ctx->se3RecsPerItem = records;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points) {
+  LSD_ARG(ctx);
+  LSD_ARG(points == 0 || (points >= 128 && points % 128 == 0 && points <= (1 << 20)));
+  LSD_ARG(points == 0 || (ctx->K.w[1] * ctx->K.h[1] + points - 1) / points <= 4096);  // work-item codes carry 12 bits of record index
+  ctx->se3RecordPoints = points;
   return LSD_OK;
 }
 

@@ -19,6 +19,7 @@ struct lsd_ctx {
   lsd_tracker_settings se3, sim3;
   int se3ActivePairs;  // 0: default; pairs in flight inside the persistent tracker (L2 residency)
   int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
+  int se3RecordPoints; // 0: default (4096); points per partial record = the summation order of the SE3 tracker
   // pools
   std::vector<uint8_t *> frameSlabPool;
   std::vector<uint8_t *> refSlabPool;

@@ -126,6 +126,7 @@ struct SE3Params {
   int maxChunks;           // per-pair stride of the partial records (records of the largest tracked level)
   int recsPerItem;         // records per work item: scheduling granularity only, never changes a result
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
+  int recPoints;           // points per partial record (lsd_ctx_set_se3_record_points; default SE3_REC)
 };
 
 // gpu-scope acquire-release fetch-add: releases this CTA's record stores (ordered before it by the CTA barrier)
@@ -191,7 +192,7 @@ __device__ int start_level(const SE3Pair *P, SE3State *S, int level, const SE3Pa
     mark_diverged(S);
     return 0;
   }
-  const int nRecs = (P->n[level] + SE3_REC - 1) / SE3_REC;
+  const int nRecs = (P->n[level] + prm.recPoints - 1) / prm.recPoints;
   S->nChunks = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;  // work items of this evaluation
   S->done = 0;
   return S->nChunks;
@@ -622,7 +623,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
     for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
     for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-    const int nRecs = (n + SE3_REC - 1) / SE3_REC;
+    const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
     const int rec0 = chunk * prm.recsPerItem, rec1 = min(nRecs, rec0 + prm.recsPerItem);
     for (int rec = rec0; rec < rec1; rec++) {
       if (rec > rec0) {
@@ -631,8 +632,8 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
 #pragma unroll
         for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
       }
-      const int begin = rec * SE3_REC;
-      const int end = min(n, begin + SE3_REC);
+      const int begin = rec * prm.recPoints;
+      const int end = min(n, begin + prm.recPoints);
       eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
       float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
       block_reduce_store(acc, dacc, dst, sm);
@@ -749,8 +750,10 @@ void se3_scratch_free(lsd_ctx *ctx) {
 static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
   if (!ctx->se3s) ctx->se3s = new SE3Scratch();
   SE3Scratch *s = ctx->se3s;
-  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + SE3_REC - 1) / SE3_REC;
-  if (n > s->cap) {
+  const int recPoints = ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
+  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + recPoints - 1) / recPoints;
+  if (n > s->cap || maxChunks != s->maxChunks) {
+    if (n < s->cap) n = s->cap;
     cudaFree(s->d_pairs);
     cudaFreeHost(s->h_pairs);
     cudaFree(s->d_states);
@@ -803,6 +806,7 @@ static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   prm.recsPerItem = ctx->se3RecsPerItem > 0 ? ctx->se3RecsPerItem : 1;
   prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
   prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
+  prm.recPoints = ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
   return prm;
 }
 
@@ -986,8 +990,8 @@ k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, f
   for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
   for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-  const int begin = blockIdx.x * SE3_REC;
-  const int end = min(n, begin + SE3_REC);
+  const int begin = blockIdx.x * prm.recPoints;
+  const int end = min(n, begin + prm.recPoints);
   eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
   block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sm);
 }
@@ -1030,7 +1034,7 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   LSD_CUDA(cudaStreamSynchronize(st));
   float tot[SE3_NF] = {0};
   double dtot[SE3_ND] = {0};
-  const int nch = (hnum[level] + SE3_REC - 1) / SE3_REC;
+  const int nch = (hnum[level] + prm.recPoints - 1) / prm.recPoints;
   for (int cidx = 0; cidx < nch; cidx++) {
     for (int j = 0; j < SE3_ND; j++) dtot[j] += reinterpret_cast<const double *>(&h[(size_t)cidx * SE3_NRED])[j];
     for (int j = 0; j < SE3_NF; j++) tot[j] += h[(size_t)cidx * SE3_NRED + 2 * SE3_ND + j];

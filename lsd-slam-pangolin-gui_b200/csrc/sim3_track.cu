@@ -258,7 +258,7 @@ __device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, cons
 // point that will be evaluated NEXT by this thread, so that its loads hit L2/L1 instead of paying an HBM round trip in
 // the middle of a ~300-instruction dependency chain.  Prefetches have no architectural effect: results are unchanged.
 #ifndef S3_PREFETCH
-#define S3_PREFETCH 1
+#define S3_PREFETCH 0  // measured: 2.91 ms with, 2.70 ms without (profiles/r01l_sweep.txt) -- kept for reference, off
 #endif
 __device__ __forceinline__ void s3_prefetch(const float4 raw, const S3Cmd &c, const Sim3Params &prm, int W, int H,
                                             const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR) {

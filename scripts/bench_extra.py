@@ -317,6 +317,8 @@ def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda"
         return slam, dt, t_kf
 
     ctx = lsd.Context(w, h, K, device=0)
+    rec = int(os.environ.get("EXTRA_SE3_RECORD", "1024"))
+    ctx.set_se3_record_points(rec)  # a context that tracks one live sequence: small records (include/lsd_b200.h)
     run_native(ctx, min(20, n_frames))  # warm-up (allocations, pools, lazy init)
     slam, dt, t_kf = run_native(ctx, n_frames)
     pslam, pdt, _ = run(DeviceBackend(ctx), min(n_frames, 100))  # the Python driver over the same ABI, for reference
@@ -329,7 +331,7 @@ def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda"
            "keyframes": slam.stats["keyframes"], "lost": slam.stats["lost"],
            "ms_per_keyframe_switch_frame": 1e3 * t_kf / max(1, slam.stats["keyframes"]),
            "ate_rmse_m": ate, "path_m": float(np.linalg.norm(np.diff(gt, axis=0), axis=1).sum()),
-           "h2d_bytes_per_frame": w * h, "driver": "native lock-step driver (csrc/slam.cu: lsd_slam_next_image), blocking, host images",
+           "h2d_bytes_per_frame": w * h, "se3_record_points": rec, "driver": "native lock-step driver (csrc/slam.cu: lsd_slam_next_image), blocking, host images",
            "python_driver_fps": (min(n_frames, 100) - 1) / pdt,
            "stage_ms_per_frame": {k: 1e3 * v / (n_frames - 1) for k, v in slam.stage_seconds.items()}}
     ctx.close()

@@ -146,6 +146,23 @@ def test_batch_equals_single_and_is_deterministic(lsd, oracle):
         assert np.array_equal(np.array(rs.frameToRef), p1[i]), "batch result must not depend on batch composition"
         ores, _ = oracle.se3_track(ds[i]["oref"], ds[i]["ofr"], inits[i], 2)
         assert np.linalg.norm(p1[i][4:] - np.array(ores.frameToRef)[4:]) <= POSE_TOL
+    # Record size is the one knob that DEFINES the summation order (lsd_ctx_set_se3_record_points): for each value the
+    # result is again independent of batch composition / scheduling, and it stays within the pose tolerance of the oracle.
+    for pts in (1024, 256):
+        ctx.set_se3_record_points(pts)
+        rb = ctx.se3_track_batch(refs, frs, inits)
+        pb = np.array([list(r.frameToRef) for r in rb])
+        ctx.set_se3_work_item_records(4)
+        assert np.array_equal(np.array([list(r.frameToRef) for r in ctx.se3_track_batch(refs, frs, inits)]), pb)
+        ctx.set_se3_work_item_records(0)
+        for i in range(6):
+            assert np.array_equal(np.array(ctx.se3_track(refs[i], frs[i], inits[i]).frameToRef), pb[i])
+            ores, _ = oracle.se3_track(ds[i]["oref"], ds[i]["ofr"], inits[i], 2)
+            assert np.linalg.norm(pb[i][4:] - np.array(ores.frameToRef)[4:]) <= POSE_TOL
+    ctx.set_se3_record_points(0)
+    assert np.array_equal(np.array([list(r.frameToRef) for r in ctx.se3_track_batch(refs, frs, inits)]), p1)
+    with pytest.raises(lsd.LsdError):
+        ctx.set_se3_record_points(100)
     ctx.close()
 
 
