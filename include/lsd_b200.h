@@ -159,6 +159,19 @@ int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *co
 /* host images in, poses out: ingest (H2D + pyramids) and tracking pipelined over two streams */
 int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const uint8_t *const *images, size_t pitch,
                                const double *init_frameToRef, lsd_se3_result *results);
+/* [UP] SE3Tracker::trackFrameOnPermaref(reference, frame, referenceToFrame): the quick single-level test track
+ * (QUICK_KF_CHECK_LVL = 4) the constraint search and the Relocalizer run against a keyframe's permanent reference,
+ * n candidates in ONE launch.  init and results[i].frameToRef both hold referenceToFrame
+ * (upstream returns it un-inverted); the frames, their masks and the keyframes' counters are left untouched.
+ * Settings: the "test track" members of DenseDepthTrackerSettings (lsd_default_permaref_settings). */
+int lsd_default_permaref_settings(lsd_tracker_settings *s);
+int lsd_ctx_set_permaref_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
+int lsd_se3_track_permaref_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames,
+                                 const double *init_refToFrame /* n*7 */, lsd_se3_result *results,
+                                 lsd_trace_entry *traces /* n*LSD_TRACE_CAP or NULL */);
+/* [UP] SE3Tracker::checkPermaRefOverlap: mean min(1, z_ref / z') over the level-4 points that land inside the image */
+int lsd_se3_check_permaref_overlap_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const double *refToFrame /* n*7 */,
+                                         float *pointUsage /* n */);
 /* one fused LM evaluation (calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate)
  * at a fixed pose; A36/b6 as after NormalEquationsLeastSquares::finish(); scalars[12] =
  * {error, meanSqRes, bufSize, good, bad, pointUsage, meanRes, a_lastIt, b_lastIt, lsError, 0, 0} */

@@ -176,6 +176,20 @@ int lsd_default_tracker_settings(lsd_tracker_settings *s) {
   return LSD_OK;
 }
 
+// the "test track" members of [UP] DenseDepthTrackerSettings: maxItsTestTrack 5, stepSizeMinTestTrack 1e-3,
+// convergenceEpsTestTrack 0.98, lambdaInitialTestTrack 0 -- installed at every level (only QUICK_KF_CHECK_LVL is used)
+int lsd_default_permaref_settings(lsd_tracker_settings *s) {
+  int rc = lsd_default_tracker_settings(s);
+  if (rc) return rc;
+  for (int l = 0; l < NL; l++) {
+    s->stepSizeMin[l] = 1e-3f;
+    s->convergenceEps[l] = 0.98f;
+    s->maxItsPerLvl[l] = 5;
+    s->lambdaInitial[l] = 0;
+  }
+  return LSD_OK;
+}
+
 int lsd_ctx_create(int device, int width, int height, const float K[4], void *stream, lsd_ctx **out) {
   LSD_ARG(out && K);
   LSD_ARG(width > 0 && height > 0 && width % 16 == 0 && height % 16 == 0);
@@ -215,6 +229,8 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->launches = 0;
   lsd_default_tracker_settings(&ctx->se3);
   lsd_default_tracker_settings(&ctx->sim3);
+  lsd_default_permaref_settings(&ctx->permaref);
+  ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
   ctx->se3ActivePairs = 0;
@@ -657,6 +673,28 @@ int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *co
   LSD_ARG(ctx && refs && frames && init_frameToRef && results && n >= 0);
   LSD_CUDA(cudaSetDevice(ctx->device));
   return se3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, results, traces, ctx->stream);
+}
+
+int lsd_ctx_set_permaref_settings(lsd_ctx *ctx, const lsd_tracker_settings *s) {
+  LSD_ARG(ctx && s);
+  ctx->permaref = *s;
+  return LSD_OK;
+}
+
+int lsd_se3_track_permaref_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init_refToFrame,
+                                 lsd_se3_result *results, lsd_trace_entry *traces) {
+  LSD_ARG(ctx && refs && frames && init_refToFrame && results && n >= 0);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  ctx->se3Permaref = true;
+  const int rc = se3_track_batch_impl(ctx, n, refs, frames, init_refToFrame, results, traces, ctx->stream);
+  ctx->se3Permaref = false;
+  return rc;
+}
+
+int lsd_se3_check_permaref_overlap_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const double *refToFrame, float *pointUsage) {
+  LSD_ARG(ctx && refs && refToFrame && pointUsage && n >= 0);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  return se3_permaref_overlap_impl(ctx, n, refs, refToFrame, pointUsage);
 }
 
 int lsd_se3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[7], lsd_se3_result *result,

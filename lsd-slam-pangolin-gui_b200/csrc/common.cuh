@@ -45,6 +45,7 @@ void set_error(const std::string &msg);
 #define LSD_VAR_GT_INIT_INITIAL (0.01f * 0.01f)
 #define LSD_SE3TRACKING_MIN_LEVEL 1
 #define LSD_SE3TRACKING_MAX_LEVEL 5
+#define LSD_QUICK_KF_CHECK_LVL 4
 
 // Per-level pinhole intrinsics (Frame::initialize): fx_l = fx_{l-1}/2, cx_l = (cx_0+.5)/2^l - .5
 struct Intrinsics {

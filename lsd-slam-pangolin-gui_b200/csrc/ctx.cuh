@@ -16,7 +16,8 @@ struct lsd_ctx {
   cudaStream_t copyStream;  // second stream for the pipelined host-image path
   cudaEvent_t evA, evB, evPipe[4];
   long long launches;
-  lsd_tracker_settings se3, sim3;
+  lsd_tracker_settings se3, sim3, permaref;
+  bool se3Permaref;    // set for the duration of lsd_se3_track_permaref_batch
   int se3ActivePairs;  // 0: default; pairs in flight inside the persistent tracker (L2 residency)
   int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
   int se3RecordPoints; // 0: default (4096); points per partial record = the summation order of the SE3 tracker
@@ -74,5 +75,6 @@ int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
                   float *A36, float *b6, float *scalars);
 void se3_scratch_free(lsd_ctx *ctx);
+int se3_permaref_overlap_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, const double *refToFrame, float *pointUsage);
 
 }  // namespace lsd

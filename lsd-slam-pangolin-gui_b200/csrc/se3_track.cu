@@ -127,6 +127,7 @@ struct SE3Params {
   int recsPerItem;         // records per work item: scheduling granularity only, never changes a result
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
   int recPoints;           // points per partial record (lsd_ctx_set_se3_record_points; default SE3_REC)
+  int permaref;            // SE3Tracker::trackFrameOnPermaref: single level, no frame side effects, referenceToFrame returned
 };
 
 // gpu-scope acquire-release fetch-add: releases this CTA's record stores (ordered before it by the CTA barrier)
@@ -173,6 +174,14 @@ __device__ void finish_pair(SE3State *S, const SE3Params &prm) {
   S->trackingWasGood = !S->diverged && lastGood / (prm.K.w[l1] * prm.K.h[l1]) > LSD_MIN_GOODPERALL_PIXEL &&
                        lastGood / (lastGood + lastBad) > LSD_MIN_GOODPERGOODBAD_PIXEL;
   S->initialTrackedResidual = S->last_residual / S->pointUsage;
+  if (prm.permaref) {  // trackFrameOnPermaref returns referenceToFrame itself
+#pragma unroll
+    for (int i = 0; i < 4; i++) S->outq[i] = S->q_cur[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) S->outt[i] = S->t_cur[i];
+    S->finished = 1;
+    return;
+  }
   // frameToRef = referenceToFrame.inverse()  (float)
   QuatT<float> qc = {-S->q_cur[0], -S->q_cur[1], -S->q_cur[2], S->q_cur[3]};
   float R[9], nt[3] = {-S->t_cur[0], -S->t_cur[1], -S->t_cur[2]}, ot[3];
@@ -615,7 +624,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
     EvalConst c;
     load_eval_const(prm, level, h0, h1, h2, h3, c);
     const int n = P->n[level];
-    uint8_t *mask = (level == prm.minLevel) ? P->mask : nullptr;
+    uint8_t *mask = (level == prm.minLevel && !prm.permaref) ? P->mask : nullptr;  // permaref: idxBuf == nullptr upstream
 
     float acc[SE3_NF];
     double dacc[SE3_ND];
@@ -799,7 +808,7 @@ static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
 static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   SE3Params prm;
   prm.K = ctx->K;
-  prm.s = ctx->se3;
+  prm.s = ctx->se3Permaref ? ctx->permaref : ctx->se3;
   prm.maxChunks = ctx->se3s->maxChunks;
   // Work-item size: one 4096-point record per item measured best at every batch size on B200 (profiles/);
   // the knob stays for experiments.
@@ -807,6 +816,8 @@ static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
   prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
   prm.recPoints = ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
+  prm.permaref = ctx->se3Permaref ? 1 : 0;
+  if (prm.permaref) prm.minLevel = prm.maxLevel = LSD_QUICK_KF_CHECK_LVL;
   return prm;
 }
 
@@ -873,7 +884,12 @@ int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
     }
     P.d_num = refs[i]->d_num;
     P.mask = frames[i]->slab + lay.mask;
-    invert_pose_to_float(init + 7 * i, P.q0, P.t0);
+    if (ctx->se3Permaref) {  // the caller hands referenceToFrame: cast only
+      for (int k = 0; k < 4; k++) P.q0[k] = (float)init[7 * i + k];
+      for (int k = 0; k < 3; k++) P.t0[k] = (float)init[7 * i + 4 + k];
+    } else {
+      invert_pose_to_float(init + 7 * i, P.q0, P.t0);
+    }
   }
   LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
   return LSD_OK;
@@ -939,6 +955,7 @@ int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
     refs[i]->numValid = true;
     r.traceLen = P.traceLen;
     // Frame bookkeeping done by SE3Tracker::trackFrame
+    if (ctx->se3Permaref) continue;  // trackFrameOnPermaref leaves the frame and the keyframe counters alone
     lsd_frame *f = frames[i];
     if (!P.diverged) {
       f->initialTrackedResidual = P.initialTrackedResidual;
@@ -959,8 +976,10 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
   if (n == 0) return LSD_OK;
   int rc = se3_prepare(ctx, n, refs, frames, init, traces != nullptr, st);
   if (rc) return rc;
-  rc = init_masks(ctx, n, frames, st);
-  if (rc) return rc;
+  if (!ctx->se3Permaref) {
+    rc = init_masks(ctx, n, frames, st);
+    if (rc) return rc;
+  }
   LSD_CUDA(cudaEventRecord(ctx->evA, st));
   rc = se3_launch(ctx, 0, n, traces != nullptr, st);
   if (rc) return rc;
@@ -969,6 +988,72 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
   return se3_collect(ctx, n, refs, frames, results, traces, st, ms);
+}
+
+// ---------------------------------------------------------------------------------------
+// SE3Tracker::checkPermaRefOverlap (B7): mean of min(1, z_ref / z') over the level-4 points that project inside
+// (0, w-1) x (0, h-1).  One CTA per candidate; per-thread strided fp32 sums and a fixed tree: deterministic.
+// ---------------------------------------------------------------------------------------
+struct OverlapJob {
+  const RefPoint *pts;
+  const int *d_num;
+  float R[9], t[3];
+};
+
+__global__ void __launch_bounds__(128) k_permaref_overlap(const OverlapJob *__restrict__ jobs, float *__restrict__ out, const Intrinsics K) {
+  __shared__ float swarp[4];
+  const OverlapJob &J = jobs[blockIdx.x];
+  const int lvl = LSD_QUICK_KF_CHECK_LVL;
+  const int n = J.d_num[lvl];
+  const float w2 = (float)(K.w[lvl] - 1), h2 = (float)(K.h[lvl] - 1);
+  const float fx = K.fx[lvl], fy = K.fy[lvl], cx = K.cx[lvl], cy = K.cy[lvl];
+  float usage = 0.0f;
+  for (int i = threadIdx.x; i < n; i += 128) {
+    const RefPoint p = J.pts[i];
+    const int x = p.xy & 0xffff, y = p.xy >> 16;
+    const float px = p.invDepth * (K.fxi[lvl] * x + K.cxi[lvl]), py = p.invDepth * (K.fyi[lvl] * y + K.cyi[lvl]), pz = p.invDepth * 1.0f;
+    const float Wx = (J.R[0] * px + J.R[1] * py + J.R[2] * pz) + J.t[0];
+    const float Wy = (J.R[3] * px + J.R[4] * py + J.R[5] * pz) + J.t[1];
+    const float Wz = (J.R[6] * px + J.R[7] * py + J.R[8] * pz) + J.t[2];
+    const float u_new = (Wx / Wz) * fx + cx, v_new = (Wy / Wz) * fy + cy;
+    if (u_new > 0 && v_new > 0 && u_new < w2 && v_new < h2) {
+      const float depthChange = pz / Wz;
+      usage += depthChange < 1 ? depthChange : 1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) usage += __shfl_down_sync(0xffffffffu, usage, o);
+  if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5] = usage;
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = n > 0 ? (((swarp[0] + swarp[1]) + swarp[2]) + swarp[3]) / (float)n : 0.0f;
+}
+
+int se3_permaref_overlap_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, const double *refToFrame, float *pointUsage) {
+  if (n == 0) return LSD_OK;
+  cudaStream_t st = ctx->stream;
+  const size_t jobBytes = (sizeof(OverlapJob) * (size_t)n + 255) / 256 * 256;
+  int rc = ensure_table(ctx, jobBytes + sizeof(float) * (size_t)n);
+  if (rc) return rc;
+  OverlapJob *h = reinterpret_cast<OverlapJob *>(ctx->h_table);
+  for (int i = 0; i < n; i++) {
+    LSD_ARG(refs[i]);
+    h[i].pts = reinterpret_cast<const RefPoint *>(refs[i]->slab + refs[i]->offPts[LSD_QUICK_KF_CHECK_LVL]);
+    h[i].d_num = refs[i]->d_num;
+    const double *p = refToFrame + 7 * (size_t)i;
+    QuatT<float> q = {(float)p[0], (float)p[1], (float)p[2], (float)p[3]};  // SE3d -> SE3f, then rotationMatrix()
+    qtoR(q, h[i].R);
+    for (int k = 0; k < 3; k++) h[i].t[k] = (float)p[4 + k];
+  }
+  float *d_out = reinterpret_cast<float *>((char *)ctx->d_table + jobBytes);
+  float *h_out = reinterpret_cast<float *>((char *)ctx->h_table + jobBytes);
+  LSD_CUDA(cudaMemcpyAsync(ctx->d_table, h, sizeof(OverlapJob) * (size_t)n, cudaMemcpyHostToDevice, st));
+  k_permaref_overlap<<<n, 128, 0, st>>>(reinterpret_cast<const OverlapJob *>(ctx->d_table), d_out, ctx->K);
+  ctx->launches++;
+  LSD_CUDA(cudaGetLastError());
+  LSD_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(pointUsage, h_out, sizeof(float) * (size_t)n);
+  return LSD_OK;
 }
 
 // ---------------------------------------------------------------------------------------

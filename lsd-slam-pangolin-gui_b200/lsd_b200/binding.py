@@ -90,6 +90,10 @@ SYMBOLS = {
     "lsd_se3_track": (_ip, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lsd_se3_track_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _vp, _vp]),
     "lsd_se3_track_images_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _vp, _vp]),
+    "lsd_default_permaref_settings": (_ip, [_vp]),
+    "lsd_ctx_set_permaref_settings": (_ip, [_vp, _vp]),
+    "lsd_se3_track_permaref_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _vp, _vp]),
+    "lsd_se3_check_permaref_overlap_batch": (_ip, [_vp, _ip, _vp, _vp, _vp]),
     "lsd_se3_eval": (_ip, [_vp, _vp, _vp, _vp, _ip, _fp, _fp, _vp, _vp, _vp]),
     "lsd_se3_last_stats": (_ip, [_vp, _vp, _vp, _vp]),
     "lsd_ctx_set_sim3_settings": (_ip, [_vp, _vp]),
@@ -333,6 +337,29 @@ class Context:
                                 tr[i * TRACE_CAP + k].lam, tr[i * TRACE_CAP + k].bufSize) for k in range(m)])
             return res, traces
         return res
+
+    def se3_track_permaref_batch(self, refs, frames, inits_ref_to_frame, want_trace=False):
+        """SE3Tracker::trackFrameOnPermaref for n (keyframe reference, frame) candidates; frameToRef holds referenceToFrame."""
+        n = len(refs)
+        rp = (C.c_void_p * n)(*[r.p for r in refs])
+        fp = (C.c_void_p * n)(*[f.p for f in frames])
+        init = np.ascontiguousarray(inits_ref_to_frame, np.float64).reshape(n, 7)
+        res = (SE3Result * n)()
+        tr = (TraceEntry * (TRACE_CAP * n))() if want_trace else None
+        _chk(self.L.lsd_se3_track_permaref_batch(self.p, n, rp, fp, _ptr(init), res, tr))
+        if want_trace:
+            return res, [[(tr[i * TRACE_CAP + k].level, tr[i * TRACE_CAP + k].accepted, tr[i * TRACE_CAP + k].error,
+                           tr[i * TRACE_CAP + k].lam, tr[i * TRACE_CAP + k].bufSize) for k in range(min(res[i].traceLen, TRACE_CAP))]
+                         for i in range(n)]
+        return res
+
+    def check_permaref_overlap_batch(self, refs, ref_to_frame):
+        n = len(refs)
+        rp = (C.c_void_p * n)(*[r.p for r in refs])
+        p = np.ascontiguousarray(ref_to_frame, np.float64).reshape(n, 7)
+        out = np.zeros(n, np.float32)
+        _chk(self.L.lsd_se3_check_permaref_overlap_batch(self.p, n, rp, _ptr(p), _ptr(out)))
+        return out
 
     def prepare_batch(self, refs, frames, inits):
         """Pre-marshal a batch so repeated calls cost no Python work (bench.py)."""

@@ -144,6 +144,36 @@ int lsdo_se3_track(void *refp, void *framep, const double init[7], int mode, lsd
   return 0;
 }
 
+// SE3Tracker::trackFrameOnPermaref with the "test track" settings of DenseDepthTrackerSettings (maxItsTestTrack 5,
+// stepSizeMinTestTrack 1e-3, convergenceEpsTestTrack 0.98, lambdaInitialTestTrack 0) at QUICK_KF_CHECK_LVL.
+// out->frameToRef receives the returned referenceToFrame.
+int lsdo_se3_track_permaref(void *refp, void *framep, const double init_refToFrame[7], int mode, lsdo_se3_result *out,
+                            lsdo_trace_entry *trace, int traceCap) {
+  auto *ref = (TrackingReference *)refp;
+  Frame *frame = (Frame *)framep;
+  SE3Tracker t(frame->w[0], frame->h[0]);
+  t.mode = (ReduceMode)mode;
+  t.settings.maxItsPerLvl[QUICK_KF_CHECK_LVL] = 5;
+  t.settings.stepSizeMin[QUICK_KF_CHECK_LVL] = 1e-3f;
+  t.settings.convergenceEps[QUICK_KF_CHECK_LVL] = 0.98f;
+  t.settings.lambdaInitial[QUICK_KF_CHECK_LVL] = 0;
+  const float itr = frame->initialTrackedResidual;
+  const SE3<double> res = t.trackFrameOnPermaref(ref->keyframe, ref, frame, pose_in(init_refToFrame));
+  fill_result(t, frame, res, out);
+  out->initialTrackedResidual = itr;
+  if (trace)
+    for (int i = 0; i < (int)t.trace.size() && i < traceCap; i++)
+      trace[i] = {t.trace[i].level, t.trace[i].accepted, t.trace[i].error, t.trace[i].lambda, t.trace[i].bufSize};
+  return 0;
+}
+
+// SE3Tracker::checkPermaRefOverlap
+float lsdo_check_permaref_overlap(void *refp, const double refToFrame[7]) {
+  auto *ref = (TrackingReference *)refp;
+  SE3Tracker t(ref->keyframe->w[0], ref->keyframe->h[0]);
+  return t.checkPermaRefOverlap(ref->keyframe, ref, pose_in(refToFrame));
+}
+
 // One LM evaluation at a fixed pose (B3+B4+B5) -- used by the parity tests to compare the fused GPU
 // evaluation against the three reference passes.  out38: see tests/test_se3_eval.py for the order.
 int lsdo_se3_eval(void *refp, void *framep, const double refToFrame[7], int level, float affine_a, float affine_b, int mode,

@@ -90,6 +90,9 @@ def lib(fast: bool = False):
     L.lsdo_ref_num.argtypes = [vp, ip]
     L.lsdo_ref_get.argtypes = [vp, ip, vp, vp, vp, vp]
     L.lsdo_se3_track.argtypes = [vp, vp, vp, ip, vp, vp, ip]
+    L.lsdo_se3_track_permaref.argtypes = [vp, vp, vp, ip, vp, vp, ip]
+    L.lsdo_check_permaref_overlap.restype = fp
+    L.lsdo_check_permaref_overlap.argtypes = [vp, vp]
     L.lsdo_se3_eval.argtypes = [vp, vp, vp, ip, fp, fp, ip, vp, vp, vp]
     L.lsdo_se3_track_batch.restype = dp
     L.lsdo_se3_track_batch.argtypes = [ip, vp, vp, vp, ip, ip, vp]
@@ -231,6 +234,21 @@ def se3_track(ref: Ref, frame: Frame, init7, mode=0, trace_cap=2048):
     ref.L.lsdo_se3_track(ref.p, frame.p, _ptr(init), mode, C.byref(res), tr, trace_cap)
     trace = [(tr[i].level, tr[i].accepted, tr[i].error, tr[i].lam, tr[i].bufSize) for i in range(min(res.traceLen, trace_cap))]
     return res, trace
+
+
+def se3_track_permaref(ref: Ref, frame: Frame, init_ref_to_frame7, mode=0, trace_cap=2048):
+    """SE3Tracker::trackFrameOnPermaref (test-track settings); the result's frameToRef holds referenceToFrame."""
+    res = SE3Result()
+    tr = (TraceEntry * trace_cap)()
+    init = np.ascontiguousarray(init_ref_to_frame7, np.float64)
+    ref.L.lsdo_se3_track_permaref(ref.p, frame.p, _ptr(init), mode, C.byref(res), tr, trace_cap)
+    trace = [(tr[i].level, tr[i].accepted, tr[i].error, tr[i].lam, tr[i].bufSize) for i in range(min(res.traceLen, trace_cap))]
+    return res, trace
+
+
+def check_permaref_overlap(ref: Ref, ref_to_frame7):
+    p = np.ascontiguousarray(ref_to_frame7, np.float64)
+    return float(ref.L.lsdo_check_permaref_overlap(ref.p, _ptr(p)))
 
 
 def se3_eval(ref: Ref, frame: Frame, refToFrame7, level, a=1.0, b=0.0, mode=0):

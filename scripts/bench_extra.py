@@ -185,6 +185,17 @@ def sim3_bench(ctx, lsd, n_cand=64, reps=3, device="cuda", cpu=True):
            "candidates_per_s": n_cand / t, "kernel_ms": kms_, "evaluations": evals, "alg_bytes": byts,
            "achieved_GBs": byts / (kms_ * 1e-3) / 1e9, "frac_of_" + src + "_peak": byts / (kms_ * 1e-3) / 1e9 / pk,
            "diverged": int(sum(r.diverged for r in res)), "median_scale_err": scale_err, "median_translation_err_m": terr}
+    # the cheap pre-filter of the same search: SE3Tracker::trackFrameOnPermaref (level 4 only) + checkPermaRefOverlap
+    pinits = np.concatenate([inits_ba[:, :7], inits_ab[:, :7]])
+    tp = []
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        pres = ctx.se3_track_permaref_batch(refs, frames, pinits)
+        usage = ctx.check_permaref_overlap_batch(refs, np.array([list(r.frameToRef) for r in pres]))
+        tp.append(time.perf_counter() - t0)
+    out["permaref_quick_check"] = {"tracks": 2 * n_cand, "ms": 1e3 * float(np.median(tp[1:])), "kernel_ms": ctx.se3_last_stats()[2],
+                                   "tracks_per_s": 2 * n_cand / float(np.median(tp[1:])), "good": int(sum(r.trackingWasGood for r in pres)),
+                                   "mean_overlap": float(usage.mean())}
     if cpu:
         from oracle import pyoracle as O
         O.build()
@@ -202,6 +213,10 @@ def sim3_bench(ctx, lsd, n_cand=64, reps=3, device="cuda", cpu=True):
                 r.num(l)
         ii = np.concatenate([inits_ab[:m], inits_ba[:m]])
         secs, outs = O.sim3_track_batch(orA + orB, oB + oA, ii, 4, 1, 0, threads)
+        t0 = time.perf_counter()
+        for i in range(2 * m):
+            O.se3_track_permaref((orA + orB)[i], (oB + oA)[i], np.concatenate([inits_ba[:m, :7], inits_ab[:m, :7]])[i], 0)
+        out["permaref_quick_check"]["cpu_port_tracks_per_s"] = 2 * m / (time.perf_counter() - t0)
         out["cpu_port"] = {"candidates_per_s": m / secs, "threads": threads, "kind": "port", "sample": f"{m} candidates x 2 directions",
                            "max_scale_diff_vs_gpu": float(max(abs(outs[i].frameToRef[7] - res[i].frameToRef[7]) for i in range(m)))}
     return out

@@ -199,3 +199,46 @@ def test_host_image_entry_point(lsd, oracle):
     for i in range(4):
         assert list(a[i].frameToRef) == list(b[i].frameToRef)
     ctx.close()
+
+
+def test_permaref_quick_track_and_overlap_batch(lsd, oracle):
+    """SE3Tracker::trackFrameOnPermaref / checkPermaRefOverlap (SURVEY.md 8a B7, 8f N4): level-4 test track of n candidates
+    in one launch.  referenceToFrame comes back un-inverted, LM traces match the oracle's evaluation by evaluation, and
+    the tracked frames / keyframe counters are left untouched."""
+    w, h = 320, 240
+    ds = [make_oracle_pair(70 + s, w, h, max_t=0.05, max_r=np.radians(2.0)) for s in range(5)]
+    ctx = lsd.Context(w, h, ds[0]["pr"]["K"])
+    kfs = ctx.create_frames([d["kf_img"] for d in ds])
+    frs = ctx.create_frames([d["fr_img"] for d in ds])
+    for k, d in zip(kfs, ds):
+        k.set_idepth(d["idepth"], d["var"])
+    refs = ctx.create_refs(kfs)
+    rng = np.random.default_rng(3)
+    inits = np.tile(np.array([0, 0, 0, 1, 0, 0, 0.0]), (5, 1))
+    inits[:, 4:] = rng.normal(size=(5, 3)) * 0.01
+    before = [(f.tracking_meta(), k.counters()) for f, k in zip(frs, kfs)]
+    res, traces = ctx.se3_track_permaref_batch(refs, frs, inits, want_trace=True)
+    usage = ctx.check_permaref_overlap_batch(refs, np.array([list(r.frameToRef) for r in res]))
+    for i, d in enumerate(ds):
+        ores, otrace = oracle.se3_track_permaref(d["oref"], d["ofr"], inits[i], 2)
+        assert res[i].diverged == ores.diverged == 0
+        assert res[i].trackingWasGood == ores.trackingWasGood
+        assert [t[0] for t in traces[i]] == [4] * len(traces[i]) and len(traces[i]) == len(otrace) >= 2
+        for tg, to in zip(traces[i], otrace):  # (level, accepted, error, lambda, bufSize)
+            assert tg[1] == to[1] and tg[4] == to[4], (tg, to)
+            assert abs(tg[2] - to[2]) <= RES_RTOL * abs(to[2]) + 1e-6
+        pg, po = np.array(res[i].frameToRef), np.array(ores.frameToRef)
+        assert np.linalg.norm(pg[4:] - po[4:]) <= POSE_TOL and quat_angle(pg[:4], po[:4]) <= POSE_TOL
+        accepted = [t[2] for t in traces[i] if t[1] != 0]
+        assert all(b < a for a, b in zip(accepted, accepted[1:])), "accepted LM steps must decrease the residual"
+        ou = oracle.check_permaref_overlap(d["oref"], po)
+        assert 0.3 < usage[i] <= 1.0 and abs(usage[i] - ou) <= 1e-5 * max(1.0, ou)
+    after = [(f.tracking_meta(), k.counters()) for f, k in zip(frs, kfs)]
+    for b, a in zip(before, after):
+        assert b[0][0] == a[0][0] and np.array_equal(b[0][1], a[0][1]) and b[1] == a[1]
+    # a batch of one equals its entry in the batch; the regular tracker is unaffected by the mode switch
+    single = ctx.se3_track_permaref_batch([refs[2]], [frs[2]], [inits[2]])
+    assert np.array_equal(np.array(single[0].frameToRef), np.array(res[2].frameToRef))
+    full = ctx.se3_track(refs[2], frs[2], np.array([0, 0, 0, 1, 0, 0, 0.0]))
+    assert full.trackingWasGood and sum(full.numResidualCalls[1:4]) > 0
+    ctx.close()

