@@ -244,8 +244,6 @@ def main():
         ctx.set_se3_active_pairs(args.active)
     if args.recs:
         ctx.set_se3_work_item_records(args.recs)
-    if os.environ.get("LSD_B200_SE3_SELF"):  # experiment knob: self-continuation mode of the persistent tracker (scheduling only)
-        ctx.set_se3_self_continue(int(os.environ["LSD_B200_SE3_SELF"]))
     # resident state: keyframes (with depth) -> tracking references; new frames with prebuilt pyramids
     kfs = ctx.create_frames_device(kf.data_ptr(), n)
     ctx.set_idepth_batch_device(kfs, idp.data_ptr(), var.data_ptr())

@@ -100,10 +100,6 @@ int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
 /* scheduling knob of the persistent tracker: 4096-point records per work item (0 = automatic).  Never
  * changes a result (the summation order is fixed by the records), only latency vs throughput. */
 int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
-/* Self-continuation of the persistent tracker: the CTA that completes an LM evaluation runs the pair's next evaluation
- * itself when that is a single work item, skipping the device queue.  0 = automatic (batches of <= 64 pairs), 1 = always,
- * -1 = never.  Scheduling only: results are bit-identical for every value. */
-int lsd_ctx_set_se3_self_continue(lsd_ctx *ctx, int mode);
 /* Points per partial record of the SE3 tracker (0 = default 4096; multiple of 128).  A record is reduced by one CTA and
  * records are summed in order, so this value DEFINES the fp32 summation order: for a given value results are
  * bit-identical for every batch size and scheduling; between values they differ by reassociation only.  Large records

@@ -233,7 +233,6 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
-  ctx->se3SelfContinue = 0;
   ctx->se3ActivePairs = 0;
   ctx->refSlabBytes = 0;
   ctx->h_stage = ctx->d_stage = nullptr;
@@ -287,12 +286,6 @@ int lsd_ctx_set_se3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s) {
 int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records) {
   LSD_ARG(ctx && records >= 0 && records <= 64);
   ctx->se3RecsPerItem = records;
-  return LSD_OK;
-}
-
-int lsd_ctx_set_se3_self_continue(lsd_ctx *ctx, int mode) {
-  LSD_ARG(ctx && mode >= -1 && mode <= 1);
-  ctx->se3SelfContinue = mode;
   return LSD_OK;
 }
 

@@ -20,7 +20,6 @@ struct lsd_ctx {
   bool se3Permaref;    // set for the duration of lsd_se3_track_permaref_batch
   int se3ActivePairs;  // 0: default; pairs in flight inside the persistent tracker (L2 residency)
   int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
-  int se3SelfContinue; // 0 automatic (small batches), 1 always, -1 never: scheduling only
   int se3RecordPoints; // 0: default (4096); points per partial record = the summation order of the SE3 tracker
   // pools
   std::vector<uint8_t *> frameSlabPool;

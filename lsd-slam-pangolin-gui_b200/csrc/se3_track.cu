@@ -44,9 +44,6 @@ namespace lsd {
 #ifndef SE3_REC
 #define SE3_REC 4096      // points per partial record: FIXED, it defines the summation order (see above)
 #endif
-#ifndef SE3_SELF_CONTINUE_MAX_PAIRS
-#define SE3_SELF_CONTINUE_MAX_PAIRS 64  // automatic self-continuation below this batch size (lsd_ctx_set_se3_self_continue)
-#endif
 #define SE3_DEFAULT_ACTIVE 1000000  // pairs in flight (lsd_ctx_set_se3_active_pairs)
 #define SE3_NRED 44       // floats per partial record: 5 doubles (affine sums) + 33 floats + pad
 #define SE3_NF 33         // fp32 sums per record
@@ -130,7 +127,6 @@ struct SE3Params {
   int recsPerItem;         // records per work item: scheduling granularity only, never changes a result
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
   int recPoints;           // points per partial record (lsd_ctx_set_se3_record_points; default SE3_REC)
-  int selfContinue;        // a CTA that finishes an evaluation runs the pair's next one itself when it is a single work item
   int permaref;            // SE3Tracker::trackFrameOnPermaref: single level, no frame side effects, referenceToFrame returned
 };
 
@@ -593,20 +589,13 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
   __shared__ __align__(16) SE3Smem sm;
   __shared__ float stot[SE3_NF];
   __shared__ double sdtot[SE3_ND];
-  __shared__ int sCode, sIsLast, sSelf;
+  __shared__ int sCode, sIsLast;
 
   unsigned ticket = 0;
   if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
-  if (threadIdx.x == 0) sSelf = -1;
   for (;;) {
     // ---- fetch the next work item (thread 0 spins on its ticket's slot) ----
-    if (threadIdx.x == 0 && sSelf >= 0) {
-      // Self-continuation: this CTA just finished the pair's previous evaluation and the next one is a single work item
-      // (levels 3-4, sparse level 2): it runs it directly -- no queue push / poll / pop round trips through L2.  The
-      // ticket it already holds is consumed afterwards.  Scheduling only: records and their order are unchanged.
-      sCode = sSelf;
-      sSelf = -1;
-    } else if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
       const unsigned slot = ticket & (q.cap - 1), seq = ticket / q.cap + 1;
       const volatile unsigned long long *sp = reinterpret_cast<const volatile unsigned long long *>(&q.slots[slot]);
       int code = -1;
@@ -680,9 +669,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
         state_load(&L, S);
         const int next = lm_step(P, &L, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
         state_store(S, &L);
-        if (next == 1 && prm.selfContinue) {
-          sSelf = pairIdx << 12;  // work item 0 of the pair's next evaluation
-        } else if (next > 0) {
+        if (next > 0) {
           q_push(q, pairIdx, next);
         } else {
           // Admission control: the number of pairs in flight is bounded so that their level data stays in L2
@@ -829,7 +816,6 @@ static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
   prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
   prm.recPoints = ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
-  prm.selfContinue = ctx->se3SelfContinue > 0 || (ctx->se3SelfContinue == 0 && nPairs <= SE3_SELF_CONTINUE_MAX_PAIRS);
   prm.permaref = ctx->se3Permaref ? 1 : 0;
   if (prm.permaref) prm.minLevel = prm.maxLevel = LSD_QUICK_KF_CHECK_LVL;
   return prm;

@@ -71,7 +71,6 @@ SYMBOLS = {
     "lsd_ctx_set_se3_work_item_records": (_ip, [_vp, _ip]),
     "lsd_ctx_set_se3_active_pairs": (_ip, [_vp, _ip]),
     "lsd_ctx_set_se3_record_points": (_ip, [_vp, _ip]),
-    "lsd_ctx_set_se3_self_continue": (_ip, [_vp, _ip]),
     "lsd_frame_create": (_ip, [_vp, _ip, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch_device": (_ip, [_vp, _ip, _vp, _vp, _u, _vp]),
@@ -240,9 +239,6 @@ class Context:
 
     def set_se3_active_pairs(self, n):
         _chk(self.L.lsd_ctx_set_se3_active_pairs(self.p, int(n)))
-
-    def set_se3_self_continue(self, mode):
-        _chk(self.L.lsd_ctx_set_se3_self_continue(self.p, int(mode)))
 
     def set_se3_record_points(self, n):
         _chk(self.L.lsd_ctx_set_se3_record_points(self.p, int(n)))

@@ -333,8 +333,6 @@ def pipeline_bench(lsd, w=640, h=480, n_frames=500, cpu_frames=60, device="cuda"
 
     ctx = lsd.Context(w, h, K, device=0)
     rec = int(os.environ.get("EXTRA_SE3_RECORD", "1024"))
-    if os.environ.get("LSD_B200_SE3_SELF"):
-        ctx.set_se3_self_continue(int(os.environ["LSD_B200_SE3_SELF"]))
     ctx.set_se3_record_points(rec)  # a context that tracks one live sequence: small records (include/lsd_b200.h)
     run_native(ctx, min(20, n_frames))  # warm-up (allocations, pools, lazy init)
     slam, dt, t_kf = run_native(ctx, n_frames)

@@ -141,10 +141,6 @@ def test_batch_equals_single_and_is_deterministic(lsd, oracle):
         r3 = ctx.se3_track_batch(refs, frs, inits)
         assert np.array_equal(np.array([list(r.frameToRef) for r in r3]), p1), f"result depends on work-item size {recs}"
     ctx.set_se3_work_item_records(0)
-    for mode in (1, -1, 0):  # self-continuation (CTA runs the pair's next single-item evaluation itself): scheduling only
-        ctx.set_se3_self_continue(mode)
-        r4 = ctx.se3_track_batch(refs, frs, inits)
-        assert np.array_equal(np.array([list(r.frameToRef) for r in r4]), p1), f"result depends on self-continuation mode {mode}"
     for i in range(6):
         rs = ctx.se3_track(refs[i], frs[i], inits[i])
         assert np.array_equal(np.array(rs.frameToRef), p1[i]), "batch result must not depend on batch composition"
