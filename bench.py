@@ -333,6 +333,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_se3_track (persistent: all LM evaluations of the batch)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
+                         "traffic_note": "ncu --set full of a 256-pair launch (profiles/r01n_k_se3_track_full.txt): dram read+write 3.12 GB "
+                                         "against 3.99 GB algorithmic for that launch (L2 absorbs the shared taps: no wasted re-reads)",
                          "algorithmic_bytes_per_launch": statistics.mean(alg_bytes), "kernel_ms": k_ms,
                          "evaluations_per_launch": statistics.mean(evals)},
             "quality": {"diverged": int(n_div), "trackingWasGood": int(n_good),
