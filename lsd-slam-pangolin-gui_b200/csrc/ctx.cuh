@@ -55,6 +55,11 @@ void launch_ingest(lsd_ctx *ctx, const uint8_t *d_src, size_t srcPitch, size_t s
 void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st);
 void launch_maxgrad0(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
 void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
+struct IdepthMapSrc {  // hypothesis planes Frame::setDepth reads (depth.cuh layout)
+  const uint32_t *meta;
+  const float *ids, *vars;
+};
+void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st);
 void launch_set_depth_gt(lsd_ctx *ctx, uint8_t *slab, const float *d_depth, float cov, cudaStream_t st);
 void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
 void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st);

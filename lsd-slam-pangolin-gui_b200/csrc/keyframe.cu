@@ -11,7 +11,7 @@
 // frame's planes directly (the pack is only produced when a host consumer asks for it), so a keyframe costs
 // 12 B/px of reads + 16 B per emitted vertex.
 //
-// k_vbo_extract is ONE pass: a CTA owns a 1024-pixel raster chunk (256 threads x one float4 of each plane), counts
+// k_vbo_extract is ONE pass: a CTA owns a 4096-pixel raster chunk (256 threads x four float4 groups of each plane), counts
 // its survivors, and obtains its output offset by decoupled look-back over the chunks before it (chunk ids are
 // handed out by an atomic ticket, so every predecessor is already resident and the spin cannot deadlock).  The
 // vertices therefore land in exactly the reference's raster order and `points` is exact.  blockIdx.y = keyframe.
@@ -25,7 +25,8 @@ namespace lsd {
 
 #define VBO_THREADS 256
 #define VBO_PX_PER_THREAD 4
-#define VBO_CHUNK (VBO_THREADS * VBO_PX_PER_THREAD)
+#define VBO_SUB 4  // 1024-pixel sub-chunks per CTA: one ticket and one look-back per 4096 pixels
+#define VBO_CHUNK (VBO_THREADS * VBO_PX_PER_THREAD * VBO_SUB)
 #define VBO_VALUE_MASK LSD_LB_MASK
 
 struct VboJob {
@@ -43,88 +44,100 @@ struct VboK {
   int minNearSupport, contractFma;
 };
 
+// per-pixel filter (Keyframe.h:95-134) on 4 consecutive pixels of one row.  Every load of the thread is issued up front
+// and unconditionally (one memory round trip instead of three dependent ones): 3 rows of idepth, var, image.
+__device__ __forceinline__ unsigned vbo_filter4(const VboJob &J, const VboK &P, int p0, int N, float depthK[4], unsigned &colPacked) {
+  unsigned keep = 0;
+  colPacked = 0;
+  if (p0 >= N) return 0;
+  const int y = p0 / P.W, x0 = p0 - y * P.W;
+  if (y < 1 || y >= P.H - 1) return 0;
+  float nb[3][6];  // rows y-1, y, y+1 x columns x0-1 .. x0+4 of idepth
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const float *row = J.idepth + p0 + (r - 1) * P.W;
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(row));
+    nb[r][1] = q.x; nb[r][2] = q.y; nb[r][3] = q.z; nb[r][4] = q.w;
+    nb[r][0] = x0 > 0 ? __ldg(row - 1) : 0.0f;          // unused when x0 == 0 (pixel x = 0 is never emitted)
+    nb[r][5] = x0 + 4 < P.W ? __ldg(row + 4) : 0.0f;    // unused when x0 + 3 == W - 1
+  }
+  const float4 v4 = __ldg(reinterpret_cast<const float4 *>(J.var + p0));
+  const float4 c4 = __ldg(reinterpret_cast<const float4 *>(J.img + p0));
+  const float vc[4] = {v4.x, v4.y, v4.z, v4.w};
+  // publishKeyframe: float -> unsigned char (truncation)
+  colPacked = (unsigned)(unsigned char)c4.x | ((unsigned)(unsigned char)c4.y << 8) | ((unsigned)(unsigned char)c4.z << 16) |
+              ((unsigned)(unsigned char)c4.w << 24);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int x = x0 + j;
+    const float idc = nb[1][j + 1];
+    if (x < 1 || x >= P.W - 1) continue;
+    if (idc <= 0) continue;
+    const float depth = 1 / idc;
+    float depth4 = depth * depth;
+    depth4 *= depth4;
+    if (vc[j] * depth4 > P.scaledTH) continue;
+    if (vc[j] * depth4 * J.scale * J.scale > P.absTH) continue;
+    if (P.minNearSupport > 1) {
+      int nearSupport = 0;
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+          const float nid = nb[dy][j + dx];
+          if (nid > 0) {
+            const float diff = nid - 1.0f / depth;
+            if (diff * diff < 2 * vc[j]) nearSupport++;
+          }
+        }
+      if (nearSupport < P.minNearSupport) continue;
+    }
+    keep |= 1u << j;
+    depthK[j] = depth;
+  }
+  return keep;
+}
+
 __global__ void __launch_bounds__(VBO_THREADS) k_vbo_extract(const VboJob *__restrict__ jobs, const VboK P) {
   __shared__ unsigned s_chunk, s_base;
-  __shared__ unsigned s_warp[VBO_THREADS / 32];
+  __shared__ unsigned s_cnt[VBO_SUB][VBO_THREADS / 32];  // survivors per (sub-chunk, warp); exclusive offsets after the scan
   const VboJob J = jobs[blockIdx.y];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_chunk = atomicAdd(J.state + P.nChunks, 1u);
   __syncthreads();
   const unsigned chunk = s_chunk;
   const int N = P.W * P.H;
-  const int p0 = (int)chunk * VBO_CHUNK + tid * VBO_PX_PER_THREAD;
 
-  // ---- per-pixel filter (Keyframe.h:95-134) on 4 consecutive pixels of one row.  Every load of the thread is issued
-  // up front and unconditionally (one memory round trip per CTA instead of three dependent ones; the kernel is bound by
-  // per-CTA latency, not by bytes): 3 rows of idepth, var, image.
-  float depthK[4];
-  float col[4] = {0, 0, 0, 0};
-  unsigned keep = 0;
-  int y = 0, x0 = 0;
-  if (p0 < N) {
-    y = p0 / P.W;
-    x0 = p0 - y * P.W;
-    if (y >= 1 && y < P.H - 1) {
-      float nb[3][6];  // rows y-1, y, y+1 x columns x0-1 .. x0+4 of idepth
+  float depthK[VBO_SUB][4];
+  unsigned keep[VBO_SUB], col[VBO_SUB], inclW[VBO_SUB];
 #pragma unroll
-      for (int r = 0; r < 3; r++) {
-        const float *row = J.idepth + p0 + (r - 1) * P.W;
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(row));
-        nb[r][1] = q.x; nb[r][2] = q.y; nb[r][3] = q.z; nb[r][4] = q.w;
-        nb[r][0] = x0 > 0 ? __ldg(row - 1) : 0.0f;          // unused when x0 == 0 (pixel x = 0 is never emitted)
-        nb[r][5] = x0 + 4 < P.W ? __ldg(row + 4) : 0.0f;    // unused when x0 + 3 == W - 1
-      }
-      const float4 v4 = __ldg(reinterpret_cast<const float4 *>(J.var + p0));
-      const float4 c4 = __ldg(reinterpret_cast<const float4 *>(J.img + p0));
-      const float vc[4] = {v4.x, v4.y, v4.z, v4.w};
-      col[0] = c4.x; col[1] = c4.y; col[2] = c4.z; col[3] = c4.w;
+  for (int sb = 0; sb < VBO_SUB; sb++) {
+    const int p0 = (int)chunk * VBO_CHUNK + sb * (VBO_THREADS * VBO_PX_PER_THREAD) + tid * VBO_PX_PER_THREAD;
+    keep[sb] = vbo_filter4(J, P, p0, N, depthK[sb], col[sb]);
+    unsigned incl = __popc(keep[sb]);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int x = x0 + j;
-        const float idc = nb[1][j + 1];
-        if (x < 1 || x >= P.W - 1) continue;
-        if (idc <= 0) continue;
-        const float depth = 1 / idc;
-        float depth4 = depth * depth;
-        depth4 *= depth4;
-        if (vc[j] * depth4 > P.scaledTH) continue;
-        if (vc[j] * depth4 * J.scale * J.scale > P.absTH) continue;
-        if (P.minNearSupport > 1) {
-          int nearSupport = 0;
-#pragma unroll
-          for (int dx = 0; dx < 3; dx++)
-#pragma unroll
-            for (int dy = 0; dy < 3; dy++) {
-              const float nid = nb[dy][j + dx];
-              if (nid > 0) {
-                const float diff = nid - 1.0f / depth;
-                if (diff * diff < 2 * vc[j]) nearSupport++;
-              }
-            }
-          if (nearSupport < P.minNearSupport) continue;
-        }
-        keep |= 1u << j;
-        depthK[j] = depth;
-      }
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
+    inclW[sb] = incl;
+    if (lane == 31) s_cnt[sb][warp] = incl;
   }
-
-  // ---- CTA-exclusive scan of the survivor counts
-  const unsigned cnt = __popc(keep);
-  unsigned incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
 
-  // ---- decoupled look-back (warp 0): offset of this chunk in the keyframe's vertex array
+  // ---- raster order inside the chunk = sub-chunk, then warp: scan the 32 (sub-chunk, warp) totals, then one
+  // ---- decoupled look-back for the whole 4096-pixel chunk (warp 0)
   if (warp == 0) {
-    unsigned total = 0;
+    unsigned *flat = &s_cnt[0][0];  // VBO_SUB * 8 == 32 entries
+    const unsigned v = flat[lane];
+    unsigned incl = v;
 #pragma unroll
-    for (int k = 0; k < VBO_THREADS / 32; k++) total += s_warp[k];
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    flat[lane] = incl - v;
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
     const unsigned excl = lookback_exclusive(J.state, chunk, total, lane);
     if (lane == 0) {
       s_base = excl;
@@ -134,14 +147,17 @@ __global__ void __launch_bounds__(VBO_THREADS) k_vbo_extract(const VboJob *__res
   __syncthreads();
 
   // ---- emit (Keyframe.h:136-143)
-  if (keep) {
-    unsigned o = s_base + (incl - cnt);
-    for (int k = 0; k < warp; k++) o += s_warp[k];
+#pragma unroll
+  for (int sb = 0; sb < VBO_SUB; sb++) {
+    if (!keep[sb]) continue;
+    const int p0 = (int)chunk * VBO_CHUNK + sb * (VBO_THREADS * VBO_PX_PER_THREAD) + tid * VBO_PX_PER_THREAD;
+    const int y = p0 / P.W, x0 = p0 - y * P.W;
+    unsigned o = s_base + s_cnt[sb][warp] + (inclW[sb] - __popc(keep[sb]));
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      if (!(keep >> j & 1u)) continue;
+      if (!(keep[sb] >> j & 1u)) continue;
       const int x = x0 + j;
-      const float depth = depthK[j];
+      const float depth = depthK[sb][j];
       float px, py;
       if (P.contractFma) {
         px = __fmaf_rn((float)x, P.fxi, P.cxi) * depth;
@@ -150,7 +166,7 @@ __global__ void __launch_bounds__(VBO_THREADS) k_vbo_extract(const VboJob *__res
         px = (x * P.fxi + P.cxi) * depth;
         py = (y * P.fyi + P.cyi) * depth;
       }
-      const unsigned g = (unsigned)(unsigned char)col[j];  // publishKeyframe: float -> unsigned char (truncation)
+      const unsigned g = (col[sb] >> (8 * j)) & 0xffu;
       uint4 vtx;
       vtx.x = __float_as_uint(px);
       vtx.y = __float_as_uint(py);

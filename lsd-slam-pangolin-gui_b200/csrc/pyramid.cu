@@ -227,7 +227,12 @@ __device__ __forceinline__ void fuse4(const float id[4], const float var[4], flo
   }
 }
 
-__global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restrict__ slabs, FrameLayout lay, int W, int H) {
+// FROM_MAP: level 0 does not exist yet -- it is Frame::setDepth of the keyframe's depth map (hypothesis planes meta / idepth_smoothed
+// / idepth_var_smoothed), computed here, written to the level-0 planes and consumed from registers: one pass over the map instead
+// of k_depth_set_depth followed by a re-read of the two planes it wrote.
+template <bool FROM_MAP>
+__global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restrict__ slabs, const IdepthMapSrc *__restrict__ srcs,
+                                                        FrameLayout lay, int W, int H) {
   __shared__ float a1[TILE_H / 2][TILE_W / 2], b1[TILE_H / 2][TILE_W / 2];
   __shared__ float a2[TILE_H / 4][TILE_W / 4], b2[TILE_H / 4][TILE_W / 4];
   __shared__ float a3[TILE_H / 8][TILE_W / 8], b3[TILE_H / 8][TILE_W / 8];
@@ -240,11 +245,26 @@ __global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restri
     const int x = (x0 >> 1) + tx, y = (y0 >> 1) + ty;
     float oid = -1, ovar = -1;
     if (x < (W >> 1) && y < (H >> 1)) {
-      const float *ID = reinterpret_cast<const float *>(slab + lay.idepth[0]);
-      const float *VR = reinterpret_cast<const float *>(slab + lay.idvar[0]);
+      float *ID = reinterpret_cast<float *>(slab + lay.idepth[0]);
+      float *VR = reinterpret_cast<float *>(slab + lay.idvar[0]);
       const size_t base = (size_t)(2 * y) * W + 2 * x;
-      const float2 i0 = *reinterpret_cast<const float2 *>(ID + base), i1 = *reinterpret_cast<const float2 *>(ID + base + W);
-      const float2 v0 = *reinterpret_cast<const float2 *>(VR + base), v1 = *reinterpret_cast<const float2 *>(VR + base + W);
+      float2 i0, i1, v0, v1;
+      if (FROM_MAP) {
+        const IdepthMapSrc S = srcs[f];
+        const uint2 m0 = *reinterpret_cast<const uint2 *>(S.meta + base), m1 = *reinterpret_cast<const uint2 *>(S.meta + base + W);
+        i0 = *reinterpret_cast<const float2 *>(S.ids + base); i1 = *reinterpret_cast<const float2 *>(S.ids + base + W);
+        v0 = *reinterpret_cast<const float2 *>(S.vars + base); v1 = *reinterpret_cast<const float2 *>(S.vars + base + W);
+        // Frame::setDepth: valid hypotheses with idepth_smoothed >= -0.05 carry (idepth_smoothed, idepth_var_smoothed), the rest (-1, -1)
+        if (!((m0.x & 1u) && i0.x >= -0.05f)) i0.x = v0.x = -1;
+        if (!((m0.y & 1u) && i0.y >= -0.05f)) i0.y = v0.y = -1;
+        if (!((m1.x & 1u) && i1.x >= -0.05f)) i1.x = v1.x = -1;
+        if (!((m1.y & 1u) && i1.y >= -0.05f)) i1.y = v1.y = -1;
+        *reinterpret_cast<float2 *>(ID + base) = i0; *reinterpret_cast<float2 *>(ID + base + W) = i1;
+        *reinterpret_cast<float2 *>(VR + base) = v0; *reinterpret_cast<float2 *>(VR + base + W) = v1;
+      } else {
+        i0 = *reinterpret_cast<const float2 *>(ID + base); i1 = *reinterpret_cast<const float2 *>(ID + base + W);
+        v0 = *reinterpret_cast<const float2 *>(VR + base); v1 = *reinterpret_cast<const float2 *>(VR + base + W);
+      }
       const float id[4] = {i0.x, i0.y, i1.x, i1.y}, var[4] = {v0.x, v0.y, v1.x, v1.y};
       fuse4(id, var, oid, ovar);
       reinterpret_cast<float *>(slab + lay.idepth[1])[(size_t)y * (W >> 1) + x] = oid;
@@ -300,7 +320,14 @@ __global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restri
 
 void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st) {
   dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
-  k_idepth_pyramid<<<grid, 256, 0, st>>>(d_slabs, ctx->lay, ctx->w, ctx->h);
+  k_idepth_pyramid<false><<<grid, 256, 0, st>>>(d_slabs, nullptr, ctx->lay, ctx->w, ctx->h);
+  ctx->launches++;
+}
+
+// Frame::setDepth(depth map) + buildIDepthAndIDepthVar in one pass (d_srcs[i]: the hypothesis planes of keyframe i's map)
+void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st) {
+  dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
+  k_idepth_pyramid<true><<<grid, 256, 0, st>>>(d_slabs, d_srcs, ctx->lay, ctx->w, ctx->h);
   ctx->launches++;
 }
 
