@@ -19,6 +19,9 @@ from common import hyp_from_idepth, make_oracle_depth_scene, make_oracle_pair, m
 from oracle import pyoracle as O  # noqa: E402
 
 
+PAIR_W, PAIR_H = 320, 240
+
+
 def sha(a):
     return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
 
@@ -36,12 +39,13 @@ def canonical_map(m):
 def build():
     out = {}
     w, h = 160, 112
-    # ---- Frame pyramids + SE3 tracker (EXACT accumulation mode = the order-independent value)
-    d = make_oracle_pair(5, w, h)
-    out["pair/kf_img"] = d["kf_img"]
-    out["pair/fr_img"] = d["fr_img"]
-    out["pair/idepth"] = d["idepth"]
-    out["pair/var"] = d["var"]
+    # ---- Frame pyramids + SE3 tracker (EXACT accumulation mode = the order-independent value).  320x240: level 4 of a
+    # smaller image holds a few dozen points and the LM path becomes summation-order sensitive.  Inputs are regenerated
+    # from the seed (tests/common.make_oracle_pair); their digests are stored so a drifting generator is noticed.
+    d = make_oracle_pair(5, PAIR_W, PAIR_H)
+    out["pair/sha_kf_img"] = sha(d["kf_img"])
+    out["pair/sha_fr_img"] = sha(d["fr_img"])
+    out["pair/sha_idepth"] = sha(d["idepth"])
     out["pair/K"] = np.array(d["pr"]["K"], np.float64)
     for l in range(5):
         out[f"pair/sha_image_L{l}"] = sha(d["okf"].get(O.IMAGE, l))
@@ -59,7 +63,7 @@ def build():
     out["pair/permaref_refToFrame"] = np.array(pres.frameToRef)
     out["pair/permaref_overlap"] = np.array(O.check_permaref_overlap(d["oref"], np.array(pres.frameToRef)))
     # ---- Sim3 tracker
-    s = make_sim3_pair(O, 8, w, h, c=0.95)
+    s = make_sim3_pair(O, 8, PAIR_W, PAIR_H, c=0.95)
     sres, _ = O.sim3_track(s["oref"], s["ofr"], s["gt8"] * np.array([1, 1, 1, 1, 1, 1, 1, 1.03]), 4, 1, 2)
     out["sim3/seed_c"] = np.array([8, 0.95])
     out["sim3/frameToRef"] = np.array(sres.frameToRef)

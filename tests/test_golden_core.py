@@ -28,18 +28,20 @@ def test_oracle_reproduces_committed_vectors(oracle):
 @pytest.mark.gpu
 def test_device_matches_committed_vectors(lsd, oracle):
     import make_golden_core as M
-    from common import hyp_from_idepth, make_oracle_depth_scene
+    from common import hyp_from_idepth, make_oracle_depth_scene, make_oracle_pair
     w, h = 160, 112
     K = tuple(float(k) for k in G["pair/K"])
-    ctx = lsd.Context(w, h, K)
-    kf = ctx.create_frame(G["pair/kf_img"], 10, flags=lsd.BUILD_MAXGRAD0 | lsd.BUILD_GRAD0)
-    fr = ctx.create_frame(G["pair/fr_img"], 11)
+    d = make_oracle_pair(5, M.PAIR_W, M.PAIR_H)
+    assert np.array_equal(M.sha(d["kf_img"]), G["pair/sha_kf_img"]) and np.array_equal(M.sha(d["idepth"]), G["pair/sha_idepth"])
+    ctx = lsd.Context(M.PAIR_W, M.PAIR_H, K)
+    kf = ctx.create_frame(d["kf_img"], 10, flags=lsd.BUILD_MAXGRAD0 | lsd.BUILD_GRAD0)
+    fr = ctx.create_frame(d["fr_img"], 11)
     for l in range(5):
         assert np.array_equal(M.sha(kf.image(l)), G[f"pair/sha_image_L{l}"]), f"image L{l}"
         assert np.array_equal(M.sha(kf.gradients(l)), G[f"pair/sha_gradients_L{l}"]), f"gradients L{l}"
     assert np.array_equal(M.sha(kf.maxGradients(0)), G["pair/sha_maxgrad_L0"])
     assert kf.num_mappable_pixels() == int(G["pair/num_mappable"])
-    kf.set_idepth(G["pair/idepth"], G["pair/var"])
+    kf.set_idepth(d["idepth"], d["var"])
     ref = ctx.create_refs([kf])[0]
     assert [ref.num_data(l) for l in (1, 2, 3, 4)] == G["pair/numData"].tolist()
     init = np.array([0, 0, 0, 1, 0, 0, 0.0])
