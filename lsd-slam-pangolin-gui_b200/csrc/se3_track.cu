@@ -44,9 +44,6 @@ namespace lsd {
 #ifndef SE3_REC
 #define SE3_REC 4096      // points per partial record: FIXED, it defines the summation order (see above)
 #endif
-#ifndef SE3_SELF_MAX_PAIRS
-#define SE3_SELF_MAX_PAIRS 16  // batches up to this size run the latency variant of the tracker (see k_se3_track)
-#endif
 #define SE3_DEFAULT_ACTIVE 1000000  // pairs in flight (lsd_ctx_set_se3_active_pairs)
 #define SE3_NRED 44       // floats per partial record: 5 doubles (affine sums) + 33 floats + pad
 #define SE3_NF 33         // fp32 sums per record
@@ -142,11 +139,11 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned *p, unsigned v) {
 }
 
 // Publish the chunks of the pair's next evaluation.  The caller has stored the pair's state already.
-__device__ void q_push(const SE3Queue &q, int pairIdx, int nch, int first = 0) {
+__device__ void q_push(const SE3Queue &q, int pairIdx, int nch) {
   __threadfence();  // state (and everything before) visible before any consumer can see the items
-  const unsigned base = atomicAdd(q.tail, (unsigned)(nch - first));
-  for (int c = first; c < nch; c++) {
-    const unsigned t = base + (c - first);
+  const unsigned base = atomicAdd(q.tail, (unsigned)nch);
+  for (int c = 0; c < nch; c++) {
+    const unsigned t = base + c;
     const unsigned long long v = ((unsigned long long)(t / q.cap + 1) << 32) | (unsigned)((pairIdx << 12) | c);
     *reinterpret_cast<volatile unsigned long long *>(&q.slots[t & (q.cap - 1)]) = v;
   }
@@ -586,28 +583,19 @@ __device__ __forceinline__ void load_eval_const(const SE3Params &prm, int level,
   c.H = prm.K.h[level];
 }
 
-// SELF (latency variant, launched for small batches): the CTA that completes an evaluation keeps work item 0 of the pair's
-// next evaluation for itself -- no queue round trip on the critical path of a single live track -- and publishes only the
-// remaining items.  Scheduling only: records, their contents and their summation order are the same in both variants
-// (the batch variant is compiled without the extra state so that its register allocation is untouched).
-template <bool SELF>
 __global__ void __launch_bounds__(SE3_THREADS, SE3_MINB)
 k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials, const SE3Queue q,
             const __grid_constant__ SE3Params prm, lsd_trace_entry *traces) {
   __shared__ __align__(16) SE3Smem sm;
   __shared__ float stot[SE3_NF];
   __shared__ double sdtot[SE3_ND];
-  __shared__ int sCode, sIsLast, sSelf;
-  if (SELF && threadIdx.x == 0) sSelf = -1;
+  __shared__ int sCode, sIsLast;
 
   unsigned ticket = 0;
   if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
   for (;;) {
     // ---- fetch the next work item (thread 0 spins on its ticket's slot) ----
-    if (SELF && threadIdx.x == 0 && sSelf >= 0) {
-      sCode = sSelf;  // work item 0 of the evaluation this CTA has just set up (see below)
-      sSelf = -1;
-    } else if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
       const unsigned slot = ticket & (q.cap - 1), seq = ticket / q.cap + 1;
       const volatile unsigned long long *sp = reinterpret_cast<const volatile unsigned long long *>(&q.slots[slot]);
       int code = -1;
@@ -681,10 +669,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
         state_load(&L, S);
         const int next = lm_step(P, &L, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
         state_store(S, &L);
-        if (SELF && next > 0) {
-          if (next > 1) q_push(q, pairIdx, next, 1);
-          sSelf = pairIdx << 12;
-        } else if (next > 0) {
+        if (next > 0) {
           q_push(q, pairIdx, next);
         } else {
           // Admission control: the number of pairs in flight is bounded so that their level data stays in L2
@@ -810,7 +795,7 @@ static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
   }
   if (!s->gridBlocks) {
     int perSM = 0;
-    LSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_se3_track<false>, SE3_THREADS, 0));
+    LSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_se3_track, SE3_THREADS, 0));
     if (perSM < 1) {
       set_error("k_se3_track cannot be resident");
       return LSD_ERR_CUDA;
@@ -929,12 +914,8 @@ int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
   k_se3_reset<<<1, 1, 0, st>>>(s->d_ctrs, (unsigned)m, (unsigned)active);
   k_se3_init<<<(m + 127) / 128, 128, 0, st>>>(s->d_pairs + i0, s->d_states + i0, m, q, prm, active);
   lsd_trace_entry *d_tr = wantTrace ? s->d_traces + (size_t)i0 * LSD_TRACE_CAP : nullptr;
-  if (m <= SE3_SELF_MAX_PAIRS)
-    k_se3_track<true><<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs + i0, s->d_states + i0,
-                                                            s->d_partials + (size_t)i0 * prm.maxChunks * SE3_NRED, q, prm, d_tr);
-  else
-    k_se3_track<false><<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs + i0, s->d_states + i0,
-                                                             s->d_partials + (size_t)i0 * prm.maxChunks * SE3_NRED, q, prm, d_tr);
+  k_se3_track<<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs + i0, s->d_states + i0, s->d_partials + (size_t)i0 * prm.maxChunks * SE3_NRED,
+                                                    q, prm, d_tr);
   LSD_CUDA(cudaGetLastError());
   ctx->launches += 3;
   return LSD_OK;
