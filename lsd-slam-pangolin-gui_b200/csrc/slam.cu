@@ -145,10 +145,14 @@ static int first_keyframe(lsd_slam *s, int id, const uint8_t *image, size_t pitc
   int rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_MAXGRAD0 | LSD_BUILD_GRAD0, &kf);
   if (rc) return rc;
   if (depth) {  // SlamSystem::gtDepthInit: Frame::setDepthFromGroundTruth + DepthMap::initializeFromGTDepth
-    if ((rc = lsd_frame_set_depth_from_gt(s->ctx, kf, depth, 1.0f))) return rc;
-    if ((rc = lsd_depth_initialize_from_gt(s->ctx, s->dm, kf))) return rc;
+    rc = lsd_frame_set_depth_from_gt(s->ctx, kf, depth, 1.0f);
+    if (!rc) rc = lsd_depth_initialize_from_gt(s->ctx, s->dm, kf);
   } else {  // SlamSystem::randomInit
-    if ((rc = lsd_depth_initialize_randomly(s->ctx, s->dm, kf))) return rc;
+    rc = lsd_depth_initialize_randomly(s->ctx, s->dm, kf);
+  }
+  if (rc) {
+    lsd_frame_release(s->ctx, kf);
+    return rc;
   }
   s->kf = kf;
   s->nKeyframes = 1;
@@ -185,6 +189,12 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
   };
   if ((rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_MAXGRAD0, &f))) return rc;
   lap(0);
+  struct FrameGuard {  // the new frame is dropped on every error exit below
+    lsd_ctx *ctx;
+    lsd_frame *&f;
+    bool armed;
+    ~FrameGuard() { if (armed && f) lsd_frame_release(ctx, f); }
+  } guard = {ctx, f, true};
 
   // ---- SlamSystem::trackFrame
   if (!s->ref || s->refKfId != s->kf->id || s->kf->depthHasBeenUpdatedFlag) {
@@ -200,9 +210,8 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
   lap(2);
   if (res.diverged || !res.trackingWasGood) {  // upstream hands over to the Relocalizer (out of scope): drop the frame
     s->lost++;
-    lsd_frame_release(ctx, f);
     fill_status(s, id, 0, 0, s->lastToKf, &res, 0.0f, st);
-    return LSD_OK;
+    return LSD_OK;  // guard releases the frame
   }
   s->tracked++;
   double toKf[8];
@@ -242,6 +251,7 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     if (s->keepFinishedKeyframes) s->keyframes.push_back(s->kf);
     else lsd_frame_release(ctx, s->kf);
     s->kf = f;
+    guard.armed = false;  // the frame lives on as the current keyframe
     s->nKeyframes++;
     s->kfMeanValid = false;
     sim3_identity(s->lastToKf);
@@ -257,6 +267,7 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     if (setsDepth) s->kfMeanValid = false;
     fill_status(s, id, 1, 0, toKf, &res, score, st);
     lsd_frame_release(ctx, f);
+    guard.armed = false;
     lap(3);
   }
   return LSD_OK;

@@ -122,6 +122,8 @@ using namespace lsd;
 
 extern "C" {
 
+int lsd_undistorter_destroy(lsd_ctx *ctx, lsd_undistorter *u);
+
 int lsd_undistorter_create_from_maps(lsd_ctx *ctx, int inWidth, int inHeight, const int16_t *map1, const uint16_t *map2,
                                      lsd_undistorter **out) {
   LSD_ARG(ctx && map1 && map2 && out && inWidth > 0 && inHeight > 0);
@@ -131,11 +133,19 @@ int lsd_undistorter_create_from_maps(lsd_ctx *ctx, int inWidth, int inHeight, co
   u->inW = inWidth; u->inH = inHeight;
   u->outW = ctx->w; u->outH = ctx->h;
   const size_t N = (size_t)u->outW * u->outH;
-  LSD_CUDA(cudaMalloc(&u->d_map1, N * sizeof(short2)));
-  LSD_CUDA(cudaMalloc(&u->d_map2, N * sizeof(uint16_t)));
-  LSD_CUDA(cudaMemcpyAsync(u->d_map1, map1, N * sizeof(short2), cudaMemcpyHostToDevice, ctx->stream));
-  LSD_CUDA(cudaMemcpyAsync(u->d_map2, map2, N * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  auto upload = [&]() -> int {
+    LSD_CUDA(cudaMalloc(&u->d_map1, N * sizeof(short2)));
+    LSD_CUDA(cudaMalloc(&u->d_map2, N * sizeof(uint16_t)));
+    LSD_CUDA(cudaMemcpyAsync(u->d_map1, map1, N * sizeof(short2), cudaMemcpyHostToDevice, ctx->stream));
+    LSD_CUDA(cudaMemcpyAsync(u->d_map2, map2, N * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LSD_OK;
+  };
+  const int rc = upload();
+  if (rc) {
+    lsd_undistorter_destroy(ctx, u);
+    return rc;
+  }
   *out = u;
   return LSD_OK;
 }
@@ -155,7 +165,8 @@ int lsd_undistorter_destroy(lsd_ctx *ctx, lsd_undistorter *u) {
   if (!u) return LSD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(u->d_map1); cudaFree(u->d_map2);
+  if (u->d_map1) cudaFree(u->d_map1);
+  if (u->d_map2) cudaFree(u->d_map2);
   if (u->d_src) cudaFree(u->d_src);
   if (u->d_dst) cudaFree(u->d_dst);
   if (u->h_src) cudaFreeHost(u->h_src);
