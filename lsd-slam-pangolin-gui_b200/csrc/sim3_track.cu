@@ -140,9 +140,35 @@ __device__ void s3_make_cmd(const double q[4], const double t[3], double s, floa
   c.op = 0;
 }
 
-__device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, const S3Cmd &c, const Sim3Params &prm, int W, int H,
-                                         const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR,
-                                         float acc[S3_NF], double dacc[S3_ND]) {
+// Per-thread accumulators.  S3_SMEM_ACC = 1 keeps the 46 fp32 sums of a thread in ITS column of the shared-memory
+// reduction buffer (conflict-free: consecutive threads, consecutive banks) instead of in registers: the register budget
+// drops by ~50, twice the CTAs are resident, and the sequence of additions per thread -- hence every bit of the result
+// -- is unchanged (the block reduction then reads the buffer in place).
+#ifndef S3_SMEM_ACC
+#define S3_SMEM_ACC 1
+#endif
+#if S3_SMEM_ACC
+struct S3Acc {
+  float *col;  // &sm.f[0][threadIdx.x]
+  __device__ __forceinline__ float &operator[](int j) const { return col[j * S3_THREADS]; }
+};
+#else
+typedef float *S3Acc;
+#endif
+
+// One reference point: its warp and the loads issued for it (stage A), consumed by stage B.  Running stage A of point
+// k+1 before stage B of point k (a two-deep software pipeline) was measured SLOWER (2.29 vs 2.13 ms: the 18 extra live
+// registers spill), so the two stages run back to back; only the 24-byte point record is fetched one iteration ahead.
+struct S3Warp {
+  float Wx, Wy, Wz, pz, u_new, v_new;
+  float4 p00, p10, p01, p11;
+  float var_frameDepth, id_frameDepth;
+  bool inside;
+};
+
+__device__ __forceinline__ void s3_stage_a(const float4 raw, const S3Cmd &c, const Sim3Params &prm, int W, int H,
+                                           const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR,
+                                           S3Warp &w) {
   const int lvl = c.level;
   const float fx_l = prm.K.fx[lvl], fy_l = prm.K.fy[lvl], cx_l = prm.K.cx[lvl], cy_l = prm.K.cy[lvl];
   const uint32_t xy = __float_as_uint(raw.x);
@@ -151,17 +177,34 @@ __device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, cons
   const float px = inv * (prm.K.fxi[lvl] * x + prm.K.cxi[lvl]);
   const float py = inv * (prm.K.fyi[lvl] * y + prm.K.cyi[lvl]);
   const float pz = inv * 1.0f;
-  const float Wx = (c.Rs[0] * px + c.Rs[1] * py + c.Rs[2] * pz) + c.t[0];
-  const float Wy = (c.Rs[3] * px + c.Rs[4] * py + c.Rs[5] * pz) + c.t[1];
-  const float Wz = (c.Rs[6] * px + c.Rs[7] * py + c.Rs[8] * pz) + c.t[2];
-  const float u_new = (Wx / Wz) * fx_l + cx_l;
-  const float v_new = (Wy / Wz) * fy_l + cy_l;
-  if (!(u_new > 1 && v_new > 1 && u_new < W - 2 && v_new < H - 2)) return;
-  // getInterpolatedElement43
+  w.pz = pz;
+  w.Wx = (c.Rs[0] * px + c.Rs[1] * py + c.Rs[2] * pz) + c.t[0];
+  w.Wy = (c.Rs[3] * px + c.Rs[4] * py + c.Rs[5] * pz) + c.t[1];
+  w.Wz = (c.Rs[6] * px + c.Rs[7] * py + c.Rs[8] * pz) + c.t[2];
+  w.u_new = (w.Wx / w.Wz) * fx_l + cx_l;
+  w.v_new = (w.Wy / w.Wz) * fy_l + cy_l;
+  w.inside = w.u_new > 1 && w.v_new > 1 && w.u_new < W - 2 && w.v_new < H - 2;
+  if (!w.inside) return;
+  // getInterpolatedElement43 taps + the frame's own (idepth, var) at the nearest pixel, all in ONE memory round trip
+  // (ncu source view of the first version: point record, taps, var, idepth were four serial HBM latencies per point)
+  const int ix = (int)w.u_new, iy = (int)w.v_new;
+  const float4 *bp = G + ix + iy * W;
+  w.p00 = __ldg(bp); w.p10 = __ldg(bp + 1); w.p01 = __ldg(bp + W); w.p11 = __ldg(bp + 1 + W);
+  const int idx_rounded = (int)(w.u_new + 0.5f) + W * (int)(w.v_new + 0.5f);
+  w.var_frameDepth = __ldg(FVAR + idx_rounded);
+  w.id_frameDepth = __ldg(FID + idx_rounded);
+}
+
+__device__ __forceinline__ void s3_stage_b(const float4 raw, const float2 rg, const S3Warp &w, const S3Cmd &c, const Sim3Params &prm,
+                                           S3Acc acc, double dacc[S3_ND]) {
+  if (!w.inside) return;
+  const int lvl = c.level;
+  const float fx_l = prm.K.fx[lvl], fy_l = prm.K.fy[lvl];
+  const float Wx = w.Wx, Wy = w.Wy, Wz = w.Wz, pz = w.pz, u_new = w.u_new, v_new = w.v_new;
+  const float4 p00 = w.p00, p10 = w.p10, p01 = w.p01, p11 = w.p11;
+  const float var_frameDepth = w.var_frameDepth, id_frameDepth = w.id_frameDepth;
   const int ix = (int)u_new, iy = (int)v_new;
   const float dx = u_new - ix, dy = v_new - iy, dxdy = dx * dy;
-  const float4 *bp = G + ix + iy * W;
-  const float4 p00 = __ldg(bp), p10 = __ldg(bp + 1), p01 = __ldg(bp + W), p11 = __ldg(bp + 1 + W);
   const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
   const float gxI = w11 * p11.x + w01 * p01.x + w10 * p10.x + w00 * p00.x;
   const float gyI = w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y;
@@ -183,13 +226,11 @@ __device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, cons
   dacc[4] += (double)weight;
 
   // depth residual against the frame's own inverse depth (nearest pixel)
-  const int idx_rounded = (int)(u_new + 0.5f) + W * (int)(v_new + 0.5f);
-  const float var_frameDepth = __ldg(FVAR + idx_rounded);
   const float ref_idepth = 1.0f / Wz;
   const float d = 1.0f / pz;
   float rd, svw;
   if (var_frameDepth > 0) {
-    rd = ref_idepth - __ldg(FID + idx_rounded);
+    rd = ref_idepth - id_frameDepth;
     svw = var_frameDepth;
   } else {
     rd = -1;
@@ -254,6 +295,14 @@ __device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, cons
   }
 }
 
+__device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, const S3Cmd &c, const Sim3Params &prm, int W, int H,
+                                         const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR,
+                                         S3Acc acc, double dacc[S3_ND]) {
+  S3Warp w;
+  s3_stage_a(raw, c, prm, W, H, G, FID, FVAR, w);
+  s3_stage_b(raw, rg, w, c, prm, acc, dacc);
+}
+
 // Address-only twin of s3_point's projection: touches the four gradient taps and the nearest idepth / var cell of the
 // point that will be evaluated NEXT by this thread, so that its loads hit L2/L1 instead of paying an HBM round trip in
 // the middle of a ~300-instruction dependency chain.  Prefetches have no architectural effect: results are unchanged.
@@ -286,9 +335,16 @@ __device__ __forceinline__ void s3_prefetch(const float4 raw, const S3Cmd &c, co
   asm volatile("prefetch.global.L1 [%0];" ::"l"(FID + idx_rounded));
 }
 
+// S3_DSHUF = 1: the five fp64 affine sums are reduced with warp shuffles + an 8-entry table per sum instead of a
+// [5][256] double buffer (10 KB): the dynamic shared memory of a CTA drops to 46 KB so that FOUR CTAs fit on an SM.
+#ifndef S3_DSHUF
+#define S3_DSHUF 1
+#endif
 struct S3Smem {
   float f[S3_NF][S3_THREADS];
+#if !S3_DSHUF
   double d[S3_ND][S3_THREADS];
+#endif
 };
 
 __device__ __forceinline__ bool s3_too_few(int size, int lvl, const Sim3Params &prm) {
@@ -509,6 +565,7 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const
   __shared__ S3Cmd cmd;
   __shared__ float part[S3_NF];
   __shared__ double dpart[S3_ND];
+  __shared__ double dwarp[S3_ND][S3_THREADS / 32];
   __shared__ float tot[S3_NF];
   __shared__ double dtot[S3_ND];
   __shared__ S3State S;  // used by thread 0 of rank 0 only
@@ -553,7 +610,12 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const
     // contiguous part of this CTA (multiple of 32 points)
     const int per = (((n + S3_CL - 1) / S3_CL) + 31) & ~31;
     const int begin = min(n, (int)rank * per), end = min(n, begin + per);
-    float acc[S3_NF];
+#if S3_SMEM_ACC
+    S3Acc acc = {&sm.f[0][threadIdx.x]};
+#else
+    float accReg[S3_NF];
+    S3Acc acc = accReg;
+#endif
     double dacc[S3_ND];
 #pragma unroll
     for (int j = 0; j < S3_NF; j++) acc[j] = 0.0f;
@@ -581,16 +643,50 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const
       }
     }
 #else
-    for (int i = begin + threadIdx.x; i < end; i += S3_THREADS)
-      s3_point(__ldg(pts4 + i), __ldg(rg + i), cmd, prm, W, H, J->fgrad[lvl], J->fid[lvl], J->fvar[lvl], acc, dacc);
+    {  // the next point's record (reference point + gradient) is loaded while the current point is evaluated
+      const float4 *G = J->fgrad[lvl];
+      const float *FID = J->fid[lvl], *FVAR = J->fvar[lvl];
+      int i = begin + threadIdx.x;
+      float4 rawC = make_float4(0, 0, 0, 0);
+      float2 rgC = make_float2(0, 0);
+      if (i < end) { rawC = __ldg(pts4 + i); rgC = __ldg(rg + i); }
+      for (; i < end; i += S3_THREADS) {
+        float4 rawN = rawC;
+        float2 rgN = rgC;
+        if (i + S3_THREADS < end) { rawN = __ldg(pts4 + i + S3_THREADS); rgN = __ldg(rg + i + S3_THREADS); }
+        s3_point(rawC, rgC, cmd, prm, W, H, G, FID, FVAR, acc, dacc);
+        rawC = rawN;
+        rgC = rgN;
+      }
+    }
 #endif
     // block reduction in a fixed order (same scheme as the SE3 tracker)
+#if !S3_SMEM_ACC
 #pragma unroll
     for (int j = 0; j < S3_NF; j++) sm.f[j][threadIdx.x] = acc[j];
+#endif
+#if S3_DSHUF
+#pragma unroll
+    for (int j = 0; j < S3_ND; j++) {
+      double v = dacc[j];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) dwarp[j][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < S3_ND) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < S3_THREADS / 32; k++) v += dwarp[threadIdx.x][k];
+      dpart[threadIdx.x] = v;
+    }
+    for (int row = wid; row < S3_NF; row += S3_THREADS / 32) {
+#else
 #pragma unroll
     for (int j = 0; j < S3_ND; j++) sm.d[j][threadIdx.x] = dacc[j];
     __syncthreads();
     for (int row = wid; row < S3_NF + S3_ND; row += S3_THREADS / 32) {
+#endif
       if (row < S3_NF) {
         float v = 0.0f;
 #pragma unroll
@@ -598,7 +694,9 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) part[row] = v;
-      } else {
+      }
+#if !S3_DSHUF
+      else {
         const int r = row - S3_NF;
         double v = 0.0;
 #pragma unroll
@@ -607,6 +705,7 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const
         for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) dpart[r] = v;
       }
+#endif
     }
     cluster.sync();  // every CTA's partial is in its shared memory
     if (rank == 0) {
