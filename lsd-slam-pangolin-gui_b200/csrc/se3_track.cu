@@ -592,20 +592,15 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
   __shared__ int sCode, sIsLast;
 
   unsigned ticket = 0;
-  unsigned long long peek = 0;  // thread 0: the NEXT ticket's slot, read while the current item is being evaluated
   if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
   for (;;) {
     // ---- fetch the next work item (thread 0 spins on its ticket's slot) ----
-    // ncu source view: 20 % of all warp samples sat at the barrier below while thread 0 paid the L2 round trips of the
-    // slot poll.  The slot of the already-reserved next ticket is therefore read early (SE3_PEEK, below) and the value is
-    // tried first: when the item had been published by then, the fetch costs no memory latency at all.
     if (threadIdx.x == 0) {
       const unsigned slot = ticket & (q.cap - 1), seq = ticket / q.cap + 1;
       const volatile unsigned long long *sp = reinterpret_cast<const volatile unsigned long long *>(&q.slots[slot]);
       int code = -1;
       for (;;) {
-        const unsigned long long v = ((unsigned)(peek >> 32) == seq) ? peek : *sp;
-        peek = 0;
+        const unsigned long long v = *sp;
         if ((unsigned)(v >> 32) == seq) {
           code = (int)(unsigned)v;
           break;
@@ -619,8 +614,6 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
     __syncthreads();
     const int code = sCode;
     if (code < 0) break;
-    if (threadIdx.x == 0)  // SE3_PEEK: issued now, consumed at the next fetch (the load is in flight during eval_range)
-      peek = *reinterpret_cast<const volatile unsigned long long *>(&q.slots[ticket & (q.cap - 1)]);
     const int pairIdx = code >> 12, chunk = code & 0xfff;
     const SE3Pair *P = pairs + pairIdx;
     SE3State *S = states + pairIdx;
