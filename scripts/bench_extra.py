@@ -375,7 +375,7 @@ def main():
     ctx = lsd_b200.Context(W, H, synth.default_K(W, H), device=0)
     reps = int(os.environ.get("EXTRA_REPS", "5"))
     cpu = os.environ.get("EXTRA_NO_CPU", "") == ""
-    parts = os.environ.get("EXTRA_PARTS", "depthmap,sim3,vbo").split(",")
+    parts = os.environ.get("EXTRA_PARTS", "depthmap,sim3,vbo,pipeline").split(",")
     B = int(os.environ.get("EXTRA_B", "64"))
     out = {}
     if "depthmap" in parts:
