@@ -26,7 +26,9 @@ namespace cg = cooperative_groups;
 
 namespace lsd {
 
+#ifndef S3_THREADS
 #define S3_THREADS 256
+#endif
 // CTAs per cluster = per track.  Measured on B200 (64 candidates x 2 directions, levels 4->1): 8 CTAs 2.96 ms, 4 CTAs
 // 2.70 ms, 2 CTAs 3.22 ms, 1 CTA 6.2 ms (profiles/r01j_sim3_cluster_sweep.txt)
 #ifndef S3_CL
