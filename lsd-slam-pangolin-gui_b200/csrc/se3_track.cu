@@ -724,6 +724,7 @@ struct SE3ScratchImpl {
   SE3Pair *h_pairs = nullptr;  // pinned
   SE3State *d_states = nullptr;
   SE3State *h_states = nullptr;  // pinned
+  uint8_t **d_maskTab = nullptr, **h_maskTab = nullptr;  // frames whose refPixelWasGood mask is created by this call (pinned / device)
   int cap = 0;
   float *d_partials = nullptr;
   int maxChunks = 0;
@@ -748,6 +749,8 @@ void se3_scratch_free(lsd_ctx *ctx) {
   cudaFreeHost(s->h_pairs);
   cudaFree(s->d_states);
   cudaFreeHost(s->h_states);
+  cudaFree(s->d_maskTab);
+  cudaFreeHost(s->h_maskTab);
   cudaFree(s->d_partials);
   cudaFree(s->d_slots);
   cudaFree(s->d_ctrs);
@@ -767,6 +770,8 @@ static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
     cudaFreeHost(s->h_pairs);
     cudaFree(s->d_states);
     cudaFreeHost(s->h_states);
+    cudaFree(s->d_maskTab);
+    cudaFreeHost(s->h_maskTab);
     cudaFree(s->d_partials);
     cudaFree(s->d_slots);
     int cap = n < 16 ? 16 : n;
@@ -774,6 +779,8 @@ static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
     LSD_CUDA(cudaMallocHost(&s->h_pairs, sizeof(SE3Pair) * cap));
     LSD_CUDA(cudaMalloc(&s->d_states, sizeof(SE3State) * cap));
     LSD_CUDA(cudaMallocHost(&s->h_states, sizeof(SE3State) * cap));
+    LSD_CUDA(cudaMalloc(&s->d_maskTab, sizeof(uint8_t *) * cap));
+    LSD_CUDA(cudaMallocHost(&s->h_maskTab, sizeof(uint8_t *) * cap));
     LSD_CUDA(cudaMalloc(&s->d_partials, (size_t)cap * maxChunks * SE3_NRED * sizeof(float)));
     s->maxChunks = maxChunks;
     unsigned need = (unsigned)cap * (unsigned)maxChunks + 4096u, qcap = 1;
@@ -839,20 +846,19 @@ static double alg_bytes_level(const lsd_ctx *ctx, int l, int n) {
 }
 
 static int init_masks(lsd_ctx *ctx, int n, lsd_frame *const *frames, cudaStream_t st) {
-  // masks are created 0xFF on first use (Frame::refPixelWasGood())
-  std::vector<uint8_t *> need;
+  // masks are created 0xFF on first use (Frame::refPixelWasGood()).  The pointer list has its own pinned / device table
+  // in the tracker scratch (sized for the batch by se3_scratch_ensure), so no host synchronisation is needed here: the
+  // table is next written by the next tracking call, which starts after this call's final synchronisation.
+  SE3Scratch *s = ctx->se3s;
+  int m = 0;
   for (int i = 0; i < n; i++)
     if (!(frames[i]->built & FB_MASK)) {
-      need.push_back(frames[i]->slab);
+      s->h_maskTab[m++] = frames[i]->slab;
       frames[i]->built |= FB_MASK;
     }
-  if (need.empty()) return LSD_OK;
-  int rc = ensure_table(ctx, need.size() * sizeof(void *));
-  if (rc) return rc;
-  std::memcpy(ctx->h_table, need.data(), need.size() * sizeof(void *));
-  LSD_CUDA(cudaMemcpyAsync(ctx->d_table, ctx->h_table, need.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
-  launch_mask_init(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), (int)need.size(), st);
-  LSD_CUDA(cudaStreamSynchronize(st));  // h_table is reused by callers
+  if (m == 0) return LSD_OK;
+  LSD_CUDA(cudaMemcpyAsync(s->d_maskTab, s->h_maskTab, sizeof(uint8_t *) * (size_t)m, cudaMemcpyHostToDevice, st));
+  launch_mask_init(ctx, s->d_maskTab, m, st);
   return LSD_OK;
 }
 
