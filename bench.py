@@ -332,9 +332,12 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_se3_track (persistent: all LM evaluations of the batch)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
-                         "traffic_note": "ncu --set full of a 256-pair launch (profiles/r01n_k_se3_track_full.txt): dram read+write 3.12 GB "
-                                         "against 3.99 GB algorithmic for that launch (L2 absorbs the shared taps: no wasted re-reads)",
+                         "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of k_se3_track from one `ncu --set full` capture of THIS workload
+                         # (1000 pairs; profiles/r01z_k_se3_track_full_1000pairs.txt); other batch sizes: not captured -> null
+                         "traffic": 13311593712.0 if n == 1000 else None,
+                         "traffic_source": "profiles/r01z_k_se3_track_full_1000pairs.txt (12.88 GB read + 0.43 GB written per launch; below the "
+                                           "15.55 GB algorithmic figure because L2 absorbs taps shared by neighbouring points: no wasted re-reads)",
                          "algorithmic_bytes_per_launch": statistics.mean(alg_bytes), "kernel_ms": k_ms,
                          "evaluations_per_launch": statistics.mean(evals)},
             "quality": {"diverged": int(n_div), "trackingWasGood": int(n_good),
