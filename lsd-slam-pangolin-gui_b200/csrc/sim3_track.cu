@@ -305,38 +305,6 @@ __device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, cons
   s3_stage_b(raw, rg, w, c, prm, acc, dacc);
 }
 
-// Address-only twin of s3_point's projection: touches the four gradient taps and the nearest idepth / var cell of the
-// point that will be evaluated NEXT by this thread, so that its loads hit L2/L1 instead of paying an HBM round trip in
-// the middle of a ~300-instruction dependency chain.  Prefetches have no architectural effect: results are unchanged.
-#ifndef S3_PREFETCH
-#define S3_PREFETCH 0  // measured: 2.91 ms with, 2.70 ms without (profiles/r01l_sweep.txt) -- kept for reference, off
-#endif
-__device__ __forceinline__ void s3_prefetch(const float4 raw, const S3Cmd &c, const Sim3Params &prm, int W, int H,
-                                            const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR) {
-  const int lvl = c.level;
-  const uint32_t xy = __float_as_uint(raw.x);
-  const int x = xy & 0xffff, y = xy >> 16;
-  const float inv = raw.y;
-  const float px = inv * (prm.K.fxi[lvl] * x + prm.K.cxi[lvl]);
-  const float py = inv * (prm.K.fyi[lvl] * y + prm.K.cyi[lvl]);
-  const float pz = inv;
-  const float Wx = (c.Rs[0] * px + c.Rs[1] * py + c.Rs[2] * pz) + c.t[0];
-  const float Wy = (c.Rs[3] * px + c.Rs[4] * py + c.Rs[5] * pz) + c.t[1];
-  const float Wz = (c.Rs[6] * px + c.Rs[7] * py + c.Rs[8] * pz) + c.t[2];
-  const float u_new = __fdividef(Wx, Wz) * prm.K.fx[lvl] + prm.K.cx[lvl];
-  const float v_new = __fdividef(Wy, Wz) * prm.K.fy[lvl] + prm.K.cy[lvl];
-  if (!(u_new > 1 && v_new > 1 && u_new < W - 2 && v_new < H - 2)) return;
-  const int ix = (int)u_new, iy = (int)v_new;
-  const float4 *bp = G + ix + iy * W;
-  const int idx_rounded = (int)(u_new + 0.5f) + W * (int)(v_new + 0.5f);
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(bp));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(bp + 1));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(bp + W));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(bp + W + 1));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(FVAR + idx_rounded));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(FID + idx_rounded));
-}
-
 // S3_DSHUF = 1: the five fp64 affine sums are reduced with warp shuffles + an 8-entry table per sum instead of a
 // [5][256] double buffer (10 KB): the dynamic shared memory of a CTA drops to 46 KB so that FOUR CTAs fit on an SM.
 #ifndef S3_DSHUF
@@ -625,26 +593,6 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const
     for (int j = 0; j < S3_ND; j++) dacc[j] = 0.0;
     const float4 *pts4 = reinterpret_cast<const float4 *>(J->pts[lvl]);
     const float2 *rg = J->rgrad[lvl];
-#if S3_PREFETCH
-    {  // two-deep software pipeline: point k is evaluated while the taps of k+1 are prefetched and the record of k+2 loads
-      const float4 *G = J->fgrad[lvl];
-      const float *FID = J->fid[lvl], *FVAR = J->fvar[lvl];
-      int i = begin + threadIdx.x;
-      float4 rawC = make_float4(0, 0, 0, 0), rawN = rawC;
-      float2 rgC = make_float2(0, 0), rgN = rgC;
-      if (i < end) { rawC = __ldg(pts4 + i); rgC = __ldg(rg + i); }
-      if (i + S3_THREADS < end) { rawN = __ldg(pts4 + i + S3_THREADS); rgN = __ldg(rg + i + S3_THREADS); }
-      for (; i < end; i += S3_THREADS) {
-        float4 rawNN = rawN;
-        float2 rgNN = rgN;
-        if (i + 2 * S3_THREADS < end) { rawNN = __ldg(pts4 + i + 2 * S3_THREADS); rgNN = __ldg(rg + i + 2 * S3_THREADS); }
-        if (i + S3_THREADS < end) s3_prefetch(rawN, cmd, prm, W, H, G, FID, FVAR);
-        s3_point(rawC, rgC, cmd, prm, W, H, G, FID, FVAR, acc, dacc);
-        rawC = rawN; rgC = rgN;
-        rawN = rawNN; rgN = rgNN;
-      }
-    }
-#else
     {  // the next point's record (reference point + gradient) is loaded while the current point is evaluated
       const float4 *G = J->fgrad[lvl];
       const float *FID = J->fid[lvl], *FVAR = J->fvar[lvl];
@@ -661,7 +609,6 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const
         rgC = rgN;
       }
     }
-#endif
     // block reduction in a fixed order (same scheme as the SE3 tracker)
 #if !S3_SMEM_ACC
 #pragma unroll
