@@ -233,6 +233,9 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
+  ctx->d_stats = nullptr;
+  LSD_CUDA(cudaMalloc(&ctx->d_stats, 16 + 16 * (size_t)ctx->numSMs));
+  LSD_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 16 + 16 * (size_t)ctx->numSMs, ctx->stream));
   ctx->se3ActivePairs = 0;
   ctx->refSlabBytes = 0;
   ctx->h_stage = ctx->d_stage = nullptr;
@@ -260,6 +263,7 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_table) cudaFreeHost(ctx->h_table);
   if (ctx->d_table) cudaFree(ctx->d_table);
+  if (ctx->d_stats) cudaFree(ctx->d_stats);
   cudaEventDestroy(ctx->evA);
   cudaEventDestroy(ctx->evB);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->evPipe[i]);

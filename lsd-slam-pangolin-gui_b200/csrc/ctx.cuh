@@ -34,6 +34,7 @@ struct lsd_ctx {
   void *h_table;
   void *d_table;
   size_t tableBytes;
+  uint8_t *d_stats;  // k_idepth_stats: ticket (16 B) + per-CTA partial sums
   bool stageTimed;  // evA/evB bracket the kernels of the last depth stage
   int descSlot;  // rotating slot of the depth-map descriptor uploads (depth.cu)
   SE3Scratch *se3s;

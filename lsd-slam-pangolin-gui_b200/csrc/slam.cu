@@ -187,7 +187,9 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     s->stageSec[k] += std::chrono::duration<double>(t1 - t0).count();
     t0 = t1;
   };
-  if ((rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_MAXGRAD0, &f))) return rc;
+  // a tracked frame needs image + gradient pyramids only; maxGradients(0) / gradients(0) are built lazily if it is promoted
+  // to keyframe (propagateDepth asks for them)
+  if ((rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_TRACKING, &f))) return rc;
   lap(0);
   struct FrameGuard {  // the new frame is dropped on every error exit below
     lsd_ctx *ctx;
