@@ -24,6 +24,7 @@
 // residual, isGood) is bit-identical to the oracle's (-ffp-contract=off); weights, Jacobian rows and the
 // accumulated terms use explicit fmaf and MUFU approximations (see accumulate_point).
 #include <cmath>
+#include <cstdlib>
 #include <cstddef>
 #include <cstring>
 
@@ -920,7 +921,13 @@ int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
   k_se3_reset<<<1, 1, 0, st>>>(s->d_ctrs, (unsigned)m, (unsigned)active);
   k_se3_init<<<(m + 127) / 128, 128, 0, st>>>(s->d_pairs + i0, s->d_states + i0, m, q, prm, active);
   lsd_trace_entry *d_tr = wantTrace ? s->d_traces + (size_t)i0 * LSD_TRACE_CAP : nullptr;
-  k_se3_track<<<s->gridBlocks, SE3_THREADS, 0, st>>>(s->d_pairs + i0, s->d_states + i0, s->d_partials + (size_t)i0 * prm.maxChunks * SE3_NRED,
+  // every launched CTA polls the queue while idle: a small batch gets only as many CTAs as it can ever have work items in
+  // flight (one evaluation per pair, at most maxChunks items each), not the whole machine
+  const long long useful = (long long)m * prm.maxChunks;
+  int grid = (int)(useful < (long long)s->gridBlocks ? (useful < 32 ? 32 : useful) : s->gridBlocks);
+  static const int envGrid = getenv("LSD_B200_SE3_GRID") ? atoi(getenv("LSD_B200_SE3_GRID")) : 0;  // experiments only
+  if (envGrid > 0 && envGrid <= s->gridBlocks) grid = envGrid;
+  k_se3_track<<<grid, SE3_THREADS, 0, st>>>(s->d_pairs + i0, s->d_states + i0, s->d_partials + (size_t)i0 * prm.maxChunks * SE3_NRED,
                                                     q, prm, d_tr);
   LSD_CUDA(cudaGetLastError());
   ctx->launches += 3;
