@@ -52,3 +52,23 @@ def test_cpp_adapter_compiles_and_links():
     out = subprocess.run([os.path.join(pkg, "build", "adapter_check")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "no device" in out.stdout or "tracked:" in out.stdout
+
+
+def test_library_holds_sm_100a_code_for_every_kernel():
+    """The shipped library carries sm_100a SASS only (no other arch, no PTX-only fallback) and one entry per kernel named in
+    DESIGN.md section 4 -- a kernel silently dropped from the build would otherwise only show up on the GPU box."""
+    import shutil
+    import subprocess
+    import pytest
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "lsd-slam-pangolin-gui_b200", "liblsd_b200.so")
+    elfs = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout.split()
+    archs = {m for e in elfs for m in re.findall(r"sm_\d+a?", e)}
+    assert archs == {"sm_100a"}, archs
+    syms = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    for k in ("k_ingest", "k_gradients", "k_maxgrad0", "k_idepth_pyramid", "k_make_pointcloud", "k_se3_track", "k_sim3_track",
+              "k_depth_observe", "k_depth_fill_holes", "k_depth_regularize", "k_prop_scatter", "k_prop_reserve", "k_prop_fill",
+              "k_prop_replay", "k_depth_sums", "k_depth_set_depth", "k_vbo_extract", "k_publish_pack", "k_remap_u8",
+              "k_permaref_overlap", "k_idepth_stats"):
+        assert k in syms, f"kernel {k} missing from liblsd_b200.so"
