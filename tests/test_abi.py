@@ -72,3 +72,29 @@ def test_library_holds_sm_100a_code_for_every_kernel():
               "k_prop_replay", "k_depth_sums", "k_depth_set_depth", "k_vbo_extract", "k_publish_pack", "k_remap_u8",
               "k_permaref_overlap", "k_idepth_stats"):
         assert k in syms, f"kernel {k} missing from liblsd_b200.so"
+
+
+def test_pose_line_format_equals_ostream_default(lsd, tmp_path):
+    """TextOutputIOWrapper::publishTrackedFrame streams `id << "," << trans.x() << ...` with ostream's default formatting
+    (/root/reference/lib/Pangolin_IOWrapper/TextOutputIOWrapper.cpp:100-120).  lsd_slam_pose_line must produce the same
+    characters: checked against a real std::ostream compiled here, on values that exercise %g's corner cases."""
+    import ctypes as C
+    import subprocess
+    vals = [0.0, -0.0, 1.0, -1.5, 0.1, 1e-5, 1.23456789e-5, 123456.7, 1234567.8, 0.000123456789, 3.14159265358979, -2.5e10, 1e100, 5e-324]
+    src = tmp_path / "fmt.cpp"
+    src.write_text('#include <iostream>\n#include <cstdlib>\nint main(int c, char** v){ std::cout << atoi(v[1]);'
+                   ' for (int i = 2; i < c; i++) std::cout << "," << strtod(v[i], nullptr); std::cout << std::endl; }\n')
+    exe = tmp_path / "fmt"
+    subprocess.check_call(["g++", "-O1", str(src), "-o", str(exe)])
+    L = lsd.load()
+    for k in range(0, len(vals) - 5):
+        six = vals[k:k + 6]
+        st = lsd.SlamStatus()
+        st.frameId = 40 + k
+        for i in range(3):
+            st.camToWorld[4 + i] = six[i]
+            st.thisToParent_raw[4 + i] = six[3 + i]
+        buf = C.create_string_buffer(256)
+        assert L.lsd_slam_pose_line(C.byref(st), buf, 256) == 0
+        want = subprocess.run([str(exe), str(40 + k)] + [repr(v) for v in six], capture_output=True, text=True).stdout
+        assert buf.value.decode() == want, (buf.value, want)
