@@ -223,6 +223,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
     ctx->ownStream = true;
   }
   LSD_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  LSD_CUDA(cudaStreamCreateWithFlags(&ctx->trackStream, cudaStreamNonBlocking));
   LSD_CUDA(cudaEventCreate(&ctx->evA));
   LSD_CUDA(cudaEventCreate(&ctx->evB));
   for (int i = 0; i < 4; i++) LSD_CUDA(cudaEventCreateWithFlags(&ctx->evPipe[i], cudaEventDisableTiming));
@@ -268,6 +269,7 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
   cudaEventDestroy(ctx->evB);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->evPipe[i]);
   cudaStreamDestroy(ctx->copyStream);
+  cudaStreamDestroy(ctx->trackStream);
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return LSD_OK;
@@ -784,6 +786,14 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     LSD_CUDA(cudaEventRecord(copied[c], ctx->copyStream));
     return LSD_OK;
   };
+  // LSD_B200_E2E_STREAM=0 selects the older schedule (one tracker launch per chunk); default: ONE persistent tracker fed chunk by chunk
+  static const bool streamed = !(getenv("LSD_B200_E2E_STREAM") && atoi(getenv("LSD_B200_E2E_STREAM")) == 0);
+  if (streamed && nChunks > 1) {
+    LSD_CUDA(cudaStreamWaitEvent(ctx->trackStream, ctx->evPipe[0], 0));  // pair table uploaded
+    rc = se3_stream_begin(ctx, n, ctx->trackStream, ctx->evPipe[1]);
+    if (rc) return rc;
+    LSD_CUDA(cudaStreamWaitEvent(st, ctx->evPipe[1], 0));  // queue armed before the first feed
+  }
   for (int c = 0; c < nChunks; c++) {
     const int i0 = c * CH, m = (n - i0) < CH ? (n - i0) : CH;
     rc = issue_copy(c);
@@ -794,8 +804,12 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     LSD_CUDA(cudaEventRecord(consumed[c], st));
     launch_gradients(ctx, d_slabs + i0, m, 1, NL - 1, st);
     launch_mask_init(ctx, d_slabs + i0, m, st);
-    rc = se3_launch(ctx, i0, m, false, st);
+    rc = (streamed && nChunks > 1) ? se3_stream_feed(ctx, i0, m, n, st) : se3_launch(ctx, i0, m, false, st);
     if (rc) return rc;
+  }
+  if (streamed && nChunks > 1) {
+    LSD_CUDA(cudaEventRecord(ctx->evPipe[2], ctx->trackStream));  // completes when the persistent tracker has drained
+    LSD_CUDA(cudaStreamWaitEvent(st, ctx->evPipe[2], 0));
   }
   rc = se3_collect(ctx, n, refs, fr.data(), results, nullptr, st, 0.0f);
   for (int c = 0; c < nChunks; c++) {

@@ -14,6 +14,7 @@ struct lsd_ctx {
   cudaStream_t stream;
   bool ownStream;
   cudaStream_t copyStream;  // second stream for the pipelined host-image path
+  cudaStream_t trackStream; // third stream: the persistent tracker of the streamed host-image path
   cudaEvent_t evA, evB, evPipe[4];
   long long launches;
   lsd_tracker_settings se3, sim3, permaref;
@@ -76,6 +77,8 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
 int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init, bool wantTrace,
                 cudaStream_t st);
 int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st);
+int se3_stream_begin(lsd_ctx *ctx, int n, cudaStream_t trackSt, cudaEvent_t armed);
+int se3_stream_feed(lsd_ctx *ctx, int i0, int m, int n, cudaStream_t st);
 int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, lsd_se3_result *results, lsd_trace_entry *traces,
                 cudaStream_t st, float kernelMs);
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,

@@ -696,10 +696,13 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
 }
 
 // Build the initial state of every pair and publish the first evaluations (level maxLevel).
+// `base`: index of the first pair this launch initialises inside the arrays / the queue's pair numbering (0 for a whole batch;
+// the streamed host-image path feeds one chunk at a time into a tracker that is already running).
 __global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, const SE3Queue q, SE3Params prm,
-                           int active) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                           int active, int base) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= n) return;
+  const int i = base + li;
   SE3Pair *P = pairs + i;
   SE3State L;
   memset(&L, 0, sizeof(L));
@@ -714,7 +717,7 @@ __global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ s
   L.trackingWasGood = 1;
   const int next = start_level(P, &L, prm.maxLevel, prm);
   state_store(states + i, &L);
-  if (i < active) {  // the rest is admitted by finishing pairs (k_se3_track)
+  if (li < active) {  // the rest is admitted by finishing pairs (k_se3_track)
     if (next > 0) q_push(q, i, next);
     else atomicSub(q.remaining, 1);
   }
@@ -919,7 +922,7 @@ int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
   if (active > m) active = m;
   LSD_CUDA(cudaMemsetAsync(s->d_slots, 0, sizeof(unsigned long long) * q.cap, st));
   k_se3_reset<<<1, 1, 0, st>>>(s->d_ctrs, (unsigned)m, (unsigned)active);
-  k_se3_init<<<(m + 127) / 128, 128, 0, st>>>(s->d_pairs + i0, s->d_states + i0, m, q, prm, active);
+  k_se3_init<<<(m + 127) / 128, 128, 0, st>>>(s->d_pairs + i0, s->d_states + i0, m, q, prm, active, 0);
   lsd_trace_entry *d_tr = wantTrace ? s->d_traces + (size_t)i0 * LSD_TRACE_CAP : nullptr;
   // every launched CTA polls the queue while idle: a small batch gets only as many CTAs as it can ever have work items in
   // flight (one evaluation per pair, at most maxChunks items each), not the whole machine
@@ -931,6 +934,46 @@ int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
                                                     q, prm, d_tr);
   LSD_CUDA(cudaGetLastError());
   ctx->launches += 3;
+  return LSD_OK;
+}
+
+// ---- streamed variant for the host-image path: ONE persistent launch for all n prepared pairs, started before any
+// ---- frame has arrived; chunks of pairs are fed into its queue (k_se3_init with a base index) as their frames have been
+// ---- ingested on another stream.  The tracker leaves one CTA slot per SM free so that the ingest kernels of later chunks
+// ---- can become resident next to it (a tracker that filled the machine would wait forever for work nobody can produce).
+static SE3Queue make_queue(SE3Scratch *s, int nPairs) {
+  SE3Queue q;
+  q.slots = s->d_slots;
+  q.head = s->d_ctrs;
+  q.tail = s->d_ctrs + 1;
+  q.remaining = reinterpret_cast<int *>(s->d_ctrs + 2);
+  q.nextPair = s->d_ctrs + 3;
+  q.nPairs = nPairs;
+  q.cap = s->qcap;
+  return q;
+}
+
+int se3_stream_begin(lsd_ctx *ctx, int n, cudaStream_t trackSt, cudaEvent_t armed) {
+  SE3Scratch *s = ctx->se3s;
+  SE3Params prm = make_params(ctx, n);
+  const SE3Queue q = make_queue(s, n);
+  LSD_CUDA(cudaMemsetAsync(s->d_slots, 0, sizeof(unsigned long long) * q.cap, trackSt));
+  k_se3_reset<<<1, 1, 0, trackSt>>>(s->d_ctrs, (unsigned)n, (unsigned)n);  // remaining = n; admission is by feeding, not by nextPair
+  LSD_CUDA(cudaEventRecord(armed, trackSt));  // feeders may push from here on (recorded BEFORE the persistent kernel)
+  const int grid = s->gridBlocks - ctx->numSMs > ctx->numSMs ? s->gridBlocks - ctx->numSMs : ctx->numSMs;
+  k_se3_track<<<grid, SE3_THREADS, 0, trackSt>>>(s->d_pairs, s->d_states, s->d_partials, q, prm, nullptr);
+  LSD_CUDA(cudaGetLastError());
+  ctx->launches += 2;
+  return LSD_OK;
+}
+
+int se3_stream_feed(lsd_ctx *ctx, int i0, int m, int n, cudaStream_t st) {
+  SE3Scratch *s = ctx->se3s;
+  SE3Params prm = make_params(ctx, n);
+  const SE3Queue q = make_queue(s, n);
+  k_se3_init<<<(m + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, m, q, prm, m, i0);
+  LSD_CUDA(cudaGetLastError());
+  ctx->launches++;
   return LSD_OK;
 }
 
