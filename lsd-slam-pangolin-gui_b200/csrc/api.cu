@@ -738,7 +738,12 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
   LSD_CUDA(cudaSetDevice(ctx->device));
   const size_t fbytes = (size_t)ctx->w * ctx->h;
   static const int envChunk = getenv("LSD_B200_E2E_CHUNK") ? atoi(getenv("LSD_B200_E2E_CHUNK")) : 0;
-  const int chunk = envChunk > 0 ? envChunk : 250;
+  // LSD_B200_E2E_STREAM=0 selects the older schedule (one tracker launch per chunk); default: ONE persistent tracker fed chunk by chunk
+  static const bool streamed = !(getenv("LSD_B200_E2E_STREAM") && atoi(getenv("LSD_B200_E2E_STREAM")) == 0);
+  // chunk = frames per H2D copy / ingest launch.  Measured on B200, 1000 pairs (profiles/): per-chunk tracker launches want big
+  // chunks (250: 127 k frames/s); the streamed tracker wants small ones so that work arrives early and evenly
+  // (250: 123 k, 125: 134 k, 63: 144 k, 48: 145 k, 32: 147 k, 20: 146 k)
+  const int chunk = envChunk > 0 ? envChunk : (streamed ? 48 : 250);
   const int CH = n < chunk ? n : chunk;
   int rc = ensure_stage(ctx, 0, 2 * fbytes * CH);
   if (rc) return rc;
@@ -786,8 +791,6 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     LSD_CUDA(cudaEventRecord(copied[c], ctx->copyStream));
     return LSD_OK;
   };
-  // LSD_B200_E2E_STREAM=0 selects the older schedule (one tracker launch per chunk); default: ONE persistent tracker fed chunk by chunk
-  static const bool streamed = !(getenv("LSD_B200_E2E_STREAM") && atoi(getenv("LSD_B200_E2E_STREAM")) == 0);
   if (streamed && nChunks > 1) {
     LSD_CUDA(cudaStreamWaitEvent(ctx->trackStream, ctx->evPipe[0], 0));  // pair table uploaded
     rc = se3_stream_begin(ctx, n, ctx->trackStream, ctx->evPipe[1]);
