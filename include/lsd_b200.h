@@ -156,7 +156,9 @@ int lsd_se3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ini
 int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames,
                         const double *init_frameToRef /* n*7 */, lsd_se3_result *results,
                         lsd_trace_entry *traces /* n*LSD_TRACE_CAP or NULL */);
-/* host images in, poses out: ingest (H2D + pyramids) and tracking pipelined over two streams */
+/* host images in, poses out.  Three streams: the copy engine moves 48-frame chunks, the context's stream builds their pyramids
+ * and feeds the pairs into ONE persistent tracker that was started up front on a third stream and leaves one CTA slot per SM to
+ * the ingest kernels (LSD_B200_E2E_STREAM=0: one tracker launch per 250-frame chunk).  Same poses as lsd_se3_track_batch. */
 int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const uint8_t *const *images, size_t pitch,
                                const double *init_frameToRef, lsd_se3_result *results);
 /* [UP] SE3Tracker::trackFrameOnPermaref(reference, frame, referenceToFrame): the quick single-level test track
