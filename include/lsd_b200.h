@@ -161,6 +161,11 @@ int lsd_se3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *co
  * the ingest kernels (LSD_B200_E2E_STREAM=0: one tracker launch per 250-frame chunk).  Same poses as lsd_se3_track_batch. */
 int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const uint8_t *const *images, size_t pitch,
                                const double *init_frameToRef, lsd_se3_result *results);
+/* scheduling of lsd_se3_track_images_batch (never changes a result): frames per H2D copy / ingest launch (0 = default);
+ * streamed = 1 one persistent tracker fed chunk by chunk, 0 one tracker launch per chunk, -1 automatic (streamed unless
+ * kernels are known to be serialised: CUDA_LAUNCH_BLOCKING, profiler / sanitizer injection); watchdogSeconds (0 = keep, default
+ * 2 s): a streamed tracker that waits that long for work stops itself and the batch is re-run with an ordinary launch. */
+int lsd_ctx_set_image_pipeline(lsd_ctx *ctx, int chunkFrames, int streamed, double watchdogSeconds);
 /* [UP] SE3Tracker::trackFrameOnPermaref(reference, frame, referenceToFrame): the quick single-level test track
  * (QUICK_KF_CHECK_LVL = 4) the constraint search and the Relocalizer run against a keyframe's permanent reference,
  * n candidates in ONE launch.  init and results[i].frameToRef both hold referenceToFrame
@@ -325,6 +330,9 @@ typedef struct lsd_slam_status {
   double keyframeRescale;     /* isKeyframe: the mean-idepth rescale createKeyFrame folded into the new keyframe's pose */
 } lsd_slam_status;
 int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out); /* SlamSystem::SlamSystem() */
+/* [UP] TrackableKeyFrameSearch::getRefFrameScore(distanceSquared, usage) = distSq*KFDistWeight^2 + (1-usage)^2*KFUsageWeight^2
+ * (KFDistWeight 4, KFUsageWeight 3): the closeness score nextImage compares with minVal to decide on a new keyframe */
+float lsd_slam_ref_frame_score(float distanceSquared, float usage);
 int lsd_slam_destroy(lsd_slam *s);                 /* fullReset() = destroy + create */
 /* keep finished keyframes alive (upstream: KeyFrameGraph::keyframesAll) -- default 1; 0 frees them for long benches */
 int lsd_slam_set_keep_keyframes(lsd_slam *s, int keep);

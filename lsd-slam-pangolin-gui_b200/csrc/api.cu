@@ -234,6 +234,9 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
+  ctx->imageChunk = 0;
+  ctx->imageStreamed = -1;
+  ctx->streamWatchdogNs = 2000000000ull;
   ctx->d_stats = nullptr;
   LSD_CUDA(cudaMalloc(&ctx->d_stats, 16 + 16 * (size_t)ctx->numSMs));
   LSD_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 16 + 16 * (size_t)ctx->numSMs, ctx->stream));
@@ -728,8 +731,28 @@ int lsd_se3_last_stats(lsd_ctx *ctx, double *algorithmic_bytes, long long *evalu
 //     image copy is queued, so that no kernel launch ever waits behind a bulk transfer on the copy engine;
 //   * images go up chunk by chunk on the copy stream (frames that are contiguous in host memory in one
 //     cudaMemcpyAsync), double-buffered staging, event-ordered against the ingest that consumes them;
-//   * per chunk the compute stream runs ingest -> gradients -> mask init -> tracker launch back to back;
+//   * per chunk the compute stream runs ingest -> gradients -> mask init -> tracker feed / launch back to back;
 //   * the host synchronises once, at the end, and reads all results in one device->host copy.
+// Streamed schedule (default): ONE persistent tracker is started up front on a third stream and fed chunk by chunk.  It needs
+// the feeding kernels to become co-resident with it, which CUDA does not promise: where kernels are known to be serialised
+// (CUDA_LAUNCH_BLOCKING, a profiler / sanitizer injected into the process) the per-chunk schedule is used instead, and a
+// tracker that starves anyway stops itself (SE3Params::watchdogNs) and the batch is re-run with one ordinary launch.
+static bool kernels_may_overlap() {
+  const char *b = getenv("CUDA_LAUNCH_BLOCKING");
+  if (b && atoi(b) != 0) return false;
+  if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE"))
+    return false;  // ncu / compute-sanitizer / nsys serialise kernels
+  return true;
+}
+
+int lsd_ctx_set_image_pipeline(lsd_ctx *ctx, int chunkFrames, int streamed, double watchdogSeconds) {
+  LSD_ARG(ctx && chunkFrames >= 0 && streamed >= -1 && streamed <= 1 && watchdogSeconds >= 0);
+  ctx->imageChunk = chunkFrames;
+  ctx->imageStreamed = streamed;
+  if (watchdogSeconds > 0) ctx->streamWatchdogNs = (unsigned long long)(watchdogSeconds * 1e9);
+  return LSD_OK;
+}
+
 int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const uint8_t *const *images, size_t pitch,
                                const double *init_frameToRef, lsd_se3_result *results) {
   LSD_ARG(ctx && refs && images && init_frameToRef && results && n >= 0);
@@ -738,19 +761,39 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
   LSD_CUDA(cudaSetDevice(ctx->device));
   const size_t fbytes = (size_t)ctx->w * ctx->h;
   static const int envChunk = getenv("LSD_B200_E2E_CHUNK") ? atoi(getenv("LSD_B200_E2E_CHUNK")) : 0;
-  // LSD_B200_E2E_STREAM=0 selects the older schedule (one tracker launch per chunk); default: ONE persistent tracker fed chunk by chunk
-  static const bool streamed = !(getenv("LSD_B200_E2E_STREAM") && atoi(getenv("LSD_B200_E2E_STREAM")) == 0);
+  static const int envStream = getenv("LSD_B200_E2E_STREAM") ? atoi(getenv("LSD_B200_E2E_STREAM")) : -1;
+  const int wantStream = ctx->imageStreamed >= 0 ? ctx->imageStreamed : envStream;
+  const bool streamedCfg = wantStream >= 0 ? wantStream != 0 : kernels_may_overlap();
   // chunk = frames per H2D copy / ingest launch.  Measured on B200, 1000 pairs (profiles/): per-chunk tracker launches want big
   // chunks (250: 127 k frames/s); the streamed tracker wants small ones so that work arrives early and evenly
   // (250: 123 k, 125: 134 k, 63: 144 k, 48: 145 k, 32: 147 k, 20: 146 k)
-  const int chunk = envChunk > 0 ? envChunk : (streamed ? 48 : 250);
+  const int chunk = ctx->imageChunk > 0 ? ctx->imageChunk : (envChunk > 0 ? envChunk : (streamedCfg ? 48 : 250));
   const int CH = n < chunk ? n : chunk;
   int rc = ensure_stage(ctx, 0, 2 * fbytes * CH);
   if (rc) return rc;
   const int nChunks = (n + CH - 1) / CH;
+  const bool streamed = streamedCfg && nChunks > 1;
   cudaStream_t st = ctx->stream;
+
+  // everything this call creates is released on every exit path; a persistent tracker that was started is drained first
+  struct Scope {
+    lsd_ctx *ctx;
+    std::vector<lsd_frame *> fr;
+    std::vector<cudaEvent_t> copied, consumed;
+    bool trackerRunning = false;
+    ~Scope() {
+      if (trackerRunning) se3_stream_abort(ctx, ctx->trackStream, ctx->copyStream);
+      cudaStreamSynchronize(ctx->copyStream);
+      cudaStreamSynchronize(ctx->stream);
+      for (cudaEvent_t e : copied) if (e) cudaEventDestroy(e);
+      for (cudaEvent_t e : consumed) if (e) cudaEventDestroy(e);
+      for (lsd_frame *f : fr) if (f) lsd_frame_release(ctx, f);
+    }
+  } sc;
+  sc.ctx = ctx;
+  sc.fr.assign(n, nullptr);
+  std::vector<lsd_frame *> &fr = sc.fr;
   // frames + all tables first
-  std::vector<lsd_frame *> fr(n, nullptr);
   std::vector<void *> slabs(n);
   for (int i = 0; i < n; i++) {
     uint8_t *s = nullptr;
@@ -766,7 +809,9 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
   if (rc) return rc;
   LSD_CUDA(cudaEventRecord(ctx->evPipe[0], st));
   LSD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evPipe[0], 0));  // tables precede the bulk copies on the copy engine
-  std::vector<cudaEvent_t> copied(nChunks), consumed(nChunks);
+  sc.copied.assign(nChunks, nullptr);
+  sc.consumed.assign(nChunks, nullptr);
+  std::vector<cudaEvent_t> &copied = sc.copied, &consumed = sc.consumed;
   for (int c = 0; c < nChunks; c++) {
     LSD_CUDA(cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming));
     LSD_CUDA(cudaEventCreateWithFlags(&consumed[c], cudaEventDisableTiming));
@@ -779,6 +824,7 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     int i = 0;
     while (i < m) {  // runs of frames that are back to back in host memory
       int j = i + 1;
+      LSD_ARG(images[i0 + i]);
       if (pitch == (size_t)ctx->w) {
         while (j < m && images[i0 + j] == images[i0 + j - 1] + fbytes) j++;
         LSD_CUDA(cudaMemcpyAsync(dst + fbytes * i, images[i0 + i], fbytes * (size_t)(j - i), cudaMemcpyHostToDevice, ctx->copyStream));
@@ -791,10 +837,11 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     LSD_CUDA(cudaEventRecord(copied[c], ctx->copyStream));
     return LSD_OK;
   };
-  if (streamed && nChunks > 1) {
+  if (streamed) {
     LSD_CUDA(cudaStreamWaitEvent(ctx->trackStream, ctx->evPipe[0], 0));  // pair table uploaded
     rc = se3_stream_begin(ctx, n, ctx->trackStream, ctx->evPipe[1]);
     if (rc) return rc;
+    sc.trackerRunning = true;
     LSD_CUDA(cudaStreamWaitEvent(st, ctx->evPipe[1], 0));  // queue armed before the first feed
   }
   for (int c = 0; c < nChunks; c++) {
@@ -807,20 +854,22 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     LSD_CUDA(cudaEventRecord(consumed[c], st));
     launch_gradients(ctx, d_slabs + i0, m, 1, NL - 1, st);
     launch_mask_init(ctx, d_slabs + i0, m, st);
-    rc = (streamed && nChunks > 1) ? se3_stream_feed(ctx, i0, m, n, st) : se3_launch(ctx, i0, m, false, st);
+    rc = streamed ? se3_stream_feed(ctx, i0, m, n, st) : se3_launch(ctx, i0, m, false, st);
     if (rc) return rc;
   }
-  if (streamed && nChunks > 1) {
+  if (streamed) {
     LSD_CUDA(cudaEventRecord(ctx->evPipe[2], ctx->trackStream));  // completes when the persistent tracker has drained
     LSD_CUDA(cudaStreamWaitEvent(st, ctx->evPipe[2], 0));
+    int starved = 0;
+    rc = se3_stream_starved(ctx, st, &starved);  // synchronises: the tracker has exited
+    sc.trackerRunning = false;
+    if (rc) return rc;
+    if (starved) {  // the producers never ran next to the tracker: every frame is ingested by now, track them in one launch
+      rc = se3_launch(ctx, 0, n, false, st);
+      if (rc) return rc;
+    }
   }
-  rc = se3_collect(ctx, n, refs, fr.data(), results, nullptr, st, 0.0f);
-  for (int c = 0; c < nChunks; c++) {
-    cudaEventDestroy(copied[c]);
-    cudaEventDestroy(consumed[c]);
-  }
-  for (int i = 0; i < n; i++) lsd_frame_release(ctx, fr[i]);
-  return rc;
+  return se3_collect(ctx, n, refs, fr.data(), results, nullptr, st, 0.0f);
 }
 
 }  // extern "C"

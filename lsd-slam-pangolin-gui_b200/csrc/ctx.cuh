@@ -22,6 +22,9 @@ struct lsd_ctx {
   int se3ActivePairs;  // 0: default; pairs in flight inside the persistent tracker (L2 residency)
   int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
   int se3RecordPoints; // 0: default (4096); points per partial record = the summation order of the SE3 tracker
+  int imageChunk;      // 0: default; frames per H2D copy / ingest launch of lsd_se3_track_images_batch
+  int imageStreamed;   // -1: default (streamed when the platform runs kernels concurrently); 0 / 1: forced
+  unsigned long long streamWatchdogNs;  // give-up time of the streamed tracker's work-item wait
   // pools
   std::vector<uint8_t *> frameSlabPool;
   std::vector<uint8_t *> refSlabPool;
@@ -79,6 +82,8 @@ int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
 int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st);
 int se3_stream_begin(lsd_ctx *ctx, int n, cudaStream_t trackSt, cudaEvent_t armed);
 int se3_stream_feed(lsd_ctx *ctx, int i0, int m, int n, cudaStream_t st);
+int se3_stream_abort(lsd_ctx *ctx, cudaStream_t trackSt, cudaStream_t sideSt);
+int se3_stream_starved(lsd_ctx *ctx, cudaStream_t st, int *starved);
 int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, lsd_se3_result *results, lsd_trace_entry *traces,
                 cudaStream_t st, float kernelMs);
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,

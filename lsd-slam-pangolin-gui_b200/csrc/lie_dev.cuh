@@ -146,22 +146,32 @@ __host__ __device__ inline void sim3_exp_compose(const S inc[7], const QuatT<S> 
   to[0] = dt[0] + rt[0] * scale; to[1] = dt[1] + rt[1] * scale; to[2] = dt[2] + rt[2] * scale;
 }
 
-// LDL^T solve, no pivoting (A symmetric positive definite, row-major N x N)
+// LDL^T solve (A symmetric positive semi-definite, row-major N x N).  No pivoting, but rank deficiency is handled the way
+// Eigen::LDLT (upstream's A.ldlt().solve(b)) handles it: a pivot with |d| <= 1 / highest() leaves its column undivided and the
+// solve applies the pseudo-inverse of D (that component of x is 0).  For a Gram matrix a zero diagonal entry means a zero
+// row and column, so this equals Eigen's pivoted result: Sim3 tracking with no depth residual under the warped points
+// (scale row of A = 0) takes a finite step with inc[6] = 0 instead of NaN.
+template <typename S> struct LdltTol;
+template <> struct LdltTol<float> { __host__ __device__ static float v() { return 1.0f / 3.402823466e+38f; } };
+template <> struct LdltTol<double> { __host__ __device__ static double v() { return 1.0 / 1.7976931348623157e+308; } };
+
 template <typename S, int N> __host__ __device__ inline void ldlt_solve(const S *A, const S *b, S *x) {
   S L[N * N];
   S D[N];
+  const S tol = LdltTol<S>::v();
 #pragma unroll
   for (int j = 0; j < N; j++) {
     S d = A[j * N + j];
 #pragma unroll
     for (int k = 0; k < j; k++) d -= L[j * N + k] * L[j * N + k] * D[k];
     D[j] = d;
+    const bool pivotValid = fabs(d) > tol;
 #pragma unroll
     for (int i = j + 1; i < N; i++) {
       S v = A[i * N + j];
 #pragma unroll
       for (int k = 0; k < j; k++) v -= L[i * N + k] * L[j * N + k] * D[k];
-      L[i * N + j] = v / d;
+      L[i * N + j] = pivotValid ? v / d : v;
     }
   }
   S y[N];
@@ -173,7 +183,7 @@ template <typename S, int N> __host__ __device__ inline void ldlt_solve(const S 
     y[i] = v;
   }
 #pragma unroll
-  for (int i = 0; i < N; i++) y[i] = y[i] / D[i];
+  for (int i = 0; i < N; i++) y[i] = fabs(D[i]) > tol ? y[i] / D[i] : S(0);
 #pragma unroll
   for (int i = N - 1; i >= 0; i--) {
     S v = y[i];

@@ -57,14 +57,16 @@ enum { R_A = 0, R_B = 21, R_SUMRES = 27, R_SUMUNW = 28, R_SUMSGN = 29, R_USAGE =
 // everything else is consumed without cancellation and stays fp32.
 enum { D_SXX = 0, D_SYY = 1, D_SX = 2, D_SY = 3, D_SW = 4 };
 
-// Immutable while the persistent kernel runs (host + k_se3_init write it): read with plain loads.
+// Written by the host only, before any kernel that reads it is launched: immutable on the device, read with plain loads.
+// (numData lives in the pair's SE3State, which is only ever read through L2: in the streamed host-image path k_se3_init fills
+// it while the persistent tracker is already running, and a plain load could be served from a stale L1 line.)
 struct SE3Pair {
   const RefPoint *pts[NL];
   const float4 *fgrad[NL];
   const int *d_num;  // ref numData[NL] on device
   uint8_t *mask;
   float q0[4], t0[3];  // initial referenceToFrame (float)
-  int n[NL];
+  int pad_;
 };
 
 // Mutable LM state: other SMs update it between evaluations, so inside the persistent kernel it is
@@ -74,7 +76,7 @@ struct __align__(16) SE3State {
   float R[9], t[3];  // pose of the evaluation in flight
   float aff_a, aff_b;
   int level;
-  int nChunks;
+  int nPts;  // numData[level]: every CTA derives the records / work items of the evaluation from it
   // --- LM bookkeeping (touched only by the thread running the LM step) ---
   float q_try[4];
   float q_cur[4], t_cur[3];
@@ -89,8 +91,9 @@ struct __align__(16) SE3State {
   int traceLen;
   float outq[4], outt[3];  // frameToRef (float)
   float initialTrackedResidual;
-  int n[NL];  // copy of numData for the host
-  int pad_[2];
+  int n[NL];  // numData of the reference (read from the reference's device counters by k_se3_init)
+  int nChunks;  // work items of the evaluation in flight
+  int pad_[1];
 };
 static_assert(sizeof(SE3State) % 16 == 0, "SE3State must be int4-copyable");
 static_assert(offsetof(SE3State, q_try) == 64, "evaluation header must be the first 64 bytes");
@@ -117,6 +120,7 @@ struct SE3Queue {
   unsigned *tail;  // producer reservations
   int *remaining;  // pairs not finished yet
   unsigned *nextPair;  // admission: next pair to start when an active one finishes
+  int *starved;        // set by the watchdog of a streamed launch (see SE3Params::watchdogNs)
   int nPairs;
   unsigned cap;    // power of two
 };
@@ -129,7 +133,19 @@ struct SE3Params {
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
   int recPoints;           // points per partial record (lsd_ctx_set_se3_record_points; default SE3_REC)
   int permaref;            // SE3Tracker::trackFrameOnPermaref: single level, no frame side effects, referenceToFrame returned
+  // Streamed launches only (0 otherwise): a CTA that has waited this long for a work item while pairs are still outstanding
+  // gives up and stops the whole launch.  The streamed host-image path starts the tracker BEFORE its producers (ingest kernels
+  // on another stream) and relies on them becoming co-resident; where the platform serialises kernels instead (profilers,
+  // sanitizers, CUDA_LAUNCH_BLOCKING, an exhausted SM) the tracker would otherwise spin forever.  The host then re-runs the
+  // batch with ordinary per-launch scheduling.
+  unsigned long long watchdogNs;
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 // gpu-scope acquire-release fetch-add: releases this CTA's record stores (ordered before it by the CTA barrier)
 // and, for the CTA that takes the last ticket, acquires every other CTA's.
@@ -193,16 +209,17 @@ __device__ void finish_pair(SE3State *S, const SE3Params &prm) {
   S->finished = 1;
 }
 
-// S is a thread-local copy.  Returns the number of chunks to publish (0: the pair is finished).
-__device__ int start_level(const SE3Pair *P, SE3State *S, int level, const SE3Params &prm) {
+// S: the CTA's shared-memory copy of the state (or a thread-local one in k_se3_init).  Returns the number of chunks to publish (0: the pair is finished).
+__device__ int start_level(SE3State *S, int level, const SE3Params &prm) {
   S->level = level;
+  S->nPts = S->n[level];
   S->phase = 0;
   set_eval_pose(S, S->q_cur, S->t_cur);
-  if (P->n[level] == 0) {  // calcResidualAndBuffers on an empty cloud: buf_warped_size 0 < 1% => diverged
+  if (S->n[level] == 0) {  // calcResidualAndBuffers on an empty cloud: buf_warped_size 0 < 1% => diverged
     mark_diverged(S);
     return 0;
   }
-  const int nRecs = (P->n[level] + prm.recPoints - 1) / prm.recPoints;
+  const int nRecs = (S->n[level] + prm.recPoints - 1) / prm.recPoints;
   S->nChunks = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;  // work items of this evaluation
   S->done = 0;
   return S->nChunks;
@@ -210,15 +227,14 @@ __device__ int start_level(const SE3Pair *P, SE3State *S, int level, const SE3Pa
 
 // The LM state machine, run by one thread after the last chunk of an evaluation (tot = summed partials).
 // Returns the number of chunks of the next evaluation (0: pair finished).
-__device__ int lm_step(const SE3Pair *P, SE3State *S, const float *tot, const double *dtot, const SE3Params &prm,
-                       lsd_trace_entry *trace) {
+__device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const SE3Params &prm, lsd_trace_entry *trace) {
   const int lvl = S->level;
   const float good = tot[R_GOOD], bad = tot[R_BAD];
   const int size = (int)(good + bad);
   S->bufSize = size;
   S->good = good;
   S->bad = bad;
-  S->pointUsage = tot[R_USAGE] / (float)P->n[lvl];
+  S->pointUsage = tot[R_USAGE] / (float)S->n[lvl];
   S->meanRes = tot[R_SUMSGN] / good;
   // closed form evaluated in fp64 (upstream: fp32; mathematically identical, see DESIGN.md "affine lighting")
   const double sxx = dtot[D_SXX], syy = dtot[D_SYY], sx = dtot[D_SX], sy = dtot[D_SY], sw = dtot[D_SW];
@@ -284,7 +300,7 @@ __device__ int lm_step(const SE3Pair *P, SE3State *S, const float *tot, const do
       finish_pair(S, prm);
       return 0;
     }
-    return start_level(P, S, lvl - 1, prm);
+    return start_level(S, lvl - 1, prm);
   }
   if (takeNormalEq) {  // NormalEquationsLeastSquares::finish(): divide by num_constraints
     const float nf = (float)size;
@@ -590,7 +606,8 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
   __shared__ __align__(16) SE3Smem sm;
   __shared__ float stot[SE3_NF];
   __shared__ double sdtot[SE3_ND];
-  __shared__ int sCode, sIsLast;
+  __shared__ int sCode, sIsLast, sNext;
+  __shared__ __align__(16) SE3State sState;  // the LM step works on a shared-memory copy (a thread-local one lived in local memory)
 
   unsigned ticket = 0;
   if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
@@ -600,6 +617,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
       const unsigned slot = ticket & (q.cap - 1), seq = ticket / q.cap + 1;
       const volatile unsigned long long *sp = reinterpret_cast<const volatile unsigned long long *>(&q.slots[slot]);
       int code = -1;
+      unsigned long long waitStart = 0;
       for (;;) {
         const unsigned long long v = *sp;
         if ((unsigned)(v >> 32) == seq) {
@@ -607,6 +625,16 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
           break;
         }
         if (*reinterpret_cast<const volatile int *>(q.remaining) <= 0) break;
+        if (prm.watchdogNs) {
+          const unsigned long long now = global_timer_ns();
+          if (!waitStart) waitStart = now;
+          else if (now - waitStart > prm.watchdogNs) {  // producers never became resident: stop the launch (see SE3Params)
+            atomicExch(q.starved, 1);
+            atomicExch(q.remaining, -(1 << 30));
+            __threadfence();
+            break;
+          }
+        }
         __nanosleep(40);
       }
       sCode = code;
@@ -621,10 +649,9 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
     // evaluation header: 4 x LDG.128 through L2
     const int4 *hp = reinterpret_cast<const int4 *>(S);
     const int4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1), h2 = __ldcg(hp + 2), h3 = __ldcg(hp + 3);
-    const int level = h3.z, nch = h3.w;
+    const int level = h3.z, n = h3.w;
     EvalConst c;
     load_eval_const(prm, level, h0, h1, h2, h3, c);
-    const int n = P->n[level];
     uint8_t *mask = (level == prm.minLevel && !prm.permaref) ? P->mask : nullptr;  // permaref: idxBuf == nullptr upstream
 
     float acc[SE3_NF];
@@ -634,6 +661,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
 #pragma unroll
     for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
     const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
+    const int nch = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;
     const int rec0 = chunk * prm.recsPerItem, rec1 = min(nRecs, rec0 + prm.recsPerItem);
     for (int rec = rec0; rec < rec1; rec++) {
       if (rec > rec0) {
@@ -663,13 +691,19 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
         float s = 0.0f;
         for (int cidx = 0; cidx < nRecs; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
         stot[j] = s;
+      } else if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(SE3State) / 16)) {
+        // the pair's state comes in with one LDG.128 per thread of warps 2-3 while warps 0-1 sum the records
+        const int k = threadIdx.x - 64;
+        reinterpret_cast<int4 *>(&sState)[k] = __ldcg(reinterpret_cast<const int4 *>(S) + k);
       }
       __syncthreads();
+      if (threadIdx.x == 0) sNext = lm_step(&sState, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
+      __syncthreads();
+      if (threadIdx.x < (int)(sizeof(SE3State) / 16))
+        reinterpret_cast<int4 *>(S)[threadIdx.x] = reinterpret_cast<const int4 *>(&sState)[threadIdx.x];
+      __syncthreads();  // the state stores precede thread 0's fence + publication below
       if (threadIdx.x == 0) {
-        SE3State L;
-        state_load(&L, S);
-        const int next = lm_step(P, &L, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
-        state_store(S, &L);
+        const int next = sNext;
         if (next > 0) {
           q_push(q, pairIdx, next);
         } else {
@@ -698,24 +732,21 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
 // Build the initial state of every pair and publish the first evaluations (level maxLevel).
 // `base`: index of the first pair this launch initialises inside the arrays / the queue's pair numbering (0 for a whole batch;
 // the streamed host-image path feeds one chunk at a time into a tracker that is already running).
-__global__ void k_se3_init(SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, const SE3Queue q, SE3Params prm,
+__global__ void k_se3_init(const SE3Pair *__restrict__ pairs, SE3State *__restrict__ states, int n, const SE3Queue q, SE3Params prm,
                            int active, int base) {
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= n) return;
   const int i = base + li;
-  SE3Pair *P = pairs + i;
+  const SE3Pair *P = pairs + i;
   SE3State L;
   memset(&L, 0, sizeof(L));
-  for (int l = 0; l < NL; l++) {
-    P->n[l] = P->d_num[l];
-    L.n[l] = P->n[l];
-  }
+  for (int l = 0; l < NL; l++) L.n[l] = P->d_num[l];
   for (int k = 0; k < 4; k++) L.q_cur[k] = P->q0[k];
   for (int k = 0; k < 3; k++) L.t_cur[k] = P->t0[k];
   L.aff_a = 1;
   L.aff_a_lastIt = 1;
   L.trackingWasGood = 1;
-  const int next = start_level(P, &L, prm.maxLevel, prm);
+  const int next = start_level(&L, prm.maxLevel, prm);
   state_store(states + i, &L);
   if (li < active) {  // the rest is admitted by finishing pairs (k_se3_track)
     if (next > 0) q_push(q, i, next);
@@ -734,7 +765,7 @@ struct SE3ScratchImpl {
   int maxChunks = 0;
   unsigned long long *d_slots = nullptr;
   unsigned qcap = 0;
-  unsigned *d_ctrs = nullptr;  // head, tail, remaining, pad
+  unsigned *d_ctrs = nullptr;  // head, tail, remaining, nextPair, starved, pad[3]
   lsd_trace_entry *d_traces = nullptr;
   size_t tracesBytes = 0;
   int gridBlocks = 0;
@@ -798,7 +829,7 @@ static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
       s->tracesBytes = 0;
     }
   }
-  if (!s->d_ctrs) LSD_CUDA(cudaMalloc(&s->d_ctrs, sizeof(unsigned) * 4));
+  if (!s->d_ctrs) LSD_CUDA(cudaMalloc(&s->d_ctrs, sizeof(unsigned) * 8));
   if (wantTrace && s->tracesBytes < sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)s->cap) {
     cudaFree(s->d_traces);
     s->tracesBytes = sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)s->cap;
@@ -829,6 +860,7 @@ static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   prm.recPoints = ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
   prm.permaref = ctx->se3Permaref ? 1 : 0;
   if (prm.permaref) prm.minLevel = prm.maxLevel = LSD_QUICK_KF_CHECK_LVL;
+  prm.watchdogNs = 0;
   return prm;
 }
 
@@ -872,6 +904,7 @@ __global__ void k_se3_reset(unsigned *ctrs, unsigned n, unsigned active) {
   ctrs[1] = 0u;
   ctrs[2] = n;
   ctrs[3] = active;
+  ctrs[4] = 0u;
 }
 
 // ---- the batch API in three steps, so that the host-image pipeline can queue several launches without a host
@@ -905,19 +938,25 @@ int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
   return LSD_OK;
 }
 
-// tracks pairs [i0, i0 + m) of the prepared table; everything it touches (queue, counters, partial records, states) is
-// private to the launch or indexed by pair, and all of it is ordered on `st`
-int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
-  SE3Scratch *s = ctx->se3s;
-  SE3Params prm = make_params(ctx, m);
+static SE3Queue make_queue(SE3Scratch *s, int nPairs) {
   SE3Queue q;
   q.slots = s->d_slots;
   q.head = s->d_ctrs;
   q.tail = s->d_ctrs + 1;
   q.remaining = reinterpret_cast<int *>(s->d_ctrs + 2);
   q.nextPair = s->d_ctrs + 3;
-  q.nPairs = m;
+  q.starved = reinterpret_cast<int *>(s->d_ctrs + 4);
+  q.nPairs = nPairs;
   q.cap = s->qcap;
+  return q;
+}
+
+// tracks pairs [i0, i0 + m) of the prepared table; everything it touches (queue, counters, partial records, states) is
+// private to the launch or indexed by pair, and all of it is ordered on `st`
+int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
+  SE3Scratch *s = ctx->se3s;
+  SE3Params prm = make_params(ctx, m);
+  const SE3Queue q = make_queue(s, m);
   int active = ctx->se3ActivePairs > 0 ? ctx->se3ActivePairs : SE3_DEFAULT_ACTIVE;
   if (active > m) active = m;
   LSD_CUDA(cudaMemsetAsync(s->d_slots, 0, sizeof(unsigned long long) * q.cap, st));
@@ -941,21 +980,10 @@ int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
 // ---- frame has arrived; chunks of pairs are fed into its queue (k_se3_init with a base index) as their frames have been
 // ---- ingested on another stream.  The tracker leaves one CTA slot per SM free so that the ingest kernels of later chunks
 // ---- can become resident next to it (a tracker that filled the machine would wait forever for work nobody can produce).
-static SE3Queue make_queue(SE3Scratch *s, int nPairs) {
-  SE3Queue q;
-  q.slots = s->d_slots;
-  q.head = s->d_ctrs;
-  q.tail = s->d_ctrs + 1;
-  q.remaining = reinterpret_cast<int *>(s->d_ctrs + 2);
-  q.nextPair = s->d_ctrs + 3;
-  q.nPairs = nPairs;
-  q.cap = s->qcap;
-  return q;
-}
-
 int se3_stream_begin(lsd_ctx *ctx, int n, cudaStream_t trackSt, cudaEvent_t armed) {
   SE3Scratch *s = ctx->se3s;
   SE3Params prm = make_params(ctx, n);
+  prm.watchdogNs = ctx->streamWatchdogNs;
   const SE3Queue q = make_queue(s, n);
   LSD_CUDA(cudaMemsetAsync(s->d_slots, 0, sizeof(unsigned long long) * q.cap, trackSt));
   k_se3_reset<<<1, 1, 0, trackSt>>>(s->d_ctrs, (unsigned)n, (unsigned)n);  // remaining = n; admission is by feeding, not by nextPair
@@ -974,6 +1002,28 @@ int se3_stream_feed(lsd_ctx *ctx, int i0, int m, int n, cudaStream_t st) {
   k_se3_init<<<(m + 127) / 128, 128, 0, st>>>(s->d_pairs, s->d_states, m, q, prm, m, i0);
   LSD_CUDA(cudaGetLastError());
   ctx->launches++;
+  return LSD_OK;
+}
+
+// Error path of the streamed host-image pipeline: makes the persistent tracker drain (remaining = 0 is its exit condition)
+// and waits for it, so that no kernel is left spinning when the entry point returns early.  Ordered on a stream of its own:
+// the tracker's stream is occupied by the tracker itself and the feeding stream may be blocked behind a failed step.
+int se3_stream_abort(lsd_ctx *ctx, cudaStream_t trackSt, cudaStream_t sideSt) {
+  SE3Scratch *s = ctx->se3s;
+  if (!s || !s->d_ctrs) return LSD_OK;
+  cudaMemsetAsync(s->d_ctrs + 2, 0, sizeof(unsigned), sideSt);
+  cudaStreamSynchronize(sideSt);
+  cudaStreamSynchronize(trackSt);
+  return LSD_OK;
+}
+
+// 1 when the watchdog of the last streamed launch fired (the launch was stopped before every pair finished)
+int se3_stream_starved(lsd_ctx *ctx, cudaStream_t st, int *starved) {
+  SE3Scratch *s = ctx->se3s;
+  int h = 0;
+  LSD_CUDA(cudaMemcpyAsync(&h, s->d_ctrs + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaStreamSynchronize(st));
+  *starved = h;
   return LSD_OK;
 }
 

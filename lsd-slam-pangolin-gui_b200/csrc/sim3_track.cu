@@ -738,11 +738,8 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
   lsd_trace_entry *dtr = traces ? reinterpret_cast<lsd_trace_entry *>(ctx->d_stage + off2) : nullptr;
   LSD_CUDA(cudaMemcpyAsync(dj, hj, jobBytes, cudaMemcpyHostToDevice, st));
   LSD_CUDA(cudaEventRecord(ctx->evA, st));
-  static bool attrSet = false;
-  if (!attrSet) {
-    LSD_CUDA(cudaFuncSetAttribute(k_sim3_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S3Smem)));
-    attrSet = true;
-  }
+  // per device, not per process: set on every call (cheap) so that a second context on another device works too
+  LSD_CUDA(cudaFuncSetAttribute(k_sim3_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S3Smem)));
   k_sim3_track<<<n * S3_CL, S3_THREADS, sizeof(S3Smem), st>>>(dj, dout, prm, dtr);
   LSD_CUDA(cudaGetLastError());
   ctx->launches++;

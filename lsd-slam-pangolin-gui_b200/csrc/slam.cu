@@ -68,6 +68,12 @@ struct lsd_slam {
 
 extern "C" {
 
+// [UP] TrackableKeyFrameSearch::getRefFrameScore(distanceSquared, usage) with KFDistWeight 4, KFUsageWeight 3 (float arithmetic,
+// upstream's operation order)
+float lsd_slam_ref_frame_score(float distanceSquared, float usage) {
+  return distanceSquared * KF_DIST_WEIGHT * KF_DIST_WEIGHT + (1 - usage) * (1 - usage) * KF_USAGE_WEIGHT * KF_USAGE_WEIGHT;
+}
+
 int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out) {
   LSD_ARG(ctx && out);
   lsd_slam *s = new lsd_slam();
@@ -233,8 +239,8 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     const double d[3] = {toKf[4] * m, toKf[5] * m, toKf[6] * m};
     float minVal = std::fmin(0.2f + s->nKeyframes * 0.8f / INITIALIZATION_PHASE_COUNT, 1.0f);
     if (s->nKeyframes < INITIALIZATION_PHASE_COUNT) minVal *= 0.7f;
-    const double usage = 1.0 - (double)res.pointUsage;
-    score = (float)(KF_DIST_WEIGHT * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) + KF_USAGE_WEIGHT * usage * usage);
+    // TrackableKeyFrameSearch::getRefFrameScore: distSq * KFDistWeight^2 + (1 - usage)^2 * KFUsageWeight^2  (16 and 9)
+    score = lsd_slam_ref_frame_score((float)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), res.pointUsage);
     create = score > minVal;
   }
 

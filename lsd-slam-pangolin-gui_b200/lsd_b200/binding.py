@@ -90,6 +90,7 @@ SYMBOLS = {
     "lsd_se3_track": (_ip, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lsd_se3_track_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _vp, _vp]),
     "lsd_se3_track_images_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _vp, _vp]),
+    "lsd_ctx_set_image_pipeline": (_ip, [_vp, _ip, _ip, _dp]),
     "lsd_default_permaref_settings": (_ip, [_vp]),
     "lsd_ctx_set_permaref_settings": (_ip, [_vp, _vp]),
     "lsd_se3_track_permaref_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _vp, _vp]),
@@ -123,6 +124,7 @@ SYMBOLS = {
     "lsd_ctx_last_stage_ms": (_ip, [_vp, _vp]),
     "lsd_depth_stage_batch": (_ip, [_vp, _ip, _vp, _ip, _ip, _ip, _vp]),
     "lsd_slam_create": (_ip, [_vp, _vp]),
+    "lsd_slam_ref_frame_score": (_fp, [_fp, _fp]),
     "lsd_slam_destroy": (_ip, [_vp]),
     "lsd_slam_set_keep_keyframes": (_ip, [_vp, _ip]),
     "lsd_slam_set_undistorter": (_ip, [_vp, _vp]),
@@ -239,6 +241,10 @@ class Context:
 
     def set_se3_active_pairs(self, n):
         _chk(self.L.lsd_ctx_set_se3_active_pairs(self.p, int(n)))
+
+    def set_image_pipeline(self, chunk_frames=0, streamed=-1, watchdog_seconds=0.0):
+        """Scheduling of se3_track_images_batch (results never change): see lsd_ctx_set_image_pipeline."""
+        _chk(self.L.lsd_ctx_set_image_pipeline(self.p, int(chunk_frames), int(streamed), float(watchdog_seconds)))
 
     def set_se3_record_points(self, n):
         _chk(self.L.lsd_ctx_set_se3_record_points(self.p, int(n)))

@@ -19,6 +19,14 @@ INITIALIZATION_PHASE_COUNT = 5
 MIN_NUM_MAPPED = 5
 
 
+def ref_frame_score(distance_squared, usage):
+    """[UP] TrackableKeyFrameSearch::getRefFrameScore: distSq * KFDistWeight^2 + (1 - usage)^2 * KFUsageWeight^2, in float32."""
+    f = np.float32
+    d2, u = f(distance_squared), f(usage)
+    w1, w2 = f(KF_DIST_WEIGHT), f(KF_USAGE_WEIGHT)
+    return float(d2 * w1 * w1 + (f(1) - u) * (f(1) - u) * w2 * w2)
+
+
 def quat_mul(a, b):
     ax, ay, az, aw = a
     bx, by, bz, bw = b
@@ -167,7 +175,7 @@ class LockStepSlam:
             min_val = min(0.2 + self.n_keyframes * 0.8 / INITIALIZATION_PHASE_COUNT, 1.0)
             if self.n_keyframes < INITIALIZATION_PHASE_COUNT:
                 min_val *= 0.7
-            score = KF_DIST_WEIGHT * float(dist @ dist) + KF_USAGE_WEIGHT * (1.0 - res.pointUsage) ** 2
+            score = ref_frame_score(float(dist @ dist), res.pointUsage)
             create = score > min_val
         # mapping, lock-step
         if create:

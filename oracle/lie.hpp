@@ -252,19 +252,27 @@ template <typename S> struct Sim3 {
 template <typename S> inline SE3<S> se3FromSim3(const Sim3<S> &s) { return SE3<S>(s.q, s.t); }
 template <typename S> inline Sim3<S> sim3FromSE3(const SE3<S> &e, S scale) { return Sim3<S>(e.q, e.t, scale); }
 
-// In-place LDL^T solve of the symmetric positive definite N x N system A x = b (no pivoting;
-// Eigen's ldlt() pivots, which only reorders roundoff for these well-conditioned SPD systems).
+// LDL^T solve of the symmetric positive semi-definite N x N system A x = b.  No pivoting (Eigen's ldlt() pivots, which only
+// reorders roundoff for these Gram matrices), but rank deficiency is handled the way Eigen::LDLT does it: a pivot with
+// |d| <= 1 / highest() leaves its column undivided, and solve() applies the pseudo-inverse of D (that component is 0).
+// A Gram matrix with a zero diagonal entry has a zero row and column, so the result equals Eigen's: e.g. Sim3 tracking
+// when no warped point has a depth residual (scale row of A = 0) takes a finite step with inc[6] = 0 instead of NaN.
+template <typename S> inline S ldlt_tolerance();
+template <> inline float ldlt_tolerance<float>() { return 1.0f / 3.402823466e+38f; }
+template <> inline double ldlt_tolerance<double>() { return 1.0 / 1.7976931348623157e+308; }
 template <typename S, int N> inline void ldlt_solve(const S A_in[N][N], const S b[N], S x[N]) {
   S L[N][N];
   S D[N];
+  const S tol = ldlt_tolerance<S>();
   for (int j = 0; j < N; j++) {
     S d = A_in[j][j];
     for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k] * D[k];
     D[j] = d;
+    const bool pivotValid = std::fabs(d) > tol;
     for (int i = j + 1; i < N; i++) {
       S v = A_in[i][j];
       for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * D[k];
-      L[i][j] = v / d;
+      L[i][j] = pivotValid ? v / d : v;
     }
   }
   S y[N];
@@ -273,7 +281,7 @@ template <typename S, int N> inline void ldlt_solve(const S A_in[N][N], const S 
     for (int k = 0; k < i; k++) v -= L[i][k] * y[k];
     y[i] = v;
   }
-  for (int i = 0; i < N; i++) y[i] = y[i] / D[i];
+  for (int i = 0; i < N; i++) y[i] = std::fabs(D[i]) > tol ? y[i] / D[i] : S(0);
   for (int i = N - 1; i >= 0; i--) {
     S v = y[i];
     for (int k = i + 1; k < N; k++) v -= L[k][i] * x[k];

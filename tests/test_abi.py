@@ -98,3 +98,19 @@ def test_pose_line_format_equals_ostream_default(lsd, tmp_path):
         assert L.lsd_slam_pose_line(C.byref(st), buf, 256) == 0
         want = subprocess.run([str(exe), str(40 + k)] + [repr(v) for v in six], capture_output=True, text=True).stdout
         assert buf.value.decode() == want, (buf.value, want)
+
+
+def test_ref_frame_score_is_the_16_9_formula(lsd):
+    """[UP] TrackableKeyFrameSearch::getRefFrameScore = distSq * KFDistWeight^2 + (1 - usage)^2 * KFUsageWeight^2 with
+    KFDistWeight 4 / KFUsageWeight 3: the C driver and the Python mirror must both use 16 and 9."""
+    import numpy as np
+    from lsd_b200 import pipeline
+    L = lsd.load()
+    f = np.float32
+    for d2, u in [(0.0, 1.0), (0.01, 0.9), (0.0234, 0.61), (0.5, 0.3), (1e-4, 0.999)]:
+        want = float(f(d2) * f(4) * f(4) + (f(1) - f(u)) * (f(1) - f(u)) * f(3) * f(3))
+        assert L.lsd_slam_ref_frame_score(d2, u) == want
+        assert pipeline.ref_frame_score(d2, u) == want
+        assert abs(want - (16.0 * d2 + 9.0 * (1.0 - u) ** 2)) < 1e-5
+    # usage 0.6 with no motion must already trigger a keyframe after the initialisation phase (9 * 0.16 = 1.44 > 1)
+    assert L.lsd_slam_ref_frame_score(0.0, 0.6) > 1.0

@@ -203,6 +203,56 @@ def test_host_image_entry_point(lsd, oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", ["streamed", "per_chunk", "starved", "non_pinned_pitch"])
+def test_host_image_pipeline_schedules(lsd, oracle, mode):
+    """Every schedule of lsd_se3_track_images_batch with MORE THAN ONE chunk gives the poses of se3_track_batch bit for bit:
+    the persistent tracker fed chunk by chunk (default), one tracker launch per chunk, the watchdog fallback (a streamed
+    tracker whose producers never arrive stops itself and the batch is re-run: forced here with a 1 ns watchdog), and a
+    pitched pageable source.  An argument error in the middle of the pipeline must return (not hang) and leave the context usable."""
+    w, h = 320, 240
+    n = 7
+    ds = [make_oracle_pair(170 + s, w, h) for s in range(n)]
+    ctx = lsd.Context(w, h, ds[0]["pr"]["K"])
+    kfs = ctx.create_frames([d["kf_img"] for d in ds])
+    for k, d in zip(kfs, ds):
+        k.set_idepth(d["idepth"], d["var"])
+    refs = ctx.create_refs(kfs)
+    frs = ctx.create_frames([d["fr_img"] for d in ds])
+    inits = np.tile(np.array([0, 0, 0, 1, 0, 0, 0.0]), (n, 1))
+    a = ctx.se3_track_batch(refs, frs, inits)
+    pitch = w
+    if mode == "non_pinned_pitch":
+        pitch = w + 32
+        imgs = []
+        for d in ds:
+            buf = np.full((h, pitch), 255, np.uint8)
+            buf[:, :w] = d["fr_img"]
+            imgs.append(buf)
+        ctx.set_image_pipeline(chunk_frames=3, streamed=1)
+    else:
+        imgs = [np.ascontiguousarray(d["fr_img"]) for d in ds]
+        if mode == "streamed":
+            ctx.set_image_pipeline(chunk_frames=2, streamed=1)
+        elif mode == "per_chunk":
+            ctx.set_image_pipeline(chunk_frames=2, streamed=0)
+        else:
+            ctx.set_image_pipeline(chunk_frames=2, streamed=1, watchdog_seconds=1e-9)
+    for rep in range(2):  # twice: the second call reuses pooled slabs and the tracker scratch
+        b = ctx.se3_track_images_batch(refs, [im.ctypes.data for im in imgs], pitch, inits)
+        for i in range(n):
+            assert list(a[i].frameToRef) == list(b[i].frameToRef), (mode, rep, i)
+            assert a[i].lastGoodCount == b[i].lastGoodCount and a[i].lastBadCount == b[i].lastBadCount
+    # an argument error in the middle of the pipeline (a null image in the second chunk) must come back as an error, not hang,
+    # and must leave the context usable
+    ptrs = [im.ctypes.data for im in imgs]
+    ptrs[3] = None
+    with pytest.raises(lsd.LsdError):
+        ctx.se3_track_images_batch(refs, ptrs, pitch, inits)
+    b = ctx.se3_track_images_batch(refs, [im.ctypes.data for im in imgs], pitch, inits)
+    assert all(list(a[i].frameToRef) == list(b[i].frameToRef) for i in range(n))
+    ctx.close()
+
+
 def test_permaref_quick_track_and_overlap_batch(lsd, oracle):
     """SE3Tracker::trackFrameOnPermaref / checkPermaRefOverlap (SURVEY.md 8a B7, 8f N4): level-4 test track of n candidates
     in one launch.  referenceToFrame comes back un-inverted, LM traces match the oracle's evaluation by evaluation, and
