@@ -136,6 +136,8 @@ int lsd_frame_set_idepth(lsd_ctx *ctx, lsd_frame *f, const float *idepth, const 
 int lsd_frame_set_idepth_batch_device(lsd_ctx *ctx, int n, lsd_frame *const *f, const void *d_idepth,
                                       const void *d_idepthVar);
 int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *numPoints);
+/* n frames, one host synchronisation */
+int lsd_frame_mean_idepth_batch(lsd_ctx *ctx, int n, lsd_frame *const *f, float *meanIdepth /* n or NULL */, int *numPoints /* n or NULL */);
 
 /* ---- TrackingReference ---------------------------------------------------------------------- */
 /* [UP] TrackingReference::importFrame + makePointCloud(level) for levels 1..4 */
@@ -269,6 +271,14 @@ int lsd_depth_update_keyframe(lsd_ctx *ctx, lsd_depthmap *dm, int n, lsd_frame *
  * thisToParent_raw exactly like upstream and also returned. */
 int lsd_depth_create_keyframe(lsd_ctx *ctx, lsd_depthmap *dm, lsd_frame *new_keyframe, float *rescaleFactor);
 int lsd_depth_finalize_keyframe(lsd_ctx *ctx, lsd_depthmap *dm); /* [UP] DepthMap::finalizeKeyFrame */
+/* The three calls above on n independent depth maps of one context (the maps of n live sequences): every stage is ONE launch
+ * over all maps and the host synchronises once per call.  Map i is handled exactly as by the single-map call (bit-identical
+ * results); updateKeyframe takes one reference frame per map (the frame just tracked on that map's keyframe).  All maps must
+ * share the same lsd_depth_settings. */
+int lsd_depth_update_keyframe_batch(lsd_ctx *ctx, int n, lsd_depthmap *const *dms, lsd_frame *const *referenceFrames);
+int lsd_depth_create_keyframe_batch(lsd_ctx *ctx, int n, lsd_depthmap *const *dms, lsd_frame *const *new_keyframes,
+                                    float *rescaleFactors /* n or NULL */);
+int lsd_depth_finalize_keyframe_batch(lsd_ctx *ctx, int n, lsd_depthmap *const *dms);
 int lsd_depth_read(lsd_ctx *ctx, lsd_depthmap *dm, lsd_hypothesis *dst); /* currentDepthMap, w*h entries */
 /* [UP] DepthMap::debugPlotDepthMap -> the w*h*3 bytes lib/GUI.cpp:104-108 (updateDepthImage) consumes */
 int lsd_depth_debug_rgb(lsd_ctx *ctx, lsd_depthmap *dm, uint8_t *rgb);
@@ -344,6 +354,14 @@ int lsd_slam_gt_depth_init(lsd_slam *s, int id, const uint8_t *image, size_t pit
 int lsd_slam_random_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
 /* SlamSystem::nextImage: 8-bit grey image as handed over at lib/App/InputThread.cpp:71 */
 int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
+/* n independent live sequences that share ONE context advance by one image each: SlamSystem::nextImage for every system, with
+ * every stage batched over the sequences (one H2D + ingest, one tracking-reference import, ONE tracker launch for the n
+ * pairs, one set of DepthMap launches for the sequences that update their keyframe and one for those that switch it).
+ * Per sequence the results are bit-identical to n separate lsd_slam_next_image calls; what changes is that the GPU sees
+ * n x the work per launch (a single 640x480 sequence keeps ~2 % of a B200 busy).  Every system must be initialised
+ * (gt_depth_init / random_init) and have no undistorter attached. */
+int lsd_slam_next_image_batch(int n, lsd_slam *const *systems, const int *ids, const uint8_t *const *images, size_t pitch,
+                              lsd_slam_status *st /* n */);
 int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm);
 int lsd_slam_counters(lsd_slam *s, int *tracked, int *lost, int *keyframes);
 /* host wall time accumulated inside nextImage, by stage: {frame ingest, reference import, tracking, updateKeyframe

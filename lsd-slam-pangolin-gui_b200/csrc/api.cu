@@ -496,6 +496,30 @@ int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *nu
   return LSD_OK;
 }
 
+int lsd_frame_mean_idepth_batch(lsd_ctx *ctx, int n, lsd_frame *const *f, float *meanIdepth, int *numPoints) {
+  LSD_ARG(ctx && f && n >= 0);
+  if (n == 0) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; i++) {
+    LSD_ARG(f[i]);
+    if (!(f[i]->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
+  }
+  int rc = ensure_table(ctx, 8 * (size_t)n);
+  if (rc) return rc;
+  // the reductions share the context's ticket / partial-sum scratch: stream order serialises them
+  for (int i = 0; i < n; i++) launch_idepth_stats(ctx, f[i]->slab, reinterpret_cast<float *>(ctx->d_table) + 2 * i, ctx->stream);
+  LSD_CUDA(cudaMemcpyAsync(ctx->h_table, ctx->d_table, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  const float *h = reinterpret_cast<const float *>(ctx->h_table);
+  for (int i = 0; i < n; i++) {
+    f[i]->meanIdepth = h[2 * i];
+    std::memcpy(&f[i]->numPoints, &h[2 * i + 1], 4);
+    if (meanIdepth) meanIdepth[i] = f[i]->meanIdepth;
+    if (numPoints) numPoints[i] = f[i]->numPoints;
+  }
+  return LSD_OK;
+}
+
 int lsd_frame_set_tracking_meta(lsd_ctx *ctx, lsd_frame *f, int parentId, const double toParent[8], float initialTrackedResidual) {
   LSD_ARG(ctx && f && toParent);
   f->trackingParentId = parentId;

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "ctx.cuh"
 #include "lie_dev.cuh"
@@ -117,6 +118,8 @@ int lsd_slam_set_undistorter(lsd_slam *s, lsd_undistorter *und) {
   s->und = und;
   return LSD_OK;
 }
+
+static float slam_min_val(const lsd_slam *s);
 
 static int slam_new_frame(lsd_slam *s, int id, const uint8_t *image, size_t pitch, unsigned flags, lsd_frame **f) {
   if (s->und) return lsd_frame_create_undistorted(s->ctx, s->und, id, image, pitch, flags, nullptr, f);
@@ -237,8 +240,7 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     }
     const double m = (double)s->kfMeanIdepth;
     const double d[3] = {toKf[4] * m, toKf[5] * m, toKf[6] * m};
-    float minVal = std::fmin(0.2f + s->nKeyframes * 0.8f / INITIALIZATION_PHASE_COUNT, 1.0f);
-    if (s->nKeyframes < INITIALIZATION_PHASE_COUNT) minVal *= 0.7f;
+    const float minVal = slam_min_val(s);
     // TrackableKeyFrameSearch::getRefFrameScore: distSq * KFDistWeight^2 + (1 - usage)^2 * KFUsageWeight^2  (16 and 9)
     score = lsd_slam_ref_frame_score((float)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), res.pointUsage);
     create = score > minVal;
@@ -279,6 +281,176 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
     lap(3);
   }
   return LSD_OK;
+}
+
+// minVal of SlamSystem::trackFrame's keyframe decision
+static float slam_min_val(const lsd_slam *s) {
+  float minVal = std::fmin(0.2f + s->nKeyframes * 0.8f / INITIALIZATION_PHASE_COUNT, 1.0f);
+  if (s->nKeyframes < INITIALIZATION_PHASE_COUNT) minVal *= 0.7f;
+  return minVal;
+}
+
+// n live sequences on one context, one image each: the stages of lsd_slam_next_image, each batched over the sequences.
+int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const uint8_t *const *images, size_t pitch,
+                              lsd_slam_status *st) {
+  LSD_ARG(n >= 1 && sys && ids && images && st);
+  lsd_ctx *ctx = sys[0] ? sys[0]->ctx : nullptr;
+  LSD_ARG(ctx);
+  for (int i = 0; i < n; i++) {
+    LSD_ARG(sys[i] && images[i]);
+    LSD_ARG(sys[i]->ctx == ctx);
+    if (!sys[i]->kf || sys[i]->und) {
+      set_error("lsd_slam_next_image_batch: every system must be initialised and have no undistorter attached");
+      return LSD_ERR_STATE;
+    }
+    for (int j = 0; j < i; j++) LSD_ARG(sys[j] != sys[i]);
+  }
+  typedef std::chrono::steady_clock clk;
+  clk::time_point t0 = clk::now();
+  auto lap = [&](int k) {
+    const clk::time_point t1 = clk::now();
+    const double dt = std::chrono::duration<double>(t1 - t0).count() / n;
+    for (int i = 0; i < n; i++) sys[i]->stageSec[k] += dt;
+    t0 = t1;
+  };
+  int rc;
+  std::vector<lsd_frame *> fr(n, nullptr);
+  struct Guard {  // frames that nobody has taken over are dropped on every exit
+    lsd_ctx *ctx;
+    std::vector<lsd_frame *> &f;
+    ~Guard() { for (lsd_frame *x : f) if (x) lsd_frame_release(ctx, x); }
+  } guard = {ctx, fr};
+  if ((rc = lsd_frame_create_batch(ctx, n, ids, images, pitch, LSD_BUILD_TRACKING, fr.data()))) return rc;
+  lap(0);
+
+  // ---- SlamSystem::trackFrame: TrackingReference::importFrame where the keyframe or its depth changed
+  {
+    std::vector<lsd_frame *> kfs;
+    std::vector<int> who;
+    for (int i = 0; i < n; i++) {
+      lsd_slam *s = sys[i];
+      if (!s->ref || s->refKfId != s->kf->id || s->kf->depthHasBeenUpdatedFlag) {
+        if (s->ref) lsd_ref_release(ctx, s->ref);
+        s->ref = nullptr;
+        kfs.push_back(s->kf);
+        who.push_back(i);
+      }
+    }
+    if (!kfs.empty()) {
+      std::vector<lsd_ref *> refs(kfs.size(), nullptr);
+      if ((rc = lsd_ref_create_batch(ctx, (int)kfs.size(), kfs.data(), refs.data()))) return rc;
+      for (size_t k = 0; k < who.size(); k++) {
+        lsd_slam *s = sys[who[k]];
+        s->ref = refs[k];
+        s->refKfId = s->kf->id;
+        s->kf->depthHasBeenUpdatedFlag = false;
+      }
+    }
+  }
+  lap(1);
+  std::vector<lsd_ref *> refs(n);
+  std::vector<double> inits(7 * (size_t)n);
+  std::vector<lsd_se3_result> res(n);
+  for (int i = 0; i < n; i++) {
+    refs[i] = sys[i]->ref;
+    std::memcpy(&inits[7 * (size_t)i], sys[i]->lastToKf, sizeof(double) * 7);
+  }
+  if ((rc = lsd_se3_track_batch(ctx, n, refs.data(), fr.data(), inits.data(), res.data(), nullptr))) return rc;
+  lap(2);
+
+  // ---- per sequence: lost / keyframe decision.  The mean inverse depths the decision needs are fetched in one batch.
+  std::vector<double> toKf(8 * (size_t)n);
+  std::vector<int> needMean;
+  for (int i = 0; i < n; i++) {
+    lsd_slam *s = sys[i];
+    if (res[i].diverged || !res[i].trackingWasGood) continue;
+    if (s->kf->numMappedOnThis > MIN_NUM_MAPPED && !s->kfMeanValid) needMean.push_back(i);
+  }
+  if (!needMean.empty()) {
+    std::vector<lsd_frame *> kfs;
+    std::vector<float> means(needMean.size());
+    for (int i : needMean) kfs.push_back(sys[i]->kf);
+    if ((rc = lsd_frame_mean_idepth_batch(ctx, (int)kfs.size(), kfs.data(), means.data(), nullptr))) return rc;
+    for (size_t k = 0; k < needMean.size(); k++) {
+      sys[needMean[k]]->kfMeanIdepth = means[k];
+      sys[needMean[k]]->kfMeanValid = true;
+    }
+  }
+  std::vector<int> upd, sw;  // sequences that update their keyframe / that switch to a new one
+  std::vector<float> score(n, 0.0f);
+  for (int i = 0; i < n; i++) {
+    lsd_slam *s = sys[i];
+    if (res[i].diverged || !res[i].trackingWasGood) {
+      s->lost++;
+      fill_status(s, ids[i], 0, 0, s->lastToKf, &res[i], 0.0f, &st[i]);
+      continue;  // the guard releases the frame
+    }
+    s->tracked++;
+    double *p = &toKf[8 * (size_t)i];
+    std::memcpy(p, res[i].frameToRef, sizeof(double) * 7);
+    p[7] = 1.0;
+    std::memcpy(s->lastToKf, p, sizeof(double) * 8);
+    bool create = false;
+    if (s->kf->numMappedOnThis > MIN_NUM_MAPPED) {
+      const double m = (double)s->kfMeanIdepth;
+      const double d[3] = {p[4] * m, p[5] * m, p[6] * m};
+      score[i] = lsd_slam_ref_frame_score((float)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), res[i].pointUsage);
+      create = score[i] > slam_min_val(s);
+    }
+    (create ? sw : upd).push_back(i);
+  }
+  lap(3);
+
+  // ---- one blocking mapping iteration per sequence, batched by kind
+  if (!upd.empty()) {
+    std::vector<lsd_depthmap *> dms;
+    std::vector<lsd_frame *> frames;
+    std::vector<char> setsDepth;
+    for (int i : upd) {
+      dms.push_back(sys[i]->dm);
+      frames.push_back(fr[i]);
+      setsDepth.push_back(!sys[i]->kf->depthHasBeenUpdatedFlag);
+    }
+    if ((rc = lsd_depth_update_keyframe_batch(ctx, (int)upd.size(), dms.data(), frames.data()))) return rc;
+    for (size_t k = 0; k < upd.size(); k++) {
+      const int i = upd[k];
+      if (setsDepth[k]) sys[i]->kfMeanValid = false;
+      fill_status(sys[i], ids[i], 1, 0, &toKf[8 * (size_t)i], &res[i], score[i], &st[i]);
+    }
+    lap(3);
+  }
+  if (!sw.empty()) {
+    std::vector<lsd_depthmap *> dms;
+    std::vector<lsd_frame *> frames;
+    for (int i : sw) {
+      dms.push_back(sys[i]->dm);
+      frames.push_back(fr[i]);
+      fill_status(sys[i], ids[i], 1, 1, &toKf[8 * (size_t)i], &res[i], score[i], &st[i]);  // published with the pose it was tracked at
+    }
+    if ((rc = lsd_depth_finalize_keyframe_batch(ctx, (int)sw.size(), dms.data()))) return rc;
+    if ((rc = lsd_depth_create_keyframe_batch(ctx, (int)sw.size(), dms.data(), frames.data(), nullptr))) return rc;
+    for (int i : sw) {
+      lsd_slam *s = sys[i];
+      lsd_frame *f = fr[i];
+      double world[8];
+      sim3_mul(s->kfWorld, f->thisToParent_raw, world);
+      std::memcpy(s->kfWorld, world, sizeof(world));
+      lsd_ref_release(ctx, s->ref);
+      s->ref = nullptr;
+      if (s->keepFinishedKeyframes) s->keyframes.push_back(s->kf);
+      else lsd_frame_release(ctx, s->kf);
+      s->kf = f;
+      fr[i] = nullptr;  // lives on as the current keyframe
+      s->nKeyframes++;
+      s->kfMeanValid = false;
+      sim3_identity(s->lastToKf);
+      st[i].numKeyframes = s->nKeyframes;
+      st[i].currentKeyframeId = s->kf->id;
+      st[i].keyframeRescale = f->thisToParent_raw[7];
+    }
+    lap(4);
+  }
+  return LSD_OK;  // the guard releases every frame that did not become a keyframe
 }
 
 int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm) {

@@ -82,6 +82,7 @@ SYMBOLS = {
     "lsd_frame_set_idepth": (_ip, [_vp, _vp, _vp, _vp]),
     "lsd_frame_set_idepth_batch_device": (_ip, [_vp, _ip, _vp, _vp, _vp]),
     "lsd_frame_mean_idepth": (_ip, [_vp, _vp, _vp, _vp]),
+    "lsd_frame_mean_idepth_batch": (_ip, [_vp, _ip, _vp, _vp, _vp]),
     "lsd_ref_create": (_ip, [_vp, _vp, _vp]),
     "lsd_ref_create_batch": (_ip, [_vp, _ip, _vp, _vp]),
     "lsd_ref_release": (_ip, [_vp, _vp]),
@@ -117,6 +118,9 @@ SYMBOLS = {
     "lsd_depth_update_keyframe": (_ip, [_vp, _vp, _ip, _vp, _vp]),
     "lsd_depth_create_keyframe": (_ip, [_vp, _vp, _vp, _vp]),
     "lsd_depth_finalize_keyframe": (_ip, [_vp, _vp]),
+    "lsd_depth_update_keyframe_batch": (_ip, [_vp, _ip, _vp, _vp]),
+    "lsd_depth_create_keyframe_batch": (_ip, [_vp, _ip, _vp, _vp, _vp]),
+    "lsd_depth_finalize_keyframe_batch": (_ip, [_vp, _ip, _vp]),
     "lsd_depth_read": (_ip, [_vp, _vp, _vp]),
     "lsd_depth_debug_rgb": (_ip, [_vp, _vp, _vp]),
     "lsd_depth_prepare": (_ip, [_vp, _vp, _ip, _vp, _vp]),
@@ -131,6 +135,7 @@ SYMBOLS = {
     "lsd_slam_gt_depth_init": (_ip, [_vp, _ip, _vp, _sz, _vp, _vp]),
     "lsd_slam_random_init": (_ip, [_vp, _ip, _vp, _sz, _vp]),
     "lsd_slam_next_image": (_ip, [_vp, _ip, _vp, _sz, _vp]),
+    "lsd_slam_next_image_batch": (_ip, [_ip, _vp, _vp, _vp, _sz, _vp]),
     "lsd_slam_current_keyframe": (_ip, [_vp, _vp, _vp]),
     "lsd_slam_counters": (_ip, [_vp, _vp, _vp, _vp]),
     "lsd_slam_stage_seconds": (_ip, [_vp, _vp]),
@@ -738,6 +743,23 @@ class SlamSystem:
         st = SlamStatus()
         _chk(self.ctx.L.lsd_slam_next_image(self.p, int(fid), _ptr(im), im.shape[1], C.byref(st)))
         return self._done(st)
+
+    @staticmethod
+    def nextImageBatch(systems, images, fids, image_ptrs=None, pitch=None):
+        """lsd_slam_next_image_batch: one image for each of n systems that share a context (every stage batched over the
+        sequences).  images: n (h, w) uint8 arrays, or pass image_ptrs (host addresses) + pitch to skip the conversion."""
+        n = len(systems)
+        ctx = systems[0].ctx
+        if image_ptrs is None:
+            ims = [np.ascontiguousarray(im, np.uint8) for im in images]
+            image_ptrs = [im.ctypes.data for im in ims]
+            pitch = ims[0].shape[1]
+        sp = (C.c_void_p * n)(*[s.p for s in systems])
+        ip = (C.c_void_p * n)(*image_ptrs)
+        idv = (C.c_int * n)(*[int(f) for f in fids])
+        st = (SlamStatus * n)()
+        _chk(ctx.L.lsd_slam_next_image_batch(n, sp, idv, ip, int(pitch), st))
+        return [s._done(st[i]) for i, s in enumerate(systems)]
 
     def counters(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()

@@ -245,3 +245,25 @@ def make_depth_scene(seed: int, w: int, h: int, n_refs: int = 10, K=None, device
         img, depth = render(room, w, h, K, R1, t1, noise_seed=1000 * seed + i, sigma=sigma)
         refs.append(dict(img=img, depth=depth, toKf=pose7(dR, dt), R_w=R1, t_w=t1))
     return dict(kf_img=kf_img, kf_depth=kf_depth, refs=refs, K=K, R_w_kf=R0, t_w_kf=t0, room=room)
+
+
+def make_constraint_scene(seed: int, w: int, h: int, n_cand: int = 64, K=None, device="cpu", max_t=0.30, max_r=math.radians(10.0),
+                          sigma=1.0):
+    """Config-4 scene: ONE new keyframe and n_cand candidate keyframes of the same room within max_t / max_r
+    of it (upstream: the candidates TrackableKeyFrameSearch hands findConstraintsForNewKeyFrames).
+
+    Returns dict: new = (img, depth), cands = list of dict(img, depth, candToNew = pose7 GT candidate -> new keyframe), K.
+    """
+    K = K or default_K(w, h)
+    rng = np.random.default_rng(seed)
+    room = make_room(seed, device)
+    R0, t0 = random_camera(rng)
+    new_img, new_depth = render(room, w, h, K, R0, t0, noise_seed=7000 * seed, sigma=sigma)
+    cands = []
+    for i in range(n_cand):
+        dR, dt = small_motion(rng, max_t, max_r)  # T_new_cand: candidate -> new keyframe
+        R1 = R0 @ dR
+        t1 = t0 + R0 @ dt
+        img, depth = render(room, w, h, K, R1, t1, noise_seed=7000 * seed + 1 + i, sigma=sigma)
+        cands.append(dict(img=img, depth=depth, candToNew=pose7(dR, dt)))
+    return dict(new=(new_img, new_depth), cands=cands, K=K, room=room)

@@ -259,6 +259,21 @@ void lsdo_make_pairs(int n, const uint8_t *const *kf_imgs, const uint8_t *const 
 }
 
 
+// Frees everything the timed tracking loop never reads (the keyframe's planes once its point clouds exist; the new
+// frame's images and level-0 gradients): 1000 prepared pairs then take ~3 GB of host memory instead of ~20 GB, so that the
+// CPU arm can run the FULL BASELINE configs[1] batch.
+void lsdo_pairs_trim(int n, void **kfs, void **frs) {
+  auto drop = [](std::vector<float> &v) { std::vector<float>().swap(v); };
+  for (int i = 0; i < n; i++) {
+    Frame *kf = (Frame *)kfs[i], *fr = (Frame *)frs[i];
+    for (int l = 0; l < NL; l++) {
+      drop(kf->image[l]); drop(kf->grad[l]); drop(kf->maxGrad[l]); drop(kf->idepth[l]); drop(kf->idepthVar[l]);
+      drop(fr->image[l]); drop(fr->maxGrad[l]);
+    }
+    drop(fr->grad[0]);
+  }
+}
+
 // ---- Sim3Tracker ---------------------------------------------------------------------------------
 struct lsdo_sim3_result {
   double frameToRef[8];  // qx qy qz qw tx ty tz scale

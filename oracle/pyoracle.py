@@ -98,6 +98,8 @@ def lib(fast: bool = False):
     L.lsdo_se3_track_batch.argtypes = [ip, vp, vp, vp, ip, ip, vp]
     L.lsdo_hardware_threads.restype = ip
     L.lsdo_make_pairs.argtypes = [ip, vp, vp, vp, vp, ip, ip, vp, ip, vp, vp, vp]
+    L.lsdo_pairs_trim.restype = None
+    L.lsdo_pairs_trim.argtypes = [ip, vp, vp]
     for name, res, args in [
         ("lsdo_sim3_track", ip, [vp, vp, vp, ip, ip, ip, vp, vp, ip]),
         ("lsdo_sim3_track_batch", dp, [ip, vp, vp, vp, ip, ip, ip, ip, vp]),
@@ -274,10 +276,11 @@ def se3_track_batch(refs, frames, inits, mode=0, threads=1):
 class RawBatch:
     """n prepared (ref, frame) pairs living in the oracle library (bench.py cpu_baseline / --impl reference)."""
 
-    def __init__(self, kf_imgs, fr_imgs, idepths, vars_, K, threads, fast=True):
+    def __init__(self, kf_imgs, fr_imgs, idepths, vars_, K, threads, fast=True, trim=False):
         self.L = lib(fast)
         n = len(kf_imgs)
         self.n = n
+        self._trim = trim
         h, w = kf_imgs[0].shape
         keep = [np.ascontiguousarray(a) for a in kf_imgs], [np.ascontiguousarray(a) for a in fr_imgs], \
                [np.ascontiguousarray(a, np.float32) for a in idepths], [np.ascontiguousarray(a, np.float32) for a in vars_]
@@ -287,6 +290,8 @@ class RawBatch:
         self.ref = (C.c_void_p * n)()
         Kc = (C.c_float * 4)(*K)
         self.L.lsdo_make_pairs(n, arr[0], arr[1], arr[2], arr[3], w, h, Kc, threads, self.kf, self.fr, self.ref)
+        if trim:  # keep only what SE3Tracker::trackFrame reads (full-size batches on the CPU arm)
+            self.L.lsdo_pairs_trim(n, self.kf, self.fr)
 
     def track(self, inits, mode=0, threads=1):
         init = np.ascontiguousarray(inits, np.float64).reshape(self.n, 7)

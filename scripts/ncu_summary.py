@@ -80,5 +80,27 @@ def full(path):
                     pass
 
 
+def traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel in the report, as JSON (profiles/traffic.json
+    entries: bench.py's roofline.traffic reads them)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    u = dict(zip(hdr, units))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    res = collections.OrderedDict()
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        name = d["Kernel Name"].split("(")[0]
+        try:
+            b = sum(float(d[k].replace(",", "")) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            t = float(d["gpu__time_duration.sum"].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[u["gpu__time_duration.sum"]]
+        except (KeyError, ValueError):
+            continue
+        res.setdefault(name, []).append({"dram_bytes": b, "ncu_ms": t, "grid": d.get("Grid Size")})
+    print(json.dumps(res))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])

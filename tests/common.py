@@ -70,8 +70,8 @@ def make_oracle_depth_scene(seed, w, h, n_refs=10, noise=0.05, var=0.01, residua
     return dict(sc=sc, K=sc["K"], kf_img=kf_img, okf=okf, maxgrad=mg, idepth=idv, var=vv, refs=refs, gt_idepth=gt_idepth)
 
 
-def make_sim3_pair(oracle, seed, w, h, c=1.0, var=0.01, max_t=0.05, max_r=np.radians(2.0)):
-    d = make_oracle_pair(seed, w, h, var=var, max_t=max_t, max_r=max_r)
+def make_sim3_pair(oracle, seed, w, h, c=1.0, var=0.01, max_t=0.05, max_r=np.radians(2.0), K=None):
+    d = make_oracle_pair(seed, w, h, var=var, max_t=max_t, max_r=max_r, K=K)
     # frame B gets its own semi-dense depth, in a map whose inverse depths are c times the true ones
     mgB = d["ofr"].get(oracle.MAXGRAD, 0)
     idB, vB = synth.semidense_idepth(d["pr"]["fr_depth"], mgB, var=var)

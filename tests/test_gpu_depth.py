@@ -42,11 +42,17 @@ def gpu_scene(lsd, d, w, h):
     return ctx, kf, refs
 
 
-@pytest.mark.parametrize("wh,seed", [((320, 240), 31), ((640, 480), 32)])
+def _K_for(w, h):
+    """BASELINE configs[4] runs at 1280x960 with the d2_camera.xml-style intrinsics."""
+    from lsd_b200 import synth
+    return synth.d2_K() if (w, h) == (1280, 960) else None
+
+
+@pytest.mark.parametrize("wh,seed", [((320, 240), 31), ((640, 480), 32), ((640, 480), 37), ((1280, 960), 36)])
 def test_stages_bit_exact(lsd, oracle, wh, seed):
     w, h = wh
     oracle.set_exact_sums(1)
-    d = make_oracle_depth_scene(seed, w, h, n_refs=10)
+    d = make_oracle_depth_scene(seed, w, h, n_refs=10, K=_K_for(w, h))
     m0 = hyp_from_idepth(d["idepth"], d["var"])
     rng = np.random.default_rng(seed)
     holes = (rng.random((h, w)) < 0.15) & (m0["isValid"] > 0)
@@ -86,7 +92,7 @@ def test_stages_bit_exact(lsd, oracle, wh, seed):
 
     # propagateDepth to the farthest frame, with and without the tracker's refPixelWasGood mask
     for with_mask in (False, True):
-        d2 = make_oracle_depth_scene(seed, w, h, n_refs=10)
+        d2 = make_oracle_depth_scene(seed, w, h, n_refs=10, K=_K_for(w, h))
         o2 = oracle.DepthMap(w, h, d2["K"])
         cur = odm.read()
         o2.init_map(d2["okf"], cur)
@@ -107,11 +113,13 @@ def test_stages_bit_exact(lsd, oracle, wh, seed):
     ctx.close()
 
 
-def test_update_and_create_keyframe_sequence(lsd, oracle):
-    """The live mapping loop: 8 x updateKeyframe (one tracked frame each), then createKeyFrame on the 9th, then 1 update."""
-    w, h = 320, 240
+@pytest.mark.parametrize("wh", [(320, 240), (640, 480), (1280, 960)])
+def test_update_and_create_keyframe_sequence(lsd, oracle, wh):
+    """The live mapping loop: 8 x updateKeyframe (one tracked frame each), then createKeyFrame on the 9th, then 1 update.
+    Run at every BASELINE resolution (640x480: configs[0..3]; 1280x960 with d2 intrinsics: configs[4])."""
+    w, h = wh
     oracle.set_exact_sums(1)
-    d = make_oracle_depth_scene(33, w, h, n_refs=10, with_mask=True)
+    d = make_oracle_depth_scene(33, w, h, n_refs=10, with_mask=True, K=_K_for(w, h))
     ctx, kf, refs = gpu_scene(lsd, d, w, h)
     for f in refs:
         f.set_mask(np.ones((h >> 1, w >> 1), np.uint8))

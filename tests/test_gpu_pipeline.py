@@ -54,6 +54,62 @@ def test_lockstep_sequence_matches_oracle(lsd, oracle):
     ctx.close()
 
 
+def test_lockstep_640x480_200_frames_matches_oracle(lsd, oracle):
+    """BASELINE configs[0] shape at its own resolution: 200 frames of the 640x480 lock-step pipeline (track + map every
+    frame, keyframe switches by the upstream score) on the device and on the oracle (EXACT sums, and the fp32 SCALAR mode
+    for the envelope).  Requirements: no lost frame, the same keyframe switches at the same frames for at least three
+    switches, frame 1 within the tracker tolerance, and on the common prefix the device stays inside the envelope the
+    oracle's own two summation orders span (the loop is a feedback system: pose -> depth map -> next pose)."""
+    w, h = 640, 480
+    K = synth.default_K(w, h)
+    room = synth.make_room(0)
+    traj = synth.trajectory(800, seed=0)[::4]  # 200 frames, ~8 cm / 2 deg steps
+    frames = [synth.render(room, w, h, K, R, t, noise_seed=i) for i, (R, t) in enumerate(traj)]
+    frames = [(im.numpy(), dp.numpy() if i == 0 else None) for i, (im, dp) in enumerate(frames)]
+    oracle.set_exact_sums(1)
+    ctx = lsd.Context(w, h, K)
+    runs = []
+    for backend in (DeviceBackend(ctx), OracleBackend(w, h, K, mode=2, threads=4), OracleBackend(w, h, K, mode=0, threads=4)):
+        slam = LockStepSlam(backend)
+        slam.first_frame(frames[0][0], 0, frames[0][1])
+        for i in range(1, len(frames)):
+            slam.next_image(frames[i][0], i)
+        runs.append(slam)
+    oracle.set_exact_sums(0)
+    g, o, o0 = runs
+    assert g.stats["lost"] == 0 and o.stats["lost"] == 0
+    # common prefix of the keyframe schedule
+    nk = 0
+    while nk < min(len(g.keyframe_ids), len(o.keyframe_ids)) and g.keyframe_ids[nk] == o.keyframe_ids[nk]:
+        nk += 1
+    assert nk >= 4, ("fewer than three identical keyframe switches", g.keyframe_ids, o.keyframe_ids)
+    last_common = (min(g.keyframe_ids[nk], o.keyframe_ids[nk]) if nk < min(len(g.keyframe_ids), len(o.keyframe_ids))
+                   else len(frames))
+    assert last_common >= 100, (g.keyframe_ids, o.keyframe_ids)
+    pg = {i: p for i, p in g.world_poses}
+    po = {i: p for i, p in o.world_poses}
+    p0 = {i: p for i, p in o0.world_poses}
+    assert np.abs(pg[1][4:7] - po[1][4:7]).max() <= 1e-5
+    ids = [i for i in range(last_common) if i in pg and i in po]
+    dev = max(np.abs(pg[i][4:7] - po[i][4:7]).max() for i in ids)
+    nk0 = 0
+    while nk0 < min(len(o0.keyframe_ids), len(o.keyframe_ids)) and o0.keyframe_ids[nk0] == o.keyframe_ids[nk0]:
+        nk0 += 1
+    env = max(np.abs(p0[i][4:7] - po[i][4:7]).max() for i in ids if i in p0) if nk0 >= nk else 0.0
+    print(f"640x480 pipeline: {len(ids)} common frames, {nk - 1} identical keyframe switches, device-vs-EXACT {dev:.3e} m, "
+          f"SCALAR-vs-EXACT {env:.3e} m, keyframes {g.keyframe_ids}")
+    assert dev <= max(3.0 * env, 5e-3), (dev, env)
+    scale_dev = max(abs(pg[i][7] - po[i][7]) for i in ids)
+    assert scale_dev <= 5e-3
+    R0, t0 = traj[0]
+    gt = np.array([R0.T @ (t - t0) for _, t in traj])
+    gi = [i for i, _ in g.world_poses]
+    err = np.linalg.norm(np.array([p[4:7] for _, p in g.world_poses]) - gt[gi], axis=1)
+    path = np.linalg.norm(np.diff(gt, axis=0), axis=1).sum()
+    assert err.max() < 0.1 * path, (err.max(), path)
+    ctx.close()
+
+
 def test_native_slam_driver_equals_python_driver(lsd):
     """csrc/slam.cu (lsd_slam_next_image = SlamSystem::nextImage, lock-step) issues the same C-ABI calls as the Python
     driver: same keyframe switches, bit-identical poses, and the reference's pose.txt line format."""
@@ -83,4 +139,45 @@ def test_native_slam_driver_equals_python_driver(lsd):
     kf = nat.current_keyframe()
     assert len(kf.compute_vbo(float(sts[-1].camToWorld[7]))) > 0
     nat.close()
+    ctx.close()
+
+
+def test_batched_sequences_equal_separate_systems(lsd):
+    """lsd_slam_next_image_batch: N live sequences on one context, every stage batched over the sequences, must give each
+    sequence exactly what its own lsd_slam_next_image calls give (poses bit for bit, the same keyframe switches, the same
+    depth maps) -- including steps where some sequences switch keyframes while others update theirs."""
+    w, h = 320, 240
+    K = synth.default_K(w, h)
+    nseq, nfr = 3, 36
+    seqs = []
+    for s in range(nseq):
+        room = synth.make_room(10 + s)
+        traj = synth.trajectory(nfr * (3 + s), seed=10 + s)[::3 + s]  # different speeds: keyframe switches at different frames
+        seqs.append([synth.render(room, w, h, K, R, t, noise_seed=i) for i, (R, t) in enumerate(traj)])
+    ctx = lsd.Context(w, h, K)
+    single, batch = [lsd.SlamSystem(ctx) for _ in range(nseq)], [lsd.SlamSystem(ctx) for _ in range(nseq)]
+    for s in range(nseq):
+        for grp in (single, batch):
+            grp[s].gtDepthInit(seqs[s][0][0].numpy(), 0, seqs[s][0][1].numpy())
+    kf_switch_steps = set()
+    for i in range(1, nfr):
+        a = [single[s].nextImage(seqs[s][i][0].numpy(), i) for s in range(nseq)]
+        b = lsd.SlamSystem.nextImageBatch(batch, [seqs[s][i][0].numpy() for s in range(nseq)], [i] * nseq)
+        for s in range(nseq):
+            assert (a[s].tracked, a[s].isKeyframe, a[s].numKeyframes, a[s].currentKeyframeId) == \
+                   (b[s].tracked, b[s].isKeyframe, b[s].numKeyframes, b[s].currentKeyframeId), (i, s)
+            assert list(a[s].camToWorld) == list(b[s].camToWorld), (i, s)
+            assert list(a[s].thisToParent_raw) == list(b[s].thisToParent_raw)
+            assert a[s].keyframeScore == b[s].keyframeScore and a[s].keyframeRescale == b[s].keyframeRescale
+        if any(x.isKeyframe for x in a) and not all(x.isKeyframe for x in a):
+            kf_switch_steps.add(i)
+    assert kf_switch_steps, "the test must contain mixed steps (some sequences switch keyframes, others update)"
+    for s in range(nseq):
+        assert single[s].lines == batch[s].lines
+        assert single[s].counters() == batch[s].counters() and single[s].counters()["keyframes"] >= 1
+        ka, kb = single[s].current_keyframe(), batch[s].current_keyframe()
+        for l in range(5):
+            assert np.array_equal(ka.idepth(l), kb.idepth(l)) and np.array_equal(ka.idepthVar(l), kb.idepthVar(l))
+    for g in single + batch:
+        g.close()
     ctx.close()

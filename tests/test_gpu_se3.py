@@ -168,6 +168,65 @@ def test_batch_equals_single_and_is_deterministic(lsd, oracle):
     ctx.close()
 
 
+def test_bench_batch_parity_64_pairs(lsd, oracle):
+    """The first 64 pairs of bench.py's config-2 batch (same generator, same seeds) tracked in ONE batched launch vs the
+    parity-build oracle in EXACT mode (fp64 accumulators), pair by pair:
+      * the first LM evaluation (identical pose on both sides) has a bit-exact buf_warped_size and a residual <= 1e-4 rel;
+      * pairs whose accept / reject sequences agree end within 1e-5 of the oracle (scene units, rad);
+      * the accept / reject FLIP RATE (an LM step accepted on one side and rejected on the other, error ~ lastErr) is no
+        higher than the oracle's own fp32 modes show against EXACT, and flipped pairs still agree to 1e-2 / within the
+        triangle bound of the fp32 modes."""
+    import torch
+
+    import bench  # repo root is on sys.path (tests/conftest.py)
+    n, w, h = 64, bench.W, bench.H
+    K, kf, fr, idp, var, gt = bench.make_inputs(n, 0, torch.device("cuda", 0))
+    kf_np, fr_np, id_np, var_np = kf.cpu().numpy(), fr.cpu().numpy(), idp.cpu().numpy(), var.cpu().numpy()
+    ctx = lsd.Context(w, h, K)
+    kfs = ctx.create_frames(list(kf_np))
+    for k, a, b in zip(kfs, id_np, var_np):
+        k.set_idepth(a, b)
+    refs = ctx.create_refs(kfs)
+    frs = ctx.create_frames(list(fr_np))
+    inits = np.tile(np.array([0, 0, 0, 1, 0, 0, 0.0]), (n, 1))
+    gres, gtraces = ctx.se3_track_batch(refs, frs, inits, want_trace=True)
+    flips = {0: 0, 1: 0, "gpu": 0}
+    worst_same, worst_flip = 0.0, 0.0
+    for i in range(n):
+        okf, ofr = oracle.Frame(2 * i, kf_np[i], K), oracle.Frame(2 * i + 1, fr_np[i], K)
+        okf.build_pyramids()
+        ofr.build_pyramids()
+        okf.set_idepth(id_np[i], var_np[i])
+        oref = oracle.Ref(okf)
+        eres, etrace = oracle.se3_track(oref, ofr, inits[i], 2)
+        ep, gp = np.array(eres.frameToRef), np.array(gres[i].frameToRef)
+        gtr = gtraces[i]
+        assert gtr[0][4] == etrace[0][4], f"pair {i}: buf_warped_size of the first evaluation"
+        assert abs(gtr[0][2] - etrace[0][2]) <= RES_RTOL * abs(etrace[0][2]), f"pair {i}: first residual"
+        same = len(gtr) == len(etrace) and _agreeing_prefix(gtr, etrace) == len(etrace)
+        dg = max(np.linalg.norm(gp[4:] - ep[4:]), quat_angle(gp[:4], ep[:4]))
+        env = 0.0
+        for mode in (0, 1):
+            ores, otrace = oracle.se3_track(oref, ofr, inits[i], mode)
+            op = np.array(ores.frameToRef)
+            osame = len(otrace) == len(etrace) and _agreeing_prefix(otrace, etrace) == len(etrace)
+            flips[mode] += 0 if osame else 1
+            env = max(env, np.linalg.norm(op[4:] - ep[4:]), quat_angle(op[:4], ep[:4]))
+        if same:
+            worst_same = max(worst_same, dg)
+            assert dg <= POSE_TOL, f"pair {i}: same accept/reject sequence but pose differs by {dg}"
+            assert gres[i].lastGoodCount == eres.lastGoodCount and gres[i].lastBadCount == eres.lastBadCount
+        else:
+            flips["gpu"] += 1
+            worst_flip = max(worst_flip, dg)
+            assert dg <= max(1e-2, 3 * env), f"pair {i}: flipped LM sequence, pose differs by {dg} (fp32-mode envelope {env})"
+        assert gres[i].diverged == eres.diverged and gres[i].trackingWasGood == eres.trackingWasGood
+    print(f"bench-batch parity: {n} pairs, GPU-vs-EXACT flips {flips['gpu']}, SCALAR-vs-EXACT {flips[0]}, SSE4-vs-EXACT {flips[1]}, "
+          f"worst pose diff (same sequence) {worst_same:.2e}, (flipped) {worst_flip:.2e}")
+    assert flips["gpu"] <= max(flips[0], flips[1]) + max(3, n // 10), flips
+    ctx.close()
+
+
 def test_divergence_is_reported(lsd, oracle, synth):
     """A frame that does not overlap the keyframe at all: diverged, identity returned (upstream returns SE3())."""
     w, h = 320, 240
@@ -294,3 +353,75 @@ def test_permaref_quick_track_and_overlap_batch(lsd, oracle):
     full = ctx.se3_track(refs[2], frs[2], np.array([0, 0, 0, 1, 0, 0, 0.0]))
     assert full.trackingWasGood and sum(full.numResidualCalls[1:4]) > 0
     ctx.close()
+
+
+def test_two_contexts_run_concurrently_on_one_device(lsd, oracle):
+    """include/lsd_b200.h promises one context per calling thread with frame / reference handles shared read-only
+    (upstream runs tracking, mapping and constraint search on separate threads: the reference's publishKeyframe takes a
+    shared lock for exactly that reason, PangolinOutputIOWrapper.cpp:50).  Three host threads drive three contexts on
+    the same device at the same time -- SE3 tracking, Sim3 tracking against the SAME references, and a depth-map update --
+    and every result must equal the one obtained serially."""
+    import threading
+    from common import hyp_from_idepth, make_oracle_depth_scene, make_sim3_pair
+    w, h = 320, 240
+    n = 6
+    ds = [make_sim3_pair(oracle, 300 + s, w, h) for s in range(n)]
+    K = ds[0]["pr"]["K"]
+    ctxA, ctxB, ctxC = lsd.Context(w, h, K), lsd.Context(w, h, K), lsd.Context(w, h, K)
+    kfs = ctxA.create_frames([d["kf_img"] for d in ds])
+    frs = ctxA.create_frames([d["fr_img"] for d in ds])
+    frs_sim3 = ctxA.create_frames([d["fr_img"] for d in ds])  # Sim3 reads its frames only; SE3 writes the mask of its own
+    for k, f, d in zip(kfs, frs_sim3, ds):
+        k.set_idepth(d["idepth"], d["var"])
+        f.set_idepth(d["fr_idepth"], d["fr_var"])
+    refs = ctxA.create_refs(kfs)
+    inits7 = np.tile(np.array([0, 0, 0, 1, 0, 0, 0.0]), (n, 1))
+    inits8 = np.array([d["gt8"] for d in ds])
+    inits8[:, 7] = 1.0
+    dsc = make_oracle_depth_scene(310, w, h, n_refs=4)
+    kfC = ctxC.create_frame(dsc["kf_img"], 1000, flags=lsd.BUILD_MAXGRAD0 | lsd.BUILD_GRAD0)
+    refC = []
+    for i, r in enumerate(dsc["refs"]):
+        f = ctxC.create_frame(r["img"], 1001 + i)
+        f.set_tracking_meta(1000, r["toParent"], 1.0)
+        refC.append(f)
+    m0 = hyp_from_idepth(dsc["idepth"], dsc["var"])
+
+    def se3():
+        return [list(r.frameToRef) for r in ctxA.se3_track_batch(refs, frs, inits7)]
+
+    def sim3():
+        return [list(r.frameToRef) for r in ctxB.sim3_track_batch(refs, frs_sim3, inits8)]
+
+    def depth():
+        dm = ctxC.create_depthmap()
+        dm.initializeFromMap(kfC, m0)
+        kfC.set_depth_updated_flag(0)
+        dm.updateKeyframe(refC)
+        out = dm.read().tobytes()
+        dm.destroy()
+        return out
+
+    want = (se3(), sim3(), depth())
+    got = {0: [], 1: [], 2: []}
+    errs = []
+
+    def worker(k, fn, reps):
+        try:
+            for _ in range(reps):
+                got[k].append(fn())
+        except Exception as e:  # noqa: BLE001
+            errs.append((k, repr(e)))
+
+    ths = [threading.Thread(target=worker, args=(0, se3, 12)), threading.Thread(target=worker, args=(1, sim3, 12)),
+           threading.Thread(target=worker, args=(2, depth, 6))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=300)
+    assert not errs, errs
+    assert all(not t.is_alive() for t in ths)
+    for k in range(3):
+        assert got[k] and all(g == want[k] for g in got[k]), f"thread {k}: result changed under concurrency"
+    for c in (ctxB, ctxC, ctxA):
+        c.close()

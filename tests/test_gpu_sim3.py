@@ -36,10 +36,12 @@ def _prefix(a, b):
 
 @pytest.mark.parametrize("seed,wh,c,levels", [(81, (640, 480), 1.0, (4, 1)), (82, (640, 480), 1.04, (4, 1)),
                                                (83, (320, 240), 0.95, (4, 3)), (84, (320, 240), 1.0, (2, 2)),
-                                               (85, (320, 240), 1.02, (1, 1))])
+                                               (85, (320, 240), 1.02, (1, 1)),
+                                               (86, (1280, 960), 1.03, (4, 1)), (87, (1280, 960), 0.97, (4, 3))])
 def test_track_frame_sim3_matches_oracle(lsd, oracle, seed, wh, c, levels):
     w, h = wh
-    d = make_sim3_pair(oracle, seed, w, h, c=c)
+    from lsd_b200 import synth
+    d = make_sim3_pair(oracle, seed, w, h, c=c, K=synth.d2_K() if wh == (1280, 960) else None)  # configs[4]: d2 intrinsics
     ctx, kf, fr, ref = _gpu(lsd, d, w, h)
     init = d["gt8"].copy()
     init[4:7] += [0.004, -0.003, 0.002]
@@ -90,6 +92,31 @@ def test_sim3_batch_is_deterministic_and_composition_independent(lsd, oracle):
         rs = ctx.sim3_track(refs[i], frs[i], inits[i])
         assert np.array_equal(np.array(rs.frameToRef), p1[i])
         assert abs(p1[i][7] - ds[i]["gt8"][7]) < 3e-3
+    ctx.close()
+
+
+def test_sim3_without_depth_residuals_takes_a_finite_step(lsd, oracle):
+    """No warped point lands on a frame pixel with a depth hypothesis (numTermsD == 0): the scale row and column of the
+    7x7 system are zero.  Upstream's Eigen LDLT applies the pseudo-inverse of D there (inc[6] = 0, finite step); an
+    unguarded LDL^T would return NaN and the track would collapse to identity.  Device and oracle must both keep tracking."""
+    w, h = 320, 240
+    d = make_sim3_pair(oracle, 96, w, h)
+    none_id = np.full((h, w), -1.0, np.float32)
+    d["ofr"].set_idepth(none_id, none_id)
+    ctx, kf, fr, ref = _gpu(lsd, d, w, h)
+    fr.set_idepth(none_id, none_id)
+    init = d["gt8"].copy()
+    init[4:7] += [0.004, -0.003, 0.002]
+    init[7] = 1.0
+    g, gtrace = ctx.sim3_track(ref, fr, init, 4, 2, want_trace=True)
+    e, etrace = oracle.sim3_track(d["oref"], d["ofr"], init, 4, 2, 2)
+    gp, ep = np.array(g.frameToRef), np.array(e.frameToRef)
+    assert np.isfinite(gp).all() and np.isfinite(ep).all()
+    assert g.diverged == 0 and e.diverged == 0
+    assert len(gtrace) > 6 and any(t[1] == 1 for t in gtrace), "steps must be taken and accepted"
+    assert gp[7] == 1.0 and ep[7] == 1.0, "no depth residual: the scale must not move"
+    assert np.linalg.norm(gp[4:7] - ep[4:7]) <= POSE_TOL and quat_angle(gp[:4], ep[:4]) <= POSE_TOL
+    assert np.linalg.norm(gp[4:7] - init[4:7]) > 1e-4, "the pose must have moved"
     ctx.close()
 
 
