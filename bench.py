@@ -441,10 +441,11 @@ def leg_track_map(lsd, dev, local_rank, args, cpu):
                 kfs += sum(st.isKeyframe for st in sts)
             torch.cuda.synchronize()
             dtm = time.perf_counter() - t0
+            stage_ms = {k: 1e3 * v * m / steps for k, v in systems[0].stage_seconds().items()}  # per step, all sequences
             for s in systems:
                 s.close()
             multi[str(m)] = {"sequences": m, "frames_per_sequence": steps, "fps_total": m * steps / dtm, "fps_per_sequence": steps / dtm,
-                             "ms_per_step": 1e3 * dtm / steps, "lost": lost, "keyframes": kfs}
+                             "ms_per_step": 1e3 * dtm / steps, "lost": lost, "keyframes": kfs, "stage_ms_per_step": stage_ms}
         out["concurrent_sequences"] = multi
         out["concurrent_sequences_note"] = ("lsd_slam_next_image_batch: N lock-step sequences on ONE context; per sequence the results "
                                             "are bit-identical to N separate systems (tests/test_gpu_pipeline.py)")

@@ -201,12 +201,15 @@ typedef struct lsd_sim3_result {
 } lsd_sim3_result;
 
 int lsd_ctx_set_sim3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s);
+/* Points per partial record of the Sim3 tracker (0 = default 1024; multiple of 128): a record is reduced by one CTA and the
+ * records are summed in order, so this value DEFINES the fp32 summation order (see lsd_ctx_set_se3_record_points). */
+int lsd_ctx_set_sim3_record_points(lsd_ctx *ctx, int points);
 /* [UP] Sim3Tracker::trackFrameSim3(TrackingReference*, Frame*, const Sim3& frameToReference_initialEstimate,
  * int startLevel, int finalLevel).  `frame` must carry depth (it is a keyframe): its idepth pyramid is read. */
 int lsd_sim3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[8], int startLevel, int finalLevel,
                    lsd_sim3_result *result, lsd_trace_entry *trace /* LSD_TRACE_CAP entries or NULL */);
-/* n independent tracks, one thread-block cluster each, in ONE launch (the constraint search of
- * SlamSystem::findConstraintsForNewKeyFrames: BASELINE.json configs[3]) */
+/* n independent tracks in ONE persistent launch (the constraint search of SlamSystem::findConstraintsForNewKeyFrames:
+ * BASELINE.json configs[3]); results are bit-identical for every batch composition */
 int lsd_sim3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init_frameToRef /* n*8 */,
                          int startLevel, int finalLevel, lsd_sim3_result *results, lsd_trace_entry *traces /* n*LSD_TRACE_CAP or NULL */);
 
@@ -327,7 +330,7 @@ int lsd_keyframe_compute_vbo_batch(lsd_ctx *ctx, int n, lsd_frame *const *frames
  * system->nextImage(idx, image, camera) lib/App/InputThread.cpp:71) with its `runRealTime == false` semantics:
  * nextImage returns once the frame is tracked AND mapped.  Tracking, mapping and keyframe selection run through the
  * entry points above; pose graph, loop closure and relocalisation stay on the reference's CPU code. */
-typedef struct lsd_slam lsd_slam;
+typedef struct lsd_slam_system lsd_slam_system;
 typedef struct lsd_slam_status {
   int frameId;
   int tracked;            /* 0: tracking lost on this frame (upstream would start the Relocalizer) */
@@ -339,34 +342,34 @@ typedef struct lsd_slam_status {
   double thisToParent_raw[8]; /* frame -> keyframe (pose.txt columns 5-7)                              */
   double keyframeRescale;     /* isKeyframe: the mean-idepth rescale createKeyFrame folded into the new keyframe's pose */
 } lsd_slam_status;
-int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out); /* SlamSystem::SlamSystem() */
+int lsd_slam_create(lsd_ctx *ctx, lsd_slam_system **out); /* SlamSystem::SlamSystem() */
 /* [UP] TrackableKeyFrameSearch::getRefFrameScore(distanceSquared, usage) = distSq*KFDistWeight^2 + (1-usage)^2*KFUsageWeight^2
  * (KFDistWeight 4, KFUsageWeight 3): the closeness score nextImage compares with minVal to decide on a new keyframe */
 float lsd_slam_ref_frame_score(float distanceSquared, float usage);
-int lsd_slam_destroy(lsd_slam *s);                 /* fullReset() = destroy + create */
+int lsd_slam_destroy(lsd_slam_system *s);                 /* fullReset() = destroy + create */
 /* keep finished keyframes alive (upstream: KeyFrameGraph::keyframesAll) -- default 1; 0 frees them for long benches */
-int lsd_slam_set_keep_keyframes(lsd_slam *s, int keep);
+int lsd_slam_set_keep_keyframes(lsd_slam_system *s, int keep);
 /* optional: images handed to nextImage are still distorted and go through `und` first (undistort + ingest fused:
  * lib/App/InputThread.cpp:59-71 in one call); NULL = images are already undistorted */
-int lsd_slam_set_undistorter(lsd_slam *s, lsd_undistorter *und);
+int lsd_slam_set_undistorter(lsd_slam_system *s, lsd_undistorter *und);
 /* SlamSystem::gtDepthInit / randomInit on the first image (nextImage on an empty system = randomInit) */
-int lsd_slam_gt_depth_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st);
-int lsd_slam_random_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
+int lsd_slam_gt_depth_init(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st);
+int lsd_slam_random_init(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
 /* SlamSystem::nextImage: 8-bit grey image as handed over at lib/App/InputThread.cpp:71 */
-int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
+int lsd_slam_next_image(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st);
 /* n independent live sequences that share ONE context advance by one image each: SlamSystem::nextImage for every system, with
  * every stage batched over the sequences (one H2D + ingest, one tracking-reference import, ONE tracker launch for the n
  * pairs, one set of DepthMap launches for the sequences that update their keyframe and one for those that switch it).
  * Per sequence the results are bit-identical to n separate lsd_slam_next_image calls; what changes is that the GPU sees
  * n x the work per launch (a single 640x480 sequence keeps ~2 % of a B200 busy).  Every system must be initialised
  * (gt_depth_init / random_init) and have no undistorter attached. */
-int lsd_slam_next_image_batch(int n, lsd_slam *const *systems, const int *ids, const uint8_t *const *images, size_t pitch,
+int lsd_slam_next_image_batch(int n, lsd_slam_system *const *systems, const int *ids, const uint8_t *const *images, size_t pitch,
                               lsd_slam_status *st /* n */);
-int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm);
-int lsd_slam_counters(lsd_slam *s, int *tracked, int *lost, int *keyframes);
+int lsd_slam_current_keyframe(lsd_slam_system *s, lsd_frame **kf, lsd_depthmap **dm);
+int lsd_slam_counters(lsd_slam_system *s, int *tracked, int *lost, int *keyframes);
 /* host wall time accumulated inside nextImage, by stage: {frame ingest, reference import, tracking, updateKeyframe
  * (incl. keyframe selection), keyframe switch (finalize + createKeyFrame)} */
-int lsd_slam_stage_seconds(lsd_slam *s, double out[5]);
+int lsd_slam_stage_seconds(lsd_slam_system *s, double out[5]);
 /* "id,tx,ty,tz,rawtx,rawty,rawtz\n" as written by TextOutputIOWrapper::publishTrackedFrame
  * (lib/Pangolin_IOWrapper/TextOutputIOWrapper.cpp:100-120) */
 int lsd_slam_pose_line(const lsd_slam_status *st, char *buf, size_t n);

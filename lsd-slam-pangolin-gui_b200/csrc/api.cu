@@ -1,10 +1,12 @@
 // api.cu -- extern "C" surface of liblsd_b200.so (include/lsd_b200.h): contexts, device-resident
 // frames, tracking references and the SE3 tracker entry points.  No CPU fallback exists: every
 // entry point either runs the sm_100a kernels or returns an error.
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "ctx.cuh"
 
@@ -249,6 +251,8 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->descSlot = 0;
   ctx->stageTimed = false;
   ctx->se3s = nullptr;
+  ctx->sim3s = nullptr;
+  ctx->sim3RecordPoints = 0;
   ctx->lastAlgBytes = 0;
   ctx->lastEvals = 0;
   ctx->lastKernelMs = 0;
@@ -261,6 +265,7 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   se3_scratch_free(ctx);
+  sim3_scratch_free(ctx);
   for (auto p : ctx->frameSlabPool) cudaFree(p);
   for (auto p : ctx->refSlabPool) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -798,6 +803,22 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
   const int nChunks = (n + CH - 1) / CH;
   const bool streamed = streamedCfg && nChunks > 1;
   cudaStream_t st = ctx->stream;
+  // Pageable caller memory (a cv::Mat handed to SlamSystem::nextImage is not pinned: lib/App/InputThread.cpp:58-71): a
+  // cudaMemcpyAsync from it is staged by the driver on the calling thread, chunk by chunk, and blocks it (measured: 34 k
+  // frames/s against 147 k from pinned memory).  Such images go through a pinned ring owned by the context instead, filled
+  // by a few host threads while earlier chunks are on the copy engine.
+  bool pageable = false;
+  {
+    cudaPointerAttributes a0, a1;
+    const cudaError_t e0 = cudaPointerGetAttributes(&a0, images[0]), e1 = cudaPointerGetAttributes(&a1, images[n - 1]);
+    if (e0 != cudaSuccess || e1 != cudaSuccess) cudaGetLastError();
+    pageable = (e0 != cudaSuccess || a0.type == cudaMemoryTypeUnregistered) || (e1 != cudaSuccess || a1.type == cudaMemoryTypeUnregistered);
+  }
+  const int RING = 3;  // ring slots of CH frames each
+  if (pageable) {
+    rc = ensure_stage(ctx, (size_t)RING * fbytes * CH, 0);
+    if (rc) return rc;
+  }
 
   // everything this call creates is released on every exit path; a persistent tracker that was started is drained first
   struct Scope {
@@ -805,7 +826,12 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     std::vector<lsd_frame *> fr;
     std::vector<cudaEvent_t> copied, consumed;
     bool trackerRunning = false;
+    std::vector<std::thread> stagers;  // pinned-ring staging of pageable images (below); joined before anything is released
+    std::atomic<int> stageStop{0}, nextFrame{0}, freeUpTo{0};
+    std::vector<std::atomic<int>> staged;
     ~Scope() {
+      stageStop.store(1);
+      for (std::thread &t : stagers) if (t.joinable()) t.join();
       if (trackerRunning) se3_stream_abort(ctx, ctx->trackStream, ctx->copyStream);
       cudaStreamSynchronize(ctx->copyStream);
       cudaStreamSynchronize(ctx->stream);
@@ -841,10 +867,50 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
     LSD_CUDA(cudaEventCreateWithFlags(&consumed[c], cudaEventDisableTiming));
   }
   uint8_t *const *d_slabs = reinterpret_cast<uint8_t *const *>(ctx->d_table);
+  // pinned-ring staging of pageable images: workers take frames in order; frame i may be written once the ring slot of its
+  // chunk is free (freeUpTo), and chunk c may be copied once all of its frames are staged (staged[c])
+  std::vector<std::atomic<int>> &staged = sc.staged;
+  std::atomic<int> &nextFrame = sc.nextFrame, &freeUpTo = sc.freeUpTo;
+  freeUpTo.store(RING - 1);
+  if (pageable) {
+    staged = std::vector<std::atomic<int>>(nChunks);
+    for (auto &a : staged) a.store(0);
+    static const int envT = getenv("LSD_B200_STAGE_THREADS") ? atoi(getenv("LSD_B200_STAGE_THREADS")) : 0;
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = envT > 0 ? envT : (int)(hw / 2 < 1 ? 1 : (hw / 2 > 8 ? 8 : hw / 2));
+    for (int i = 0; i < n; i++) LSD_ARG(images[i]);
+    for (int t = 0; t < T; t++)
+      sc.stagers.emplace_back([&, fbytes, CH]() {
+        for (;;) {
+          const int i = nextFrame.fetch_add(1);
+          if (i >= n) return;
+          const int c = i / CH;
+          while (freeUpTo.load(std::memory_order_acquire) < c) {
+            if (sc.stageStop.load()) return;
+            std::this_thread::yield();
+          }
+          uint8_t *dst = ctx->h_stage + ((size_t)(c % RING) * CH + (size_t)(i - c * CH)) * fbytes;
+          const uint8_t *src = images[i];
+          if (pitch == (size_t)ctx->w) std::memcpy(dst, src, fbytes);
+          else for (int y = 0; y < ctx->h; y++) std::memcpy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
+          staged[c].fetch_add(1, std::memory_order_release);
+        }
+      });
+  }
   auto issue_copy = [&](int c) -> int {
     const int i0 = c * CH, m = (n - i0) < CH ? (n - i0) : CH;
     uint8_t *dst = ctx->d_stage + (size_t)(c & 1) * fbytes * CH;
     if (c >= 2) LSD_CUDA(cudaStreamWaitEvent(ctx->copyStream, consumed[c - 2], 0));  // staging half free again
+    if (pageable) {
+      while (staged[c].load(std::memory_order_acquire) < m) std::this_thread::yield();
+      LSD_CUDA(cudaMemcpyAsync(dst, ctx->h_stage + (size_t)(c % RING) * CH * fbytes, fbytes * (size_t)m, cudaMemcpyHostToDevice, ctx->copyStream));
+      LSD_CUDA(cudaEventRecord(copied[c], ctx->copyStream));
+      if (c >= 1) {  // the ring slot of chunk c - 1 is free once its copy has completed: chunk c - 1 + RING may be staged
+        LSD_CUDA(cudaEventSynchronize(copied[c - 1]));
+        freeUpTo.store(c - 1 + RING, std::memory_order_release);
+      }
+      return LSD_OK;
+    }
     int i = 0;
     while (i < m) {  // runs of frames that are back to back in host memory
       int j = i + 1;

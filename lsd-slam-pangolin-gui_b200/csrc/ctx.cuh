@@ -2,7 +2,8 @@
 #pragma once
 #include "common.cuh"
 
-struct SE3Scratch;  // se3_track.cu
+struct SE3Scratch;   // se3_track.cu
+struct Sim3Scratch;  // sim3_track.cu
 struct DepthScratch;
 
 struct lsd_ctx {
@@ -42,6 +43,8 @@ struct lsd_ctx {
   bool stageTimed;  // evA/evB bracket the kernels of the last depth stage
   int descSlot;  // rotating slot of the depth-map descriptor uploads (depth.cu)
   SE3Scratch *se3s;
+  Sim3Scratch *sim3s;
+  int sim3RecordPoints;  // 0: default (1024); points per partial record = the summation order of the Sim3 tracker
   // last-call stats
   double lastAlgBytes;
   long long lastEvals;
@@ -89,6 +92,7 @@ int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
                   float *A36, float *b6, float *scalars);
 void se3_scratch_free(lsd_ctx *ctx);
+void sim3_scratch_free(lsd_ctx *ctx);
 int se3_permaref_overlap_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, const double *refToFrame, float *pointUsage);
 
 }  // namespace lsd

@@ -6,43 +6,47 @@
 // calcSim3Buffers (12 SoA buffers) -> calcSim3WeightsAndResidual -> calcSim3LGS (LGS6 + LGS4 -> LGS7), with
 // the 7x7 LDLT and the fp64 Sim3 exponential on the host in between.
 //
-// B200 structure: ONE THREAD-BLOCK CLUSTER (S3_CL = 4 CTAs x 256 threads) PER TRACK, the whole coarse-to-fine LM
-// loop on device.  Every evaluation is cut into S3_CL contiguous parts, one per CTA of the cluster; each CTA
-// fuses the three reference passes per point (no buffers are materialised), reduces its 41 normal-equation
-// terms + residual sums in a fixed order, and CTA 0 gathers the S3_CL partials over distributed shared memory
-// in rank order, runs accept / reject, the 7x7 LDL^T solve and the fp64 Sim3 exponential, and broadcasts the
-// next pose into every CTA's shared memory.  Two cluster barriers per evaluation, no global-memory round
-// trip, no host involvement, bit-reproducible (the decomposition never depends on the batch).
-// Compiled -fmad=false: per-point values are IEEE-identical to the oracle's; only summation order differs.
-#include <cooperative_groups.h>
-
+// B200 structure (round 2; round 1 ran one 4-CTA cluster per track with two cluster barriers per evaluation and sat at
+// 0.17 of the HBM roofline): the persistent work-queue scheme of the SE3 tracker (se3_track.cu).
+//  * the three reference passes are fused into one per-point evaluation that never materialises the buffers;
+//  * an evaluation is cut into RECORDS of recPoints consecutive points (default 1024: a constraint search is at most a few
+//    hundred tracks, so an evaluation is spread over many CTAs instead of four); every record is reduced by one CTA in a
+//    fixed order and the records are summed in record order: bit-reproducible, independent of batch and scheduling;
+//  * work items are (track, record); CTAs of one grid-resident kernel pull them from a device ring queue.  The CTA that
+//    completes a track's last record runs accept / reject, the 7x7 LDL^T and the fp64 Sim3 exponential and publishes the
+//    next evaluation.  Tracks advance independently: no cluster barrier, no grid barrier, no host round trip;
+//  * per point, both global-memory latencies (point record; four gradient taps + the frame's own idepth / var at the
+//    nearest pixel) are in flight two points ahead (cp.async into per-thread shared-memory slots).
+// Arithmetic tiers as in the SE3 tracker: everything a discrete output depends on (warp, projection, in-image test, the
+// bilinear sample, both residuals and the depth-validity tests) is IEEE-identical to the oracle (-fmad=false, correctly
+// rounded division); weights, Huber factors and Jacobian rows -- which only enter sums whose order already differs from the
+// reference's -- use fmaf and MUFU reciprocal / rsqrt (2^-22 relative, far inside the 1e-4 residual tolerance).
 #include <cmath>
+#include <cstddef>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.cuh"
 #include "lie_dev.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace lsd {
 
 #ifndef S3_THREADS
-#define S3_THREADS 256
+#define S3_THREADS 128
 #endif
-// CTAs per cluster = per track.  Measured on B200 (64 candidates x 2 directions, levels 4->1): 8 CTAs 2.96 ms, 4 CTAs
-// 2.70 ms, 2 CTAs 3.22 ms, 1 CTA 6.2 ms (profiles/r01j_sim3_cluster_sweep.txt)
-#ifndef S3_CL
-#define S3_CL 4
+#ifndef S3_D
+#define S3_D 2            // software-pipeline depth of s3_eval_range
 #endif
-// resident CTAs per SM the register allocation is capped for (221 registers uncapped = ONE 256-thread CTA per SM, i.e.
-// 18 clusters on the whole GPU; the cap trades a few spills in the single-thread LM step for 2-4x the clusters in flight)
 #ifndef S3_MINB
-#define S3_MINB 2
+#define S3_MINB 3         // resident CTAs per SM the register budget is sized for
 #endif
+#define S3_REC_DEFAULT 1024
 // fp32 sums
 enum { Q_A6 = 0, Q_B6 = 21, Q_A4 = 27, Q_B4 = 37, Q_RD = 41, Q_RP = 42, Q_USAGE = 43, Q_ND = 44, Q_CNT = 45, S3_NF = 46 };
 #define S3_ND 5  // fp64 affine-lighting sums (sxx, syy, sx, sy, sw), see se3_track.cu
+#define S3_NRED 64  // floats per partial record: 5 doubles + 46 floats + pad (256 B)
 
+// Written by the host before the launch: immutable on the device.
 struct Sim3Job {
   const RefPoint *pts[NL];
   const float2 *rgrad[NL];
@@ -66,16 +70,21 @@ struct Sim3Params {
   Intrinsics K;
   lsd_tracker_settings s;
   int startLevel, finalLevel;
+  int recPoints;  // points per partial record: defines the summation order
+  int maxRecs;    // per-track stride of the partial records
 };
 
-// what every CTA of the cluster needs for one evaluation
+// what every CTA working on a track's current evaluation needs: the first 96 bytes of the track state
 struct S3Cmd {
   float Rs[9], t[3];  // scaled rotation (rxso3) and translation, float
   float roll[4];      // xRoll0, xRoll1, yRoll0, yRoll1
   float a, b;
   int level;
-  int op;  // 0 evaluate, 1 finished
+  int op;    // 0 evaluate, 1 finished
+  int nPts;  // numData[level]
+  int pad_[3];
 };
+static_assert(sizeof(S3Cmd) == 96, "evaluation header = 6 x int4");
 
 struct S3Res {
   float sumResD, sumResP;
@@ -93,6 +102,29 @@ struct S3State {
   S3Res lastErr, finalRes;
   float sums[41];  // A6, b6, A4, b4 of the evaluation the current outer iteration started from (undivided)
   int nc;
+  // outputs that accumulate over the track: kept here (the state is only ever read through L2) and written to Sim3Out once,
+  // when the track finishes -- a read-modify-write of Sim3Out from whichever SM runs the LM step could hit a stale L1 line
+  int n[NL], nRes[NL], nWarp[NL];
+  int traceLen;
+  float pointUsage;
+  int pad_[1];
+};
+static_assert(sizeof(S3State) % 16 == 0, "S3State must be int4-copyable");
+
+// Mutable per-track state in global memory: only ever read through L2 (__ldcg) inside the persistent kernel.
+struct __align__(16) S3Track {
+  S3Cmd cmd;
+  unsigned done;  // records of the evaluation in flight that have been reduced
+  int pad_[3];
+  S3State st;
+};
+static_assert(sizeof(S3Track) % 16 == 0 && offsetof(S3Track, st) % 16 == 0, "S3Track must be int4-copyable");
+
+struct S3Queue {
+  unsigned long long *slots;  // {sequence : 32, item : 32}; valid for ticket T when sequence == T / cap + 1
+  unsigned *head, *tail;
+  int *remaining;  // tracks not finished yet
+  unsigned cap;    // power of two >= tracks * maxRecs
 };
 
 __device__ void s3_make_cmd(const double q[4], const double t[3], double s, float a, float b, int level, S3Cmd &c) {
@@ -142,138 +174,169 @@ __device__ void s3_make_cmd(const double q[4], const double t[3], double s, floa
   c.op = 0;
 }
 
-// Per-thread accumulators.  S3_SMEM_ACC = 1 keeps the 46 fp32 sums of a thread in ITS column of the shared-memory
-// reduction buffer (conflict-free: consecutive threads, consecutive banks) instead of in registers: the register budget
-// drops by ~50, twice the CTAs are resident, and the sequence of additions per thread -- hence every bit of the result
-// -- is unchanged (the block reduction then reads the buffer in place).
-#ifndef S3_SMEM_ACC
-#define S3_SMEM_ACC 1
-#endif
-#if S3_SMEM_ACC
-struct S3Acc {
-  float *col;  // &sm.f[0][threadIdx.x]
-  __device__ __forceinline__ float &operator[](int j) const { return col[j * S3_THREADS]; }
-};
-#else
-typedef float *S3Acc;
-#endif
 
-// One reference point: its warp and the loads issued for it (stage A), consumed by stage B.  Running stage A of point
-// k+1 before stage B of point k (a two-deep software pipeline) was measured SLOWER (2.29 vs 2.13 ms: the 18 extra live
-// registers spill), so the two stages run back to back; only the 24-byte point record is fetched one iteration ahead.
-struct S3Warp {
-  float Wx, Wy, Wz, pz, u_new, v_new;
-  float4 p00, p10, p01, p11;
-  float var_frameDepth, id_frameDepth;
-  bool inside;
+__device__ __forceinline__ unsigned s3_atom_add_acq_rel(unsigned *p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
+// publish the records of a track's next evaluation (its state has been stored already)
+__device__ void s3_push(const S3Queue &q, int track, int nRecs) {
+  __threadfence();
+  const unsigned base = atomicAdd(q.tail, (unsigned)nRecs);
+  for (int c = 0; c < nRecs; c++) {
+    const unsigned t = base + c;
+    const unsigned long long v = ((unsigned long long)(t / q.cap + 1) << 32) | (unsigned)((track << 12) | c);
+    *reinterpret_cast<volatile unsigned long long *>(&q.slots[t & (q.cap - 1)]) = v;
+  }
+}
+
+__device__ __forceinline__ void s3_cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void s3_cp_async4(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void s3_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void s3_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct S3Const {  // per-evaluation constants in registers
+  float Rs[9], t[3], roll[4];
+  float a, b;
+  float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
+  float var_weight, huber;
+  int W, H;
 };
 
-__device__ __forceinline__ void s3_stage_a(const float4 raw, const S3Cmd &c, const Sim3Params &prm, int W, int H,
-                                           const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR,
-                                           S3Warp &w) {
-  const int lvl = c.level;
-  const float fx_l = prm.K.fx[lvl], fy_l = prm.K.fy[lvl], cx_l = prm.K.cx[lvl], cy_l = prm.K.cy[lvl];
+// what the warp stage of a point hands to its accumulate stage
+struct S3Pending {
+  float Wx, Wy, Wz, pz, dx, dy, color, var;
+  float2 rg;
+  int st;  // 1: loads in flight, 0: projects outside the image, -1: no point
+};
+
+// per-thread staging slots: [stage][tap][thread] float4 (conflict-free rows) and [stage][idepth|var][thread] float
+struct S3Slots {
+  float4 taps[S3_D * 4 * S3_THREADS];
+  float dv[S3_D * 2 * S3_THREADS];
+};
+
+// EXACT tier: warp, projection, in-image test.  The four bilinear taps and the frame's own (idepth, var) at the nearest
+// pixel go straight from global memory into this thread's slot.
+__device__ __forceinline__ void s3_warp_point(const float4 raw, const float2 rg, const S3Const &c, const float4 *__restrict__ G,
+                                              const float *__restrict__ FID, const float *__restrict__ FVAR, float4 *tapSlot,
+                                              float *dvSlot, S3Pending &w) {
   const uint32_t xy = __float_as_uint(raw.x);
   const int x = xy & 0xffff, y = xy >> 16;
   const float inv = raw.y;  // RefPoint::invDepth
-  const float px = inv * (prm.K.fxi[lvl] * x + prm.K.cxi[lvl]);
-  const float py = inv * (prm.K.fyi[lvl] * y + prm.K.cyi[lvl]);
+  const float px = inv * (c.fxi * x + c.cxi);
+  const float py = inv * (c.fyi * y + c.cyi);
   const float pz = inv * 1.0f;
   w.pz = pz;
   w.Wx = (c.Rs[0] * px + c.Rs[1] * py + c.Rs[2] * pz) + c.t[0];
   w.Wy = (c.Rs[3] * px + c.Rs[4] * py + c.Rs[5] * pz) + c.t[1];
   w.Wz = (c.Rs[6] * px + c.Rs[7] * py + c.Rs[8] * pz) + c.t[2];
-  w.u_new = (w.Wx / w.Wz) * fx_l + cx_l;
-  w.v_new = (w.Wy / w.Wz) * fy_l + cy_l;
-  w.inside = w.u_new > 1 && w.v_new > 1 && w.u_new < W - 2 && w.v_new < H - 2;
-  if (!w.inside) return;
-  // getInterpolatedElement43 taps + the frame's own (idepth, var) at the nearest pixel, all in ONE memory round trip
-  // (ncu source view of the first version: point record, taps, var, idepth were four serial HBM latencies per point)
-  const int ix = (int)w.u_new, iy = (int)w.v_new;
-  const float4 *bp = G + ix + iy * W;
-  w.p00 = __ldg(bp); w.p10 = __ldg(bp + 1); w.p01 = __ldg(bp + W); w.p11 = __ldg(bp + 1 + W);
-  const int idx_rounded = (int)(w.u_new + 0.5f) + W * (int)(w.v_new + 0.5f);
-  w.var_frameDepth = __ldg(FVAR + idx_rounded);
-  w.id_frameDepth = __ldg(FID + idx_rounded);
+  w.color = raw.z;
+  w.var = raw.w;
+  w.rg = rg;
+  const float u_new = (w.Wx / w.Wz) * c.fx + c.cx;
+  const float v_new = (w.Wy / w.Wz) * c.fy + c.cy;
+  if (!(u_new > 1 && v_new > 1 && u_new < c.W - 2 && v_new < c.H - 2)) {
+    w.st = 0;
+    return;
+  }
+  const int ix = (int)u_new, iy = (int)v_new;
+  w.dx = u_new - ix;
+  w.dy = v_new - iy;
+  w.st = 1;
+  const float4 *bp = G + (ix + iy * c.W);
+  s3_cp_async16(tapSlot, bp);
+  s3_cp_async16(tapSlot + S3_THREADS, bp + 1);
+  s3_cp_async16(tapSlot + 2 * S3_THREADS, bp + c.W);
+  s3_cp_async16(tapSlot + 3 * S3_THREADS, bp + c.W + 1);
+  const int idx_rounded = (int)(u_new + 0.5f) + c.W * (int)(v_new + 0.5f);
+  s3_cp_async4(dvSlot, FID + idx_rounded);
+  s3_cp_async4(dvSlot + S3_THREADS, FVAR + idx_rounded);
 }
 
-__device__ __forceinline__ void s3_stage_b(const float4 raw, const float2 rg, const S3Warp &w, const S3Cmd &c, const Sim3Params &prm,
-                                           S3Acc acc, double dacc[S3_ND]) {
-  if (!w.inside) return;
-  const int lvl = c.level;
-  const float fx_l = prm.K.fx[lvl], fy_l = prm.K.fy[lvl];
-  const float Wx = w.Wx, Wy = w.Wy, Wz = w.Wz, pz = w.pz, u_new = w.u_new, v_new = w.v_new;
-  const float4 p00 = w.p00, p10 = w.p10, p01 = w.p01, p11 = w.p11;
-  const float var_frameDepth = w.var_frameDepth, id_frameDepth = w.id_frameDepth;
-  const int ix = (int)u_new, iy = (int)v_new;
-  const float dx = u_new - ix, dy = v_new - iy, dxdy = dx * dy;
-  const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+__device__ __forceinline__ float s3_rcp(float x) { return __fdividef(1.0f, x); }
+
+__device__ __forceinline__ void s3_accumulate(const S3Pending &w, const float4 p00, const float4 p10, const float4 p01, const float4 p11,
+                                              const float id_frameDepth, const float var_frameDepth, const S3Const &c,
+                                              float acc[S3_NF], double dacc[S3_ND]) {
+  // ---- EXACT: getInterpolatedElement43 (this weight form and summation order), both residuals, the validity tests
+  const float dxdy = w.dx * w.dy;
+  const float w11 = dxdy, w01 = w.dy - dxdy, w10 = w.dx - dxdy, w00 = 1 - w.dx - w.dy + dxdy;
   const float gxI = w11 * p11.x + w01 * p01.x + w10 * p10.x + w00 * p00.x;
   const float gyI = w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y;
   const float cI = w11 * p11.z + w01 * p01.z + w10 * p10.z + w00 * p00.z;
-  // USE_ESM_TRACKING: mean of the frame gradient and the rolled reference gradient
-  const float rotatedGradX = c.roll[0] * rg.x + c.roll[1] * rg.y;
-  const float rotatedGradY = c.roll[2] * rg.x + c.roll[3] * rg.y;
-  const float gx = fx_l * 0.5f * (gxI + rotatedGradX);
-  const float gy = fy_l * 0.5f * (gyI + rotatedGradY);
-
-  const float c1 = c.a * raw.z + c.b;
+  const float Wx = w.Wx, Wy = w.Wy, Wz = w.Wz, pz = w.pz;
+  const float c1 = c.a * w.color + c.b;
   const float c2 = cI;
   const float rp = c1 - c2;
-  const float weight = fabsf(rp) < 2.0f ? 1 : 2.0f / fabsf(rp);
-  dacc[0] += (double)(c1 * c1 * weight);
-  dacc[1] += (double)(c2 * c2 * weight);
-  dacc[2] += (double)(c1 * weight);
-  dacc[3] += (double)(c2 * weight);
-  dacc[4] += (double)weight;
-
-  // depth residual against the frame's own inverse depth (nearest pixel)
-  const float ref_idepth = 1.0f / Wz;
-  const float d = 1.0f / pz;
-  float rd, svw;
-  if (var_frameDepth > 0) {
-    rd = ref_idepth - id_frameDepth;
-    svw = var_frameDepth;
-  } else {
-    rd = -1;
-    svw = -1;
-  }
+  const float z = 1.0f / Wz;  // ref_idepth (IEEE: rd below is a difference of two nearly equal inverse depths)
+  const bool hasDepth = var_frameDepth > 0;
+  const float rd = hasDepth ? z - id_frameDepth : -1.0f;
   acc[Q_CNT] += 1.0f;
-  const float depthChange = pz / Wz;
+  if (hasDepth) acc[Q_ND] += 1.0f;
+
+  // ---- RELAXED from here on
+  const float arp = fabsf(rp);
+  const float weight = arp < 2.0f ? 1.0f : 2.0f * s3_rcp(arp);  // affine-lighting Huber weight (k = 2)
+  const float c1w = c1 * weight, c2w = c2 * weight;
+  dacc[0] += (double)(c1 * c1w);
+  dacc[1] += (double)(c2 * c2w);
+  dacc[2] += (double)c1w;
+  dacc[3] += (double)c2w;
+  dacc[4] += (double)weight;
+  const float depthChange = pz * z;
   acc[Q_USAGE] += depthChange < 1 ? depthChange : 1;
 
-  // calcSim3WeightsAndResidual
-  const float s = prm.s.var_weight * raw.w;
-  const float sv = prm.s.var_weight * svw;
-  const float g0 = (c.t[0] * Wz - c.t[2] * Wx) / (Wz * Wz * d);
-  const float g1 = (c.t[1] * Wz - c.t[2] * Wy) / (Wz * Wz * d);
-  const float g2 = (Wz - c.t[2]) / (Wz * Wz * d);
-  const float drpdd = gx * g0 + gy * g1;
-  const float w_p = 1.0f / (LSD_CAMERA_PIXEL_NOISE2 + s * drpdd * drpdd);
-  const float w_d = 1.0f / (sv + g2 * g2 * s);
-  const float weighted_rd = fabsf(rd * sqrtf(w_d));
-  const float weighted_rp = fabsf(rp * sqrtf(w_p));
-  const float weighted_abs_res = sv > 0 ? weighted_rd + weighted_rp : weighted_rp;
-  const float wh = fabsf(weighted_abs_res < prm.s.huber_d ? 1 : prm.s.huber_d / weighted_abs_res);
-  float wd = 0;
-  if (sv > 0) {
-    acc[Q_RD] += wh * w_d * rd * rd;
-    acc[Q_ND] += 1.0f;
-    wd = wh * w_d;
-  }
-  acc[Q_RP] += wh * w_p * rp * rp;
-  const float wp = wh * w_p;
+  // USE_ESM_TRACKING: mean of the frame gradient and the rolled reference gradient
+  const float rotatedGradX = fmaf(c.roll[0], w.rg.x, c.roll[1] * w.rg.y);
+  const float rotatedGradY = fmaf(c.roll[2], w.rg.x, c.roll[3] * w.rg.y);
+  const float gx = c.fx * 0.5f * (gxI + rotatedGradX);
+  const float gy = c.fy * 0.5f * (gyI + rotatedGradY);
 
-  // calcSim3LGS
-  const float z = 1.0f / Wz;
-  const float z_sqr = 1.0f / (Wz * Wz);
+  // calcSim3WeightsAndResidual: g = (.) / (z'^2 d) with d = 1 / p_z  =>  (.) * p_z / z'^2
+  const float z_sqr = z * z;
+  const float kk = z_sqr * pz;
+  const float g0 = fmaf(c.t[0], Wz, -c.t[2] * Wx) * kk;
+  const float g1 = fmaf(c.t[1], Wz, -c.t[2] * Wy) * kk;
+  const float g2 = (Wz - c.t[2]) * kk;
+  const float drpdd = fmaf(gx, g0, gy * g1);
+  const float s = c.var_weight * w.var;
+  const float rsp = rsqrtf(fmaf(s * drpdd, drpdd, LSD_CAMERA_PIXEL_NOISE2));  // sqrt(w_p)
+  const float w_p = rsp * rsp;
+  const float weighted_rp = arp * rsp;
+  float w_d = 0.0f, weighted_rd = 0.0f;
+  if (hasDepth) {
+    const float sv = c.var_weight * var_frameDepth;
+    const float rsd = rsqrtf(fmaf(g2 * g2, s, sv));  // sqrt(w_d)
+    w_d = rsd * rsd;
+    weighted_rd = fabsf(rd) * rsd;
+  }
+  const float war = weighted_rd + weighted_rp;
+  const float wh = war < c.huber ? 1.0f : c.huber * s3_rcp(war);
+  const float wd = wh * w_d;  // 0 without a depth residual
+  const float wp = wh * w_p;
+  acc[Q_RD] = fmaf(wd * rd, rd, acc[Q_RD]);
+  acc[Q_RP] = fmaf(wp * rp, rp, acc[Q_RP]);
+
+  // calcSim3LGS (regrouped as in the SE3 tracker)
   float v[6], v4[4];
-  v[0] = z * gx + 0;
-  v[1] = 0 + z * gy;
-  v[2] = (-Wx * z_sqr) * gx + (-Wy * z_sqr) * gy;
-  v[3] = (float)((double)((-Wx * Wy * z_sqr) * gx) + (-(1.0 + (double)(Wy * Wy * z_sqr))) * (double)gy);
-  v[4] = (float)((1.0 + (double)(Wx * Wx * z_sqr)) * (double)gx + (double)((Wx * Wy * z_sqr) * gy));
-  v[5] = (-Wy * z) * gx + (Wx * z) * gy;
+  v[0] = z * gx;
+  v[1] = z * gy;
+  v[2] = -z * fmaf(Wx, v[0], Wy * v[1]);
+  v[3] = fmaf(Wy, v[2], -gy);
+  v[4] = fmaf(-Wx, v[2], gx);
+  v[5] = fmaf(Wx, v[1], -Wy * v[0]);
   v4[0] = z_sqr;
   v4[1] = z_sqr * Wy;
   v4[2] = -z_sqr * Wx;
@@ -297,25 +360,87 @@ __device__ __forceinline__ void s3_stage_b(const float4 raw, const float2 rg, co
   }
 }
 
-__device__ __forceinline__ void s3_point(const float4 raw, const float2 rg, const S3Cmd &c, const Sim3Params &prm, int W, int H,
-                                         const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR,
-                                         S3Acc acc, double dacc[S3_ND]) {
-  S3Warp w;
-  s3_stage_a(raw, c, prm, W, H, G, FID, FVAR, w);
-  s3_stage_b(raw, rg, w, c, prm, acc, dacc);
+// All points [begin, end) of one record.  Thread t takes points begin + t + m * S3_THREADS in order of m (part of the summation
+// order).  Software pipeline as in se3_track.cu: the point record one stage ahead of its warp stage, the taps S3_D - 1 points
+// ahead of their accumulate stage; a thread only reads slots it filled itself, so there is no CTA barrier inside the loop.
+__device__ __forceinline__ void s3_eval_range(const RefPoint *__restrict__ pts, const float2 *__restrict__ rgrad, int begin, int end,
+                                              const float4 *__restrict__ G, const float *__restrict__ FID, const float *__restrict__ FVAR,
+                                              const S3Const &c, float acc[S3_NF], double dacc[S3_ND], S3Slots &slots) {
+  const float4 *pts4 = reinterpret_cast<const float4 *>(pts);
+  float4 *myTap = slots.taps + threadIdx.x;
+  float *myDv = slots.dv + threadIdx.x;
+  S3Pending pd[S3_D];
+  int iLoad = begin + threadIdx.x;
+  float4 rawNext = make_float4(0, 0, 0, 0);
+  float2 rgNext = make_float2(0, 0);
+  if (iLoad < end) { rawNext = __ldg(pts4 + iLoad); rgNext = __ldg(rgrad + iLoad); }
+  auto issue = [&](const int s) {
+    const float4 raw = rawNext;
+    const float2 rg = rgNext;
+    const bool have = iLoad < end;
+    iLoad += S3_THREADS;
+    if (iLoad < end) { rawNext = __ldg(pts4 + iLoad); rgNext = __ldg(rgrad + iLoad); }
+    if (have) s3_warp_point(raw, rg, c, G, FID, FVAR, myTap + s * 4 * S3_THREADS, myDv + s * 2 * S3_THREADS, pd[s]);
+    else pd[s].st = -1;
+    s3_cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < S3_D - 1; s++) issue(s);
+  const int steps = (end - begin + S3_THREADS - 1) / S3_THREADS;  // CTA-uniform
+  for (int m0 = 0; m0 < steps; m0 += S3_D) {
+#pragma unroll
+    for (int s = 0; s < S3_D; s++) {
+      issue((s + S3_D - 1) % S3_D);
+      s3_cp_async_wait<S3_D - 1>();
+      if (pd[s].st > 0) {
+        const float4 *sl = myTap + s * 4 * S3_THREADS;
+        const float *dv = myDv + s * 2 * S3_THREADS;
+        s3_accumulate(pd[s], sl[0], sl[S3_THREADS], sl[2 * S3_THREADS], sl[3 * S3_THREADS], dv[0], dv[S3_THREADS], c, acc, dacc);
+      }
+    }
+  }
+  s3_cp_async_wait<0>();
 }
 
-// S3_DSHUF = 1: the five fp64 affine sums are reduced with warp shuffles + an 8-entry table per sum instead of a
-// [5][256] double buffer (10 KB): the dynamic shared memory of a CTA drops to 46 KB so that FOUR CTAs fit on an SM.
-#ifndef S3_DSHUF
-#define S3_DSHUF 1
-#endif
-struct S3Smem {
+struct S3Red {
   float f[S3_NF][S3_THREADS];
-#if !S3_DSHUF
   double d[S3_ND][S3_THREADS];
-#endif
 };
+union S3Smem {  // staging slots and reduction scratch are never live at the same time (one CTA barrier separates them)
+  S3Slots slots;
+  S3Red red;
+};
+
+// fixed-order block reduction of the per-thread sums into one partial record (same scheme as the SE3 tracker)
+__device__ __forceinline__ void s3_block_reduce_store(const float acc[S3_NF], const double dacc[S3_ND], float *__restrict__ dst, S3Smem &smu) {
+  S3Red &sm = smu.red;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < S3_NF; j++) sm.f[j][threadIdx.x] = acc[j];
+#pragma unroll
+  for (int j = 0; j < S3_ND; j++) sm.d[j][threadIdx.x] = dacc[j];
+  __syncthreads();
+  for (int row = wid; row < S3_NF + S3_ND; row += S3_THREADS / 32) {
+    if (row < S3_NF) {
+      float v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < S3_THREADS / 32; k++) v += sm.f[row][lane + 32 * k];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) dst[2 * S3_ND + row] = v;
+    } else {
+      const int r = row - S3_NF;
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < S3_THREADS / 32; k++) v += sm.d[r][lane + 32 * k];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) reinterpret_cast<double *>(dst)[r] = v;
+    }
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ bool s3_too_few(int size, int lvl, const Sim3Params &prm) {
   return size < 0.5 * LSD_MIN_GOODPERALL_PIXEL_ABSMIN * prm.K.w[lvl] * prm.K.h[lvl] || size < 10;
@@ -362,11 +487,24 @@ __device__ void s3_finish(const S3State &S, Sim3Out *O) {
 }
 
 // The LM state machine after one evaluation.  Returns false when the track is finished.
+// the accumulated outputs of a finished track (see S3State)
+__device__ void s3_flush(const S3State &S, Sim3Out *O) {
+  O->pointUsage = S.pointUsage;
+  O->affine_a = S.a;
+  O->affine_b = S.b;
+  O->traceLen = S.traceLen;
+  for (int l = 0; l < NL; l++) {
+    O->n[l] = S.n[l];
+    O->nRes[l] = S.nRes[l];
+    O->nWarp[l] = S.nWarp[l];
+  }
+}
+
 __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *tot, const double *dtot, const Sim3Params &prm,
                         lsd_trace_entry *trace, S3Cmd &next) {
   const int lvl = S.level;
   const int size = (int)tot[Q_CNT];
-  O->pointUsage = tot[Q_USAGE] / (float)O->n[lvl];
+  S.pointUsage = tot[Q_USAGE] / (float)S.n[lvl];
   const double sxx = dtot[0], syy = dtot[1], sx = dtot[2], sy = dtot[3], sw = dtot[4];
   const double aLd = sqrt((syy - sy * sy / sw) / (sxx - sx * sx / sw));
   const float aL = (float)aLd, bL = (float)((sy - aLd * sx) / sw);
@@ -383,8 +521,6 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
     S.finalRes = err;
 #pragma unroll
     for (int k = 0; k < 41; k++) S.sums[k] = tot[k];
-    O->affine_a = S.a;
-    O->affine_b = S.b;
     s3_finish(S, O);
     return false;
   }
@@ -393,7 +529,7 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
     s3_identity_out(O);
     return false;
   }
-  O->nRes[lvl]++;
+  S.nRes[lvl]++;
   const int maxIts = prm.s.maxItsPerLvl[lvl];
   bool take = false;
   int accepted;
@@ -435,10 +571,8 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
       S.lambda *= f;
     }
   }
-  if (trace && O->traceLen < LSD_TRACE_CAP) trace[O->traceLen] = {lvl, accepted, err.mean, traceLambda, size};
-  O->traceLen++;
-  O->affine_a = S.a;
-  O->affine_b = S.b;
+  if (trace && S.traceLen < LSD_TRACE_CAP) trace[S.traceLen] = {lvl, accepted, err.mean, traceLambda, size};
+  S.traceLen++;
 
   if (S.iteration >= maxIts) {
     // next level with iterations (upstream `continue`s over levels whose maxItsPerLvl is 0)
@@ -447,7 +581,7 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
     if (nl >= prm.finalLevel) {
       S.level = nl;
       S.phase = 0;
-      if (O->n[nl] == 0) {
+      if (S.n[nl] == 0) {
         O->diverged = 1;
         s3_identity_out(O);
         return false;
@@ -468,7 +602,7 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
 #pragma unroll
     for (int k = 0; k < 41; k++) S.sums[k] = tot[k];
     S.nc = 2 * size;
-    O->nWarp[lvl]++;
+    S.nWarp[lvl]++;
     S.incTry = 0;
     S.upToDate = true;
   }
@@ -522,163 +656,185 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
   return true;
 }
 
-__global__ void __cluster_dims__(S3_CL, 1, 1) __launch_bounds__(S3_THREADS, S3_MINB)
-k_sim3_track(const Sim3Job *__restrict__ jobs, Sim3Out *__restrict__ outs, const __grid_constant__ Sim3Params prm,
-             lsd_trace_entry *__restrict__ traces) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned rank = cluster.block_rank();
-  const int jobIdx = blockIdx.x / S3_CL;
-  const Sim3Job *J = jobs + jobIdx;
-  Sim3Out *O = outs + jobIdx;
-  extern __shared__ __align__(16) unsigned char s3_dyn_smem[];  // 56 KB: above the static limit
-  S3Smem &sm = *reinterpret_cast<S3Smem *>(s3_dyn_smem);
-  __shared__ S3Cmd cmd;
-  __shared__ float part[S3_NF];
-  __shared__ double dpart[S3_ND];
-  __shared__ double dwarp[S3_ND][S3_THREADS / 32];
-  __shared__ float tot[S3_NF];
-  __shared__ double dtot[S3_ND];
-  __shared__ S3State S;  // used by thread 0 of rank 0 only
 
-  if (rank == 0 && threadIdx.x == 0) {
-    memset(&S, 0, sizeof(S));
-    for (int i = 0; i < 4; i++) S.q[i] = J->init[i];
-    for (int i = 0; i < 3; i++) S.t[i] = J->init[4 + i];
-    S.s = J->init[7];
-    S.a = 1;
-    S.b = 0;
-    memset(O, 0, sizeof(Sim3Out));
-    for (int l = 0; l < NL; l++) O->n[l] = J->d_num[l];
-    O->affine_a = 1;
-    S3Cmd first;
-    int lvl = prm.startLevel;
-    while (lvl >= prm.finalLevel && prm.s.maxItsPerLvl[lvl] == 0) lvl--;
-    if (lvl < prm.finalLevel) {
-      // no level has iterations: upstream still evaluates once at finalLevel (!warp_update_up_to_date)
-      S.phase = 2;
-      S.level = prm.finalLevel;
-      s3_make_cmd(S.q, S.t, S.s, S.a, S.b, prm.finalLevel, first);
-    } else if (O->n[lvl] == 0) {
-      O->diverged = 1;
-      s3_identity_out(O);
-      first.op = 1;
-    } else {
-      S.level = lvl;
-      S.phase = 0;
-      s3_make_cmd(S.q, S.t, S.s, S.a, S.b, lvl, first);
-    }
-    for (unsigned r = 0; r < S3_CL; r++) *cluster.map_shared_rank(&cmd, r) = first;
-  }
-  cluster.sync();
+__global__ void __launch_bounds__(S3_THREADS, S3_MINB)
+k_sim3_track(const Sim3Job *__restrict__ jobs, S3Track *tracks, Sim3Out *outs, float *partials, const S3Queue q,
+             const __grid_constant__ Sim3Params prm, lsd_trace_entry *traces) {
+  __shared__ __align__(16) S3Smem sm;
+  __shared__ float stot[S3_NF];
+  __shared__ double sdtot[S3_ND];
+  __shared__ int sCode, sIsLast, sMore;
+  __shared__ __align__(16) S3State sState;
+  __shared__ __align__(16) S3Cmd sNext;
 
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned ticket = 0;
+  if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
   for (;;) {
-    if (cmd.op != 0) break;
-    const int lvl = cmd.level;
-    const int n = J->d_num[lvl];
-    const int W = prm.K.w[lvl], H = prm.K.h[lvl];
-    // contiguous part of this CTA (multiple of 32 points)
-    const int per = (((n + S3_CL - 1) / S3_CL) + 31) & ~31;
-    const int begin = min(n, (int)rank * per), end = min(n, begin + per);
-#if S3_SMEM_ACC
-    S3Acc acc = {&sm.f[0][threadIdx.x]};
-#else
-    float accReg[S3_NF];
-    S3Acc acc = accReg;
-#endif
+    if (threadIdx.x == 0) {  // fetch the next work item: thread 0 spins on its ticket's slot
+      const unsigned slot = ticket & (q.cap - 1), seq = ticket / q.cap + 1;
+      const volatile unsigned long long *sp = reinterpret_cast<const volatile unsigned long long *>(&q.slots[slot]);
+      int code = -1;
+      for (;;) {
+        const unsigned long long v = *sp;
+        if ((unsigned)(v >> 32) == seq) {
+          code = (int)(unsigned)v;
+          break;
+        }
+        if (*reinterpret_cast<const volatile int *>(q.remaining) <= 0) break;
+        __nanosleep(40);
+      }
+      sCode = code;
+      if (code >= 0) ticket = atomicAdd(q.head, 1u);
+    }
+    __syncthreads();
+    const int code = sCode;
+    if (code < 0) break;
+    const int track = code >> 12, rec = code & 0xfff;
+    const Sim3Job *J = jobs + track;
+    S3Track *T = tracks + track;
+    // evaluation header: 6 x LDG.128 through L2
+    S3Const c;
+    int lvl, n;
+    {
+      const int4 *hp = reinterpret_cast<const int4 *>(T);
+      const int4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1), h2 = __ldcg(hp + 2), h3 = __ldcg(hp + 3), h4 = __ldcg(hp + 4);
+      c.Rs[0] = __int_as_float(h0.x); c.Rs[1] = __int_as_float(h0.y); c.Rs[2] = __int_as_float(h0.z); c.Rs[3] = __int_as_float(h0.w);
+      c.Rs[4] = __int_as_float(h1.x); c.Rs[5] = __int_as_float(h1.y); c.Rs[6] = __int_as_float(h1.z); c.Rs[7] = __int_as_float(h1.w);
+      c.Rs[8] = __int_as_float(h2.x); c.t[0] = __int_as_float(h2.y); c.t[1] = __int_as_float(h2.z); c.t[2] = __int_as_float(h2.w);
+      c.roll[0] = __int_as_float(h3.x); c.roll[1] = __int_as_float(h3.y); c.roll[2] = __int_as_float(h3.z); c.roll[3] = __int_as_float(h3.w);
+      c.a = __int_as_float(h4.x); c.b = __int_as_float(h4.y);
+      lvl = h4.z;
+      n = __ldcg(&T->cmd.nPts);
+    }
+    c.fx = prm.K.fx[lvl]; c.fy = prm.K.fy[lvl]; c.cx = prm.K.cx[lvl]; c.cy = prm.K.cy[lvl];
+    c.fxi = prm.K.fxi[lvl]; c.fyi = prm.K.fyi[lvl]; c.cxi = prm.K.cxi[lvl]; c.cyi = prm.K.cyi[lvl];
+    c.var_weight = prm.s.var_weight;
+    c.huber = prm.s.huber_d;
+    c.W = prm.K.w[lvl];
+    c.H = prm.K.h[lvl];
+
+    float acc[S3_NF];
     double dacc[S3_ND];
 #pragma unroll
     for (int j = 0; j < S3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
     for (int j = 0; j < S3_ND; j++) dacc[j] = 0.0;
-    const float4 *pts4 = reinterpret_cast<const float4 *>(J->pts[lvl]);
-    const float2 *rg = J->rgrad[lvl];
-    {  // the next point's record (reference point + gradient) is loaded while the current point is evaluated
-      const float4 *G = J->fgrad[lvl];
-      const float *FID = J->fid[lvl], *FVAR = J->fvar[lvl];
-      int i = begin + threadIdx.x;
-      float4 rawC = make_float4(0, 0, 0, 0);
-      float2 rgC = make_float2(0, 0);
-      if (i < end) { rawC = __ldg(pts4 + i); rgC = __ldg(rg + i); }
-      for (; i < end; i += S3_THREADS) {
-        float4 rawN = rawC;
-        float2 rgN = rgC;
-        if (i + S3_THREADS < end) { rawN = __ldg(pts4 + i + S3_THREADS); rgN = __ldg(rg + i + S3_THREADS); }
-        s3_point(rawC, rgC, cmd, prm, W, H, G, FID, FVAR, acc, dacc);
-        rawC = rawN;
-        rgC = rgN;
-      }
-    }
-    // block reduction in a fixed order (same scheme as the SE3 tracker)
-#if !S3_SMEM_ACC
-#pragma unroll
-    for (int j = 0; j < S3_NF; j++) sm.f[j][threadIdx.x] = acc[j];
-#endif
-#if S3_DSHUF
-#pragma unroll
-    for (int j = 0; j < S3_ND; j++) {
-      double v = dacc[j];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) dwarp[j][wid] = v;
-    }
+    const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
+    const int begin = rec * prm.recPoints, end = min(n, begin + prm.recPoints);
+    s3_eval_range(J->pts[lvl], J->rgrad[lvl], begin, end, J->fgrad[lvl], J->fid[lvl], J->fvar[lvl], c, acc, dacc, sm.slots);
+    float *recBase = partials + (size_t)track * prm.maxRecs * S3_NRED;
+    s3_block_reduce_store(acc, dacc, recBase + (size_t)rec * S3_NRED, sm);
+    if (threadIdx.x == 0) sIsLast = (s3_atom_add_acq_rel(&T->done, 1u) == (unsigned)(nRecs - 1));
     __syncthreads();
-    if (threadIdx.x < S3_ND) {
-      double v = 0.0;
-#pragma unroll
-      for (int k = 0; k < S3_THREADS / 32; k++) v += dwarp[threadIdx.x][k];
-      dpart[threadIdx.x] = v;
-    }
-    for (int row = wid; row < S3_NF; row += S3_THREADS / 32) {
-#else
-#pragma unroll
-    for (int j = 0; j < S3_ND; j++) sm.d[j][threadIdx.x] = dacc[j];
-    __syncthreads();
-    for (int row = wid; row < S3_NF + S3_ND; row += S3_THREADS / 32) {
-#endif
-      if (row < S3_NF) {
-        float v = 0.0f;
-#pragma unroll
-        for (int k = 0; k < S3_THREADS / 32; k++) v += sm.f[row][lane + 32 * k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) part[row] = v;
-      }
-#if !S3_DSHUF
-      else {
-        const int r = row - S3_NF;
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < S3_THREADS / 32; k++) v += sm.d[r][lane + 32 * k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) dpart[r] = v;
-      }
-#endif
-    }
-    cluster.sync();  // every CTA's partial is in its shared memory
-    if (rank == 0) {
-      if (threadIdx.x < S3_NF) {
-        float v = 0.0f;
-        for (unsigned r = 0; r < S3_CL; r++) v += *cluster.map_shared_rank(&part[threadIdx.x], r);
-        tot[threadIdx.x] = v;
-      } else if (threadIdx.x < S3_NF + S3_ND) {
-        const int j = threadIdx.x - S3_NF;
-        double v = 0.0;
-        for (unsigned r = 0; r < S3_CL; r++) v += *cluster.map_shared_rank(&dpart[j], r);
-        dtot[j] = v;
+    if (sIsLast) {
+      if (threadIdx.x < S3_ND) {
+        const double *src = reinterpret_cast<const double *>(recBase) + threadIdx.x;
+        double s = 0.0;
+        for (int r = 0; r < nRecs; r++) s += __ldcg(src + (size_t)r * (S3_NRED / 2));
+        sdtot[threadIdx.x] = s;
+      } else if (threadIdx.x < S3_ND + S3_NF) {
+        const int j = threadIdx.x - S3_ND;
+        const float *src = recBase + 2 * S3_ND + j;
+        float s = 0.0f;
+        for (int r = 0; r < nRecs; r++) s += __ldcg(src + (size_t)r * S3_NRED);
+        stot[j] = s;
+      } else if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(S3State) / 16)) {
+        const int k = threadIdx.x - 64;
+        reinterpret_cast<int4 *>(&sState)[k] = __ldcg(reinterpret_cast<const int4 *>(&T->st) + k);
       }
       __syncthreads();
       if (threadIdx.x == 0) {
         S3Cmd next;
         next.op = 1;
-        const bool more = s3_step(J, S, O, tot, dtot, prm, traces ? traces + (size_t)jobIdx * LSD_TRACE_CAP : nullptr, next);
-        if (!more) next.op = 1;
-        for (unsigned r = 0; r < S3_CL; r++) *cluster.map_shared_rank(&cmd, r) = next;
+        next.nPts = 0;
+        const bool more = s3_step(J, sState, outs + track, stot, sdtot, prm, traces ? traces + (size_t)track * LSD_TRACE_CAP : nullptr, next);
+        if (!more) {
+          next.op = 1;
+          s3_flush(sState, outs + track);
+        } else {
+          next.nPts = sState.n[next.level];
+        }
+        sNext = next;
+        sMore = more ? 1 : 0;
+      }
+      __syncthreads();
+      if (sMore) {  // store the state and the next evaluation's header, then publish its records
+        if (threadIdx.x < (int)(sizeof(S3State) / 16))
+          reinterpret_cast<int4 *>(&T->st)[threadIdx.x] = reinterpret_cast<const int4 *>(&sState)[threadIdx.x];
+        else if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(S3Cmd) / 16))
+          reinterpret_cast<int4 *>(&T->cmd)[threadIdx.x - 64] = reinterpret_cast<const int4 *>(&sNext)[threadIdx.x - 64];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          T->done = 0;
+          s3_push(q, track, (sNext.nPts + prm.recPoints - 1) / prm.recPoints);
+        }
+      } else if (threadIdx.x == 0) {
+        __threadfence();  // the track's outputs precede the completion count
+        atomicSub(q.remaining, 1);
       }
     }
-    cluster.sync();  // next command visible everywhere; partials may be overwritten
+    __syncthreads();  // sCode / sIsLast / sm are reused by the next item
   }
+}
+
+// Initial state of every track and its first evaluation.
+__global__ void k_sim3_init(const Sim3Job *__restrict__ jobs, S3Track *__restrict__ tracks, Sim3Out *__restrict__ outs, int n,
+                            const S3Queue q, const Sim3Params prm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Sim3Job *J = jobs + i;
+  S3Track *T = tracks + i;
+  Sim3Out *O = outs + i;
+  S3State S;
+  memset(&S, 0, sizeof(S));
+  for (int k = 0; k < 4; k++) S.q[k] = J->init[k];
+  for (int k = 0; k < 3; k++) S.t[k] = J->init[4 + k];
+  S.s = J->init[7];
+  S.a = 1;
+  S.b = 0;
+  memset(O, 0, sizeof(Sim3Out));
+  for (int l = 0; l < NL; l++) S.n[l] = J->d_num[l];
+  S3Cmd first;
+  memset(&first, 0, sizeof(first));
+  first.op = 0;
+  int lvl = prm.startLevel;
+  while (lvl >= prm.finalLevel && prm.s.maxItsPerLvl[lvl] == 0) lvl--;
+  if (lvl < prm.finalLevel) {
+    // no level has iterations: upstream still evaluates once at finalLevel (!warp_update_up_to_date)
+    S.phase = 2;
+    S.level = prm.finalLevel;
+    s3_make_cmd(S.q, S.t, S.s, S.a, S.b, prm.finalLevel, first);
+  } else if (S.n[lvl] == 0) {
+    O->diverged = 1;
+    s3_identity_out(O);
+    first.op = 1;
+  } else {
+    S.level = lvl;
+    S.phase = 0;
+    s3_make_cmd(S.q, S.t, S.s, S.a, S.b, lvl, first);
+  }
+  if (first.op == 0 && S.n[first.level] == 0) {  // an empty cloud at the only level to evaluate
+    O->diverged = 1;
+    s3_identity_out(O);
+    first.op = 1;
+  }
+  first.nPts = first.op == 0 ? S.n[first.level] : 0;
+  T->cmd = first;
+  T->done = 0;
+  T->st = S;
+  if (first.op == 0) {
+    s3_push(q, i, (first.nPts + prm.recPoints - 1) / prm.recPoints);
+  } else {
+    s3_flush(S, O);
+    atomicSub(q.remaining, 1);
+  }
+}
+
+__global__ void k_sim3_reset(unsigned *ctrs, unsigned n) {
+  ctrs[0] = 0u;
+  ctrs[1] = 0u;
+  ctrs[2] = n;
+  ctrs[3] = 0u;
 }
 
 static void sim3_inverse_host(const double p[8], double o[8]) {
@@ -692,10 +848,71 @@ static void sim3_inverse_host(const double p[8], double o[8]) {
   o[7] = si;
 }
 
+struct Sim3ScratchImpl {
+  S3Track *d_tracks = nullptr;
+  float *d_partials = nullptr;
+  unsigned long long *d_slots = nullptr;
+  unsigned *d_ctrs = nullptr;  // head, tail, remaining, pad
+  int cap = 0, maxRecs = 0;
+  unsigned qcap = 0;
+  int gridBlocks = 0;
+};
+
+}  // namespace lsd
+
+struct Sim3Scratch : lsd::Sim3ScratchImpl {};
+
+namespace lsd {
+
+void sim3_scratch_free(lsd_ctx *ctx) {
+  Sim3Scratch *s = ctx->sim3s;
+  if (!s) return;
+  cudaFree(s->d_tracks);
+  cudaFree(s->d_partials);
+  cudaFree(s->d_slots);
+  cudaFree(s->d_ctrs);
+  delete s;
+  ctx->sim3s = nullptr;
+}
+
+static int sim3_scratch_ensure(lsd_ctx *ctx, int n, int recPoints) {
+  if (!ctx->sim3s) ctx->sim3s = new Sim3Scratch();
+  Sim3Scratch *s = ctx->sim3s;
+  const int maxRecs = (ctx->K.w[1] * ctx->K.h[1] + recPoints - 1) / recPoints;
+  if (n > s->cap || maxRecs != s->maxRecs) {
+    cudaFree(s->d_tracks);
+    cudaFree(s->d_partials);
+    cudaFree(s->d_slots);
+    s->d_tracks = nullptr; s->d_partials = nullptr; s->d_slots = nullptr;
+    int cap = n < s->cap ? s->cap : n;
+    if (cap < 16) cap = 16;
+    LSD_CUDA(cudaMalloc(&s->d_tracks, sizeof(S3Track) * (size_t)cap));
+    LSD_CUDA(cudaMalloc(&s->d_partials, sizeof(float) * S3_NRED * (size_t)cap * maxRecs));
+    unsigned need = (unsigned)cap * (unsigned)maxRecs + 1024u, qcap = 1;
+    while (qcap < need) qcap <<= 1;
+    LSD_CUDA(cudaMalloc(&s->d_slots, sizeof(unsigned long long) * qcap));
+    s->qcap = qcap;
+    s->cap = cap;
+    s->maxRecs = maxRecs;
+  }
+  if (!s->d_ctrs) LSD_CUDA(cudaMalloc(&s->d_ctrs, sizeof(unsigned) * 4));
+  if (!s->gridBlocks) {
+    int perSM = 0;
+    LSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sim3_track, S3_THREADS, 0));
+    if (perSM < 1) {
+      set_error("k_sim3_track cannot be resident");
+      return LSD_ERR_CUDA;
+    }
+    s->gridBlocks = perSM * ctx->numSMs;  // every CTA resident: spinning consumers never starve producers
+  }
+  return LSD_OK;
+}
+
 int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
                           int startLevel, int finalLevel, lsd_sim3_result *results, lsd_trace_entry *traces) {
   if (n == 0) return LSD_OK;
   LSD_ARG(startLevel >= finalLevel && finalLevel >= 1 && startLevel < NL);
+  LSD_ARG(n < (1 << 19));
   cudaStream_t st = ctx->stream;
   const FrameLayout &lay = ctx->lay;
   // frames need their idepth pyramid (frame->idepth(level), idepthVar(level))
@@ -709,10 +926,14 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
     int rc = frame_ensure_built(ctx, frames[i], FB_IDEPTH_PYR);
     if (rc) return rc;
   }
+  const int recPoints = ctx->sim3RecordPoints > 0 ? ctx->sim3RecordPoints : S3_REC_DEFAULT;
+  int rc = sim3_scratch_ensure(ctx, n, recPoints);
+  if (rc) return rc;
+  Sim3Scratch *sc = ctx->sim3s;
   const size_t jobBytes = sizeof(Sim3Job) * (size_t)n, outBytes = sizeof(Sim3Out) * (size_t)n;
   const size_t trBytes = traces ? sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)n : 0;
   const size_t off1 = (jobBytes + 255) / 256 * 256, off2 = off1 + (outBytes + 255) / 256 * 256;
-  int rc = ensure_stage(ctx, off2, off2 + trBytes);
+  rc = ensure_stage(ctx, off2, off2 + trBytes);
   if (rc) return rc;
   Sim3Job *hj = reinterpret_cast<Sim3Job *>(ctx->h_stage);
   for (int i = 0; i < n; i++) {
@@ -733,16 +954,30 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
   prm.s = ctx->sim3;
   prm.startLevel = startLevel;
   prm.finalLevel = finalLevel;
+  prm.recPoints = recPoints;
+  prm.maxRecs = sc->maxRecs;
+  S3Queue q;
+  q.slots = sc->d_slots;
+  q.head = sc->d_ctrs;
+  q.tail = sc->d_ctrs + 1;
+  q.remaining = reinterpret_cast<int *>(sc->d_ctrs + 2);
+  q.cap = sc->qcap;
   Sim3Job *dj = reinterpret_cast<Sim3Job *>(ctx->d_stage);
   Sim3Out *dout = reinterpret_cast<Sim3Out *>(ctx->d_stage + off1);
   lsd_trace_entry *dtr = traces ? reinterpret_cast<lsd_trace_entry *>(ctx->d_stage + off2) : nullptr;
   LSD_CUDA(cudaMemcpyAsync(dj, hj, jobBytes, cudaMemcpyHostToDevice, st));
   LSD_CUDA(cudaEventRecord(ctx->evA, st));
-  // per device, not per process: set on every call (cheap) so that a second context on another device works too
-  LSD_CUDA(cudaFuncSetAttribute(k_sim3_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S3Smem)));
-  k_sim3_track<<<n * S3_CL, S3_THREADS, sizeof(S3Smem), st>>>(dj, dout, prm, dtr);
+  LSD_CUDA(cudaMemsetAsync(sc->d_slots, 0, sizeof(unsigned long long) * q.cap, st));
+  k_sim3_reset<<<1, 1, 0, st>>>(sc->d_ctrs, (unsigned)n);
+  k_sim3_init<<<(n + 63) / 64, 64, 0, st>>>(dj, sc->d_tracks, dout, n, q, prm);
+  // every launched CTA polls the queue while idle: a small batch gets only as many CTAs as it can have records in flight
+  const long long useful = (long long)n * prm.maxRecs;
+  int grid = (int)(useful < (long long)sc->gridBlocks ? (useful < 32 ? 32 : useful) : sc->gridBlocks);
+  static const int envGrid = getenv("LSD_B200_SIM3_GRID") ? atoi(getenv("LSD_B200_SIM3_GRID")) : 0;  // experiments only
+  if (envGrid > 0 && envGrid <= sc->gridBlocks) grid = envGrid;
+  k_sim3_track<<<grid, S3_THREADS, 0, st>>>(dj, sc->d_tracks, dout, sc->d_partials, q, prm, dtr);
   LSD_CUDA(cudaGetLastError());
-  ctx->launches++;
+  ctx->launches += 3;
   LSD_CUDA(cudaEventRecord(ctx->evB, st));
   Sim3Out *ho = reinterpret_cast<Sim3Out *>(ctx->h_stage + off1);
   LSD_CUDA(cudaMemcpyAsync(ho, dout, outBytes, cudaMemcpyDeviceToHost, st));
@@ -792,6 +1027,14 @@ extern "C" {
 int lsd_ctx_set_sim3_settings(lsd_ctx *ctx, const lsd_tracker_settings *s) {
   LSD_ARG(ctx && s);
   ctx->sim3 = *s;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_sim3_record_points(lsd_ctx *ctx, int points) {
+  LSD_ARG(ctx);
+  LSD_ARG(points == 0 || (points >= 128 && points % 128 == 0 && points <= (1 << 20)));
+  LSD_ARG(points == 0 || (ctx->K.w[1] * ctx->K.h[1] + points - 1) / points <= 4096);  // work-item codes carry 12 bits of record index
+  ctx->sim3RecordPoints = points;
   return LSD_OK;
 }
 

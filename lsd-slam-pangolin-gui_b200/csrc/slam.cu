@@ -50,7 +50,7 @@ static void sim3_mul(const double a[8], const double b[8], double o[8]) {
 
 using namespace lsd;
 
-struct lsd_slam {
+struct lsd_slam_system {
   lsd_ctx *ctx;
   lsd_depthmap *dm;
   lsd_frame *kf;       // current keyframe
@@ -75,9 +75,9 @@ float lsd_slam_ref_frame_score(float distanceSquared, float usage) {
   return distanceSquared * KF_DIST_WEIGHT * KF_DIST_WEIGHT + (1 - usage) * (1 - usage) * KF_USAGE_WEIGHT * KF_USAGE_WEIGHT;
 }
 
-int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out) {
+int lsd_slam_create(lsd_ctx *ctx, lsd_slam_system **out) {
   LSD_ARG(ctx && out);
-  lsd_slam *s = new lsd_slam();
+  lsd_slam_system *s = new lsd_slam_system();
   s->ctx = ctx;
   s->dm = nullptr;
   s->kf = nullptr;
@@ -97,7 +97,7 @@ int lsd_slam_create(lsd_ctx *ctx, lsd_slam **out) {
   return LSD_OK;
 }
 
-int lsd_slam_destroy(lsd_slam *s) {
+int lsd_slam_destroy(lsd_slam_system *s) {
   if (!s) return LSD_OK;
   if (s->ref) lsd_ref_release(s->ctx, s->ref);
   for (lsd_frame *f : s->keyframes) lsd_frame_release(s->ctx, f);
@@ -107,26 +107,26 @@ int lsd_slam_destroy(lsd_slam *s) {
   return LSD_OK;
 }
 
-int lsd_slam_set_keep_keyframes(lsd_slam *s, int keep) {
+int lsd_slam_set_keep_keyframes(lsd_slam_system *s, int keep) {
   LSD_ARG(s);
   s->keepFinishedKeyframes = keep;
   return LSD_OK;
 }
 
-int lsd_slam_set_undistorter(lsd_slam *s, lsd_undistorter *und) {
+int lsd_slam_set_undistorter(lsd_slam_system *s, lsd_undistorter *und) {
   LSD_ARG(s);
   s->und = und;
   return LSD_OK;
 }
 
-static float slam_min_val(const lsd_slam *s);
+static float slam_min_val(const lsd_slam_system *s);
 
-static int slam_new_frame(lsd_slam *s, int id, const uint8_t *image, size_t pitch, unsigned flags, lsd_frame **f) {
+static int slam_new_frame(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, unsigned flags, lsd_frame **f) {
   if (s->und) return lsd_frame_create_undistorted(s->ctx, s->und, id, image, pitch, flags, nullptr, f);
   return lsd_frame_create(s->ctx, id, image, pitch, flags, f);
 }
 
-static void fill_status(lsd_slam *s, int id, int tracked, int isKeyframe, const double toKf[8], const lsd_se3_result *r, float score,
+static void fill_status(lsd_slam_system *s, int id, int tracked, int isKeyframe, const double toKf[8], const lsd_se3_result *r, float score,
                         lsd_slam_status *st) {
   if (!st) return;
   std::memset(st, 0, sizeof(*st));
@@ -147,7 +147,7 @@ static void fill_status(lsd_slam *s, int id, int tracked, int isKeyframe, const 
   }
 }
 
-static int first_keyframe(lsd_slam *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st) {
+static int first_keyframe(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st) {
   LSD_ARG(s && image);
   if (s->kf) { set_error("SlamSystem already initialised (fullReset = destroy + create)"); return LSD_ERR_STATE; }
   lsd_frame *kf = nullptr;
@@ -174,16 +174,16 @@ static int first_keyframe(lsd_slam *s, int id, const uint8_t *image, size_t pitc
   return LSD_OK;
 }
 
-int lsd_slam_gt_depth_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st) {
+int lsd_slam_gt_depth_init(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, const float *depth, lsd_slam_status *st) {
   LSD_ARG(depth);
   return first_keyframe(s, id, image, pitch, depth, st);
 }
 
-int lsd_slam_random_init(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st) {
+int lsd_slam_random_init(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st) {
   return first_keyframe(s, id, image, pitch, nullptr, st);
 }
 
-int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st) {
+int lsd_slam_next_image(lsd_slam_system *s, int id, const uint8_t *image, size_t pitch, lsd_slam_status *st) {
   LSD_ARG(s && image);
   if (!s->kf) return first_keyframe(s, id, image, pitch, nullptr, st);  // SlamSystem::nextImage: randomInit on the first image
   lsd_ctx *ctx = s->ctx;
@@ -284,14 +284,14 @@ int lsd_slam_next_image(lsd_slam *s, int id, const uint8_t *image, size_t pitch,
 }
 
 // minVal of SlamSystem::trackFrame's keyframe decision
-static float slam_min_val(const lsd_slam *s) {
+static float slam_min_val(const lsd_slam_system *s) {
   float minVal = std::fmin(0.2f + s->nKeyframes * 0.8f / INITIALIZATION_PHASE_COUNT, 1.0f);
   if (s->nKeyframes < INITIALIZATION_PHASE_COUNT) minVal *= 0.7f;
   return minVal;
 }
 
 // n live sequences on one context, one image each: the stages of lsd_slam_next_image, each batched over the sequences.
-int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const uint8_t *const *images, size_t pitch,
+int lsd_slam_next_image_batch(int n, lsd_slam_system *const *sys, const int *ids, const uint8_t *const *images, size_t pitch,
                               lsd_slam_status *st) {
   LSD_ARG(n >= 1 && sys && ids && images && st);
   lsd_ctx *ctx = sys[0] ? sys[0]->ctx : nullptr;
@@ -328,7 +328,7 @@ int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const
     std::vector<lsd_frame *> kfs;
     std::vector<int> who;
     for (int i = 0; i < n; i++) {
-      lsd_slam *s = sys[i];
+      lsd_slam_system *s = sys[i];
       if (!s->ref || s->refKfId != s->kf->id || s->kf->depthHasBeenUpdatedFlag) {
         if (s->ref) lsd_ref_release(ctx, s->ref);
         s->ref = nullptr;
@@ -340,7 +340,7 @@ int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const
       std::vector<lsd_ref *> refs(kfs.size(), nullptr);
       if ((rc = lsd_ref_create_batch(ctx, (int)kfs.size(), kfs.data(), refs.data()))) return rc;
       for (size_t k = 0; k < who.size(); k++) {
-        lsd_slam *s = sys[who[k]];
+        lsd_slam_system *s = sys[who[k]];
         s->ref = refs[k];
         s->refKfId = s->kf->id;
         s->kf->depthHasBeenUpdatedFlag = false;
@@ -362,7 +362,7 @@ int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const
   std::vector<double> toKf(8 * (size_t)n);
   std::vector<int> needMean;
   for (int i = 0; i < n; i++) {
-    lsd_slam *s = sys[i];
+    lsd_slam_system *s = sys[i];
     if (res[i].diverged || !res[i].trackingWasGood) continue;
     if (s->kf->numMappedOnThis > MIN_NUM_MAPPED && !s->kfMeanValid) needMean.push_back(i);
   }
@@ -379,7 +379,7 @@ int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const
   std::vector<int> upd, sw;  // sequences that update their keyframe / that switch to a new one
   std::vector<float> score(n, 0.0f);
   for (int i = 0; i < n; i++) {
-    lsd_slam *s = sys[i];
+    lsd_slam_system *s = sys[i];
     if (res[i].diverged || !res[i].trackingWasGood) {
       s->lost++;
       fill_status(s, ids[i], 0, 0, s->lastToKf, &res[i], 0.0f, &st[i]);
@@ -430,7 +430,7 @@ int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const
     if ((rc = lsd_depth_finalize_keyframe_batch(ctx, (int)sw.size(), dms.data()))) return rc;
     if ((rc = lsd_depth_create_keyframe_batch(ctx, (int)sw.size(), dms.data(), frames.data(), nullptr))) return rc;
     for (int i : sw) {
-      lsd_slam *s = sys[i];
+      lsd_slam_system *s = sys[i];
       lsd_frame *f = fr[i];
       double world[8];
       sim3_mul(s->kfWorld, f->thisToParent_raw, world);
@@ -453,20 +453,20 @@ int lsd_slam_next_image_batch(int n, lsd_slam *const *sys, const int *ids, const
   return LSD_OK;  // the guard releases every frame that did not become a keyframe
 }
 
-int lsd_slam_current_keyframe(lsd_slam *s, lsd_frame **kf, lsd_depthmap **dm) {
+int lsd_slam_current_keyframe(lsd_slam_system *s, lsd_frame **kf, lsd_depthmap **dm) {
   LSD_ARG(s);
   if (kf) *kf = s->kf;
   if (dm) *dm = s->dm;
   return LSD_OK;
 }
 
-int lsd_slam_stage_seconds(lsd_slam *s, double out[5]) {
+int lsd_slam_stage_seconds(lsd_slam_system *s, double out[5]) {
   LSD_ARG(s && out);
   for (int i = 0; i < 5; i++) out[i] = s->stageSec[i];
   return LSD_OK;
 }
 
-int lsd_slam_counters(lsd_slam *s, int *tracked, int *lost, int *keyframes) {
+int lsd_slam_counters(lsd_slam_system *s, int *tracked, int *lost, int *keyframes) {
   LSD_ARG(s);
   if (tracked) *tracked = s->tracked;
   if (lost) *lost = s->lost;

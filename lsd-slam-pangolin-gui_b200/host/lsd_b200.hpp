@@ -24,6 +24,17 @@
 #ifdef LSD_B200_WITH_SOPHUS
 #include "util/SophusUtil.h"
 #endif
+// LSD_B200_LSDSLAM_COMPAT (set by host/compat/DataStructures/Frame.h): Frame additionally carries everything the reference's
+// consumers read through the lsd-slam headers -- fx/fy/cx/cy(level), getCamToWorld(), getActiveLock(), pose->thisToParent_raw
+// (/root/reference/lib/Pangolin_IOWrapper/PangolinOutputIOWrapper.cpp:50-63, TextOutputIOWrapper.cpp:107,114) -- in the types
+// those files expect (Sophus::Sim3d, boost::shared_lock).
+#ifdef LSD_B200_LSDSLAM_COMPAT
+#include <Eigen/Core>
+#include <boost/thread/shared_mutex.hpp>
+#include <cmath>
+
+#include "sophus/sim3.hpp"
+#endif
 
 namespace lsd_b200 {
 
@@ -69,18 +80,66 @@ class Context {
   Context(int width, int height, float fx, float fy, float cx, float cy, int device = 0, void *stream = nullptr) : w_(width), h_(height) {
     const float K[4] = {fx, fy, cx, cy};
     check(lsd_ctx_create(device, width, height, K, stream, &c_));
+    // [UP] Frame::initialize: fx_l = fx_{l-1} * 0.5, cx_l = (cx_0 + 0.5) / 2^l - 0.5 (the values the device uses, csrc/api.cu)
+    for (int l = 0; l < LSD_PYRAMID_LEVELS; l++) {
+      fx_[l] = l ? (float)(fx_[l - 1] * 0.5) : fx;
+      fy_[l] = l ? (float)(fy_[l - 1] * 0.5) : fy;
+      cx_[l] = l ? (float)((cx + 0.5) / (1 << l) - 0.5) : cx;
+      cy_[l] = l ? (float)((cy + 0.5) / (1 << l) - 0.5) : cy;
+    }
+    if (!current()) current() = this;
   }
-  ~Context() { lsd_ctx_destroy(c_); }
+  ~Context() {
+    if (current() == this) current() = nullptr;
+    lsd_ctx_destroy(c_);
+  }
   Context(const Context &) = delete;
   Context &operator=(const Context &) = delete;
   lsd_ctx *c() const { return c_; }
   int width() const { return w_; }
   int height() const { return h_; }
+  float fx(int level = 0) const { return fx_[level]; }
+  float fy(int level = 0) const { return fy_[level]; }
+  float cx(int level = 0) const { return cx_[level]; }
+  float cy(int level = 0) const { return cy_[level]; }
+  // The context of the calling thread (one context per worker thread, include/lsd_b200.h): what the upstream-shaped Frame
+  // constructor, which carries no context argument, builds its frame on.  The first context a thread creates becomes current.
+  static Context *&current() {
+    static thread_local Context *cur = nullptr;
+    return cur;
+  }
+  void makeCurrent() { current() = this; }
 
  private:
   lsd_ctx *c_ = nullptr;
   int w_, h_;
+  float fx_[LSD_PYRAMID_LEVELS], fy_[LSD_PYRAMID_LEVELS], cx_[LSD_PYRAMID_LEVELS], cy_[LSD_PYRAMID_LEVELS];
 };
+
+#ifdef LSD_B200_LSDSLAM_COMPAT
+inline Sophus::Sim3d toSophus(const double d[8]) {
+  return Sophus::Sim3d(Sophus::RxSO3d(d[7], Eigen::Quaterniond(d[3], d[0], d[1], d[2])), Eigen::Vector3d(d[4], d[5], d[6]));
+}
+inline void fromSophus(const Sophus::Sim3d &s, double d[8]) {
+  const Eigen::Quaterniond q = s.quaternion();  // RxSO3: squared norm = scale
+  const double n = std::sqrt(q.squaredNorm());
+  d[0] = q.x() / n; d[1] = q.y() / n; d[2] = q.z() / n; d[3] = q.w() / n;
+  d[4] = s.translation()[0]; d[5] = s.translation()[1]; d[6] = s.translation()[2];
+  d[7] = s.scale();
+}
+// [UP] lsd_slam::FramePoseStruct: frame -> tracking parent chain; the pose graph (camToWorld_new, graphVertex) stays upstream
+struct FramePoseStruct {
+  FramePoseStruct *trackingParent = nullptr;
+  Sophus::Sim3d thisToParent_raw;
+  int frameID = -1;
+  bool isRegisteredToGraph = false;
+  Sophus::Sim3d camToWorld;  // absolute pose of a registered keyframe (set by the owner of the graph)
+  Sophus::Sim3d getCamToWorld() const {
+    if (isRegisteredToGraph || !trackingParent) return camToWorld;
+    return trackingParent->getCamToWorld() * thisToParent_raw;
+  }
+};
+#endif
 
 // [UP] lsd_slam::Frame.  Pyramids live on the device; accessors copy a level to a host cache on first use.
 class Frame {
@@ -91,6 +150,15 @@ class Frame {
       : ctx_(ctx), id_(id), timestamp_(timestamp) {
     check(lsd_frame_create(ctx.c(), id, image, pitch ? pitch : (size_t)ctx.width(), keyframeCandidate ? LSD_BUILD_MAXGRAD0 : LSD_BUILD_TRACKING, &f_));
   }
+#ifdef LSD_B200_LSDSLAM_COMPAT
+  // [UP] Frame(int id, int width, int height, const Eigen::Matrix3f& K, double timestamp, const unsigned char* image): the frame is
+  // built on the calling thread's current context, which must have been created for the same image size and camera
+  Frame(int id, int width, int height, const Eigen::Matrix3f &K, double timestamp, const unsigned char *image)
+      : ctx_(requireContext(width, height, K(0, 0), K(1, 1), K(0, 2), K(1, 2))), id_(id), timestamp_(timestamp) {
+    check(lsd_frame_create(ctx_.c(), id, image, (size_t)width, LSD_BUILD_MAXGRAD0, &f_));
+    pose_.frameID = id;
+  }
+#endif
   ~Frame() { lsd_frame_release(ctx_.c(), f_); }
   Frame(const Frame &) = delete;
   Frame &operator=(const Frame &) = delete;
@@ -130,8 +198,36 @@ class Frame {
   void invalidate() { cache_.clear(); }  // device planes changed (setDepth, tracking mask)
   lsd_frame *handle() const { return f_; }
   Context &context() const { return ctx_; }
+  // per-level intrinsics, as [UP] Frame::fx(level) ... (read at PangolinOutputIOWrapper.cpp:60-63)
+  float fx(int level = 0) const { return ctx_.fx(level); }
+  float fy(int level = 0) const { return ctx_.fy(level); }
+  float cx(int level = 0) const { return ctx_.cx(level); }
+  float cy(int level = 0) const { return ctx_.cy(level); }
+#ifdef LSD_B200_LSDSLAM_COMPAT
+  FramePoseStruct *pose = &pose_;  // [UP] Frame::pose (TextOutputIOWrapper.cpp:114 reads pose->thisToParent_raw)
+  Sophus::Sim3d getCamToWorld() const { return pose_.getCamToWorld(); }  // [UP] Frame::getCamToWorld()
+  // [UP] Frame::getActiveLock(): readers hold it while they copy planes; the mapping side takes the unique lock around setDepth
+  boost::shared_lock<boost::shared_mutex> getActiveLock() { return boost::shared_lock<boost::shared_mutex>(activeMutex); }
+  boost::shared_mutex activeMutex;
+  // pulls thisToParent_raw (written on the device-side handle by SE3Tracker::trackFrame / DepthMap::createKeyFrame) into pose
+  void syncPoseFromDevice(FramePoseStruct *parent) {
+    const Sim3 s = thisToParent_raw();
+    pose_.thisToParent_raw = toSophus(s.d);
+    if (parent) pose_.trackingParent = parent;
+  }
+#endif
 
  private:
+#ifdef LSD_B200_LSDSLAM_COMPAT
+  static Context &requireContext(int width, int height, float fx, float fy, float cx, float cy) {
+    Context *c = Context::current();
+    if (!c) throw Error("lsd_b200::Frame: no current Context on this thread (create one, or call Context::makeCurrent())");
+    if (c->width() != width || c->height() != height || c->fx() != fx || c->fy() != fy || c->cx() != cx || c->cy() != cy)
+      throw Error("lsd_b200::Frame: image size / camera matrix differ from the current Context's");
+    return *c;
+  }
+  FramePoseStruct pose_;
+#endif
   const float *plane(int field, int level, int comps) {
     const int key = field * 8 + level;
     for (auto &e : cache_)
@@ -196,6 +292,9 @@ class SE3Tracker {
     affineEstimation_a = r.affine_a;
     affineEstimation_b = r.affine_b;
     frame->invalidate();
+#ifdef LSD_B200_LSDSLAM_COMPAT
+    if (!diverged) frame->syncPoseFromDevice(reference->keyframe ? reference->keyframe->pose : nullptr);
+#endif
     SE3 out;
     std::memcpy(out.d, r.frameToRef, sizeof(out.d));
     return out;
@@ -261,6 +360,9 @@ class DepthMap {
     float rescale = 1;
     check(lsd_depth_create_keyframe(ctx_.c(), d_, new_keyframe->handle(), &rescale));
     new_keyframe->invalidate();
+#ifdef LSD_B200_LSDSLAM_COMPAT
+    new_keyframe->syncPoseFromDevice(nullptr);  // thisToParent_raw now carries the mean-idepth rescale factor
+#endif
   }
   void finalizeKeyFrame() { check(lsd_depth_finalize_keyframe(ctx_.c(), d_)); }
   // int debugPlotDepthMap(): fills the RGB image handed to OutputIOWrapper::updateDepthImage (lib/GUI.cpp:104-108)
@@ -333,7 +435,7 @@ class SlamSystem {
 
  private:
   Context &ctx_;
-  lsd_slam *s_ = nullptr;
+  lsd_slam_system *s_ = nullptr;
 };
 
 }  // namespace lsd_b200

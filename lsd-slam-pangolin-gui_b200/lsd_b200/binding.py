@@ -99,6 +99,7 @@ SYMBOLS = {
     "lsd_se3_eval": (_ip, [_vp, _vp, _vp, _vp, _ip, _fp, _fp, _vp, _vp, _vp]),
     "lsd_se3_last_stats": (_ip, [_vp, _vp, _vp, _vp]),
     "lsd_ctx_set_sim3_settings": (_ip, [_vp, _vp]),
+    "lsd_ctx_set_sim3_record_points": (_ip, [_vp, _ip]),
     "lsd_sim3_track": (_ip, [_vp, _vp, _vp, _vp, _ip, _ip, _vp, _vp]),
     "lsd_sim3_track_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _ip, _ip, _vp, _vp]),
     "lsd_frame_set_tracking_meta": (_ip, [_vp, _vp, _ip, _vp, _fp]),
@@ -406,6 +407,9 @@ class Context:
         return res
 
     # ---- Sim3 tracking
+    def set_sim3_record_points(self, n):
+        _chk(self.L.lsd_ctx_set_sim3_record_points(self.p, int(n)))
+
     def set_sim3_settings(self, s):
         _chk(self.L.lsd_ctx_set_sim3_settings(self.p, C.byref(s)))
 
