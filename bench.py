@@ -620,27 +620,21 @@ def leg_sim3_search(lsd, dev, local_rank, rank, world, cpu, n_cand=64, steps=10)
     c2n[:, 7] = 1.0 + rng.uniform(-0.05, 0.05, size=n_cand)
     m = len(mine)
 
+    # testConstraint for my candidates: tryTrackSim3 at [4,3], [2], [1]; each stage tracks candidate->new on the new keyframe's
+    # reference and new->candidate on the candidate's reference, starting from the previous stage's results
+    CtoF0 = c2n[mine].copy() if m else np.zeros((0, 8))
+    FtoC0 = np.array([sim3_inv(p) for p in CtoF0]).reshape(-1, 8)
+    s_refs = [ref_new] * m + [ref_c[i] for i in mine]
+    s_frames = [cands[i] for i in mine] + [new] * m
+    s_inits = np.concatenate([CtoF0, FtoC0])
+
     def search():
-        """testConstraint for my candidates: tryTrackSim3 at [4,3], [2], [1]; each stage tracks candidate->new on the new
-        keyframe's reference and new->candidate on the candidate's reference, starting from the previous stage's results."""
         if m == 0:
             return None, 0.0, 0.0, 0
-        CtoF = c2n[mine].copy()
-        FtoC = np.array([sim3_inv(p) for p in CtoF])
-        refs = [ref_new] * m + [ref_c[i] for i in mine]
-        frames = [cands[i] for i in mine] + [new] * m
-        byts = kms = 0.0
-        evals = 0
-        res = None
-        for (ls, le) in ((4, 3), (2, 2), (1, 1)):
-            res = ctx.sim3_track_batch(refs, frames, np.concatenate([CtoF, FtoC]), ls, le)
-            b, e, k = ctx.se3_last_stats()
-            byts += b
-            kms += k
-            evals += e
-            CtoF = np.array([list(res[i].frameToRef) for i in range(m)])
-            FtoC = np.array([list(res[m + i].frameToRef) for i in range(m)])
-        return res, byts, kms, evals
+        # ONE launch: every track runs its [4,3] -> [2] -> [1] chain on the device (lsd_sim3_track_stages_batch)
+        per_stage = ctx.sim3_track_stages_batch(s_refs, s_frames, s_inits, ((4, 3), (2, 2), (1, 1)))
+        byts, evals, kms = ctx.se3_last_stats()
+        return per_stage[-1], byts, kms, evals
 
     def barrier():
         if world > 1:
@@ -664,7 +658,7 @@ def leg_sim3_search(lsd, dev, local_rank, rank, world, cpu, n_cand=64, steps=10)
         out = {"candidates": n_cand, "job": "tryTrackSim3 x 3 stages ([4,3],[2],[1]) x 2 directions = 6 tracks per candidate",
                "jobs_per_s": n_cand / dt, "ms_per_search": 1e3 * dt, "n_gpus": world, "scaling": "strong",
                "sharding": "LPT on sum of numData(1..4) of the candidate, no collective (results ~600 B per candidate)",
-               "candidates_on_rank0": m, "kernel_ms_rank0_sum_of_3_stages": kms, "kernel_ms_max_over_ranks": kms_max,
+               "candidates_on_rank0": m, "kernel_ms_rank0": kms, "kernel_ms_max_over_ranks": kms_max,
                "diverged_rank0": int(sum(r.diverged for r in res)) if m else 0, "median_scale_err_rank0": scale_err}
         if m and kms > 0:
             out["roofline"] = {"bound": "hbm", "kernel": "k_sim3_track (rank 0's share)", "achieved": byts / (kms * 1e-3) / 1e9,

@@ -213,6 +213,14 @@ int lsd_sim3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double in
 int lsd_sim3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init_frameToRef /* n*8 */,
                          int startLevel, int finalLevel, lsd_sim3_result *results, lsd_trace_entry *traces /* n*LSD_TRACE_CAP or NULL */);
 
+/* [UP] SlamSystem::tryTrackSim3 chains trackFrameSim3 calls over level ranges ([4,3], [2], [1] in testConstraint), each starting
+ * from the previous call's result.  Here every track runs its whole chain inside the ONE persistent launch: stage k+1 starts
+ * from stage k's frameToRef exactly as a separate call would (bit-identical), a track that diverged / came back with an empty
+ * information matrix (upstream's rejection test) stops and reports diverged for its remaining stages.
+ * results: nStages * n, stage-major (results[k * n + i] = what the k-th call of track i would have returned). */
+int lsd_sim3_track_stages_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init_frameToRef /* n*8 */,
+                                int nStages /* <= 4 */, const int *startLevels, const int *finalLevels, lsd_sim3_result *results);
+
 /* ---- frame bookkeeping the mapping side reads ---------------------------------------------------- */
 /* What SE3Tracker::trackFrame leaves on a tracked Frame ([UP] frame->pose->thisToParent_raw,
  * trackingParent, initialTrackedResidual); settable directly for frames whose pose comes from elsewhere

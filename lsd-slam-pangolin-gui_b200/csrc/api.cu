@@ -3,6 +3,8 @@
 // entry point either runs the sm_100a kernels or returns an error.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -10,7 +12,81 @@
 
 #include "ctx.cuh"
 
+// A few persistent host threads (created on first use): copying a batch of pageable images into the pinned staging buffer is
+// the host-side cost of every multi-frame entry point (one memcpy thread moves ~10 GB/s; 32 VGA frames are 10 MB).
+struct HostPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cvWork, cvDone;
+  std::function<void(int)> fn;
+  int nTasks = 0, generation = 0, pending = 0;
+  std::atomic<int> next{0};
+  bool stop = false;
+  explicit HostPool(int threads) {
+    for (int t = 0; t < threads; t++)
+      th.emplace_back([this]() {
+        int seen = 0;
+        for (;;) {
+          {
+            std::unique_lock<std::mutex> l(mu);
+            cvWork.wait(l, [&]() { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+          }
+          work();
+          std::unique_lock<std::mutex> l(mu);
+          if (--pending == 0) cvDone.notify_all();
+        }
+      });
+  }
+  ~HostPool() {
+    {
+      std::unique_lock<std::mutex> l(mu);
+      stop = true;
+    }
+    cvWork.notify_all();
+    for (std::thread &t : th) t.join();
+  }
+  void work() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= nTasks) return;
+      fn(i);
+    }
+  }
+  // runs f(0..n-1) on the pool + the calling thread; returns when all are done
+  void run(int n, const std::function<void(int)> &f) {
+    if (n <= 0) return;
+    if (th.empty() || n == 1) {
+      for (int i = 0; i < n; i++) f(i);
+      return;
+    }
+    {
+      std::unique_lock<std::mutex> l(mu);
+      fn = f;
+      nTasks = n;
+      next.store(0);
+      pending = (int)th.size();
+      generation++;
+    }
+    cvWork.notify_all();
+    work();
+    std::unique_lock<std::mutex> l(mu);
+    cvDone.wait(l, [&]() { return pending == 0; });
+  }
+};
+
 namespace lsd {
+
+static HostPool *host_pool(lsd_ctx *ctx) {
+  if (!ctx->pool) {
+    static const int envT = getenv("LSD_B200_STAGE_THREADS") ? atoi(getenv("LSD_B200_STAGE_THREADS")) : 0;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = envT > 0 ? envT : (int)(hw / 2 < 1 ? 1 : (hw / 2 > 8 ? 8 : hw / 2));
+    ctx->pool = new HostPool(T - 1);  // the calling thread is the T-th worker
+  }
+  return ctx->pool;
+}
 
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
@@ -240,8 +316,11 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->imageStreamed = -1;
   ctx->streamWatchdogNs = 2000000000ull;
   ctx->d_stats = nullptr;
-  LSD_CUDA(cudaMalloc(&ctx->d_stats, 16 + 16 * (size_t)ctx->numSMs));
-  LSD_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 16 + 16 * (size_t)ctx->numSMs, ctx->stream));
+  ctx->statsFrames = 0;
+  {
+    const int rc = ensure_stats_scratch(ctx, 1);
+    if (rc) return rc;
+  }
   ctx->se3ActivePairs = 0;
   ctx->refSlabBytes = 0;
   ctx->h_stage = ctx->d_stage = nullptr;
@@ -250,6 +329,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->tableBytes = 0;
   ctx->descSlot = 0;
   ctx->stageTimed = false;
+  ctx->pool = nullptr;
   ctx->se3s = nullptr;
   ctx->sim3s = nullptr;
   ctx->sim3RecordPoints = 0;
@@ -266,6 +346,7 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   se3_scratch_free(ctx);
   sim3_scratch_free(ctx);
+  delete ctx->pool;
   for (auto p : ctx->frameSlabPool) cudaFree(p);
   for (auto p : ctx->refSlabPool) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -354,15 +435,15 @@ int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *c
   const int CH = 64;
   int rc = ensure_stage(ctx, fbytes * (n < CH ? n : CH), fbytes * (n < CH ? n : CH));
   if (rc) return rc;
+  for (int i = 0; i < n; i++) LSD_ARG(images[i]);
   for (int i0 = 0; i0 < n; i0 += CH) {
     const int m = (n - i0) < CH ? (n - i0) : CH;
-    for (int i = 0; i < m; i++) {
+    host_pool(ctx)->run(m, [&](int i) {
       const uint8_t *src = images[i0 + i];
-      LSD_ARG(src);
       uint8_t *dst = ctx->h_stage + fbytes * i;
       if (pitch == (size_t)ctx->w) std::memcpy(dst, src, fbytes);
       else for (int y = 0; y < ctx->h; y++) std::memcpy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
-    }
+    });
     LSD_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, fbytes * m, cudaMemcpyHostToDevice, ctx->stream));
     rc = lsd_frame_create_batch_device(ctx, m, ids ? ids + i0 : nullptr, ctx->d_stage, flags, out + i0);
     if (rc) return rc;
@@ -509,13 +590,20 @@ int lsd_frame_mean_idepth_batch(lsd_ctx *ctx, int n, lsd_frame *const *f, float 
     LSD_ARG(f[i]);
     if (!(f[i]->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
   }
-  int rc = ensure_table(ctx, 8 * (size_t)n);
+  // table: n slab pointers, then n x 2 floats of results; one launch for all frames (blockIdx.y = frame)
+  const size_t offOut = (sizeof(void *) * (size_t)n + 255) / 256 * 256;
+  int rc = ensure_table(ctx, offOut + 8 * (size_t)n);
   if (rc) return rc;
-  // the reductions share the context's ticket / partial-sum scratch: stream order serialises them
-  for (int i = 0; i < n; i++) launch_idepth_stats(ctx, f[i]->slab, reinterpret_cast<float *>(ctx->d_table) + 2 * i, ctx->stream);
-  LSD_CUDA(cudaMemcpyAsync(ctx->h_table, ctx->d_table, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = ensure_stats_scratch(ctx, n);
+  if (rc) return rc;
+  void **hp = reinterpret_cast<void **>(ctx->h_table);
+  for (int i = 0; i < n; i++) hp[i] = f[i]->slab;
+  LSD_CUDA(cudaMemcpyAsync(ctx->d_table, ctx->h_table, sizeof(void *) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  launch_idepth_stats_batch(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), n, reinterpret_cast<float *>((char *)ctx->d_table + offOut),
+                            ctx->stream);
+  LSD_CUDA(cudaMemcpyAsync((char *)ctx->h_table + offOut, (char *)ctx->d_table + offOut, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   LSD_CUDA(cudaStreamSynchronize(ctx->stream));
-  const float *h = reinterpret_cast<const float *>(ctx->h_table);
+  const float *h = reinterpret_cast<const float *>((char *)ctx->h_table + offOut);
   for (int i = 0; i < n; i++) {
     f[i]->meanIdepth = h[2 * i];
     std::memcpy(&f[i]->numPoints, &h[2 * i + 1], 4);

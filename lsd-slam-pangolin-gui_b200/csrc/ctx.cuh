@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 struct SE3Scratch;   // se3_track.cu
+struct HostPool;     // api.cu: a few host threads for staging pageable images into pinned memory
 struct Sim3Scratch;  // sim3_track.cu
 struct DepthScratch;
 
@@ -39,9 +40,11 @@ struct lsd_ctx {
   void *h_table;
   void *d_table;
   size_t tableBytes;
-  uint8_t *d_stats;  // k_idepth_stats: ticket (16 B) + per-CTA partial sums
+  uint8_t *d_stats;  // k_idepth_stats: per frame a ticket (16 B) + per-CTA partial sums
+  int statsFrames;   // frames d_stats has room for
   bool stageTimed;  // evA/evB bracket the kernels of the last depth stage
   int descSlot;  // rotating slot of the depth-map descriptor uploads (depth.cu)
+  HostPool *pool;
   SE3Scratch *se3s;
   Sim3Scratch *sim3s;
   int sim3RecordPoints;  // 0: default (1024); points per partial record = the summation order of the Sim3 tracker
@@ -71,6 +74,8 @@ void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const I
 void launch_set_depth_gt(lsd_ctx *ctx, uint8_t *slab, const float *d_depth, float cov, cudaStream_t st);
 void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
 void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st);
+void launch_idepth_stats_batch(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, float *d_out2, cudaStream_t st);
+int ensure_stats_scratch(lsd_ctx *ctx, int frames);
 
 // trackref.cu
 int pointcloud_state_words(const lsd_ctx *ctx);  // ints behind a reference's counters: numData[NL], pad, look-back state

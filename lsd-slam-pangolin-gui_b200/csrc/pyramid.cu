@@ -369,11 +369,17 @@ void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t
 // per-CTA partials to global memory, and the CTA that takes the last ticket adds them in CTA order -- deterministic and
 // order-independent to fp32 rounding (a single 1024-thread CTA took 46 us per frame on the live path).
 #define STATS_THREADS 256
-__global__ void __launch_bounds__(STATS_THREADS) k_idepth_stats(const uint8_t *slab, FrameLayout lay, int N, double *__restrict__ partial,
-                                                                unsigned *__restrict__ ticket, float *__restrict__ out2) {
+// blockIdx.y = frame: n frames in one launch, each with its own ticket / partial-sum scratch and the SAME decomposition as a
+// single-frame launch (gridDim.x CTAs, grid-strided slices), so a frame's result does not depend on how many ride along.
+__global__ void __launch_bounds__(STATS_THREADS) k_idepth_stats(uint8_t *const *__restrict__ slabs, const uint8_t *slab0, FrameLayout lay, int N,
+                                                                uint8_t *__restrict__ scratch, size_t scratchStride, float *__restrict__ out2) {
   __shared__ double ssum[STATS_THREADS / 32];
   __shared__ int scnt[STATS_THREADS / 32];
   __shared__ bool sLast;
+  const uint8_t *slab = slabs ? slabs[blockIdx.y] : slab0;
+  unsigned *ticket = reinterpret_cast<unsigned *>(scratch + scratchStride * blockIdx.y);
+  double *partial = reinterpret_cast<double *>(scratch + scratchStride * blockIdx.y + 16);
+  out2 += 2 * blockIdx.y;
   const float *ID = reinterpret_cast<const float *>(slab + lay.idepth[0]);
   const float *VR = reinterpret_cast<const float *>(slab + lay.idvar[0]);
   double s = 0;
@@ -419,10 +425,29 @@ __global__ void __launch_bounds__(STATS_THREADS) k_idepth_stats(const uint8_t *s
   }
 }
 
-// d_scratch: 16 + 16 * numSMs bytes of zero-initialised-once device memory owned by the context
+// scratch: (16 + 16 * numSMs) bytes per frame of zero-initialised-once device memory owned by the context
+static size_t stats_stride(const lsd_ctx *ctx) { return (16 + 16 * (size_t)ctx->numSMs + 255) / 256 * 256; }
+
+int ensure_stats_scratch(lsd_ctx *ctx, int frames) {
+  if (frames <= ctx->statsFrames) return LSD_OK;
+  if (ctx->d_stats) cudaFree(ctx->d_stats);
+  ctx->d_stats = nullptr;
+  ctx->statsFrames = 0;
+  const int cap = frames < 8 ? 8 : frames * 2;
+  LSD_CUDA(cudaMalloc(&ctx->d_stats, stats_stride(ctx) * (size_t)cap));
+  LSD_CUDA(cudaMemsetAsync(ctx->d_stats, 0, stats_stride(ctx) * (size_t)cap, ctx->stream));
+  ctx->statsFrames = cap;
+  return LSD_OK;
+}
+
 void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st) {
-  double *partial = reinterpret_cast<double *>(ctx->d_stats + 16);
-  k_idepth_stats<<<ctx->numSMs, STATS_THREADS, 0, st>>>(slab, ctx->lay, ctx->w * ctx->h, partial, reinterpret_cast<unsigned *>(ctx->d_stats), d_out2);
+  k_idepth_stats<<<ctx->numSMs, STATS_THREADS, 0, st>>>(nullptr, slab, ctx->lay, ctx->w * ctx->h, ctx->d_stats, stats_stride(ctx), d_out2);
+  ctx->launches++;
+}
+
+// n frames (d_slabs: device pointer list) in one launch; d_out2: 2 floats per frame
+void launch_idepth_stats_batch(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, float *d_out2, cudaStream_t st) {
+  k_idepth_stats<<<dim3(ctx->numSMs, n), STATS_THREADS, 0, st>>>(d_slabs, nullptr, ctx->lay, ctx->w * ctx->h, ctx->d_stats, stats_stride(ctx), d_out2);
   ctx->launches++;
 }
 

@@ -643,42 +643,49 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
     __syncthreads();
     const int code = sCode;
     if (code < 0) break;
-    const int pairIdx = code >> 12, chunk = code & 0xfff;
+    const int pairIdx = code >> 12, chunk0 = code & 0xfff;
     const SE3Pair *P = pairs + pairIdx;
     SE3State *S = states + pairIdx;
     // evaluation header: 4 x LDG.128 through L2
     const int4 *hp = reinterpret_cast<const int4 *>(S);
-    const int4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1), h2 = __ldcg(hp + 2), h3 = __ldcg(hp + 3);
-    const int level = h3.z, n = h3.w;
-    EvalConst c;
-    load_eval_const(prm, level, h0, h1, h2, h3, c);
-    uint8_t *mask = (level == prm.minLevel && !prm.permaref) ? P->mask : nullptr;  // permaref: idxBuf == nullptr upstream
+    int4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1), h2 = __ldcg(hp + 2), h3 = __ldcg(hp + 3);
+    int chunk = chunk0;
+    bool haveState = false;  // sState holds this pair's state (true while this CTA keeps evaluating the same pair)
+    // A pair whose next evaluation is ONE work item stays on this CTA: no queue hop, no state round trip through global
+    // memory.  The coarse levels (a few hundred points, a third of all evaluations) are exactly that.
+    for (;;) {
+      const int level = h3.z, n = h3.w;
+      EvalConst c;
+      load_eval_const(prm, level, h0, h1, h2, h3, c);
+      uint8_t *mask = (level == prm.minLevel && !prm.permaref) ? P->mask : nullptr;  // permaref: idxBuf == nullptr upstream
 
-    float acc[SE3_NF];
-    double dacc[SE3_ND];
+      float acc[SE3_NF];
+      double dacc[SE3_ND];
 #pragma unroll
-    for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
+      for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
-    for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-    const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
-    const int nch = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;
-    const int rec0 = chunk * prm.recsPerItem, rec1 = min(nRecs, rec0 + prm.recsPerItem);
-    for (int rec = rec0; rec < rec1; rec++) {
-      if (rec > rec0) {
+      for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
+      const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
+      const int nch = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;
+      const int rec0 = chunk * prm.recsPerItem, rec1 = min(nRecs, rec0 + prm.recsPerItem);
+      for (int rec = rec0; rec < rec1; rec++) {
+        if (rec > rec0) {
 #pragma unroll
-        for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
+          for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
+          for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
+        }
+        const int begin = rec * prm.recPoints;
+        const int end = min(n, begin + prm.recPoints);
+        eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
+        float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
+        block_reduce_store(acc, dacc, dst, sm);
       }
-      const int begin = rec * prm.recPoints;
-      const int end = min(n, begin + prm.recPoints);
-      eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
-      float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
-      block_reduce_store(acc, dacc, dst, sm);
-    }
-    if (threadIdx.x == 0) sIsLast = (atom_add_acq_rel(&S->done, 1u) == (unsigned)(nch - 1));
-    __syncthreads();
-    if (sIsLast) {
+      if (nch > 1) {
+        if (threadIdx.x == 0) sIsLast = (atom_add_acq_rel(&S->done, 1u) == (unsigned)(nch - 1));
+        __syncthreads();
+        if (!sIsLast) break;
+      }
       const float *recBase = partials + (size_t)pairIdx * prm.maxChunks * SE3_NRED;
       if (threadIdx.x < SE3_ND) {
         const double *src = reinterpret_cast<const double *>(recBase) + threadIdx.x;
@@ -691,14 +698,22 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
         float s = 0.0f;
         for (int cidx = 0; cidx < nRecs; cidx++) s += __ldcg(src + (size_t)cidx * SE3_NRED);
         stot[j] = s;
-      } else if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(SE3State) / 16)) {
+      } else if (!haveState && threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(SE3State) / 16)) {
         // the pair's state comes in with one LDG.128 per thread of warps 2-3 while warps 0-1 sum the records
         const int k = threadIdx.x - 64;
         reinterpret_cast<int4 *>(&sState)[k] = __ldcg(reinterpret_cast<const int4 *>(S) + k);
       }
       __syncthreads();
+      haveState = true;
       if (threadIdx.x == 0) sNext = lm_step(&sState, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
       __syncthreads();
+      if (sNext == 1) {  // the next evaluation is a single work item: keep it (the header is the first 64 bytes of the state)
+        const int4 *sp4 = reinterpret_cast<const int4 *>(&sState);
+        h0 = sp4[0]; h1 = sp4[1]; h2 = sp4[2]; h3 = sp4[3];
+        chunk = 0;
+        __syncthreads();  // every thread has read sNext / the header before the next LM step rewrites them
+        continue;
+      }
       if (threadIdx.x < (int)(sizeof(SE3State) / 16))
         reinterpret_cast<int4 *>(S)[threadIdx.x] = reinterpret_cast<const int4 *>(&sState)[threadIdx.x];
       __syncthreads();  // the state stores precede thread 0's fence + publication below
@@ -724,6 +739,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
           atomicSub(q.remaining, 1);
         }
       }
+      break;
     }
     __syncthreads();  // sCode / sIsLast / sm are reused by the next item
   }

@@ -69,10 +69,12 @@ struct Sim3Out {
 struct Sim3Params {
   Intrinsics K;
   lsd_tracker_settings s;
-  int startLevel, finalLevel;
+  int nStages;                      // chained trackFrameSim3 calls per track (tryTrackSim3's [4,3], [2], [1] = 3)
+  int startLevel[4], finalLevel[4];
   int recPoints;  // points per partial record: defines the summation order
   int maxRecs;    // per-track stride of the partial records
 };
+#define S3_MAX_STAGES 4
 
 // what every CTA working on a track's current evaluation needs: the first 96 bytes of the track state
 struct S3Cmd {
@@ -107,7 +109,7 @@ struct S3State {
   int n[NL], nRes[NL], nWarp[NL];
   int traceLen;
   float pointUsage;
-  int pad_[1];
+  int stage;  // which of the chained trackFrameSim3 calls this track is in
 };
 static_assert(sizeof(S3State) % 16 == 0, "S3State must be int4-copyable");
 
@@ -125,6 +127,7 @@ struct S3Queue {
   unsigned *head, *tail;
   int *remaining;  // tracks not finished yet
   unsigned cap;    // power of two >= tracks * maxRecs
+  int nTracks;
 };
 
 __device__ void s3_make_cmd(const double q[4], const double t[3], double s, float a, float b, int level, S3Cmd &c) {
@@ -577,8 +580,8 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
   if (S.iteration >= maxIts) {
     // next level with iterations (upstream `continue`s over levels whose maxItsPerLvl is 0)
     int nl = lvl - 1;
-    while (nl >= prm.finalLevel && prm.s.maxItsPerLvl[nl] == 0) nl--;
-    if (nl >= prm.finalLevel) {
+    while (nl >= prm.finalLevel[S.stage] && prm.s.maxItsPerLvl[nl] == 0) nl--;
+    if (nl >= prm.finalLevel[S.stage]) {
       S.level = nl;
       S.phase = 0;
       if (S.n[nl] == 0) {
@@ -591,8 +594,8 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
     }
     if (!S.upToDate) {
       S.phase = 2;
-      S.level = prm.finalLevel;
-      s3_make_cmd(S.q, S.t, S.s, S.a, S.b, prm.finalLevel, next);
+      S.level = prm.finalLevel[S.stage];
+      s3_make_cmd(S.q, S.t, S.s, S.a, S.b, prm.finalLevel[S.stage], next);
       return true;
     }
     s3_finish(S, O);
@@ -657,10 +660,64 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
 }
 
 
+// Starts stage `stage` of a track from the pose in S (q, t, s): the part of Sim3Tracker::trackFrameSim3 before the first
+// evaluation.  Returns false when there is nothing to evaluate (the track's outputs for this stage are then complete).
+__device__ bool s3_begin_stage(S3State &S, Sim3Out *O, const Sim3Params &prm, int stage, S3Cmd &first) {
+  S.stage = stage;
+  S.a = 1;
+  S.b = 0;
+  S.phase = S.iteration = S.incTry = 0;
+  S.upToDate = false;
+  S.lambda = S.absInc = 0;
+  S.traceLen = 0;
+  S.pointUsage = 0;
+  for (int l = 0; l < NL; l++) S.nRes[l] = S.nWarp[l] = 0;
+  memset(O, 0, sizeof(Sim3Out));
+  memset(&first, 0, sizeof(first));
+  first.op = 0;
+  const int startLevel = prm.startLevel[stage], finalLevel = prm.finalLevel[stage];
+  int lvl = startLevel;
+  while (lvl >= finalLevel && prm.s.maxItsPerLvl[lvl] == 0) lvl--;
+  if (lvl < finalLevel) {
+    // no level has iterations: upstream still evaluates once at finalLevel (!warp_update_up_to_date)
+    S.phase = 2;
+    S.level = finalLevel;
+    s3_make_cmd(S.q, S.t, S.s, S.a, S.b, finalLevel, first);
+  } else {
+    S.level = lvl;
+    S.phase = 0;
+    s3_make_cmd(S.q, S.t, S.s, S.a, S.b, lvl, first);
+  }
+  if (S.n[first.level] == 0) {  // an empty cloud at the first level to evaluate
+    O->diverged = 1;
+    s3_identity_out(O);
+    first.op = 1;
+    return false;
+  }
+  first.nPts = S.n[first.level];
+  return true;
+}
+
+// The next stage starts from the previous stage's RESULT the way the host would hand it over: frameToReference (what
+// trackFrameSim3 returned, fp64) inverted back into referenceToFrame -- the same two inversions, so a chained stage is
+// bit-identical to a separate call.
+__device__ void s3_pose_from_result(S3State &S, const Sim3Out *O) {
+  const double *p = O->frameToRef;
+  QuatT<double> qc = {-p[0], -p[1], -p[2], p[3]};
+  double R[9], nt[3] = {p[4] * -1.0, p[5] * -1.0, p[6] * -1.0}, rt[3];
+  qtoR(qc, R);
+  mat3vec(R, nt, rt);
+  const double si = 1.0 / p[7];
+  S.q[0] = qc.x; S.q[1] = qc.y; S.q[2] = qc.z; S.q[3] = qc.w;
+  S.t[0] = rt[0] * si; S.t[1] = rt[1] * si; S.t[2] = rt[2] * si;
+  S.s = si;
+}
+
 __global__ void __launch_bounds__(S3_THREADS, S3_MINB)
 k_sim3_track(const Sim3Job *__restrict__ jobs, S3Track *tracks, Sim3Out *outs, float *partials, const S3Queue q,
              const __grid_constant__ Sim3Params prm, lsd_trace_entry *traces) {
   __shared__ __align__(16) S3Smem sm;
+  __shared__ __align__(16) float srec[S3_NRED];  // the partial record of a single-record evaluation never leaves the CTA
   __shared__ float stot[S3_NF];
   __shared__ double sdtot[S3_ND];
   __shared__ int sCode, sIsLast, sMore;
@@ -689,10 +746,11 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, S3Track *tracks, Sim3Out *outs, f
     __syncthreads();
     const int code = sCode;
     if (code < 0) break;
-    const int track = code >> 12, rec = code & 0xfff;
+    const int track = code >> 12;
+    int rec = code & 0xfff;
     const Sim3Job *J = jobs + track;
     S3Track *T = tracks + track;
-    // evaluation header: 6 x LDG.128 through L2
+    // evaluation header through L2: 5 x LDG.128 + the point count
     S3Const c;
     int lvl, n;
     {
@@ -706,72 +764,129 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, S3Track *tracks, Sim3Out *outs, f
       lvl = h4.z;
       n = __ldcg(&T->cmd.nPts);
     }
-    c.fx = prm.K.fx[lvl]; c.fy = prm.K.fy[lvl]; c.cx = prm.K.cx[lvl]; c.cy = prm.K.cy[lvl];
-    c.fxi = prm.K.fxi[lvl]; c.fyi = prm.K.fyi[lvl]; c.cxi = prm.K.cxi[lvl]; c.cyi = prm.K.cyi[lvl];
     c.var_weight = prm.s.var_weight;
     c.huber = prm.s.huber_d;
-    c.W = prm.K.w[lvl];
-    c.H = prm.K.h[lvl];
-
-    float acc[S3_NF];
-    double dacc[S3_ND];
+    bool haveState = false;  // sState holds this track's state (true while the CTA keeps evaluating the same track)
+    // A track whose next evaluation is a single record stays on this CTA: no queue hop, no state round trip through global
+    // memory.  The coarse levels of a constraint search are exactly that: tens of tiny evaluations whose cost was all latency.
+    for (;;) {
+      c.fx = prm.K.fx[lvl]; c.fy = prm.K.fy[lvl]; c.cx = prm.K.cx[lvl]; c.cy = prm.K.cy[lvl];
+      c.fxi = prm.K.fxi[lvl]; c.fyi = prm.K.fyi[lvl]; c.cxi = prm.K.cxi[lvl]; c.cyi = prm.K.cyi[lvl];
+      c.W = prm.K.w[lvl];
+      c.H = prm.K.h[lvl];
+      float acc[S3_NF];
+      double dacc[S3_ND];
 #pragma unroll
-    for (int j = 0; j < S3_NF; j++) acc[j] = 0.0f;
+      for (int j = 0; j < S3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
-    for (int j = 0; j < S3_ND; j++) dacc[j] = 0.0;
-    const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
-    const int begin = rec * prm.recPoints, end = min(n, begin + prm.recPoints);
-    s3_eval_range(J->pts[lvl], J->rgrad[lvl], begin, end, J->fgrad[lvl], J->fid[lvl], J->fvar[lvl], c, acc, dacc, sm.slots);
-    float *recBase = partials + (size_t)track * prm.maxRecs * S3_NRED;
-    s3_block_reduce_store(acc, dacc, recBase + (size_t)rec * S3_NRED, sm);
-    if (threadIdx.x == 0) sIsLast = (s3_atom_add_acq_rel(&T->done, 1u) == (unsigned)(nRecs - 1));
-    __syncthreads();
-    if (sIsLast) {
+      for (int j = 0; j < S3_ND; j++) dacc[j] = 0.0;
+      const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
+      const int begin = rec * prm.recPoints, end = min(n, begin + prm.recPoints);
+      s3_eval_range(J->pts[lvl], J->rgrad[lvl], begin, end, J->fgrad[lvl], J->fid[lvl], J->fvar[lvl], c, acc, dacc, sm.slots);
+      float *recBase = partials + (size_t)track * prm.maxRecs * S3_NRED;
+      const bool single = nRecs == 1;
+      s3_block_reduce_store(acc, dacc, single ? srec : recBase + (size_t)rec * S3_NRED, sm);
+      if (!single) {
+        if (threadIdx.x == 0) sIsLast = (s3_atom_add_acq_rel(&T->done, 1u) == (unsigned)(nRecs - 1));
+        __syncthreads();
+        if (!sIsLast) break;
+      }
+      // ---- this CTA completed the evaluation: totals (records in record order), LM step
       if (threadIdx.x < S3_ND) {
-        const double *src = reinterpret_cast<const double *>(recBase) + threadIdx.x;
         double s = 0.0;
-        for (int r = 0; r < nRecs; r++) s += __ldcg(src + (size_t)r * (S3_NRED / 2));
+        if (single) {
+          s = reinterpret_cast<const double *>(srec)[threadIdx.x];
+        } else {
+          const double *src = reinterpret_cast<const double *>(recBase) + threadIdx.x;
+          for (int r = 0; r < nRecs; r++) s += __ldcg(src + (size_t)r * (S3_NRED / 2));
+        }
         sdtot[threadIdx.x] = s;
       } else if (threadIdx.x < S3_ND + S3_NF) {
         const int j = threadIdx.x - S3_ND;
-        const float *src = recBase + 2 * S3_ND + j;
         float s = 0.0f;
-        for (int r = 0; r < nRecs; r++) s += __ldcg(src + (size_t)r * S3_NRED);
+        if (single) {
+          s = srec[2 * S3_ND + j];
+        } else {
+          const float *src = recBase + 2 * S3_ND + j;
+          for (int r = 0; r < nRecs; r++) s += __ldcg(src + (size_t)r * S3_NRED);
+        }
         stot[j] = s;
-      } else if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(S3State) / 16)) {
+      } else if (!haveState && threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(S3State) / 16)) {
         const int k = threadIdx.x - 64;
         reinterpret_cast<int4 *>(&sState)[k] = __ldcg(reinterpret_cast<const int4 *>(&T->st) + k);
       }
       __syncthreads();
+      haveState = true;
       if (threadIdx.x == 0) {
         S3Cmd next;
         next.op = 1;
         next.nPts = 0;
-        const bool more = s3_step(J, sState, outs + track, stot, sdtot, prm, traces ? traces + (size_t)track * LSD_TRACE_CAP : nullptr, next);
-        if (!more) {
-          next.op = 1;
-          s3_flush(sState, outs + track);
-        } else {
+        Sim3Out *O = outs + (size_t)sState.stage * q.nTracks + track;
+        bool more = s3_step(J, sState, O, stot, sdtot, prm, traces ? traces + (size_t)track * LSD_TRACE_CAP : nullptr, next);
+        if (more) {
           next.nPts = sState.n[next.level];
+        } else {
+          s3_flush(sState, O);
+          // chained stages (tryTrackSim3 at [4,3], [2], [1]): the next stage starts from this stage's result; a track that
+          // diverged or returned the identity ends here and its later stages report the same
+          int stage = sState.stage;
+          while (!more && stage + 1 < prm.nStages) {
+            Sim3Out *On = outs + (size_t)(stage + 1) * q.nTracks + track;
+            // upstream's own test in SlamSystem::tryTrackSim3: diverged, a degenerate scale, or an empty information matrix
+            const bool dead = O->diverged || !(O->frameToRef[7] < 1e10) || !(O->frameToRef[7] > 1e-10) || O->H[0] == 0.0f || O->H[48] == 0.0f;
+            if (dead) {
+              *On = *O;
+              On->diverged = 1;
+              stage++;
+              O = On;
+              continue;
+            }
+            s3_pose_from_result(sState, O);
+            more = s3_begin_stage(sState, On, prm, stage + 1, next);
+            if (!more) s3_flush(sState, On);
+            stage++;
+            O = On;
+          }
+          if (!more) next.op = 1;
         }
         sNext = next;
         sMore = more ? 1 : 0;
       }
       __syncthreads();
-      if (sMore) {  // store the state and the next evaluation's header, then publish its records
-        if (threadIdx.x < (int)(sizeof(S3State) / 16))
-          reinterpret_cast<int4 *>(&T->st)[threadIdx.x] = reinterpret_cast<const int4 *>(&sState)[threadIdx.x];
-        else if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(S3Cmd) / 16))
-          reinterpret_cast<int4 *>(&T->cmd)[threadIdx.x - 64] = reinterpret_cast<const int4 *>(&sNext)[threadIdx.x - 64];
-        __syncthreads();
+      if (!sMore) {
         if (threadIdx.x == 0) {
-          T->done = 0;
-          s3_push(q, track, (sNext.nPts + prm.recPoints - 1) / prm.recPoints);
+          __threadfence();  // the track's outputs precede the completion count
+          atomicSub(q.remaining, 1);
         }
-      } else if (threadIdx.x == 0) {
-        __threadfence();  // the track's outputs precede the completion count
-        atomicSub(q.remaining, 1);
+        break;
       }
+      const int nextRecs = (sNext.nPts + prm.recPoints - 1) / prm.recPoints;
+      if (nextRecs == 1) {  // stay on this track: the header comes from shared memory
+#pragma unroll
+        for (int k = 0; k < 9; k++) c.Rs[k] = sNext.Rs[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) c.t[k] = sNext.t[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) c.roll[k] = sNext.roll[k];
+        c.a = sNext.a;
+        c.b = sNext.b;
+        lvl = sNext.level;
+        n = sNext.nPts;
+        rec = 0;
+        __syncthreads();  // every thread has read sNext / stot before the next step overwrites them
+        continue;
+      }
+      // store the state and the next evaluation's header, then publish its records
+      if (threadIdx.x < (int)(sizeof(S3State) / 16))
+        reinterpret_cast<int4 *>(&T->st)[threadIdx.x] = reinterpret_cast<const int4 *>(&sState)[threadIdx.x];
+      else if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(S3Cmd) / 16))
+        reinterpret_cast<int4 *>(&T->cmd)[threadIdx.x - 64] = reinterpret_cast<const int4 *>(&sNext)[threadIdx.x - 64];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        T->done = 0;
+        s3_push(q, track, nextRecs);
+      }
+      break;
     }
     __syncthreads();  // sCode / sIsLast / sm are reused by the next item
   }
@@ -784,50 +899,23 @@ __global__ void k_sim3_init(const Sim3Job *__restrict__ jobs, S3Track *__restric
   if (i >= n) return;
   const Sim3Job *J = jobs + i;
   S3Track *T = tracks + i;
-  Sim3Out *O = outs + i;
   S3State S;
   memset(&S, 0, sizeof(S));
   for (int k = 0; k < 4; k++) S.q[k] = J->init[k];
   for (int k = 0; k < 3; k++) S.t[k] = J->init[4 + k];
   S.s = J->init[7];
-  S.a = 1;
-  S.b = 0;
-  memset(O, 0, sizeof(Sim3Out));
   for (int l = 0; l < NL; l++) S.n[l] = J->d_num[l];
   S3Cmd first;
-  memset(&first, 0, sizeof(first));
-  first.op = 0;
-  int lvl = prm.startLevel;
-  while (lvl >= prm.finalLevel && prm.s.maxItsPerLvl[lvl] == 0) lvl--;
-  if (lvl < prm.finalLevel) {
-    // no level has iterations: upstream still evaluates once at finalLevel (!warp_update_up_to_date)
-    S.phase = 2;
-    S.level = prm.finalLevel;
-    s3_make_cmd(S.q, S.t, S.s, S.a, S.b, prm.finalLevel, first);
-  } else if (S.n[lvl] == 0) {
-    O->diverged = 1;
-    s3_identity_out(O);
-    first.op = 1;
-  } else {
-    S.level = lvl;
-    S.phase = 0;
-    s3_make_cmd(S.q, S.t, S.s, S.a, S.b, lvl, first);
+  const bool more = s3_begin_stage(S, outs + i, prm, 0, first);
+  if (!more) {  // nothing to evaluate: stage 0 reports diverged, and so do the chained stages
+    s3_flush(S, outs + i);
+    for (int stage = 1; stage < prm.nStages; stage++) outs[(size_t)stage * n + i] = outs[i];
   }
-  if (first.op == 0 && S.n[first.level] == 0) {  // an empty cloud at the only level to evaluate
-    O->diverged = 1;
-    s3_identity_out(O);
-    first.op = 1;
-  }
-  first.nPts = first.op == 0 ? S.n[first.level] : 0;
   T->cmd = first;
   T->done = 0;
   T->st = S;
-  if (first.op == 0) {
-    s3_push(q, i, (first.nPts + prm.recPoints - 1) / prm.recPoints);
-  } else {
-    s3_flush(S, O);
-    atomicSub(q.remaining, 1);
-  }
+  if (more) s3_push(q, i, (first.nPts + prm.recPoints - 1) / prm.recPoints);
+  else atomicSub(q.remaining, 1);
 }
 
 __global__ void k_sim3_reset(unsigned *ctrs, unsigned n) {
@@ -908,10 +996,12 @@ static int sim3_scratch_ensure(lsd_ctx *ctx, int n, int recPoints) {
   return LSD_OK;
 }
 
-int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
-                          int startLevel, int finalLevel, lsd_sim3_result *results, lsd_trace_entry *traces) {
+int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init, int nStages,
+                          const int *startLevels, const int *finalLevels, lsd_sim3_result *results, lsd_trace_entry *traces) {
   if (n == 0) return LSD_OK;
-  LSD_ARG(startLevel >= finalLevel && finalLevel >= 1 && startLevel < NL);
+  LSD_ARG(nStages >= 1 && nStages <= S3_MAX_STAGES && startLevels && finalLevels);
+  LSD_ARG(nStages == 1 || traces == nullptr);  // LM traces are per trackFrameSim3 call
+  for (int k = 0; k < nStages; k++) LSD_ARG(startLevels[k] >= finalLevels[k] && finalLevels[k] >= 1 && startLevels[k] < NL);
   LSD_ARG(n < (1 << 19));
   cudaStream_t st = ctx->stream;
   const FrameLayout &lay = ctx->lay;
@@ -930,7 +1020,7 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
   int rc = sim3_scratch_ensure(ctx, n, recPoints);
   if (rc) return rc;
   Sim3Scratch *sc = ctx->sim3s;
-  const size_t jobBytes = sizeof(Sim3Job) * (size_t)n, outBytes = sizeof(Sim3Out) * (size_t)n;
+  const size_t jobBytes = sizeof(Sim3Job) * (size_t)n, outBytes = sizeof(Sim3Out) * (size_t)n * nStages;
   const size_t trBytes = traces ? sizeof(lsd_trace_entry) * LSD_TRACE_CAP * (size_t)n : 0;
   const size_t off1 = (jobBytes + 255) / 256 * 256, off2 = off1 + (outBytes + 255) / 256 * 256;
   rc = ensure_stage(ctx, off2, off2 + trBytes);
@@ -952,8 +1042,11 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
   Sim3Params prm;
   prm.K = ctx->K;
   prm.s = ctx->sim3;
-  prm.startLevel = startLevel;
-  prm.finalLevel = finalLevel;
+  prm.nStages = nStages;
+  for (int k = 0; k < S3_MAX_STAGES; k++) {
+    prm.startLevel[k] = k < nStages ? startLevels[k] : 0;
+    prm.finalLevel[k] = k < nStages ? finalLevels[k] : 0;
+  }
   prm.recPoints = recPoints;
   prm.maxRecs = sc->maxRecs;
   S3Queue q;
@@ -962,6 +1055,7 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
   q.tail = sc->d_ctrs + 1;
   q.remaining = reinterpret_cast<int *>(sc->d_ctrs + 2);
   q.cap = sc->qcap;
+  q.nTracks = n;
   Sim3Job *dj = reinterpret_cast<Sim3Job *>(ctx->d_stage);
   Sim3Out *dout = reinterpret_cast<Sim3Out *>(ctx->d_stage + off1);
   lsd_trace_entry *dtr = traces ? reinterpret_cast<lsd_trace_entry *>(ctx->d_stage + off2) : nullptr;
@@ -987,7 +1081,7 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
   cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
   double bytes = 0;
   long long evals = 0;
-  for (int i = 0; i < n; i++) {
+  for (int i = 0; i < n * nStages; i++) {  // stage-major: results[stage * n + track]
     const Sim3Out &o = ho[i];
     lsd_sim3_result &r = results[i];
     for (int k = 0; k < 8; k++) r.frameToRef[k] = o.frameToRef[k];
@@ -1008,9 +1102,9 @@ int sim3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *
       const double per = 20.0 * nn + 16.0 * (4.0 * nn < N ? 4.0 * nn : N) + 8.0 * nn + 8.0 * (nn < N ? nn : N) + 140.0;
       bytes += o.nRes[l] * per;
       evals += o.nRes[l];
-      refs[i]->num[l] = o.n[l];
+      if (i < n) refs[i]->num[l] = o.n[l];
     }
-    refs[i]->numValid = true;
+    if (i < n) refs[i]->numValid = true;
   }
   ctx->lastAlgBytes = bytes;
   ctx->lastEvals = evals;
@@ -1042,7 +1136,14 @@ int lsd_sim3_track_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
                          int startLevel, int finalLevel, lsd_sim3_result *results, lsd_trace_entry *traces) {
   LSD_ARG(ctx && refs && frames && init_frameToRef && results && n >= 0);
   LSD_CUDA(cudaSetDevice(ctx->device));
-  return sim3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, startLevel, finalLevel, results, traces);
+  return sim3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, 1, &startLevel, &finalLevel, results, traces);
+}
+
+int lsd_sim3_track_stages_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init_frameToRef,
+                                int nStages, const int *startLevels, const int *finalLevels, lsd_sim3_result *results) {
+  LSD_ARG(ctx && refs && frames && init_frameToRef && results && n >= 0);
+  LSD_CUDA(cudaSetDevice(ctx->device));
+  return sim3_track_batch_impl(ctx, n, refs, frames, init_frameToRef, nStages, startLevels, finalLevels, results, nullptr);
 }
 
 int lsd_sim3_track(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double init_frameToRef[8], int startLevel, int finalLevel,

@@ -102,6 +102,7 @@ SYMBOLS = {
     "lsd_ctx_set_sim3_record_points": (_ip, [_vp, _ip]),
     "lsd_sim3_track": (_ip, [_vp, _vp, _vp, _vp, _ip, _ip, _vp, _vp]),
     "lsd_sim3_track_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _ip, _ip, _vp, _vp]),
+    "lsd_sim3_track_stages_batch": (_ip, [_vp, _ip, _vp, _vp, _vp, _ip, _vp, _vp, _vp]),
     "lsd_frame_set_tracking_meta": (_ip, [_vp, _vp, _ip, _vp, _fp]),
     "lsd_frame_get_tracking_meta": (_ip, [_vp, _vp, _vp, _vp, _vp]),
     "lsd_frame_set_mask": (_ip, [_vp, _vp, _vp]),
@@ -429,6 +430,19 @@ class Context:
                                 tr[i * TRACE_CAP + k].lam, tr[i * TRACE_CAP + k].bufSize) for k in range(m)])
             return res, traces
         return res
+
+    def sim3_track_stages_batch(self, refs, frames, inits, stages=((4, 3), (2, 2), (1, 1))):
+        """Chained trackFrameSim3 calls per track in one launch (tryTrackSim3's level schedule).  Returns a list over stages of
+        lists over tracks of Sim3Result."""
+        n, k = len(refs), len(stages)
+        rp = (C.c_void_p * n)(*[r.p for r in refs])
+        fp = (C.c_void_p * n)(*[f.p for f in frames])
+        init = np.ascontiguousarray(inits, np.float64).reshape(n, 8)
+        res = (Sim3Result * (n * k))()
+        sl = (C.c_int * k)(*[int(a) for a, _ in stages])
+        fl = (C.c_int * k)(*[int(b) for _, b in stages])
+        _chk(self.L.lsd_sim3_track_stages_batch(self.p, n, rp, fp, _ptr(init), k, sl, fl, res))
+        return [[res[s * n + i] for i in range(n)] for s in range(k)]
 
     def sim3_track(self, ref, frame, init8, start_level=4, final_level=1, want_trace=False):
         out = self.sim3_track_batch([ref], [frame], [init8], start_level, final_level, want_trace)

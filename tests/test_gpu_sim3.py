@@ -95,6 +95,43 @@ def test_sim3_batch_is_deterministic_and_composition_independent(lsd, oracle):
     ctx.close()
 
 
+def test_chained_stages_equal_separate_calls(lsd, oracle):
+    """lsd_sim3_track_stages_batch ([4,3] -> [2] -> [1], SlamSystem::tryTrackSim3's schedule, inside one launch) returns for every
+    stage exactly what the corresponding separate lsd_sim3_track_batch call returns when it is started from the previous call's
+    result; a track that diverges stops and reports diverged for its remaining stages."""
+    w, h = 640, 480
+    ds = [make_sim3_pair(oracle, 120 + i, w, h, c=1.0 + 0.01 * i) for i in range(4)]
+    ctx = lsd.Context(w, h, ds[0]["pr"]["K"])
+    kfs = ctx.create_frames([d["kf_img"] for d in ds])
+    frs = ctx.create_frames([d["fr_img"] for d in ds])
+    for k, f, d in zip(kfs, frs, ds):
+        k.set_idepth(d["idepth"], d["var"])
+        f.set_idepth(d["fr_idepth"], d["fr_var"])
+    refs = ctx.create_refs(kfs)
+    inits = np.array([d["gt8"] for d in ds])
+    inits[:, 4:7] += [0.004, -0.003, 0.002]
+    inits[:, 7] = 1.0
+    s_ = np.sin(np.pi / 4)
+    inits[3] = [0, s_, 0, s_, 0, 0, 0, 1.0]  # looks 90 degrees away: diverges in the first stage
+    stages = ((4, 3), (2, 2), (1, 1))
+    chained = ctx.sim3_track_stages_batch(refs, frs, inits, stages)
+    cur = inits.copy()
+    for k, (ls, le) in enumerate(stages):
+        sep = ctx.sim3_track_batch(refs[:3], frs[:3], cur[:3], ls, le)
+        for i in range(3):
+            a, b = chained[k][i], sep[i]
+            assert list(a.frameToRef) == list(b.frameToRef), (k, i)
+            assert list(a.lastSim3Hessian) == list(b.lastSim3Hessian)
+            assert (a.lastResidual, a.pointUsage, a.affine_a, a.affine_b, a.diverged) == (b.lastResidual, b.pointUsage, b.affine_a, b.affine_b, b.diverged)
+            assert list(a.numResidualCalls) == list(b.numResidualCalls) and list(a.numWarpUpdateCalls) == list(b.numWarpUpdateCalls)
+            cur[i] = list(b.frameToRef)
+        assert chained[k][3].diverged == 1 and list(chained[k][3].frameToRef) == [0, 0, 0, 1, 0, 0, 0, 1]
+    # and the chain ends close to the truth (scale included)
+    for i in range(3):
+        assert abs(chained[2][i].frameToRef[7] - ds[i]["gt8"][7]) < 3e-3
+    ctx.close()
+
+
 def test_sim3_without_depth_residuals_takes_a_finite_step(lsd, oracle):
     """No warped point lands on a frame pixel with a depth hypothesis (numTermsD == 0): the scale row and column of the
     7x7 system are zero.  Upstream's Eigen LDLT applies the pseudo-inverse of D there (inc[6] = 0, finite step); an
