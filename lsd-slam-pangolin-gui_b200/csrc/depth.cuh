@@ -55,6 +55,9 @@ struct DepthDesc {
   unsigned *cnt, *offs, *srcPack, *bucket, *cursor;
   float2 *rec;
   float4 *tgt;  // per TARGET pixel: (new_idepth, new_var, validity) of its rank-0 source
+  // TMA descriptors (CUtensorMap, in device memory) of the CURRENT meta / idepth / var planes for the two stencil tile shapes:
+  // [0..2] the 36x36 tile of regularizeDepthMap, [3..5] the 36x12 tile of regularizeDepthMapFillHoles
+  const void *tmap[6];
   // setDepth target
   float *frIdepth, *frVar;
   double *sums;  // [4]: sum ids (valid), n valid, sum ids (valid && ids >= -0.05), n
@@ -82,4 +85,5 @@ struct lsd_depthmap {
   // per-call device tables (refs, refById, desc)
   uint8_t *d_tab, *h_tab;  // h_tab pinned
   size_t tabBytes;
+  uint8_t *d_tmaps;  // 12 CUtensorMap (128 B each): [tile shape][plane: meta, idepth, var][copy]
 };
