@@ -197,6 +197,36 @@ static void build_planes(lsd_ctx *ctx, int n, unsigned flags, cudaStream_t st) {
   if (flags & LSD_BUILD_MAXGRAD0) launch_maxgrad0(ctx, d_slabs, n, st);
 }
 
+int schedule_mean_idepth(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, lsd_frame *const *frames, cudaStream_t st) {
+  ctx->pendingMeans.clear();  // leftovers of a call that failed before its synchronisation
+  if (n > ctx->meansCap) {
+    if (ctx->d_means) cudaFree(ctx->d_means);
+    if (ctx->h_means) cudaFreeHost(ctx->h_means);
+    ctx->d_means = ctx->h_means = nullptr;
+    ctx->meansCap = 0;
+    const int cap = n < 32 ? 32 : 2 * n;
+    LSD_CUDA(cudaMalloc(&ctx->d_means, 8 * (size_t)cap));
+    LSD_CUDA(cudaMallocHost(&ctx->h_means, 8 * (size_t)cap));
+    ctx->meansCap = cap;
+  }
+  int rc = ensure_stats_scratch(ctx, n);
+  if (rc) return rc;
+  launch_idepth_stats_batch(ctx, d_slabs, n, ctx->d_means, st);
+  LSD_CUDA(cudaMemcpyAsync(ctx->h_means, ctx->d_means, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  ctx->pendingMeans.assign(frames, frames + n);
+  return LSD_OK;
+}
+
+void resolve_pending_means(lsd_ctx *ctx) {
+  for (size_t i = 0; i < ctx->pendingMeans.size(); i++) {
+    lsd_frame *f = ctx->pendingMeans[i];
+    f->meanIdepth = ctx->h_means[2 * i];
+    std::memcpy(&f->numPoints, &ctx->h_means[2 * i + 1], 4);
+    f->meanValid = true;
+  }
+  ctx->pendingMeans.clear();
+}
+
 int frame_ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need) {
   const unsigned missing = need & ~f->built;
   if (!missing) return LSD_OK;
@@ -317,6 +347,8 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->streamWatchdogNs = 2000000000ull;
   ctx->d_stats = nullptr;
   ctx->statsFrames = 0;
+  ctx->d_means = ctx->h_means = nullptr;
+  ctx->meansCap = 0;
   {
     const int rc = ensure_stats_scratch(ctx, 1);
     if (rc) return rc;
@@ -354,6 +386,8 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
   if (ctx->h_table) cudaFreeHost(ctx->h_table);
   if (ctx->d_table) cudaFree(ctx->d_table);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->d_means) cudaFree(ctx->d_means);
+  if (ctx->h_means) cudaFreeHost(ctx->h_means);
   cudaEventDestroy(ctx->evA);
   cudaEventDestroy(ctx->evB);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->evPipe[i]);
@@ -532,6 +566,7 @@ int lsd_frame_set_depth_from_gt(lsd_ctx *ctx, lsd_frame *f, const float *depth, 
   launch_set_depth_gt(ctx, f->slab, reinterpret_cast<const float *>(ctx->d_stage), cov_scale, ctx->stream);
   LSD_CUDA(cudaStreamSynchronize(ctx->stream));
   f->built = (f->built | FB_IDEPTH0) & ~FB_IDEPTH_PYR;
+  f->meanValid = false;
   return LSD_OK;
 }
 
@@ -547,6 +582,7 @@ int lsd_frame_set_idepth(lsd_ctx *ctx, lsd_frame *f, const float *idepth, const 
   LSD_CUDA(cudaMemcpyAsync(f->slab + ctx->lay.idvar[0], ctx->h_stage + bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
   LSD_CUDA(cudaStreamSynchronize(ctx->stream));
   f->built = (f->built | FB_IDEPTH0) & ~FB_IDEPTH_PYR;
+  f->meanValid = false;
   return LSD_OK;
 }
 
@@ -560,6 +596,7 @@ int lsd_frame_set_idepth_batch_device(lsd_ctx *ctx, int n, lsd_frame *const *f, 
     LSD_CUDA(cudaMemcpyAsync(f[i]->slab + ctx->lay.idvar[0], (const char *)d_idepthVar + bytes * i, bytes, cudaMemcpyDeviceToDevice,
                              ctx->stream));
     f[i]->built = (f[i]->built | FB_IDEPTH0) & ~FB_IDEPTH_PYR;
+    f[i]->meanValid = false;
   }
   LSD_CUDA(cudaStreamSynchronize(ctx->stream));
   return LSD_OK;
@@ -568,6 +605,11 @@ int lsd_frame_set_idepth_batch_device(lsd_ctx *ctx, int n, lsd_frame *const *f, 
 int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *numPoints) {
   LSD_ARG(ctx && f);
   if (!(f->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
+  if (f->meanValid) {  // computed alongside the setDepth that produced the planes
+    if (meanIdepth) *meanIdepth = f->meanIdepth;
+    if (numPoints) *numPoints = f->numPoints;
+    return LSD_OK;
+  }
   LSD_CUDA(cudaSetDevice(ctx->device));
   int rc = ensure_table(ctx, 64);
   if (rc) return rc;
@@ -577,6 +619,7 @@ int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *nu
   LSD_CUDA(cudaStreamSynchronize(ctx->stream));
   f->meanIdepth = h[0];
   std::memcpy(&f->numPoints, &h[1], 4);
+  f->meanValid = true;
   if (meanIdepth) *meanIdepth = f->meanIdepth;
   if (numPoints) *numPoints = f->numPoints;
   return LSD_OK;
@@ -586,9 +629,18 @@ int lsd_frame_mean_idepth_batch(lsd_ctx *ctx, int n, lsd_frame *const *f, float 
   LSD_ARG(ctx && f && n >= 0);
   if (n == 0) return LSD_OK;
   LSD_CUDA(cudaSetDevice(ctx->device));
+  bool allCached = true;
   for (int i = 0; i < n; i++) {
     LSD_ARG(f[i]);
     if (!(f[i]->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
+    allCached = allCached && f[i]->meanValid;
+  }
+  if (allCached) {
+    for (int i = 0; i < n; i++) {
+      if (meanIdepth) meanIdepth[i] = f[i]->meanIdepth;
+      if (numPoints) numPoints[i] = f[i]->numPoints;
+    }
+    return LSD_OK;
   }
   // table: n slab pointers, then n x 2 floats of results; one launch for all frames (blockIdx.y = frame)
   const size_t offOut = (sizeof(void *) * (size_t)n + 255) / 256 * 256;
@@ -607,6 +659,7 @@ int lsd_frame_mean_idepth_batch(lsd_ctx *ctx, int n, lsd_frame *const *f, float 
   for (int i = 0; i < n; i++) {
     f[i]->meanIdepth = h[2 * i];
     std::memcpy(&f[i]->numPoints, &h[2 * i + 1], 4);
+    f[i]->meanValid = true;
     if (meanIdepth) meanIdepth[i] = f[i]->meanIdepth;
     if (numPoints) numPoints[i] = f[i]->numPoints;
   }

@@ -109,6 +109,7 @@ struct lsd_frame {
   int trackingParentId;
   float meanIdepth;
   int numPoints;
+  bool meanValid;  // meanIdepth / numPoints describe the current level-0 idepth planes
   int numFramesTrackedOnThis, numMappedOnThis, numMappedOnThisTotal;
   bool depthHasBeenUpdatedFlag;
 };

@@ -42,6 +42,11 @@ struct lsd_ctx {
   size_t tableBytes;
   uint8_t *d_stats;  // k_idepth_stats: per frame a ticket (16 B) + per-CTA partial sums
   int statsFrames;   // frames d_stats has room for
+  // Frame::setDepth bookkeeping (meanIdepth, numPoints) rides along with the setDepth launch: results land in pinned memory
+  // and are attached to the frames after the call's own synchronisation (no extra launch + sync when the score asks for them)
+  float *d_means, *h_means;
+  int meansCap;
+  std::vector<lsd_frame *> pendingMeans;
   bool stageTimed;  // evA/evB bracket the kernels of the last depth stage
   int descSlot;  // rotating slot of the depth-map descriptor uploads (depth.cu)
   HostPool *pool;
@@ -76,6 +81,8 @@ void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t
 void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st);
 void launch_idepth_stats_batch(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, float *d_out2, cudaStream_t st);
 int ensure_stats_scratch(lsd_ctx *ctx, int frames);
+int schedule_mean_idepth(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, lsd_frame *const *frames, cudaStream_t st);  // api.cu
+void resolve_pending_means(lsd_ctx *ctx);  // call after the stream has been synchronised
 
 // trackref.cu
 int pointcloud_state_words(const lsd_ctx *ctx);  // ints behind a reference's counters: numData[NL], pad, look-back state

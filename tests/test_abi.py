@@ -68,8 +68,7 @@ def test_library_holds_sm_100a_code_for_every_kernel():
     assert archs == {"sm_100a"}, archs
     syms = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
     for k in ("k_ingest", "k_gradients", "k_maxgrad0", "k_idepth_pyramid", "k_make_pointcloud", "k_se3_track", "k_sim3_track",
-              "k_depth_observe", "k_depth_fill_holes", "k_depth_regularize", "k_prop_scatter", "k_prop_reserve", "k_prop_fill",
-              "k_prop_replay", "k_depth_sums", "k_depth_set_depth", "k_vbo_extract", "k_publish_pack", "k_remap_u8",
+              "k_depth_observe", "k_depth_fill_holes", "k_depth_regularize", "k_prop_scatter", "k_prop_replay", "k_depth_sums", "k_depth_set_depth", "k_vbo_extract", "k_publish_pack", "k_remap_u8",
               "k_permaref_overlap", "k_idepth_stats"):
         assert k in syms, f"kernel {k} missing from liblsd_b200.so"
 
