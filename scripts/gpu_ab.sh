@@ -48,7 +48,8 @@ if [ -n "$NCU_K" ]; then  # one --set full capture of the named kernels with the
   echo "ncu exit $?"; tail -2 gpurun_out/ncu_ab.log
   python scripts/ncu_summary.py full gpurun_out/prof_${R}.ncu-rep > gpurun_out/${R}_kernels_full.txt
   for k in ${NCU_SRC_KERNELS}; do
-    ncu -i gpurun_out/prof_${R}.ncu-rep --page source --csv --kernel-name-base function -k $k -c 1 > gpurun_out/${R}_src_$k.csv 2>/dev/null
+    ncu -i gpurun_out/prof_${R}.ncu-rep --page source --csv --kernel-name-base function -k $k -c 1 > gpurun_out/src_tmp.csv 2>/dev/null
+    python scripts/ncu_summary.py srcsum gpurun_out/src_tmp.csv ${NCU_SRC_TOP:-60} > gpurun_out/${R}_src_$k.txt; rm -f gpurun_out/src_tmp.csv
   done
   rm -f gpurun_out/prof_${R}.ncu-rep
   grep -E "^## |gpu__time_duration|smsp__inst_executed.sum|issue_active|warps_active|long_scoreboard|barrier" gpurun_out/${R}_kernels_full.txt | head -80

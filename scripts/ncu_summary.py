@@ -54,6 +54,34 @@ def launches(path):
         print(f"{k:40s} {n:8d} {us:12.1f} {us / n:10.1f} {100 * us / tot:6.1f}%")
 
 
+
+def srcsum(path, top=40):
+    """Compact view of an `ncu --page source --csv` dump (SASS view): the instructions that collect the stall samples."""
+    with open(path) as f:
+        rows = list(csv.reader(f))
+    name = rows[0][1] if rows and rows[0] and rows[0][0] == "Kernel Name" else "?"
+    hdr = rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    body = []
+    for r in rows[2:]:  # the dump may hold further views (CUDA-C lines) behind the SASS view: stop at the next header
+        if len(r) != len(hdr) or r[0] == "Address" or r[0] == "Kernel Name":
+            break
+        body.append(r)
+    tot = sum(int(r[ix["# Samples"]] or 0) for r in body)
+    inst = sum(int(r[ix["Instructions Executed"]] or 0) for r in body)
+    print(f"## {name}: {len(body)} SASS instructions, {inst} warp instructions executed, {tot} stall samples")
+    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    agg = {h: sum(int(r[ix[h]] or 0) for r in body) for h in stalls}
+    print("stall totals:", ", ".join(f"{k[6:]}={v}" for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v))
+    print(f"{'line':>5s} {'samples':>8s} {'%':>6s} {'executed':>10s} {'thr/inst':>8s}  top stall    instruction")
+    order = sorted(range(len(body)), key=lambda i: -int(body[i][ix["# Samples"]] or 0))[:top]
+    for i in sorted(order):
+        r = body[i]
+        smp = int(r[ix["# Samples"]] or 0)
+        ts = max(stalls, key=lambda h: int(r[ix[h]] or 0))
+        print(f"{i:5d} {smp:8d} {100.0 * smp / max(tot, 1):6.2f} {r[ix['Instructions Executed']]:>10s} {r[ix['Avg. Threads Executed']]:>8s}  {ts[6:]:12s} {r[ix['Source']].strip()[:90]}")
+
+
 def full(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -103,4 +131,7 @@ def traffic(path):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "srcsum":
+        srcsum(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
+        sys.exit(0)
     {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
