@@ -342,6 +342,10 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
+  {
+    const char *e = std::getenv("LSD_B200_STENCIL_TMA");
+    ctx->stencilTma = e ? (std::atoi(e) != 0) : LSD_STENCIL_TMA_DEFAULT;
+  }
   ctx->imageChunk = 0;
   ctx->imageStreamed = -1;
   ctx->streamWatchdogNs = 2000000000ull;
@@ -423,6 +427,12 @@ int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points) {
   LSD_ARG(points == 0 || (points >= 128 && points % 128 == 0 && points <= (1 << 20)));
   LSD_ARG(points == 0 || (ctx->K.w[1] * ctx->K.h[1] + points - 1) / points <= 4096);  // work-item codes carry 12 bits of record index
   ctx->se3RecordPoints = points;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_stencil_tma(lsd_ctx *ctx, int enable) {
+  LSD_ARG(ctx);
+  ctx->stencilTma = enable ? 1 : 0;
   return LSD_OK;
 }
 

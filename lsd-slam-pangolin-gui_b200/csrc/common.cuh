@@ -98,6 +98,10 @@ __device__ __forceinline__ unsigned lookback_exclusive(unsigned *state, unsigned
 }
 #endif
 
+#ifndef LSD_STENCIL_TMA_DEFAULT
+#define LSD_STENCIL_TMA_DEFAULT 0  // measured choice (profiles/): see lsd_ctx_set_stencil_tma
+#endif
+
 struct lsd_frame {
   int id;
   uint8_t *slab;       // device

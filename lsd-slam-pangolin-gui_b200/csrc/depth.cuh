@@ -53,9 +53,9 @@ struct DepthDesc {
   const uint8_t *newMask;  // trackingWasGood or null
   float R[9], t[3];        // oldToNew
   unsigned *cnt;                 // per TARGET pixel: number of sources that arrived
-  unsigned *ovfHead, *ovfNext;   // overflow list of a target's third and later sources (head per target, link per source)
+  unsigned *ovfHead, *ovfNext;   // overflow list of a target's fifth and later sources (head per target, link per source)
   float4 *rec;                   // per SOURCE pixel that went to an overflow list: (new_idepth, new_var, validity, source index)
-  float4 *tgt, *tgt1;            // per TARGET pixel: the records of its rank-0 and rank-1 arrivals
+  float4 *tgt[4];                // per TARGET pixel: the records of its rank-0 .. rank-3 arrivals
   // TMA descriptors (CUtensorMap, in device memory) of the CURRENT meta / idepth / var planes for the two stencil tile shapes:
   // [0..2] the 36x36 tile of regularizeDepthMap, [3..5] the 36x12 tile of regularizeDepthMapFillHoles
   const void *tmap[6];
@@ -77,7 +77,7 @@ struct lsd_depthmap {
   int mi, di;  // current copies
   unsigned *cnt, *ovfHead, *ovfNext, *cursor;
   float4 *rec;
-  float4 *tgt, *tgt1;
+  float4 *tgt[4];
   double *sums;
   lsd_frame *activeKeyFrame;
   bool reactivated;

@@ -70,6 +70,7 @@ SYMBOLS = {
     "lsd_ctx_set_se3_settings": (_ip, [_vp, _vp]),
     "lsd_ctx_set_se3_work_item_records": (_ip, [_vp, _ip]),
     "lsd_ctx_set_se3_active_pairs": (_ip, [_vp, _ip]),
+    "lsd_ctx_set_stencil_tma": (_ip, [_vp, _ip]),
     "lsd_ctx_set_se3_record_points": (_ip, [_vp, _ip]),
     "lsd_frame_create": (_ip, [_vp, _ip, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _u, _vp]),
@@ -245,6 +246,9 @@ class Context:
 
     def set_se3_settings(self, s):
         _chk(self.L.lsd_ctx_set_se3_settings(self.p, C.byref(s)))
+
+    def set_stencil_tma(self, enable):
+        _chk(self.L.lsd_ctx_set_stencil_tma(self.p, int(bool(enable))))
 
     def set_se3_active_pairs(self, n):
         _chk(self.L.lsd_ctx_set_se3_active_pairs(self.p, int(n)))

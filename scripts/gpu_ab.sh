@@ -10,15 +10,18 @@ if [ -n "$TESTS" ]; then
   timeout 1500 python -m pytest $TESTS -m gpu -q -x > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "pytest exit $?"
   grep -E "passed|failed|error|parity:|pipeline:|Error|assert" gpurun_out/${R}_pytest_gpu.log | tail -15
 fi
-for v in ${VARIANTS}; do
+for vv in ${VARIANTS}; do  # name or name@ENV=VALUE (an environment switch on top of the library variant)
+  v=${vv%%@*}; envset=""; [ "$vv" != "$v" ] && envset=${vv#*@}
   lib=$PWD/lsd-slam-pangolin-gui_b200/build/liblsd_b200_$v.so
   [ "$v" = main ] && lib=$PWD/lsd-slam-pangolin-gui_b200/liblsd_b200.so
+  [ -n "$envset" ] && export "$envset"
   if [ -n "$VTESTS" ]; then
     LSD_B200_LIB=$lib timeout 900 python -m pytest $VTESTS -m gpu -q -x > gpurun_out/${R}_pytest_$v.log 2>&1; echo "== $v pytest exit $? $(tail -1 gpurun_out/${R}_pytest_$v.log)"
   fi
   LSD_B200_LIB=$lib timeout 900 python bench.py --no-cpu --legs $LEGS --pairs ${PAIRS:-64} --steps 3 --warmup 3 --frames ${FRAMES:-200} --multi ${MULTI:-1} \
      > gpurun_out/${R}_ab_$v.json 2> gpurun_out/${R}_ab_$v.err || { echo "variant $v FAILED"; tail -3 gpurun_out/${R}_ab_$v.err; }
-  python - gpurun_out/${R}_ab_$v.json $v <<'PY'
+  [ -n "$envset" ] && unset "${envset%%=*}"
+  python - gpurun_out/${R}_ab_$v.json $vv <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
