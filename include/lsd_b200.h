@@ -106,11 +106,11 @@ int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
  * maximise batch throughput; a context that tracks ONE live sequence (SlamSystem's tracking thread) wants small records
  * (1024): an evaluation then spreads over 4x the CTAs (measured: 0.51 -> 0.38 ms per tracked frame, batch 4.2 -> 6.1 ms). */
 int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points);
-/* Depth-map stencil kernels (regularizeDepthMap, regularizeDepthMapFillHoles): 1 = the halo tile of each CTA is fetched by
- * the TMA unit (cp.async.bulk.tensor, out-of-map cells zero-filled by the hardware), 0 = by 16-byte vector loads.  Results are
- * bit-identical; the default is the faster of the two on B200.  Environment LSD_B200_STENCIL_TMA=0/1 overrides the
- * default at context creation. */
-int lsd_ctx_set_stencil_tma(lsd_ctx *ctx, int enable);
+/* Depth-map stencil kernels: bit 0 of `mask` = regularizeDepthMap, bit 1 = regularizeDepthMapFillHoles.  A set bit makes the
+ * kernel fetch the halo tile of each CTA with the TMA unit (cp.async.bulk.tensor, out-of-map cells zero-filled by the
+ * hardware), a clear bit with 16-byte vector loads.  Results are bit-identical; the default (1) is the faster choice per kernel
+ * on B200.  Environment LSD_B200_STENCIL_TMA=<mask> overrides the default at context creation. */
+int lsd_ctx_set_stencil_tma(lsd_ctx *ctx, int mask);
 /* pairs in flight inside one lsd_se3_track_batch launch (0 = default): bounds the working set to what L2 holds.
  * Scheduling only: results are bit-identical for every value. */
 int lsd_ctx_set_se3_active_pairs(lsd_ctx *ctx, int pairs);

@@ -344,7 +344,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3RecordPoints = 0;
   {
     const char *e = std::getenv("LSD_B200_STENCIL_TMA");
-    ctx->stencilTma = e ? (std::atoi(e) != 0) : LSD_STENCIL_TMA_DEFAULT;
+    ctx->stencilTma = e ? (std::atoi(e) & 3) : LSD_STENCIL_TMA_DEFAULT;
   }
   ctx->imageChunk = 0;
   ctx->imageStreamed = -1;
@@ -430,9 +430,9 @@ int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points) {
   return LSD_OK;
 }
 
-int lsd_ctx_set_stencil_tma(lsd_ctx *ctx, int enable) {
+int lsd_ctx_set_stencil_tma(lsd_ctx *ctx, int enable) {  // `enable`: the mask of include/lsd_b200.h
   LSD_ARG(ctx);
-  ctx->stencilTma = enable ? 1 : 0;
+  ctx->stencilTma = enable & 3;
   return LSD_OK;
 }
 
@@ -480,18 +480,28 @@ int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *c
   int rc = ensure_stage(ctx, fbytes * (n < CH ? n : CH), fbytes * (n < CH ? n : CH));
   if (rc) return rc;
   for (int i = 0; i < n; i++) LSD_ARG(images[i]);
+  static const bool trace = std::getenv("LSD_B200_TRACE") != nullptr;  // host-side timing of the ingest steps on stderr
+  static int traced = 0, traced1 = 0;
   for (int i0 = 0; i0 < n; i0 += CH) {
     const int m = (n - i0) < CH ? (n - i0) : CH;
+    const auto t0 = std::chrono::steady_clock::now();
     host_pool(ctx)->run(m, [&](int i) {
       const uint8_t *src = images[i0 + i];
       uint8_t *dst = ctx->h_stage + fbytes * i;
       if (pitch == (size_t)ctx->w) std::memcpy(dst, src, fbytes);
       else for (int y = 0; y < ctx->h; y++) std::memcpy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
     });
+    const auto t1 = std::chrono::steady_clock::now();
     LSD_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, fbytes * m, cudaMemcpyHostToDevice, ctx->stream));
     rc = lsd_frame_create_batch_device(ctx, m, ids ? ids + i0 : nullptr, ctx->d_stage, flags, out + i0);
     if (rc) return rc;
     if (!ids) for (int i = 0; i < m; i++) out[i0 + i]->id = i0 + i;
+    if (trace && (m > 1 ? traced++ < 12 : traced1++ < 3)) {
+      const auto t2 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[lsd_b200] frame_create_batch n=%d: stage %.1f us (%d pool threads), h2d + kernels + sync %.1f us\n", m,
+                   1e6 * std::chrono::duration<double>(t1 - t0).count(), (int)host_pool(ctx)->th.size() + 1,
+                   1e6 * std::chrono::duration<double>(t2 - t1).count());
+    }
   }
   return LSD_OK;
 }

@@ -384,11 +384,22 @@ __global__ void __launch_bounds__(STATS_THREADS) k_idepth_stats(uint8_t *const *
   const float *VR = reinterpret_cast<const float *>(slab + lay.idvar[0]);
   double s = 0;
   int c = 0;
-  for (int i = blockIdx.x * STATS_THREADS + threadIdx.x; i < N; i += gridDim.x * STATS_THREADS) {
-    if (VR[i] > 0) {
-      s += (double)ID[i];
-      c++;
-    }
+  // 16-byte vectors of both planes, two in flight per thread (N % 4 == 0: w and h are multiples of 16); the fp64 sum of fp32
+  // values is exact far beyond the final fp32 rounding, so the grouping does not show in the result
+  const float4 *ID4 = reinterpret_cast<const float4 *>(ID), *VR4 = reinterpret_cast<const float4 *>(VR);
+  const int N4 = N >> 2, stride = gridDim.x * STATS_THREADS;
+  for (int i = blockIdx.x * STATS_THREADS + threadIdx.x; i < N4; i += 2 * stride) {
+    const bool two = i + stride < N4;
+    const float4 v0 = VR4[i], d0 = ID4[i];
+    const float4 v1 = two ? VR4[i + stride] : make_float4(0, 0, 0, 0), d1 = two ? ID4[i + stride] : make_float4(0, 0, 0, 0);
+    if (v0.x > 0) { s += (double)d0.x; c++; }
+    if (v0.y > 0) { s += (double)d0.y; c++; }
+    if (v0.z > 0) { s += (double)d0.z; c++; }
+    if (v0.w > 0) { s += (double)d0.w; c++; }
+    if (v1.x > 0) { s += (double)d1.x; c++; }
+    if (v1.y > 0) { s += (double)d1.y; c++; }
+    if (v1.z > 0) { s += (double)d1.z; c++; }
+    if (v1.w > 0) { s += (double)d1.w; c++; }
   }
   for (int o = 16; o; o >>= 1) {
     s += __shfl_down_sync(0xffffffffu, s, o);

@@ -247,8 +247,8 @@ class Context:
     def set_se3_settings(self, s):
         _chk(self.L.lsd_ctx_set_se3_settings(self.p, C.byref(s)))
 
-    def set_stencil_tma(self, enable):
-        _chk(self.L.lsd_ctx_set_stencil_tma(self.p, int(bool(enable))))
+    def set_stencil_tma(self, mask):
+        _chk(self.L.lsd_ctx_set_stencil_tma(self.p, int(mask)))
 
     def set_se3_active_pairs(self, n):
         _chk(self.L.lsd_ctx_set_se3_active_pairs(self.p, int(n)))

@@ -50,6 +50,18 @@ def _K_for(w, h):
 
 @pytest.mark.parametrize("wh,seed", [((320, 240), 31), ((640, 480), 32), ((640, 480), 37), ((1280, 960), 36)])
 def test_stages_bit_exact(lsd, oracle, wh, seed):
+    _stages_bit_exact(lsd, oracle, wh, seed, None)
+
+
+@pytest.mark.parametrize("wh,seed,tma", [((176, 144), 41, 0), ((176, 144), 41, 3), ((320, 240), 31, 0), ((320, 240), 31, 3),
+                                         ((640, 480), 32, 2)])
+def test_stencil_tile_loads_tma_and_vector(lsd, oracle, wh, seed, tma):
+    """lsd_ctx_set_stencil_tma: the TMA halo-tile path (40-wide boxes at a 16-byte aligned origin, hardware zero fill outside
+    the map, partial tiles at the right / bottom edge) and the vector-load path produce the oracle's maps bit for bit."""
+    _stages_bit_exact(lsd, oracle, wh, seed, tma)
+
+
+def _stages_bit_exact(lsd, oracle, wh, seed, tma):
     w, h = wh
     oracle.set_exact_sums(1)
     d = make_oracle_depth_scene(seed, w, h, n_refs=10, K=_K_for(w, h))
@@ -61,6 +73,8 @@ def test_stages_bit_exact(lsd, oracle, wh, seed):
     odm = oracle.DepthMap(w, h, d["K"])
     odm.init_map(d["okf"], m0)
     ctx, kf, refs = gpu_scene(lsd, d, w, h)
+    if tma is not None:
+        ctx.set_stencil_tma(tma)
     gdm = ctx.create_depthmap()
     gdm.initializeFromMap(kf, m0)
     assert_maps_equal(gdm.read(), odm.read(), "import/export round trip")
