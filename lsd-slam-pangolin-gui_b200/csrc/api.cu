@@ -76,6 +76,30 @@ struct HostPool {
   }
 };
 
+
+// Copy into a pinned staging buffer with NON-TEMPORAL stores.  A buffer that host threads have just written with ordinary stores
+// sits dirty in their caches, and the DMA engine then reads it at 9-14 GB/s instead of 45-52 GB/s (measured on the pool's B200
+// boxes, scripts/probe/h2d_probe.cu: 9.8 MB written by 8 threads, then cudaMemcpyAsync); streaming stores leave nothing in the
+// caches to snoop.  dst is 16-byte aligned (cudaMallocHost, frame sizes are multiples of 256).
+#include <emmintrin.h>
+static void stage_copy(uint8_t *dst, const uint8_t *src, size_t n) {
+  size_t i = 0;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (; i + 64 <= n; i += 64) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+      const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+      const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+    }
+  }
+  if (i < n) std::memcpy(dst + i, src + i, n - i);
+  _mm_sfence();  // the streamed lines are globally visible before the copy engine is started
+}
+
 namespace lsd {
 
 static HostPool *host_pool(lsd_ctx *ctx) {
@@ -457,12 +481,33 @@ int lsd_frame_create_batch_device(lsd_ctx *ctx, int n, const int *ids, const voi
     slabs[i] = s;
     out[i] = new_frame(ids ? ids[i] : i, s);
   }
+  static const bool trace = std::getenv("LSD_B200_TRACE") != nullptr;
+  static int traced = 0;
+  static cudaEvent_t tev[3];
+  static bool tevMade = false;
+  if (trace && !tevMade) {
+    for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
+    tevMade = true;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = upload_ptrs(ctx, slabs, st);
   if (rc) return rc;
+  if (trace) cudaEventRecord(tev[0], st);
   launch_ingest(ctx, (const uint8_t *)d_images, ctx->w, (size_t)ctx->w * ctx->h, reinterpret_cast<uint8_t *const *>(ctx->d_table), n,
                 st);
+  if (trace) cudaEventRecord(tev[1], st);
   build_planes(ctx, n, flags, st);
+  if (trace) cudaEventRecord(tev[2], st);
+  const auto t1 = std::chrono::steady_clock::now();
   LSD_CUDA(cudaStreamSynchronize(st));
+  if (trace && n > 1 && traced++ < 12) {
+    const auto t2 = std::chrono::steady_clock::now();
+    float msI = 0, msG = 0;
+    cudaEventElapsedTime(&msI, tev[0], tev[1]);
+    cudaEventElapsedTime(&msG, tev[1], tev[2]);
+    std::fprintf(stderr, "[lsd_b200] frame_create_batch_device n=%d: enqueue %.1f us, wait %.1f us; device: ingest %.1f us, planes %.1f us\n", n,
+                 1e6 * std::chrono::duration<double>(t1 - t0).count(), 1e6 * std::chrono::duration<double>(t2 - t1).count(), 1e3 * msI, 1e3 * msG);
+  }
   for (int i = 0; i < n; i++)
     out[i]->built = FB_TRACKING | ((flags & LSD_BUILD_MAXGRAD0) ? FB_MAXGRAD0 : 0) | ((flags & LSD_BUILD_GRAD0) ? FB_GRAD0 : 0);
   return LSD_OK;
@@ -488,8 +533,8 @@ int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *c
     host_pool(ctx)->run(m, [&](int i) {
       const uint8_t *src = images[i0 + i];
       uint8_t *dst = ctx->h_stage + fbytes * i;
-      if (pitch == (size_t)ctx->w) std::memcpy(dst, src, fbytes);
-      else for (int y = 0; y < ctx->h; y++) std::memcpy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
+      if (pitch == (size_t)ctx->w) stage_copy(dst, src, fbytes);
+      else for (int y = 0; y < ctx->h; y++) stage_copy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
     });
     const auto t1 = std::chrono::steady_clock::now();
     LSD_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, fbytes * m, cudaMemcpyHostToDevice, ctx->stream));
@@ -801,7 +846,6 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
   int rc = upload_ptrs(ctx, tab, st);
   if (rc) return rc;
   void **d = reinterpret_cast<void **>(ctx->d_table);
-  for (int i = 0; i < n; i++) LSD_CUDA(cudaMemsetAsync(out[i]->d_num, 0, numBytes, st));
   launch_make_pointcloud(ctx, reinterpret_cast<uint8_t *const *>(d), reinterpret_cast<uint8_t *const *>(d + n),
                          reinterpret_cast<int *const *>(d + 2 * (size_t)n), n, offPts, offGrad, st);
   LSD_CUDA(cudaStreamSynchronize(st));
@@ -1052,8 +1096,8 @@ int lsd_se3_track_images_batch(lsd_ctx *ctx, int n, lsd_ref *const *refs, const 
           }
           uint8_t *dst = ctx->h_stage + ((size_t)(c % RING) * CH + (size_t)(i - c * CH)) * fbytes;
           const uint8_t *src = images[i];
-          if (pitch == (size_t)ctx->w) std::memcpy(dst, src, fbytes);
-          else for (int y = 0; y < ctx->h; y++) std::memcpy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
+          if (pitch == (size_t)ctx->w) stage_copy(dst, src, fbytes);
+          else for (int y = 0; y < ctx->h; y++) stage_copy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
           staged[c].fetch_add(1, std::memory_order_release);
         }
       });

@@ -40,7 +40,8 @@ namespace lsd {
 #define SE3_D 2           // per-thread software-pipeline depth of eval_range (points whose taps are in flight + 1)
 #endif
 #ifndef SE3_MINB
-#define SE3_MINB 4        // resident CTAs per SM the register budget is sized for
+#define SE3_MINB 5        // resident CTAs per SM the register budget is sized for (r02n, 1000 pairs: 4.37 ms at 4 / 128 registers,
+                          // 4.16 ms at 5 / 96 registers, 4.46 ms at 6 / 80, 6.66 ms at 8 / 64)
 #endif
 #ifndef SE3_REC
 #define SE3_REC 4096      // points per partial record: FIXED, it defines the summation order (see above)

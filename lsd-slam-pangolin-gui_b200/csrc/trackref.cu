@@ -103,8 +103,16 @@ int pointcloud_state_words(const lsd_ctx *ctx) {
   return 64 + NL + total;
 }
 
+// numData + look-back state of n references, zeroed in one launch (one memset per reference cost ~3 us of launch time each)
+__global__ void k_zero_ref_state(int *const *__restrict__ nums, int words) {
+  int *p = nums[blockIdx.x];
+  for (int i = threadIdx.x; i < words; i += blockDim.x) p[i] = 0;
+}
+
 void launch_make_pointcloud(lsd_ctx *ctx, uint8_t *const *d_kfSlabs, uint8_t *const *d_refSlabs, int *const *d_nums, int n,
                             const size_t *offPts, const size_t *offGrad, cudaStream_t st) {
+  k_zero_ref_state<<<n, 128, 0, st>>>(d_nums, pointcloud_state_words(ctx));
+  ctx->launches++;
   PCOffsets off;
   for (int l = 0; l < NL; l++) {
     off.pts[l] = offPts[l];
