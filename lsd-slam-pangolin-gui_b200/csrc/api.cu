@@ -221,7 +221,9 @@ static void build_planes(lsd_ctx *ctx, int n, unsigned flags, cudaStream_t st) {
   if (flags & LSD_BUILD_MAXGRAD0) launch_maxgrad0(ctx, d_slabs, n, st);
 }
 
-int schedule_mean_idepth(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, lsd_frame *const *frames, cudaStream_t st) {
+// Frame::setDepth's bookkeeping (meanIdepth, numPoints) is produced by the setDepth / pyramid launch itself (k_idepth_pyramid):
+// prepare_mean_idepth sizes the buffers before that launch, schedule_mean_idepth queues the read-back behind it.
+int prepare_mean_idepth(lsd_ctx *ctx, int n, float **d_out2) {
   ctx->pendingMeans.clear();  // leftovers of a call that failed before its synchronisation
   if (n > ctx->meansCap) {
     if (ctx->d_means) cudaFree(ctx->d_means);
@@ -235,7 +237,11 @@ int schedule_mean_idepth(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, lsd_frame
   }
   int rc = ensure_stats_scratch(ctx, n);
   if (rc) return rc;
-  launch_idepth_stats_batch(ctx, d_slabs, n, ctx->d_means, st);
+  *d_out2 = ctx->d_means;
+  return LSD_OK;
+}
+
+int schedule_mean_idepth(lsd_ctx *ctx, int n, lsd_frame *const *frames, cudaStream_t st) {
   LSD_CUDA(cudaMemcpyAsync(ctx->h_means, ctx->d_means, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
   ctx->pendingMeans.assign(frames, frames + n);
   return LSD_OK;

@@ -71,18 +71,20 @@ void launch_ingest(lsd_ctx *ctx, const uint8_t *d_src, size_t srcPitch, size_t s
                    cudaStream_t st);
 void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st);
 void launch_maxgrad0(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
-void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
+void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st, float *d_statOut2 = nullptr);
 struct IdepthMapSrc {  // hypothesis planes Frame::setDepth reads (depth.cuh layout)
   const uint32_t *meta;
   const float *ids, *vars;
 };
-void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st);
+void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st,
+                                  float *d_statOut2 = nullptr);
 void launch_set_depth_gt(lsd_ctx *ctx, uint8_t *slab, const float *d_depth, float cov, cudaStream_t st);
 void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
 void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st);
 void launch_idepth_stats_batch(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, float *d_out2, cudaStream_t st);
 int ensure_stats_scratch(lsd_ctx *ctx, int frames);
-int schedule_mean_idepth(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, lsd_frame *const *frames, cudaStream_t st);  // api.cu
+int prepare_mean_idepth(lsd_ctx *ctx, int n, float **d_out2);  // api.cu: before the setDepth launch
+int schedule_mean_idepth(lsd_ctx *ctx, int n, lsd_frame *const *frames, cudaStream_t st);  // api.cu: after it
 void resolve_pending_means(lsd_ctx *ctx);  // call after the stream has been synchronised
 
 // trackref.cu

@@ -230,10 +230,16 @@ __device__ __forceinline__ void fuse4(const float id[4], const float var[4], flo
 // FROM_MAP: level 0 does not exist yet -- it is Frame::setDepth of the keyframe's depth map (hypothesis planes meta / idepth_smoothed
 // / idepth_var_smoothed), computed here, written to the level-0 planes and consumed from registers: one pass over the map instead
 // of k_depth_set_depth followed by a re-read of the two planes it wrote.
+// STATS: Frame::setDepth's meanIdepth / numPoints (mean of idepth over the level-0 pixels with idepthVar > 0) ride along: every
+// CTA reduces its tile in a fixed order (fp64), the last CTA of a frame (ticket) sums the per-CTA partials in a fixed order.
+// scratch: per frame a 16-byte ticket + 16 bytes per CTA (stats_stride); out2: (mean, count as int bits) per frame.
 template <bool FROM_MAP>
 __global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restrict__ slabs, const IdepthMapSrc *__restrict__ srcs,
-                                                        FrameLayout lay, int W, int H) {
+                                                        FrameLayout lay, int W, int H, uint8_t *__restrict__ statScratch, size_t statStride,
+                                                        float *__restrict__ statOut2) {
   __shared__ float a1[TILE_H / 2][TILE_W / 2], b1[TILE_H / 2][TILE_W / 2];
+  __shared__ double s_wsum[8];
+  __shared__ int s_wcnt[8];
   __shared__ float a2[TILE_H / 4][TILE_W / 4], b2[TILE_H / 4][TILE_W / 4];
   __shared__ float a3[TILE_H / 8][TILE_W / 8], b3[TILE_H / 8][TILE_W / 8];
   const int f = blockIdx.z;
@@ -244,6 +250,8 @@ __global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restri
     const int tx = t & 31, ty = t >> 5;
     const int x = (x0 >> 1) + tx, y = (y0 >> 1) + ty;
     float oid = -1, ovar = -1;
+    double ssum = 0;
+    int scnt = 0;
     if (x < (W >> 1) && y < (H >> 1)) {
       float *ID = reinterpret_cast<float *>(slab + lay.idepth[0]);
       float *VR = reinterpret_cast<float *>(slab + lay.idvar[0]);
@@ -269,11 +277,68 @@ __global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restri
       fuse4(id, var, oid, ovar);
       reinterpret_cast<float *>(slab + lay.idepth[1])[(size_t)y * (W >> 1) + x] = oid;
       reinterpret_cast<float *>(slab + lay.idvar[1])[(size_t)y * (W >> 1) + x] = ovar;
+      if (statScratch) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (var[k] > 0) {
+            ssum += (double)id[k];
+            scnt++;
+          }
+      }
     }
     a1[ty][tx] = oid;
     b1[ty][tx] = ovar;
+    if (statScratch) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        ssum += __shfl_down_sync(0xffffffffu, ssum, o);
+        scnt += __shfl_down_sync(0xffffffffu, scnt, o);
+      }
+      if ((t & 31) == 0) {
+        s_wsum[t >> 5] = ssum;
+        s_wcnt[t >> 5] = scnt;
+      }
+    }
   }
   __syncthreads();
+  if (statScratch && t < 32) {  // warp 0: CTA partial, ticket, and -- in the frame's last CTA -- the total
+    unsigned *ticket = reinterpret_cast<unsigned *>(statScratch + statStride * f);
+    double *partial = reinterpret_cast<double *>(statScratch + statStride * f + 16);
+    const unsigned nCta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    unsigned last = 0;
+    if (t == 0) {
+      double S = 0;
+      int Cn = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        S += s_wsum[k];
+        Cn += s_wcnt[k];
+      }
+      partial[2 * cta] = S;
+      partial[2 * cta + 1] = (double)Cn;
+      __threadfence();
+      last = atomicAdd(ticket, 1u) == nCta - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      double S = 0, Cn = 0;
+      for (unsigned k = t; k < nCta; k += 32) {  // lane-strided, then a fixed shuffle tree: a pure function of the partials
+        S += __ldcg(partial + 2 * k);
+        Cn += __ldcg(partial + 2 * k + 1);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        S += __shfl_down_sync(0xffffffffu, S, o);
+        Cn += __shfl_down_sync(0xffffffffu, Cn, o);
+      }
+      if (t == 0) {
+        statOut2[2 * f] = (float)S / (float)Cn;  // upstream: float sum / float count
+        statOut2[2 * f + 1] = __int_as_float((int)Cn);
+        *ticket = 0;  // ready for the next call
+      }
+    }
+  }
   if (t < 64) {
     const int tx = t & 15, ty = t >> 4;
     const float id[4] = {a1[2 * ty][2 * tx], a1[2 * ty][2 * tx + 1], a1[2 * ty + 1][2 * tx], a1[2 * ty + 1][2 * tx + 1]};
@@ -318,16 +383,22 @@ __global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restri
   }
 }
 
-void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st) {
+static size_t stats_stride(const lsd_ctx *ctx);
+
+// d_statOut2 != nullptr: Frame::setDepth's (meanIdepth, numPoints) of every frame as well (ensure_stats_scratch(ctx, n) first)
+void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st, float *d_statOut2) {
   dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
-  k_idepth_pyramid<false><<<grid, 256, 0, st>>>(d_slabs, nullptr, ctx->lay, ctx->w, ctx->h);
+  k_idepth_pyramid<false><<<grid, 256, 0, st>>>(d_slabs, nullptr, ctx->lay, ctx->w, ctx->h, d_statOut2 ? ctx->d_stats : nullptr,
+                                                stats_stride(ctx), d_statOut2);
   ctx->launches++;
 }
 
 // Frame::setDepth(depth map) + buildIDepthAndIDepthVar in one pass (d_srcs[i]: the hypothesis planes of keyframe i's map)
-void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st) {
+void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st,
+                                  float *d_statOut2) {
   dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
-  k_idepth_pyramid<true><<<grid, 256, 0, st>>>(d_slabs, d_srcs, ctx->lay, ctx->w, ctx->h);
+  k_idepth_pyramid<true><<<grid, 256, 0, st>>>(d_slabs, d_srcs, ctx->lay, ctx->w, ctx->h, d_statOut2 ? ctx->d_stats : nullptr,
+                                               stats_stride(ctx), d_statOut2);
   ctx->launches++;
 }
 
@@ -436,8 +507,13 @@ __global__ void __launch_bounds__(STATS_THREADS) k_idepth_stats(uint8_t *const *
   }
 }
 
-// scratch: (16 + 16 * numSMs) bytes per frame of zero-initialised-once device memory owned by the context
-static size_t stats_stride(const lsd_ctx *ctx) { return (16 + 16 * (size_t)ctx->numSMs + 255) / 256 * 256; }
+// scratch: 16 + 16 bytes per CTA of a frame, zero-initialised once, owned by the context
+// (k_idepth_stats runs numSMs CTAs per frame, k_idepth_pyramid one per 64x16 tile)
+static size_t stats_stride(const lsd_ctx *ctx) {
+  const size_t tiles = (size_t)((ctx->w + TILE_W - 1) / TILE_W) * ((ctx->h + TILE_H - 1) / TILE_H);
+  const size_t ctas = tiles > (size_t)ctx->numSMs ? tiles : (size_t)ctx->numSMs;
+  return (16 + 16 * ctas + 255) / 256 * 256;
+}
 
 int ensure_stats_scratch(lsd_ctx *ctx, int frames) {
   if (frames <= ctx->statsFrames) return LSD_OK;
