@@ -316,12 +316,14 @@ __global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restri
       }
       partial[2 * cta] = S;
       partial[2 * cta + 1] = (double)Cn;
-      __threadfence();
-      last = atomicAdd(ticket, 1u) == nCta - 1;
+      // gpu-scope acquire-release ticket: releases this CTA's partial, and the CTA that takes the last ticket acquires all others
+      unsigned old;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(ticket), "r"(1u) : "memory");
+      last = old == nCta - 1;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
+    __syncwarp();  // lane 0's acquire precedes the other lanes' L2 reads of the partials
     if (last) {
-      __threadfence();
       double S = 0, Cn = 0;
       for (unsigned k = t; k < nCta; k += 32) {  // lane-strided, then a fixed shuffle tree: a pure function of the partials
         S += __ldcg(partial + 2 * k);

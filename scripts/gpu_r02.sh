@@ -41,13 +41,16 @@ if [ -z "$SKIP_NCU" ]; then
   python scripts/ncu_summary.py full gpurun_out/prof_se3_${R}.ncu-rep > gpurun_out/${R}_k_se3_track_full_1000pairs.txt
   head -50 gpurun_out/${R}_k_se3_track_full_1000pairs.txt
   python scripts/ncu_summary.py traffic gpurun_out/prof_se3_${R}.ncu-rep > gpurun_out/${R}_traffic_se3_1000pairs.json; cat gpurun_out/${R}_traffic_se3_1000pairs.json
+  ncu -i gpurun_out/prof_se3_${R}.ncu-rep --page source --csv --kernel-name-base function -k k_se3_track -c 1 > gpurun_out/src_tmp.csv 2>/dev/null
+  python scripts/ncu_summary.py srcsum gpurun_out/src_tmp.csv 60 > gpurun_out/${R}_src_k_se3_track.txt; rm -f gpurun_out/src_tmp.csv
   if [ -n "$NCU_EXTRA_K" ]; then
     timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base function -k "$NCU_EXTRA_K" -c ${NCU_EXTRA_C:-24} \
        -o gpurun_out/prof_extra_${R} -f python bench.py --pairs 64 --steps 1 --warmup 1 --no-cpu --frames 40 --multi 1 --legs ${NCU_EXTRA_LEGS:-depth_stages,sim3_search} > gpurun_out/ncu_extra_full.log 2>&1
     echo "ncu extra exit $?"; tail -2 gpurun_out/ncu_extra_full.log
     python scripts/ncu_summary.py full gpurun_out/prof_extra_${R}.ncu-rep > gpurun_out/${R}_kernels_full.txt
     for k in ${NCU_SRC_KERNELS}; do
-      ncu -i gpurun_out/prof_extra_${R}.ncu-rep --page source --csv --kernel-name-base function -k $k -c 1 > gpurun_out/${R}_src_$k.csv 2>/dev/null
+      ncu -i gpurun_out/prof_extra_${R}.ncu-rep --page source --csv --kernel-name-base function -k $k -c 1 > gpurun_out/src_tmp.csv 2>/dev/null
+      python scripts/ncu_summary.py srcsum gpurun_out/src_tmp.csv ${NCU_SRC_TOP:-40} > gpurun_out/${R}_src_$k.txt; rm -f gpurun_out/src_tmp.csv
     done
     rm -f gpurun_out/prof_extra_${R}.ncu-rep
   fi
