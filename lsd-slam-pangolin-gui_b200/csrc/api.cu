@@ -536,14 +536,19 @@ int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *c
   for (int i0 = 0; i0 < n; i0 += CH) {
     const int m = (n - i0) < CH ? (n - i0) : CH;
     const auto t0 = std::chrono::steady_clock::now();
-    host_pool(ctx)->run(m, [&](int i) {
-      const uint8_t *src = images[i0 + i];
-      uint8_t *dst = ctx->h_stage + fbytes * i;
-      if (pitch == (size_t)ctx->w) stage_copy(dst, src, fbytes);
-      else for (int y = 0; y < ctx->h; y++) stage_copy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
-    });
+    // staged and copied in up to four sub-chunks: the copy engine moves sub-chunk k while the host threads stage k + 1
+    const int SUB = m >= 8 ? (m + 3) / 4 : m;
+    for (int j0 = 0; j0 < m; j0 += SUB) {
+      const int mm = (m - j0) < SUB ? (m - j0) : SUB;
+      host_pool(ctx)->run(mm, [&](int i) {
+        const uint8_t *src = images[i0 + j0 + i];
+        uint8_t *dst = ctx->h_stage + fbytes * (j0 + i);
+        if (pitch == (size_t)ctx->w) stage_copy(dst, src, fbytes);
+        else for (int y = 0; y < ctx->h; y++) stage_copy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
+      });
+      LSD_CUDA(cudaMemcpyAsync(ctx->d_stage + fbytes * j0, ctx->h_stage + fbytes * j0, fbytes * mm, cudaMemcpyHostToDevice, ctx->stream));
+    }
     const auto t1 = std::chrono::steady_clock::now();
-    LSD_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, fbytes * m, cudaMemcpyHostToDevice, ctx->stream));
     rc = lsd_frame_create_batch_device(ctx, m, ids ? ids + i0 : nullptr, ctx->d_stage, flags, out + i0);
     if (rc) return rc;
     if (!ids) for (int i = 0; i < m; i++) out[i0 + i]->id = i0 + i;
