@@ -538,6 +538,22 @@ int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *c
     const auto t0 = std::chrono::steady_clock::now();
     // staged and copied in up to four sub-chunks: the copy engine moves sub-chunk k while the host threads stage k + 1
     const int SUB = m >= 8 ? (m + 3) / 4 : m;
+    static const int splitOne = getenv("LSD_B200_STAGE_SPLIT") ? atoi(getenv("LSD_B200_STAGE_SPLIT")) : 4;
+    if (m == 1 && splitOne > 1 && ctx->h >= 4 * splitOne) {
+      // one live frame: its rows are staged by a few pool threads at once (32 us of single-thread copy for a VGA frame otherwise)
+      const uint8_t *src = images[i0];
+      uint8_t *dst = ctx->h_stage;
+      const int rowsPer = (ctx->h + splitOne - 1) / splitOne;
+      host_pool(ctx)->run(splitOne, [&](int part) {
+        const int y0 = part * rowsPer, y1 = (y0 + rowsPer) < ctx->h ? (y0 + rowsPer) : ctx->h;
+        if (pitch == (size_t)ctx->w) {
+          if (y1 > y0) stage_copy(dst + (size_t)y0 * ctx->w, src + (size_t)y0 * ctx->w, (size_t)(y1 - y0) * ctx->w);
+        } else {
+          for (int y = y0; y < y1; y++) stage_copy(dst + (size_t)y * ctx->w, src + (size_t)y * pitch, ctx->w);
+        }
+      });
+      LSD_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else
     for (int j0 = 0; j0 < m; j0 += SUB) {
       const int mm = (m - j0) < SUB ? (m - j0) : SUB;
       host_pool(ctx)->run(mm, [&](int i) {

@@ -631,7 +631,15 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
       rhs[remap[a]] += S.sums[Q_B4 + a];
     }
     const float nc = (float)S.nc;
-    for (int i = 0; i < 49; i++) A[i] = A[i] / nc;
+    // A is symmetric by construction (both triangles were filled with the same sums): 28 divisions instead of 49, same values
+#pragma unroll
+    for (int a = 0; a < 7; a++)
+#pragma unroll
+      for (int c = a; c < 7; c++) {
+        const float v = A[a * 7 + c] / nc;
+        A[a * 7 + c] = v;
+        A[c * 7 + a] = v;
+      }
     for (int i = 0; i < 7; i++) rhs[i] = rhs[i] / nc;
     const float lam1 = 1 + S.lambda;
     for (int i = 0; i < 7; i++) A[i * 7 + i] *= lam1;
