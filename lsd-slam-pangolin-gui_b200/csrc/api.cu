@@ -538,7 +538,7 @@ int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *c
     const auto t0 = std::chrono::steady_clock::now();
     // staged and copied in up to four sub-chunks: the copy engine moves sub-chunk k while the host threads stage k + 1
     const int SUB = m >= 8 ? (m + 3) / 4 : m;
-    static const int splitOne = getenv("LSD_B200_STAGE_SPLIT") ? atoi(getenv("LSD_B200_STAGE_SPLIT")) : 4;
+    static const int splitOne = getenv("LSD_B200_STAGE_SPLIT") ? atoi(getenv("LSD_B200_STAGE_SPLIT")) : 1;  // r02v: 55 us (4 parts) vs 57 us (1): not worth waking the pool
     if (m == 1 && splitOne > 1 && ctx->h >= 4 * splitOne) {
       // one live frame: its rows are staged by a few pool threads at once (32 us of single-thread copy for a VGA frame otherwise)
       const uint8_t *src = images[i0];
