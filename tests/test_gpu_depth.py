@@ -127,6 +127,52 @@ def _stages_bit_exact(lsd, oracle, wh, seed, tma):
     ctx.close()
 
 
+@pytest.mark.parametrize("back,expect_max", [(2.5, 5), (6.0, 9)])
+def test_propagate_many_sources_per_target(lsd, oracle, back, expect_max):
+    """propagateDepth onto a view far BEHIND the keyframe: the map shrinks towards the image centre and up to a dozen sources
+    land on one target pixel, so the replay's three paths all run -- one record, 2..4 records ordered in registers, and the
+    overflow list of a fifth and later arrival -- and upstream's raster-order merge / occlusion rules must come out bit for bit."""
+    w, h = 320, 240
+    oracle.set_exact_sums(1)
+    d = make_oracle_depth_scene(52, w, h, n_refs=2, noise=0.0)
+    m0 = hyp_from_idepth(d["idepth"], d["var"])
+    odm = oracle.DepthMap(w, h, d["K"])
+    odm.init_map(d["okf"], m0)
+    ctx, kf, refs = gpu_scene(lsd, d, w, h)
+    gdm = ctx.create_depthmap()
+    gdm.initializeFromMap(kf, m0)
+    # the new frame sits `back` metres behind the keyframe, same orientation: thisToParent = (identity, (0, 0, -back))
+    toParent = np.array([0, 0, 0, 1, 0, 0, -back, 1.0])
+    new_o, new_g = d["refs"][-1]["of"], refs[-1]
+    new_o.set_track_meta(1.0, 1000, toParent)
+    new_g.set_tracking_meta(1000, toParent, 1.0)
+    mask = np.ones((h >> 1, w >> 1), np.uint8)  # tracked-on-this-keyframe path: no photometric test between the two views
+    new_o.set_mask(mask)
+    new_g.set_mask(mask)
+    # how many sources per target this really is (same projection, float64): the test must reach the overflow path
+    fx, fy, cx, cy = d["K"][:4]
+    ys, xs = np.nonzero(m0["isValid"] > 0)
+    z = 1.0 / m0["idepth_smoothed"][ys, xs].astype(np.float64)
+    u = (xs - cx) / fx * z / (z + back) * fx + cx
+    v = (ys - cy) / fy * z / (z + back) * fy + cy
+    cnt = np.bincount(((u + 0.5).astype(int) + (v + 0.5).astype(int) * w), minlength=w * h)
+    assert cnt.max() >= expect_max, cnt.max()
+    odm.stage(oracle.STAGE_PROPAGATE, frame=new_o)
+    gdm.stage(lsd.STAGE_PROPAGATE, frame=new_g)
+    go, oo = gdm.read(), odm.read()
+    assert_maps_equal(go, oo, f"propagateDepth, {back} m behind (up to {cnt.max()} sources per target)")
+    assert (oo["isValid"] > 0).sum() > 200
+    # and the scratch is clean again: a second propagate of the same map gives the same result
+    g2 = ctx.create_depthmap()
+    g2.initializeFromMap(kf, m0)
+    g2.stage(lsd.STAGE_PROPAGATE, frame=new_g)
+    gdm.initializeFromMap(kf, m0)
+    gdm.stage(lsd.STAGE_PROPAGATE, frame=new_g)
+    assert_maps_equal(gdm.read(), g2.read(), "second propagate on the same scratch")
+    oracle.set_exact_sums(0)
+    ctx.close()
+
+
 @pytest.mark.parametrize("wh", [(320, 240), (640, 480), (1280, 960)])
 def test_update_and_create_keyframe_sequence(lsd, oracle, wh):
     """The live mapping loop: 8 x updateKeyframe (one tracked frame each), then createKeyFrame on the 9th, then 1 update.
