@@ -81,9 +81,12 @@ struct HostPool {
 // sits dirty in their caches, and the DMA engine then reads it at 9-14 GB/s instead of 45-52 GB/s (measured on the pool's B200
 // boxes, scripts/probe/h2d_probe.cu: 9.8 MB written by 8 threads, then cudaMemcpyAsync); streaming stores leave nothing in the
 // caches to snoop.  dst is 16-byte aligned (cudaMallocHost, frame sizes are multiples of 256).
+#if defined(__SSE2__)
 #include <emmintrin.h>
+#endif
 static void stage_copy(uint8_t *dst, const uint8_t *src, size_t n) {
   size_t i = 0;
+#if defined(__SSE2__)
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     for (; i + 64 <= n; i += 64) {
       const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
@@ -98,6 +101,9 @@ static void stage_copy(uint8_t *dst, const uint8_t *src, size_t n) {
   }
   if (i < n) std::memcpy(dst + i, src + i, n - i);
   _mm_sfence();  // the streamed lines are globally visible before the copy engine is started
+#else
+  std::memcpy(dst, src, n);
+#endif
 }
 
 namespace lsd {
