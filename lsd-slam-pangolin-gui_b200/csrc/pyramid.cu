@@ -233,8 +233,11 @@ __device__ __forceinline__ void fuse4(const float id[4], const float var[4], flo
 // STATS: Frame::setDepth's meanIdepth / numPoints (mean of idepth over the level-0 pixels with idepthVar > 0) ride along: every
 // CTA reduces its tile in a fixed order (fp64), the last CTA of a frame (ticket) sums the per-CTA partials in a fixed order.
 // scratch: per frame a 16-byte ticket + 16 bytes per CTA (stats_stride); out2: (mean, count as int bits) per frame.
+#ifndef IDP_MINB
+#define IDP_MINB 8  // 32 registers, no spills: setDepth + pyramids 0.127 -> 0.110 ms per 64 keyframes (r02za)
+#endif
 template <bool FROM_MAP>
-__global__ void __launch_bounds__(256) k_idepth_pyramid(uint8_t *const *__restrict__ slabs, const IdepthMapSrc *__restrict__ srcs,
+__global__ void __launch_bounds__(256, IDP_MINB) k_idepth_pyramid(uint8_t *const *__restrict__ slabs, const IdepthMapSrc *__restrict__ srcs,
                                                         FrameLayout lay, int W, int H, uint8_t *__restrict__ statScratch, size_t statStride,
                                                         float *__restrict__ statOut2) {
   __shared__ float a1[TILE_H / 2][TILE_W / 2], b1[TILE_H / 2][TILE_W / 2];
