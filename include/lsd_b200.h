@@ -109,7 +109,8 @@ int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points);
 /* Depth-map stencil kernels: bit 0 of `mask` = regularizeDepthMap, bit 1 = regularizeDepthMapFillHoles.  A set bit makes the
  * kernel fetch the halo tile of each CTA with the TMA unit (cp.async.bulk.tensor, out-of-map cells zero-filled by the
  * hardware), a clear bit with 16-byte vector loads.  Results are bit-identical; the default (1) is the faster choice per kernel
- * on B200.  Environment LSD_B200_STENCIL_TMA=<mask> overrides the default at context creation. */
+ * on B200.  Environment LSD_B200_STENCIL_TMA=<mask> overrides the default at context creation.  On a driver
+ * without cuTensorMapEncodeTiled the mask is forced to 0 (vector loads). */
 int lsd_ctx_set_stencil_tma(lsd_ctx *ctx, int mask);
 /* pairs in flight inside one lsd_se3_track_batch launch (0 = default): bounds the working set to what L2 holds.
  * Scheduling only: results are bit-identical for every value. */

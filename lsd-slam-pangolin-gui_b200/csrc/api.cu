@@ -378,6 +378,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
+  ctx->tmaUnavailable = false;
   {
     const char *e = std::getenv("LSD_B200_STENCIL_TMA");
     ctx->stencilTma = e ? (std::atoi(e) & 3) : LSD_STENCIL_TMA_DEFAULT;
@@ -468,7 +469,7 @@ int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points) {
 
 int lsd_ctx_set_stencil_tma(lsd_ctx *ctx, int enable) {  // `enable`: the mask of include/lsd_b200.h
   LSD_ARG(ctx);
-  ctx->stencilTma = enable & 3;
+  ctx->stencilTma = ctx->tmaUnavailable ? 0 : (enable & 3);
   return LSD_OK;
 }
 

@@ -23,6 +23,7 @@ struct lsd_ctx {
   bool se3Permaref;    // set for the duration of lsd_se3_track_permaref_batch
   int se3ActivePairs;  // 0: default; pairs in flight inside the persistent tracker (L2 residency)
   int se3RecsPerItem;  // 0: automatic (scheduling granularity only)
+  bool tmaUnavailable; // cuTensorMapEncodeTiled missing or failing on this driver: the stencil kernels keep to vector loads
   int stencilTma;      // bit 0 / 1: regularizeDepthMap / fillHoles fetch their halo tiles with TMA (lsd_ctx_set_stencil_tma)
   int se3RecordPoints; // 0: default (4096); points per partial record = the summation order of the SE3 tracker
   int imageChunk;      // 0: default; frames per H2D copy / ingest launch of lsd_se3_track_images_batch
