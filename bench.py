@@ -403,7 +403,7 @@ def leg_track_map(lsd, dev, local_rank, args, cpu):
     n = args.frames
     frames, gt = render_sequence(W, H, K, n, 0, dev)
     ctx = lsd.Context(W, H, K, device=local_rank)
-    ctx.set_se3_record_points(1024)  # a context that tracks live sequences: small records (include/lsd_b200.h)
+    ctx.set_se3_record_points(int(os.environ.get("LSD_B200_BENCH_LIVE_REC", "512")))  # live sequences: small records (include/lsd_b200.h)
     run_native_sequence(lsd, ctx, frames, min(20, n))  # warm-up: pools, lazy allocations
     dt, stt = run_native_sequence(lsd, ctx, frames, n)
     ids = sorted(stt["est"])
@@ -606,6 +606,8 @@ def leg_sim3_search(lsd, dev, local_rank, rank, world, cpu, n_cand=64, steps=10)
     from lsd_b200.pipeline import sim3_inv
     K = synth.default_K(W, H)
     ctx = lsd.Context(W, H, K, device=local_rank)
+    if os.environ.get("LSD_B200_BENCH_SIM3_REC"):  # experiments: points per partial record of the Sim3 tracker (default 1024)
+        ctx.set_sim3_record_points(int(os.environ["LSD_B200_BENCH_SIM3_REC"]))
     sc = synth.make_constraint_scene(4, W, H, n_cand, K=K, device=dev)
     # every rank builds the new keyframe and all candidates (setup, untimed): LPT needs every candidate's numData
     new = ctx.create_frame(sc["new"][0].cpu().numpy(), 0, flags=lsd.BUILD_MAXGRAD0)
@@ -719,7 +721,7 @@ def leg_sequences(lsd, dev, local_rank, rank, world, args, cpu):
     # same semi-dense density
     frames, gt = render_sequence(w, h, K, n, rank, dev, contrast=130.0)
     ctx = lsd.Context(w, h, K, device=local_rank)
-    ctx.set_se3_record_points(1024)
+    ctx.set_se3_record_points(int(os.environ.get("LSD_B200_BENCH_LIVE_REC", "512")))
     run_native_sequence(lsd, ctx, frames, min(20, n))
     if world > 1:
         import torch.distributed as dist

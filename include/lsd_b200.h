@@ -104,7 +104,8 @@ int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
  * records are summed in order, so this value DEFINES the fp32 summation order: for a given value results are
  * bit-identical for every batch size and scheduling; between values they differ by reassociation only.  Large records
  * maximise batch throughput; a context that tracks ONE live sequence (SlamSystem's tracking thread) wants small records
- * (1024): an evaluation then spreads over 4x the CTAs (measured: 0.51 -> 0.38 ms per tracked frame, batch 4.2 -> 6.1 ms). */
+ * (512): an evaluation then spreads over 8x the CTAs (measured: 0.51 -> 0.34 ms per tracked frame; the 1000-pair batch would
+ * go from 4.1 to > 6 ms). */
 int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points);
 /* Depth-map stencil kernels: bit 0 of `mask` = regularizeDepthMap, bit 1 = regularizeDepthMapFillHoles.  A set bit makes the
  * kernel fetch the halo tile of each CTA with the TMA unit (cp.async.bulk.tensor, out-of-map cells zero-filled by the
