@@ -395,6 +395,19 @@ def run_native_sequence(lsd, ctx, frames, n):
     return dt, dict(lost=lost, keyframes=kfs, kf_seconds=t_kf, est=est, stages=stages)
 
 
+
+def set_live_records(ctx):
+    """Record sizes of a context that tracks live sequences (include/lsd_b200.h: lsd_ctx_set_live_tracking).  Experiments:
+    LSD_B200_BENCH_LIVE_REC = one size for every level, or four comma-separated sizes for levels 1..4."""
+    env = os.environ.get("LSD_B200_BENCH_LIVE_REC")
+    if not env:
+        ctx.set_live_tracking(True)
+    elif "," in env:
+        ctx.set_se3_record_points_per_level([0] + [int(v) for v in env.split(",")])
+    else:
+        ctx.set_se3_record_points(int(env))
+
+
 def leg_track_map(lsd, dev, local_rank, args, cpu):
     """configs[0] shape on the device: single live sequence (latency-bound: the GPU is mostly idle) and N concurrent sequences
     through the batched driver (what fills the GPU); CPU port (1 tracking + 4 mapping threads) on the same 500 frames."""
@@ -403,7 +416,7 @@ def leg_track_map(lsd, dev, local_rank, args, cpu):
     n = args.frames
     frames, gt = render_sequence(W, H, K, n, 0, dev)
     ctx = lsd.Context(W, H, K, device=local_rank)
-    ctx.set_se3_record_points(int(os.environ.get("LSD_B200_BENCH_LIVE_REC", "512")))  # live sequences: small records (include/lsd_b200.h)
+    set_live_records(ctx)  # live sequences: small per-level records (include/lsd_b200.h)
     run_native_sequence(lsd, ctx, frames, min(20, n))  # warm-up: pools, lazy allocations
     dt, stt = run_native_sequence(lsd, ctx, frames, n)
     ids = sorted(stt["est"])
@@ -721,7 +734,7 @@ def leg_sequences(lsd, dev, local_rank, rank, world, args, cpu):
     # same semi-dense density
     frames, gt = render_sequence(w, h, K, n, rank, dev, contrast=130.0)
     ctx = lsd.Context(w, h, K, device=local_rank)
-    ctx.set_se3_record_points(int(os.environ.get("LSD_B200_BENCH_LIVE_REC", "512")))
+    set_live_records(ctx)
     run_native_sequence(lsd, ctx, frames, min(20, n))
     if world > 1:
         import torch.distributed as dist

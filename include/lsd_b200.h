@@ -107,6 +107,22 @@ int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
  * (512): an evaluation then spreads over 8x the CTAs (measured: 0.51 -> 0.34 ms per tracked frame; the 1000-pair batch would
  * go from 4.1 to > 6 ms). */
 int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points);
+/* Record size per pyramid level: points[l] for level l = 1 .. LSD_PYRAMID_LEVELS - 1 (points[0] is ignored: level 0 is never
+ * tracked); 0 = the context-wide value of lsd_ctx_set_se3_record_points.  A live context wants every evaluation to be ONE
+ * record per 128-thread group of its cluster with as few points per thread as the level allows, e.g. {0, 640, 256, 128, 128}
+ * at 640x480: a coarse level then costs one point per thread instead of four.  Like the context-wide value this defines the
+ * summation order and nothing else. */
+int lsd_ctx_set_se3_record_points_per_level(lsd_ctx *ctx, const int *points);
+/* Convenience for the context of SlamSystem's tracking thread (one frame per call): picks the per-level record sizes for this
+ * image size -- ceil(0.45 * pixels(level) / 64) rounded up to a multiple of 128, i.e. {640, 256, 128, 128} at 640x480 and
+ * {2176, 640, 256, 128} at 1280x960.  enable = 0 returns to the context-wide record size. */
+int lsd_ctx_set_live_tracking(lsd_ctx *ctx, int enable);
+/* SE3 tracking calls with at most `pairs` pairs run on the live kernel: ONE thread-block cluster per pair (16 CTAs x 512 threads
+ * where the device co-schedules them, else 8), LM state in the leader CTA's shared memory, header and partial records exchanged
+ * over distributed shared memory, two cluster barriers per LM evaluation instead of the work queue's global-memory hand-offs.
+ * This is the shape of SlamSystem::trackFrame (one frame at a time).  Same records, same summation order: for a given record
+ * size both kernels return identical bits.  -1 = default (2), 0 = always the work-queue kernel. */
+int lsd_ctx_set_se3_live_pairs(lsd_ctx *ctx, int pairs);
 /* Depth-map stencil kernels: bit 0 of `mask` = regularizeDepthMap, bit 1 = regularizeDepthMapFillHoles.  A set bit makes the
  * kernel fetch the halo tile of each CTA with the TMA unit (cp.async.bulk.tensor, out-of-map cells zero-filled by the
  * hardware), a clear bit with 16-byte vector loads.  Results are bit-identical; the default (1) is the faster choice per kernel

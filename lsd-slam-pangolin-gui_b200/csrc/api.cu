@@ -378,6 +378,8 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
+  for (int &v : ctx->se3RecordPointsLvl) v = 0;
+  ctx->se3LivePairs = std::getenv("LSD_B200_SE3_LIVE_PAIRS") ? std::atoi(std::getenv("LSD_B200_SE3_LIVE_PAIRS")) : -1;
   ctx->tmaUnavailable = false;
   {
     const char *e = std::getenv("LSD_B200_STENCIL_TMA");
@@ -464,6 +466,43 @@ int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points) {
   LSD_ARG(points == 0 || (points >= 128 && points % 128 == 0 && points <= (1 << 20)));
   LSD_ARG(points == 0 || (ctx->K.w[1] * ctx->K.h[1] + points - 1) / points <= 4096);  // work-item codes carry 12 bits of record index
   ctx->se3RecordPoints = points;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_se3_record_points_per_level(lsd_ctx *ctx, const int *points) {
+  LSD_ARG(ctx && points);
+  for (int l = 1; l < NL; l++) {
+    const int p = points[l];
+    LSD_ARG(p == 0 || (p >= 128 && p % 128 == 0 && p <= (1 << 20)));
+    LSD_ARG(p == 0 || (ctx->K.w[l] * ctx->K.h[l] + p - 1) / p <= 4096);  // work-item codes carry 12 bits of record index
+  }
+  for (int l = 0; l < NL; l++) ctx->se3RecordPointsLvl[l] = l ? points[l] : 0;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_live_tracking(lsd_ctx *ctx, int enable) {
+  LSD_ARG(ctx);
+  if (!enable) {
+    for (int &v : ctx->se3RecordPointsLvl) v = 0;
+    return LSD_OK;
+  }
+  // one record per 128-thread group of a 16-CTA cluster (64 groups) when about 45 % of a level's pixels carry depth -- the density
+  // of a semi-dense keyframe; a denser level simply takes a second round
+  for (int l = 1; l < NL; l++) {
+    const long long px = (long long)ctx->K.w[l] * ctx->K.h[l];
+    long long p = (px * 45 / 100 + 63) / 64;
+    p = (p + 127) / 128 * 128;
+    if (p < 128) p = 128;
+    while ((px + p - 1) / p > 4096) p += 128;
+    ctx->se3RecordPointsLvl[l] = (int)p;
+  }
+  ctx->se3RecordPointsLvl[0] = 0;
+  return LSD_OK;
+}
+
+int lsd_ctx_set_se3_live_pairs(lsd_ctx *ctx, int pairs) {
+  LSD_ARG(ctx && pairs >= -1);
+  ctx->se3LivePairs = pairs;
   return LSD_OK;
 }
 

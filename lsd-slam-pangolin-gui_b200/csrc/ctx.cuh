@@ -26,6 +26,8 @@ struct lsd_ctx {
   bool tmaUnavailable; // cuTensorMapEncodeTiled missing or failing on this driver: the stencil kernels keep to vector loads
   int stencilTma;      // bit 0 / 1: regularizeDepthMap / fillHoles fetch their halo tiles with TMA (lsd_ctx_set_stencil_tma)
   int se3RecordPoints; // 0: default (4096); points per partial record = the summation order of the SE3 tracker
+  int se3RecordPointsLvl[5];  // per level (0: se3RecordPoints applies): lsd_ctx_set_se3_record_points_per_level
+  int se3LivePairs;    // -1: default (2); batches of at most this many pairs run on k_se3_track_live, one cluster per pair; 0: never
   int imageChunk;      // 0: default; frames per H2D copy / ingest launch of lsd_se3_track_images_batch
   int imageStreamed;   // -1: default (streamed when the platform runs kernels concurrently); 0 / 1: forced
   unsigned long long streamWatchdogNs;  // give-up time of the streamed tracker's work-item wait
@@ -107,6 +109,7 @@ int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
                 cudaStream_t st, float kernelMs);
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
                   float *A36, float *b6, float *scalars);
+int se3_record_points(const lsd_ctx *ctx, int level);
 void se3_scratch_free(lsd_ctx *ctx);
 void sim3_scratch_free(lsd_ctx *ctx);
 int se3_permaref_overlap_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, const double *refToFrame, float *pointUsage);

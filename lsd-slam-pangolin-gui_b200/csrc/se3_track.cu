@@ -24,6 +24,7 @@
 // residual, isGood) is bit-identical to the oracle's (-ffp-contract=off); weights, Jacobian rows and the
 // accumulated terms use explicit fmaf and MUFU approximations (see accumulate_point).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstddef>
 #include <cstring>
@@ -132,7 +133,7 @@ struct SE3Params {
   int maxChunks;           // per-pair stride of the partial records (records of the largest tracked level)
   int recsPerItem;         // records per work item: scheduling granularity only, never changes a result
   int minLevel, maxLevel;  // SE3TRACKING_MIN_LEVEL, SE3TRACKING_MAX_LEVEL-1
-  int recPoints;           // points per partial record (lsd_ctx_set_se3_record_points; default SE3_REC)
+  int recPointsLvl[NL];    // points per partial record at each level (lsd_ctx_set_se3_record_points[_per_level]; default SE3_REC)
   int permaref;            // SE3Tracker::trackFrameOnPermaref: single level, no frame side effects, referenceToFrame returned
   // Streamed launches only (0 otherwise): a CTA that has waited this long for a work item while pairs are still outstanding
   // gives up and stops the whole launch.  The streamed host-image path starts the tracker BEFORE its producers (ingest kernels
@@ -220,15 +221,53 @@ __device__ int start_level(SE3State *S, int level, const SE3Params &prm) {
     mark_diverged(S);
     return 0;
   }
-  const int nRecs = (S->n[level] + prm.recPoints - 1) / prm.recPoints;
+  const int nRecs = (S->n[level] + prm.recPointsLvl[level] - 1) / prm.recPointsLvl[level];
   S->nChunks = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;  // work items of this evaluation
   S->done = 0;
   return S->nChunks;
 }
 
+// closed form of the affine-lighting estimate, evaluated in fp64 (upstream: fp32; mathematically identical, see DESIGN.md "affine lighting")
+__device__ __forceinline__ void affine_estimate(const double *dtot, float *aL, float *bL) {
+  const double sxx = dtot[D_SXX], syy = dtot[D_SYY], sx = dtot[D_SX], sy = dtot[D_SY], sw = dtot[D_SW];
+  const double aLd = sqrt((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+  *aL = (float)aLd;
+  *bL = (float)((sy - aLd * sx) / sw);
+}
+
+// What two other warps of the CTA compute WHILE thread 0 runs the LM decision logic (lm_step consumes it when it gets there):
+//   pre[0..26] = the 21 + 6 normal-equation sums divided by num_constraints (27 IEEE divisions, one per lane of helper warp 1)
+//   pre[27..28] = affine-lighting estimate (fp64 square root + four fp64 divisions, one lane of helper warp 2)
+// Same operations on the same operands as the one-thread path: not a bit changes, the serial tail of an evaluation gets shorter.
+// `ready[k] == seq` publishes part k of evaluation number `seq` of this CTA (seq only ever grows: no reset, no ABA).
+struct LmPre {
+  volatile float pre[32];
+  volatile int ready[2];
+};
+__device__ __forceinline__ void lm_prework(const float *tot, const double *dtot, LmPre *P, const int seq, const int t) {
+  if (t >= 32 && t < 64) {
+    const int k = t - 32;
+    if (k < 27) {
+      const float nf = (float)(int)(tot[R_GOOD] + tot[R_BAD]);
+      P->pre[k] = tot[R_A + k] / nf;  // R_A .. R_B + 5 are contiguous
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (k == 0) P->ready[0] = seq;
+  } else if (t == 64) {
+    float aL, bL;
+    affine_estimate(dtot, &aL, &bL);
+    P->pre[27] = aL;
+    P->pre[28] = bL;
+    __threadfence_block();
+    P->ready[1] = seq;
+  }
+}
+
 // The LM state machine, run by one thread after the last chunk of an evaluation (tot = summed partials).
-// Returns the number of chunks of the next evaluation (0: pair finished).
-__device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const SE3Params &prm, lsd_trace_entry *trace) {
+// Returns the number of chunks of the next evaluation (0: pair finished).  P (optional): see lm_prework.
+__device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const SE3Params &prm, lsd_trace_entry *trace, const LmPre *P = nullptr,
+                       const int seq = 0) {
   const int lvl = S->level;
   const float good = tot[R_GOOD], bad = tot[R_BAD];
   const int size = (int)(good + bad);
@@ -237,15 +276,26 @@ __device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const 
   S->bad = bad;
   S->pointUsage = tot[R_USAGE] / (float)S->n[lvl];
   S->meanRes = tot[R_SUMSGN] / good;
-  // closed form evaluated in fp64 (upstream: fp32; mathematically identical, see DESIGN.md "affine lighting")
-  const double sxx = dtot[D_SXX], syy = dtot[D_SYY], sx = dtot[D_SX], sy = dtot[D_SY], sw = dtot[D_SW];
-  const double aLd = sqrt((syy - sy * sy / sw) / (sxx - sx * sx / sw));
-  const float aL = (float)aLd;
-  const float bL = (float)((sy - aLd * sx) / sw);
-  S->aff_a_lastIt = aL;
-  S->aff_b_lastIt = bL;
+  bool takeAffine = false;  // the step is accepted (or the level starts): aff_a / aff_b follow this evaluation's estimate
+  auto affine = [&]() {     // runs once, right before lm_step returns: by then the helper warp has long finished
+    float aL, bL;
+    if (P) {
+      while (P->ready[1] != seq) {}
+      aL = P->pre[27];
+      bL = P->pre[28];
+    } else {
+      affine_estimate(dtot, &aL, &bL);
+    }
+    S->aff_a_lastIt = aL;
+    S->aff_b_lastIt = bL;
+    if (takeAffine) {
+      S->aff_a = aL;
+      S->aff_b = bL;
+    }
+  };
 
   if (size < LSD_MIN_GOODPERALL_PIXEL_ABSMIN * prm.K.w[lvl] * prm.K.h[lvl]) {
+    affine();
     mark_diverged(S);
     return 0;
   }
@@ -257,8 +307,7 @@ __device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const 
   int accepted;
   float traceLambda = S->lambda;
   if (S->phase == 0) {
-    S->aff_a = aL;
-    S->aff_b = bL;
+    takeAffine = true;
     S->lastErr = error;
     S->lambda = prm.s.lambdaInitial[lvl];
     S->iteration = 0;
@@ -271,8 +320,7 @@ __device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const 
     for (int i = 0; i < 4; i++) S->q_cur[i] = S->q_try[i];
 #pragma unroll
     for (int i = 0; i < 3; i++) S->t_cur[i] = S->t[i];
-    S->aff_a = aL;
-    S->aff_b = bL;
+    takeAffine = true;
     if (error / S->lastErr > prm.s.convergenceEps[lvl]) S->iteration = maxIts;
     S->last_residual = S->lastErr = error;
     if (S->lambda <= 0.2f) S->lambda = 0; else S->lambda *= prm.s.lambdaSuccessFac;
@@ -297,6 +345,7 @@ __device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const 
   S->traceLen++;
 
   if (S->iteration >= maxIts) {
+    affine();  // the next level's header carries aff_a / aff_b
     if (lvl - 1 < prm.minLevel) {
       finish_pair(S, prm);
       return 0;
@@ -304,11 +353,19 @@ __device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const 
     return start_level(S, lvl - 1, prm);
   }
   if (takeNormalEq) {  // NormalEquationsLeastSquares::finish(): divide by num_constraints
-    const float nf = (float)size;
+    if (P) {
+      while (P->ready[0] != seq) {}
 #pragma unroll
-    for (int k = 0; k < 21; k++) S->A[k] = tot[R_A + k] / nf;
+      for (int k = 0; k < 21; k++) S->A[k] = P->pre[k];
 #pragma unroll
-    for (int k = 0; k < 6; k++) S->b[k] = tot[R_B + k] / nf;
+      for (int k = 0; k < 6; k++) S->b[k] = P->pre[21 + k];
+    } else {
+      const float nf = (float)size;
+#pragma unroll
+      for (int k = 0; k < 21; k++) S->A[k] = tot[R_A + k] / nf;
+#pragma unroll
+      for (int k = 0; k < 6; k++) S->b[k] = tot[R_B + k] / nf;
+    }
     S->nWarpCalls[lvl]++;
     S->incTry = 0;
   }
@@ -340,6 +397,7 @@ __device__ int lm_step(SE3State *S, const float *tot, const double *dtot, const 
   set_eval_pose(S, S->q_try, tn);
   S->phase = 1;
   S->done = 0;  // same level => same nChunks
+  affine();
   return S->nChunks;
 }
 
@@ -506,11 +564,13 @@ __device__ __forceinline__ void accumulate_point(const Pending &w, const float4 
 // before it.  A thread only ever reads slots it filled itself: no CTA barrier inside the loop.
 __device__ __forceinline__ void eval_range(const RefPoint *__restrict__ pts, int begin, int end, const float4 *__restrict__ G,
                                            uint8_t *__restrict__ mask, const EvalConst &c, float acc[SE3_NF],
-                                           double dacc[SE3_ND], float4 *tapbuf) {
+                                           double dacc[SE3_ND], float4 *tapbuf, const int tid) {
+  // tid: the thread's index inside the SE3_THREADS-wide group that works on this range (the whole CTA in k_se3_track; one of
+  // four groups of a CTA in k_se3_track_live)
   const float4 *pts4 = reinterpret_cast<const float4 *>(pts);
-  float4 *mySlot = tapbuf + threadIdx.x;
+  float4 *mySlot = tapbuf + tid;
   Pending pd[SE3_D];
-  int iLoad = begin + threadIdx.x;
+  int iLoad = begin + tid;
   float4 rawNext = (iLoad < end) ? __ldg(pts4 + iLoad) : make_float4(0, 0, 0, 0);
   auto issue = [&](const int s) {
     const float4 raw = rawNext;
@@ -552,6 +612,61 @@ union SE3Smem {
   SE3Red red;
 };
 
+// Rows of the parked sums one warp reduces: rows wid, wid + 4, ...  All of a warp's rows go through the steps TOGETHER
+// (loads of every row, then the four ordered adds of every row, then each level of the shuffle tree for every row), so the
+// dependent latencies of a row -- LDS, 4 FADD, 5 x (SHFL + FADD) -- are paid once per warp instead of once per row: 2.0 -> 0.3 us
+// per record.  Per row the operations and their order are exactly: v = (((0 + c0) + c1) + c2) + c3 over the four columns
+// lane + 32 k, then v += shfl_down(v, 16), 8, 4, 2, 1; lane 0 holds the row's sum.
+#define SE3_ROWS_PER_WARP ((SE3_NF + SE3_ND + SE3_THREADS / 32 - 1) / (SE3_THREADS / 32))
+__device__ __forceinline__ void reduce_rows(const SE3Red &sm, float *__restrict__ dst, const int lane, const int wid) {
+  constexpr int NW = SE3_THREADS / 32;
+  constexpr int FR = (SE3_NF + NW - 1) / NW;  // float rows per warp (upper bound)
+  constexpr int DR = (SE3_ND + NW - 1) / NW;  // double rows per warp (upper bound)
+  float fv[FR];
+  double dv[DR];
+#pragma unroll
+  for (int i = 0; i < FR; i++) {
+    const int row = wid + NW * i;
+    float v = 0.0f;
+    if (row < SE3_NF) {
+#pragma unroll
+      for (int k = 0; k < NW; k++) v += sm.f[row][lane + 32 * k];
+    }
+    fv[i] = v;
+  }
+  // double rows: row index SE3_NF + r is handled by warp (SE3_NF + r) % NW in the original layout (rows wid, wid + NW, ...)
+#pragma unroll
+  for (int i = 0; i < DR; i++) {
+    // the i-th double row of this warp: smallest r >= 0 with (SE3_NF + r) % NW == wid, then + NW * i
+    const int r = ((wid - SE3_NF % NW) + NW) % NW + NW * i;
+    double v = 0.0;
+    if (r < SE3_ND) {
+#pragma unroll
+      for (int k = 0; k < NW; k++) v += sm.d[r][lane + 32 * k];
+    }
+    dv[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < FR; i++) fv[i] += __shfl_down_sync(0xffffffffu, fv[i], o);
+#pragma unroll
+    for (int i = 0; i < DR; i++) dv[i] += __shfl_down_sync(0xffffffffu, dv[i], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < FR; i++) {
+      const int row = wid + NW * i;
+      if (row < SE3_NF) dst[2 * SE3_ND + row] = fv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DR; i++) {
+      const int r = ((wid - SE3_NF % NW) + NW) % NW + NW * i;
+      if (r < SE3_ND) reinterpret_cast<double *>(dst)[r] = dv[i];
+    }
+  }
+}
+
 __device__ __forceinline__ void block_reduce_store(const float acc[SE3_NF], const double dacc[SE3_ND], float *__restrict__ dst,
                                                    SE3Smem &smu) {
   SE3Red &sm = smu.red;
@@ -562,24 +677,7 @@ __device__ __forceinline__ void block_reduce_store(const float acc[SE3_NF], cons
 #pragma unroll
   for (int j = 0; j < SE3_ND; j++) sm.d[j][threadIdx.x] = dacc[j];
   __syncthreads();
-  for (int row = wid; row < SE3_NF + SE3_ND; row += SE3_THREADS / 32) {
-    if (row < SE3_NF) {
-      float v = 0.0f;
-#pragma unroll
-      for (int k = 0; k < SE3_THREADS / 32; k++) v += sm.f[row][lane + 32 * k];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) dst[2 * SE3_ND + row] = v;
-    } else {
-      const int r = row - SE3_NF;
-      double v = 0.0;
-#pragma unroll
-      for (int k = 0; k < SE3_THREADS / 32; k++) v += sm.d[r][lane + 32 * k];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) reinterpret_cast<double *>(dst)[r] = v;
-    }
-  }
+  reduce_rows(sm, dst, lane, wid);
   // No fence here: the record is published by the release-ordered completion ticket below (the CTA barrier
   // orders these stores before thread 0's gpu-scope release; a per-thread __threadfence would also flush L1
   // -- CCTL.IVALL -- after every record and throw away the tap locality of the next one).
@@ -609,6 +707,9 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
   __shared__ double sdtot[SE3_ND];
   __shared__ int sCode, sIsLast, sNext;
   __shared__ __align__(16) SE3State sState;  // the LM step works on a shared-memory copy (a thread-local one lived in local memory)
+  __shared__ LmPre sPre;
+  int lmSeq = 0;  // LM steps this CTA has run (CTA-uniform)
+  if (threadIdx.x < 2) sPre.ready[threadIdx.x] = 0;
 
   unsigned ticket = 0;
   if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
@@ -666,7 +767,8 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
       for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
       for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-      const int nRecs = (n + prm.recPoints - 1) / prm.recPoints;
+      const int recPoints = prm.recPointsLvl[level];
+      const int nRecs = (n + recPoints - 1) / recPoints;
       const int nch = (nRecs + prm.recsPerItem - 1) / prm.recsPerItem;
       const int rec0 = chunk * prm.recsPerItem, rec1 = min(nRecs, rec0 + prm.recsPerItem);
       for (int rec = rec0; rec < rec1; rec++) {
@@ -676,9 +778,9 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
 #pragma unroll
           for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
         }
-        const int begin = rec * prm.recPoints;
-        const int end = min(n, begin + prm.recPoints);
-        eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
+        const int begin = rec * recPoints;
+        const int end = min(n, begin + recPoints);
+        eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps, threadIdx.x);
         float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
         block_reduce_store(acc, dacc, dst, sm);
       }
@@ -706,7 +808,9 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
       }
       __syncthreads();
       haveState = true;
-      if (threadIdx.x == 0) sNext = lm_step(&sState, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr);
+      lmSeq++;
+      if (threadIdx.x == 0) sNext = lm_step(&sState, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr, &sPre, lmSeq);
+      else lm_prework(stot, sdtot, &sPre, lmSeq, threadIdx.x);
       __syncthreads();
       if (sNext == 1) {  // the next evaluation is a single work item: keep it (the header is the first 64 bytes of the state)
         const int4 *sp4 = reinterpret_cast<const int4 *>(&sState);
@@ -771,6 +875,266 @@ __global__ void k_se3_init(const SE3Pair *__restrict__ pairs, SE3State *__restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The live tracker: ONE pair per thread-block cluster (SlamSystem's tracking thread has exactly one frame to track).
+// The work-queue kernel above buys batch throughput with global-memory hand-offs: every evaluation of a pair costs a
+// fence + queue publication, a poll, a header load through L2, a release ticket per record and a state round trip --
+// about 11 us of fixed latency per evaluation, 30 evaluations per frame.  Here the pair lives in one cluster:
+//   * the LM state sits in the leader CTA's shared memory; the other CTAs read the evaluation header from it over DSMEM;
+//   * a CTA is LIVE_GROUPS groups of SE3_THREADS threads; group g of CTA r takes records myGroup, myGroup + G, ... and
+//     reduces each with the SAME thread-strided order and the same tree as block_reduce_store (named barrier per group),
+//     into the CTA's own shared memory;
+//   * after one cluster barrier the leader gathers the records over DSMEM, sums them in record order and runs lm_step;
+//     a second cluster barrier publishes the next header.
+// Two hardware barriers per evaluation instead of five global-memory round trips.  Record boundaries, the order inside a
+// record and the order of the records are those of k_se3_track, so for a given record size both kernels return the same
+// bits (tests/test_gpu_se3.py::test_live_cluster_kernel_matches_queue_kernel).
+// ---------------------------------------------------------------------------------------------
+#define LIVE_GROUPS 4
+#define LIVE_THREADS (LIVE_GROUPS * SE3_THREADS)
+
+__device__ __forceinline__ void group_bar(const int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(SE3_THREADS) : "memory");
+}
+
+// block_reduce_store for one group of a larger CTA: same parking layout, same row sums, same shuffle tree
+__device__ __forceinline__ void group_reduce_store(const float acc[SE3_NF], const double dacc[SE3_ND], float *dst, SE3Red &sm,
+                                                   const int tid, const int bar) {
+  const int lane = tid & 31, wid = tid >> 5;
+  group_bar(bar);  // every thread of the group has left eval_range: the tap slots may be overwritten
+#pragma unroll
+  for (int j = 0; j < SE3_NF; j++) sm.f[j][tid] = acc[j];
+#pragma unroll
+  for (int j = 0; j < SE3_ND; j++) sm.d[j][tid] = dacc[j];
+  group_bar(bar);
+  reduce_rows(sm, dst, lane, wid);
+  group_bar(bar);  // the scratch is free for the group's next record
+}
+
+#ifndef LIVE_NP
+#define LIVE_NP 2  // points of a thread whose record loads and taps are in flight TOGETHER (r03d: 4 spills at 128 registers, 0.268 vs 0.245 ms)
+#endif
+union LiveSmem {
+  float4 taps[LIVE_NP * 4 * SE3_THREADS];  // [point][tap][thread]
+  SE3Red red;
+};
+
+// eval_range for the live kernel.  Same points per thread in the same order (thread t: begin + t + m * SE3_THREADS, m ascending),
+// so the same bits; but a live evaluation is a few points per thread and all latency, so instead of a steady-state software
+// pipeline the thread requests LIVE_NP records at once, then all their taps at once, and only then accumulates them in order:
+// two memory round trips per batch instead of one per point.
+__device__ __forceinline__ void eval_range_live(const RefPoint *__restrict__ pts, int begin, int end, const float4 *__restrict__ G,
+                                                uint8_t *__restrict__ mask, const EvalConst &c, float acc[SE3_NF], double dacc[SE3_ND],
+                                                float4 *tapbuf, const int tid) {
+  const float4 *pts4 = reinterpret_cast<const float4 *>(pts);
+  float4 *mySlot = tapbuf + tid;
+  for (int base = begin; base < end; base += LIVE_NP * SE3_THREADS) {  // group-uniform trip count
+    float4 raw[LIVE_NP];
+#pragma unroll
+    for (int s = 0; s < LIVE_NP; s++) {
+      const int i = base + tid + s * SE3_THREADS;
+      raw[s] = i < end ? __ldg(pts4 + i) : make_float4(0, 0, 0, 0);
+    }
+    Pending pd[LIVE_NP];
+#pragma unroll
+    for (int s = 0; s < LIVE_NP; s++) {
+      if (base + tid + s * SE3_THREADS < end) warp_point(raw[s], c, G, mySlot + s * 4 * SE3_THREADS, pd[s]);
+      else pd[s].st = -1;
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+#pragma unroll
+    for (int s = 0; s < LIVE_NP; s++) {
+      if (pd[s].st > 0) {
+        const float4 *sl = mySlot + s * 4 * SE3_THREADS;
+        accumulate_point(pd[s], sl[0], sl[SE3_THREADS], sl[2 * SE3_THREADS], sl[3 * SE3_THREADS], c, mask, acc, dacc);
+      } else if (pd[s].st == 0 && mask) {
+        mask[pd[s].midx] = 0;
+      }
+    }
+  }
+}
+
+#ifdef SE3_LIVE_TIMING  // variant builds only: where a live evaluation spends its time (leader thread 0, nanoseconds)
+__device__ unsigned long long g_liveNs[64];  // [0..7]: evaluations, lm_step, wait at [A], whole kernel; [8 l + k]: level l -- count, [A] -> [B],
+                                             // header, first record, its reduction, further records, wait at [B], gather + sum
+#define LIVE_T(var) const unsigned long long var = global_timer_ns()
+#else
+#define LIVE_T(var)
+#endif
+
+// Cluster barrier that orders SHARED memory only.  barrier.cluster.arrive.release would put a MEMBAR.ALL.GPU in front of every
+// arrive (a cluster-scope release has to push this thread's global stores to L2: ~1 us with the level-1 mask stores in flight),
+// and nothing this kernel exchanges between CTAs lives in global memory.  What is exchanged -- the leader's header, every CTA's
+// records -- is written to the writer's OWN shared memory: the CTA-scope fence below (MEMBAR.SC.CTA, ~40 cycles) retires those
+// stores into the SM's shared memory before the thread arrives, and a peer's distributed-shared-memory load is issued only after
+// its wait has completed, so it reads the retired value.  (The wait is an acquire: ptxas emits CCTL.IVALL with it.)
+#ifndef LIVE_RELEASE_BARRIER
+__device__ __forceinline__ void cluster_barrier() {
+  __threadfence_block();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#else
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#endif
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_size() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// generic address of `p` (a shared-memory object of this CTA) inside CTA `rank` of the cluster
+template <typename T> __device__ __forceinline__ T *dsmem_ptr(T *p, const unsigned rank) {
+  unsigned long long out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
+  return reinterpret_cast<T *>(out);
+}
+
+// recsPerCta: record slots in every CTA's shared memory (>= ceil(maxChunks / (clusterSize * LIVE_GROUPS)) * LIVE_GROUPS)
+__global__ void __launch_bounds__(LIVE_THREADS, 1)
+k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __grid_constant__ SE3Params prm, lsd_trace_entry *traces,
+                 const int recsPerCta) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  LiveSmem *gsm = reinterpret_cast<LiveSmem *>(dsm);                                  // one per group
+  float *recs = reinterpret_cast<float *>(dsm + sizeof(LiveSmem) * LIVE_GROUPS);      // [recsPerCta][SE3_NRED]
+  __shared__ __align__(16) SE3State sState;
+  __shared__ float stot[SE3_NF];
+  __shared__ double sdtot[SE3_ND];
+  __shared__ int sNext;
+  __shared__ LmPre sPre;
+  int lmSeq = 0;
+  if (threadIdx.x < 2) sPre.ready[threadIdx.x] = 0;
+
+  const unsigned CL = cluster_size(), rank = cluster_rank();
+  const int pairIdx = blockIdx.x / CL;
+  const SE3Pair *P = pairs + pairIdx;
+  const int g = threadIdx.x / SE3_THREADS, tid = threadIdx.x % SE3_THREADS;
+  const int G = (int)CL * LIVE_GROUPS, myGroup = (int)rank * LIVE_GROUPS + g;
+
+  if (rank == 0 && threadIdx.x == 0) {  // k_se3_init
+    SE3State *L = &sState;
+    memset(L, 0, sizeof(SE3State));
+    for (int l = 0; l < NL; l++) L->n[l] = P->d_num[l];
+    for (int k = 0; k < 4; k++) L->q_cur[k] = P->q0[k];
+    for (int k = 0; k < 3; k++) L->t_cur[k] = P->t0[k];
+    L->aff_a = 1;
+    L->aff_a_lastIt = 1;
+    L->trackingWasGood = 1;
+    sNext = start_level(L, prm.maxLevel, prm);
+  }
+  const int4 *leadHdr = reinterpret_cast<const int4 *>(dsmem_ptr(&sState, 0));
+  const volatile int *leadNext = dsmem_ptr(&sNext, 0);
+  // the leader's view of every CTA's record slots is only needed by the leader, computed per use (mapa is one instruction)
+  const int CAP = (int)(sizeof(LiveSmem) * LIVE_GROUPS / (SE3_NRED * sizeof(float)));  // records the gather buffer (= the group scratch) holds
+
+  LIVE_T(tStart);
+  for (;;) {
+    LIVE_T(tA0);
+    cluster_barrier();  // [A] the leader's header / sNext are final; the leader has consumed the previous records
+    LIVE_T(tA);
+    if (*leadNext <= 0) break;
+    const int4 h0 = leadHdr[0], h1 = leadHdr[1], h2 = leadHdr[2], h3 = leadHdr[3];
+    const int level = h3.z, n = h3.w;
+    EvalConst c;
+    load_eval_const(prm, level, h0, h1, h2, h3, c);
+    uint8_t *mask = (level == prm.minLevel && !prm.permaref) ? P->mask : nullptr;
+    const int recPoints = prm.recPointsLvl[level];
+    const int nRecs = (n + recPoints - 1) / recPoints;
+#ifdef SE3_LIVE_TIMING
+    unsigned long long tH = global_timer_ns(), tE = tH, tR = tH;
+#endif
+    int slot = g;
+    for (int rec = myGroup; rec < nRecs; rec += G, slot += LIVE_GROUPS) {
+      float acc[SE3_NF];
+      double dacc[SE3_ND];
+#pragma unroll
+      for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
+      const int begin = rec * recPoints;
+      const int end = min(n, begin + recPoints);
+      eval_range_live(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, gsm[g].taps, tid);
+#ifdef SE3_LIVE_TIMING
+      if (rec == myGroup) tE = global_timer_ns();
+#endif
+      group_reduce_store(acc, dacc, recs + (size_t)slot * SE3_NRED, gsm[g].red, tid, 1 + g);
+#ifdef SE3_LIVE_TIMING
+      if (rec == myGroup) tR = global_timer_ns();
+#endif
+    }
+    LIVE_T(tD);
+    cluster_barrier();  // [B] every record of the evaluation is in its CTA's shared memory
+    LIVE_T(tB);
+    if (rank == 0) {
+      // gather (all threads, independent DSMEM loads) into the group scratch, then 38 threads sum their column in record order
+      float *buf = reinterpret_cast<float *>(dsm);
+      double ds = 0.0;
+      float fs = 0.0f;
+      for (int r0 = 0; r0 < nRecs; r0 += CAP) {
+        const int m = min(CAP, nRecs - r0);
+        for (int i = threadIdx.x; i < m * (SE3_NRED / 4); i += LIVE_THREADS) {  // one float4 per step
+          const int r = r0 + i / (SE3_NRED / 4), q4 = i % (SE3_NRED / 4);
+          const int grp = r % G, round = r / G;
+          const float *src = dsmem_ptr(recs, (unsigned)(grp / LIVE_GROUPS)) + (size_t)(round * LIVE_GROUPS + grp % LIVE_GROUPS) * SE3_NRED;
+          reinterpret_cast<float4 *>(buf)[i] = reinterpret_cast<const float4 *>(src)[q4];
+        }
+        __syncthreads();
+        // strictly sequential adds (record order is the contract), but the loads of 16 records are requested before the first
+        // add of the batch needs them
+        if (threadIdx.x < SE3_ND) {
+          const double *src = reinterpret_cast<const double *>(buf) + threadIdx.x;
+          for (int k0 = 0; k0 < m; k0 += 16) {
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = (k0 + k < m) ? src[(size_t)(k0 + k) * (SE3_NRED / 2)] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+              if (k0 + k < m) ds += v[k];
+          }
+        } else if (threadIdx.x < SE3_ND + SE3_NF) {
+          const float *src = buf + 2 * SE3_ND + (threadIdx.x - SE3_ND);
+          for (int k0 = 0; k0 < m; k0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = (k0 + k < m) ? src[(size_t)(k0 + k) * SE3_NRED] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+              if (k0 + k < m) fs += v[k];
+          }
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < SE3_ND) sdtot[threadIdx.x] = ds;
+      else if (threadIdx.x < SE3_ND + SE3_NF) stot[threadIdx.x - SE3_ND] = fs;
+      __syncthreads();
+      LIVE_T(tS);
+      lmSeq++;
+      if (threadIdx.x == 0) sNext = lm_step(&sState, stot, sdtot, prm, traces ? traces + (size_t)pairIdx * LSD_TRACE_CAP : nullptr, &sPre, lmSeq);
+      else lm_prework(stot, sdtot, &sPre, lmSeq, threadIdx.x);
+#ifdef SE3_LIVE_TIMING
+      if (threadIdx.x == 0) {
+        const unsigned long long tL = global_timer_ns();
+        g_liveNs[0] += 1; g_liveNs[1] += tL - tS; g_liveNs[2] += tA - tA0;
+        unsigned long long *L = g_liveNs + 8 * level;
+        L[0] += 1; L[1] += tB - tA; L[2] += tH - tA; L[3] += tE - tH; L[4] += tR - tE; L[5] += tD - tR; L[6] += tB - tD; L[7] += tS - tB;
+      }
+#endif
+    }
+  }
+#ifdef SE3_LIVE_TIMING
+  if (rank == 0 && threadIdx.x == 0) g_liveNs[3] += global_timer_ns() - tStart;
+#endif
+  if (rank == 0 && threadIdx.x < (int)(sizeof(SE3State) / 16))
+    reinterpret_cast<int4 *>(states + pairIdx)[threadIdx.x] = reinterpret_cast<const int4 *>(&sState)[threadIdx.x];
+  cluster_barrier();  // nobody leaves while a peer may still read its shared memory
+}
+
 struct SE3ScratchImpl {
   SE3Pair *d_pairs = nullptr;
   SE3Pair *h_pairs = nullptr;  // pinned
@@ -786,6 +1150,8 @@ struct SE3ScratchImpl {
   lsd_trace_entry *d_traces = nullptr;
   size_t tracesBytes = 0;
   int gridBlocks = 0;
+  int liveCluster = -1;  // -1: not probed; 0: k_se3_track_live cannot run here; else CTAs per cluster (16 where the device schedules it, else 8)
+  int liveSmemSet = 0;   // dynamic shared memory the kernel attribute currently allows
 };
 
 }  // namespace lsd
@@ -811,11 +1177,21 @@ void se3_scratch_free(lsd_ctx *ctx) {
   ctx->se3s = nullptr;
 }
 
+// points per partial record at `level`: the per-level setting, else the context-wide one, else the default
+int se3_record_points(const lsd_ctx *ctx, int level) {
+  if (ctx->se3RecordPointsLvl[level] > 0) return ctx->se3RecordPointsLvl[level];
+  return ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
+}
+
 static int se3_scratch_ensure(lsd_ctx *ctx, int n, bool wantTrace) {
   if (!ctx->se3s) ctx->se3s = new SE3Scratch();
   SE3Scratch *s = ctx->se3s;
-  const int recPoints = ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
-  const int maxChunks = (ctx->K.w[1] * ctx->K.h[1] + recPoints - 1) / recPoints;
+  int maxChunks = 1;  // records of the level that has the most of them (worst case: every pixel of the level carries depth)
+  for (int l = 1; l < NL; l++) {
+    const int rp = se3_record_points(ctx, l);
+    const int c = (ctx->K.w[l] * ctx->K.h[l] + rp - 1) / rp;
+    if (c > maxChunks) maxChunks = c;
+  }
   if (n > s->cap || maxChunks != s->maxChunks) {
     if (n < s->cap) n = s->cap;
     cudaFree(s->d_pairs);
@@ -874,7 +1250,7 @@ static SE3Params make_params(lsd_ctx *ctx, int nPairs) {
   prm.recsPerItem = ctx->se3RecsPerItem > 0 ? ctx->se3RecsPerItem : 1;
   prm.minLevel = LSD_SE3TRACKING_MIN_LEVEL;
   prm.maxLevel = LSD_SE3TRACKING_MAX_LEVEL - 1;
-  prm.recPoints = ctx->se3RecordPoints > 0 ? ctx->se3RecordPoints : SE3_REC;
+  for (int l = 0; l < NL; l++) prm.recPointsLvl[l] = se3_record_points(ctx, l);
   prm.permaref = ctx->se3Permaref ? 1 : 0;
   if (prm.permaref) prm.minLevel = prm.maxLevel = LSD_QUICK_KF_CHECK_LVL;
   prm.watchdogNs = 0;
@@ -993,6 +1369,70 @@ int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st) {
   return LSD_OK;
 }
 
+// ---- the live tracker: one cluster per pair (k_se3_track_live).  Returns 1 in *used when the launch was made, 0 when the
+// ---- batch is not eligible (too many pairs, clusters unavailable, records of a level do not fit): the caller then takes se3_launch.
+static int live_smem_bytes(const SE3Params &prm, int cluster, int *recsPerCta) {
+  const int G = cluster * LIVE_GROUPS;
+  *recsPerCta = LIVE_GROUPS * ((prm.maxChunks + G - 1) / G);
+  return (int)(sizeof(LiveSmem) * LIVE_GROUPS + (size_t)*recsPerCta * SE3_NRED * sizeof(float));
+}
+
+static int se3_launch_live(lsd_ctx *ctx, int m, bool wantTrace, cudaStream_t st, int *used) {
+  *used = 0;
+  SE3Scratch *s = ctx->se3s;
+  const int limit = ctx->se3LivePairs < 0 ? 2 : ctx->se3LivePairs;
+  if (m > limit || s->liveCluster == 0) return LSD_OK;
+  SE3Params prm = make_params(ctx, m);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  cfg.blockDim = dim3(LIVE_THREADS, 1, 1);
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (s->liveCluster < 0) {  // probe once per context: the largest cluster this device can co-schedule
+    static const int envCl = getenv("LSD_B200_SE3_LIVE_CLUSTER") ? atoi(getenv("LSD_B200_SE3_LIVE_CLUSTER")) : 0;  // experiments: 8 or 16
+    s->liveCluster = 0;
+    cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int cl = (envCl == 8 ? 8 : 16); cl >= 8; cl -= 8) {
+      int recsPerCta = 0;
+      const int bytes = live_smem_bytes(prm, cl, &recsPerCta);
+      if (bytes > 220 * 1024) continue;
+      if (cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) continue;
+      cfg.gridDim = dim3(cl, 1, 1);
+      cfg.dynamicSmemBytes = bytes;
+      attr[0].val.clusterDim.x = cl;
+      attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+      int nClusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nClusters, k_se3_track_live, &cfg) == cudaSuccess && nClusters >= 1) {
+        s->liveCluster = cl;
+        break;
+      }
+    }
+    cudaGetLastError();  // a failed probe is not an error of the call
+    if (s->liveCluster == 0) return LSD_OK;
+  }
+  const int cl = s->liveCluster;
+  int recsPerCta = 0;
+  const int bytes = live_smem_bytes(prm, cl, &recsPerCta);
+  if (bytes > 220 * 1024) return LSD_OK;  // a record size that small for this image size: the queue kernel takes it
+  // per device, cheap: set on every launch (a process may hold contexts on several devices)
+  LSD_CUDA(cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  LSD_CUDA(cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  cfg.gridDim = dim3(cl * m, 1, 1);
+  cfg.dynamicSmemBytes = bytes;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  lsd_trace_entry *d_tr = wantTrace ? s->d_traces : nullptr;
+  const SE3Pair *d_pairs = s->d_pairs;
+  SE3State *d_states = s->d_states;
+  LSD_CUDA(cudaLaunchKernelEx(&cfg, k_se3_track_live, d_pairs, d_states, prm, d_tr, recsPerCta));
+  ctx->launches += 1;
+  *used = 1;
+  return LSD_OK;
+}
+
 // ---- streamed variant for the host-image path: ONE persistent launch for all n prepared pairs, started before any
 // ---- frame has arrived; chunks of pairs are fed into its queue (k_se3_init with a base index) as their frames have been
 // ---- ingested on another stream.  The tracker leaves one CTA slot per SM free so that the ingest kernels of later chunks
@@ -1088,6 +1528,25 @@ int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
     }
     if (P.trackingWasGood) refs[i]->keyframe->numFramesTrackedOnThis++;
   }
+#ifdef SE3_LIVE_TIMING
+  {
+    static int calls = 0;
+    if (++calls % 100 == 0) {
+      unsigned long long h[64];
+      cudaMemcpyFromSymbol(h, g_liveNs, sizeof(h));
+      const double e = (double)(h[0] ? h[0] : 1);
+      std::fprintf(stderr, "[live timing] %d calls, %.1f evaluations/call, lm_step %.2f us, wait at [A] %.2f us per evaluation; kernel %.1f us/call\n", calls,
+                   e / calls, 1e-3 * h[1] / e, 1e-3 * h[2] / e, 1e-3 * h[3] / calls);
+      for (int l = 1; l < 5; l++) {
+        const unsigned long long *L = h + 8 * l;
+        const double c = (double)(L[0] ? L[0] : 1);
+        std::fprintf(stderr, "[live timing]   level %d: %.1f evaluations/call, [A]->[B] %.2f us = header %.2f + first record %.2f + its reduction %.2f + further records %.2f "
+                     "+ wait at [B] %.2f; gather+sum %.2f us\n", l, L[0] / (double)calls, 1e-3 * L[1] / c, 1e-3 * L[2] / c, 1e-3 * L[3] / c, 1e-3 * L[4] / c,
+                     1e-3 * L[5] / c, 1e-3 * L[6] / c, 1e-3 * L[7] / c);
+      }
+    }
+  }
+#endif
   ctx->lastAlgBytes = bytes;
   ctx->lastEvals = evals;
   ctx->lastKernelMs = kernelMs;
@@ -1104,7 +1563,10 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
     if (rc) return rc;
   }
   LSD_CUDA(cudaEventRecord(ctx->evA, st));
-  rc = se3_launch(ctx, 0, n, traces != nullptr, st);
+  int live = 0;
+  rc = se3_launch_live(ctx, n, traces != nullptr, st, &live);
+  if (rc) return rc;
+  if (!live) rc = se3_launch(ctx, 0, n, traces != nullptr, st);
   if (rc) return rc;
   LSD_CUDA(cudaEventRecord(ctx->evB, st));
   LSD_CUDA(cudaEventSynchronize(ctx->evB));
@@ -1198,9 +1660,9 @@ k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, f
   for (int j = 0; j < SE3_NF; j++) acc[j] = 0.0f;
 #pragma unroll
   for (int j = 0; j < SE3_ND; j++) dacc[j] = 0.0;
-  const int begin = blockIdx.x * prm.recPoints;
-  const int end = min(n, begin + prm.recPoints);
-  eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps);
+  const int begin = blockIdx.x * prm.recPointsLvl[level];
+  const int end = min(n, begin + prm.recPointsLvl[level]);
+  eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps, threadIdx.x);
   block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sm);
 }
 
@@ -1242,7 +1704,7 @@ int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double ref
   LSD_CUDA(cudaStreamSynchronize(st));
   float tot[SE3_NF] = {0};
   double dtot[SE3_ND] = {0};
-  const int nch = (hnum[level] + prm.recPoints - 1) / prm.recPoints;
+  const int nch = (hnum[level] + prm.recPointsLvl[level] - 1) / prm.recPointsLvl[level];
   for (int cidx = 0; cidx < nch; cidx++) {
     for (int j = 0; j < SE3_ND; j++) dtot[j] += reinterpret_cast<const double *>(&h[(size_t)cidx * SE3_NRED])[j];
     for (int j = 0; j < SE3_NF; j++) tot[j] += h[(size_t)cidx * SE3_NRED + 2 * SE3_ND + j];

@@ -72,6 +72,9 @@ SYMBOLS = {
     "lsd_ctx_set_se3_active_pairs": (_ip, [_vp, _ip]),
     "lsd_ctx_set_stencil_tma": (_ip, [_vp, _ip]),
     "lsd_ctx_set_se3_record_points": (_ip, [_vp, _ip]),
+    "lsd_ctx_set_se3_live_pairs": (_ip, [_vp, _ip]),
+    "lsd_ctx_set_live_tracking": (_ip, [_vp, _ip]),
+    "lsd_ctx_set_se3_record_points_per_level": (_ip, [_vp, _vp]),
     "lsd_frame_create": (_ip, [_vp, _ip, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch": (_ip, [_vp, _ip, _vp, _vp, _sz, _u, _vp]),
     "lsd_frame_create_batch_device": (_ip, [_vp, _ip, _vp, _vp, _u, _vp]),
@@ -259,6 +262,17 @@ class Context:
 
     def set_se3_record_points(self, n):
         _chk(self.L.lsd_ctx_set_se3_record_points(self.p, int(n)))
+
+    def set_se3_record_points_per_level(self, points):
+        """points[l] for level l (5 entries, entry 0 ignored; 0 = the context-wide record size)."""
+        arr = (C.c_int * 5)(*[int(v) for v in points])
+        _chk(self.L.lsd_ctx_set_se3_record_points_per_level(self.p, arr))
+
+    def set_live_tracking(self, enable=True):
+        _chk(self.L.lsd_ctx_set_live_tracking(self.p, int(bool(enable))))
+
+    def set_se3_live_pairs(self, n):
+        _chk(self.L.lsd_ctx_set_se3_live_pairs(self.p, int(n)))
 
     def set_se3_work_item_records(self, n):
         _chk(self.L.lsd_ctx_set_se3_work_item_records(self.p, int(n)))

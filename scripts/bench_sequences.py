@@ -42,7 +42,7 @@ def main():
         img, depth = synth.render(room, W, H, K, R, t, noise_seed=i)
         frames.append((img.cpu().numpy(), depth.cpu().numpy() if i == 0 else None))
     ctx = lsd_b200.Context(W, H, K, device=local)
-    ctx.set_se3_record_points(512)  # a context that tracks one live sequence (include/lsd_b200.h)
+    ctx.set_live_tracking(True)  # a context that tracks one live sequence (include/lsd_b200.h)
 
     def run(n):
         s = lsd_b200.SlamSystem(ctx, keep_keyframes=False)

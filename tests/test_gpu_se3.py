@@ -425,3 +425,53 @@ def test_two_contexts_run_concurrently_on_one_device(lsd, oracle):
         assert got[k] and all(g == want[k] for g in got[k]), f"thread {k}: result changed under concurrency"
     for c in (ctxB, ctxC, ctxA):
         c.close()
+
+
+@pytest.mark.parametrize("seed,wh", [(61, (640, 480)), (62, (1280, 960)), (63, (320, 240))])
+def test_live_cluster_kernel_matches_queue_kernel(lsd, oracle, seed, wh):
+    """k_se3_track_live (one thread-block cluster per pair: what a one-frame SlamSystem::trackFrame call runs on) against
+    k_se3_track (the batch work-queue kernel) on the same pair: same records, same order inside a record, same record order,
+    so every output -- pose, counters, the whole accept / reject trace, the refPixelWasGood mask -- must be identical bits,
+    for every record size; and the live result stays within the pose tolerance of the EXACT oracle."""
+    import ctypes as C
+    w, h = wh
+    d = make_oracle_pair(seed, w, h)
+    ctx, kf, fr, ref = _gpu_pair(lsd, d, w, h)
+    init = np.array([0, 0, 0, 1, 0, 0, 0.0])
+    d2 = make_oracle_pair(seed + 100, w, h)
+    kf2 = ctx.create_frame(d2["kf_img"], 2)
+    fr2 = ctx.create_frame(d2["fr_img"], 3)
+    kf2.set_idepth(d2["idepth"], d2["var"])
+    ref2 = ctx.create_refs([kf2])[0]
+
+    def snap(res, trace, frame):
+        raw = bytes(C.string_at(C.addressof(res), C.sizeof(res)))
+        rows = [tuple(t) for t in trace[: res.traceLen]]
+        return raw, rows, frame.refPixelWasGood().copy()
+
+    for pts in (0, 512, "live"):
+        if pts == "live":  # per-level record sizes of a live context (lsd_ctx_set_live_tracking)
+            ctx.set_live_tracking(True)
+        else:
+            ctx.set_se3_record_points(pts)
+        ctx.set_se3_live_pairs(0)  # work-queue kernel
+        rq, tq = ctx.se3_track(ref, fr, init, want_trace=True)
+        q = snap(rq, tq, fr)
+        rq2 = ctx.se3_track_batch([ref, ref2], [fr, fr2], [init, init])
+        q2 = [bytes(C.string_at(C.addressof(r), C.sizeof(r))) for r in rq2]
+        ctx.set_se3_live_pairs(2)  # cluster kernel for one and for two pairs
+        rl, tl = ctx.se3_track(ref, fr, init, want_trace=True)
+        l = snap(rl, tl, fr)
+        assert l[1] == q[1], f"accept / reject trace differs at record size {pts}"
+        assert l[0] == q[0], f"result struct differs at record size {pts}"
+        assert np.array_equal(l[2], q[2]), "refPixelWasGood mask"
+        rl2 = ctx.se3_track_batch([ref, ref2], [fr, fr2], [init, init])
+        assert [bytes(C.string_at(C.addressof(r), C.sizeof(r))) for r in rl2] == q2, "two pairs = two clusters"
+        ores, _ = oracle.se3_track(d["oref"], d["ofr"], init, 2)
+        assert rl.diverged == ores.diverged and rl.trackingWasGood == ores.trackingWasGood
+        assert np.linalg.norm(np.array(rl.frameToRef)[4:] - np.array(ores.frameToRef)[4:]) <= POSE_TOL
+        assert quat_angle(np.array(rl.frameToRef)[:4], np.array(ores.frameToRef)[:4]) <= POSE_TOL
+    ctx.set_live_tracking(False)
+    ctx.set_se3_record_points(0)
+    ctx.set_se3_live_pairs(-1)
+    ctx.close()
