@@ -380,6 +380,12 @@ float lsd_slam_ref_frame_score(float distanceSquared, float usage);
 int lsd_slam_destroy(lsd_slam_system *s);                 /* fullReset() = destroy + create */
 /* keep finished keyframes alive (upstream: KeyFrameGraph::keyframesAll) -- default 1; 0 frees them for long benches */
 int lsd_slam_set_keep_keyframes(lsd_slam_system *s, int keep);
+/* Pipelined stages inside lsd_slam_next_image (default 1): ingest, TrackingReference::importFrame and the tracker are queued back
+ * to back and synchronised once, by the tracker's result; updateKeyframe is queued and completed by the next call into this
+ * context that needs one of its results or rewrites a table it reads (at the latest the next image, after that image has been
+ * staged into pinned memory).  Stream order is unchanged, so results are bit-identical; the caller-visible semantics stay
+ * blocking.  0 = every stage synchronises on its own (the mapping of frame k is complete when the call returns). */
+int lsd_slam_set_pipelined(lsd_slam_system *s, int enable);
 /* optional: images handed to nextImage are still distorted and go through `und` first (undistort + ingest fused:
  * lib/App/InputThread.cpp:59-71 in one call); NULL = images are already undistorted */
 int lsd_slam_set_undistorter(lsd_slam_system *s, lsd_undistorter *und);

@@ -173,7 +173,19 @@ int ensure_stage(lsd_ctx *ctx, size_t hostBytes, size_t devBytes) {
   return LSD_OK;
 }
 
+int ctx_finish_pending(lsd_ctx *ctx) {
+  if (!ctx->pendingSync) return LSD_OK;
+  ctx->pendingSync = false;
+  LSD_CUDA(cudaStreamSynchronize(ctx->stream));
+  resolve_pending_means(ctx);
+  return LSD_OK;
+}
+
 int ensure_table(lsd_ctx *ctx, size_t bytes) {
+  if (ctx->pendingSync) {  // every writer of the pinned table passes through here first
+    int rc = ctx_finish_pending(ctx);
+    if (rc) return rc;
+  }
   if (bytes > ctx->tableBytes) {
     if (ctx->h_table) cudaFreeHost(ctx->h_table);
     if (ctx->d_table) cudaFree(ctx->d_table);
@@ -230,6 +242,10 @@ static void build_planes(lsd_ctx *ctx, int n, unsigned flags, cudaStream_t st) {
 // Frame::setDepth's bookkeeping (meanIdepth, numPoints) is produced by the setDepth / pyramid launch itself (k_idepth_pyramid):
 // prepare_mean_idepth sizes the buffers before that launch, schedule_mean_idepth queues the read-back behind it.
 int prepare_mean_idepth(lsd_ctx *ctx, int n, float **d_out2) {
+  if (ctx->pendingSync) {
+    int rc = ctx_finish_pending(ctx);
+    if (rc) return rc;
+  }
   ctx->pendingMeans.clear();  // leftovers of a call that failed before its synchronisation
   if (n > ctx->meansCap) {
     if (ctx->d_means) cudaFree(ctx->d_means);
@@ -378,6 +394,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->se3Permaref = false;
   ctx->se3RecsPerItem = 0;
   ctx->se3RecordPoints = 0;
+  ctx->deferSync = ctx->pendingSync = false;
   for (int &v : ctx->se3RecordPointsLvl) v = 0;
   ctx->se3LivePairs = std::getenv("LSD_B200_SE3_LIVE_PAIRS") ? std::atoi(std::getenv("LSD_B200_SE3_LIVE_PAIRS")) : -1;
   ctx->tmaUnavailable = false;
@@ -443,6 +460,7 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
 
 int lsd_ctx_synchronize(lsd_ctx *ctx) {
   LSD_ARG(ctx);
+  if (ctx->pendingSync) return ctx_finish_pending(ctx);
   LSD_CUDA(cudaStreamSynchronize(ctx->stream));
   return LSD_OK;
 }
@@ -551,7 +569,7 @@ int lsd_frame_create_batch_device(lsd_ctx *ctx, int n, const int *ids, const voi
   build_planes(ctx, n, flags, st);
   if (trace) cudaEventRecord(tev[2], st);
   const auto t1 = std::chrono::steady_clock::now();
-  LSD_CUDA(cudaStreamSynchronize(st));
+  if (!ctx->deferSync) LSD_CUDA(cudaStreamSynchronize(st));  // pipelined driver: the planes are consumed in stream order by the tracker
   if (trace && n > 1 && traced++ < 12) {
     const auto t2 = std::chrono::steady_clock::now();
     float msI = 0, msG = 0;
@@ -743,6 +761,10 @@ int lsd_frame_set_idepth_batch_device(lsd_ctx *ctx, int n, lsd_frame *const *f, 
 int lsd_frame_mean_idepth(lsd_ctx *ctx, lsd_frame *f, float *meanIdepth, int *numPoints) {
   LSD_ARG(ctx && f);
   if (!(f->built & FB_IDEPTH0)) { set_error("frame has no depth"); return LSD_ERR_STATE; }
+  if (!f->meanValid && ctx->pendingSync) {  // the deferred updateKeyframe may carry exactly this value
+    int rc0 = ctx_finish_pending(ctx);
+    if (rc0) return rc0;
+  }
   if (f->meanValid) {  // computed alongside the setDepth that produced the planes
     if (meanIdepth) *meanIdepth = f->meanIdepth;
     if (numPoints) *numPoints = f->numPoints;
@@ -916,12 +938,14 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
     tab[n + i] = slab;
     tab[2 * (size_t)n + i] = r->d_num;
   }
-  int rc = upload_ptrs(ctx, tab, st);
+  // pipelined driver: the frame created just before may still be waiting for ITS pointer list at offset 0 of the pinned table
+  const size_t tabOff = ctx->deferSync ? 256 : 0;
+  int rc = upload_ptrs(ctx, tab, st, tabOff);
   if (rc) return rc;
-  void **d = reinterpret_cast<void **>(ctx->d_table);
+  void **d = reinterpret_cast<void **>((char *)ctx->d_table + tabOff);
   launch_make_pointcloud(ctx, reinterpret_cast<uint8_t *const *>(d), reinterpret_cast<uint8_t *const *>(d + n),
                          reinterpret_cast<int *const *>(d + 2 * (size_t)n), n, offPts, offGrad, st);
-  LSD_CUDA(cudaStreamSynchronize(st));
+  if (!ctx->deferSync) LSD_CUDA(cudaStreamSynchronize(st));
   return LSD_OK;
 }
 

@@ -51,6 +51,11 @@ struct lsd_ctx {
   float *d_means, *h_means;
   int meansCap;
   std::vector<lsd_frame *> pendingMeans;
+  // Pipelined lock-step driver (slam.cu): while deferSync is set, frame creation, reference import and updateKeyframe queue their
+  // work and leave the final synchronisation to the next call that needs a result (the tracker's).  pendingSync = mapping work
+  // of the last frame may still be in flight together with the pinned tables its uploads read from: everything that rewrites
+  // such a table (ensure_table, the depth map's reference table, the mean-idepth read-back) finishes it first.
+  bool deferSync, pendingSync;
   bool stageTimed;  // evA/evB bracket the kernels of the last depth stage
   int descSlot;  // rotating slot of the depth-map descriptor uploads (depth.cu)
   HostPool *pool;
@@ -67,6 +72,7 @@ namespace lsd {
 
 int ensure_stage(lsd_ctx *ctx, size_t hostBytes, size_t devBytes);
 int ensure_table(lsd_ctx *ctx, size_t bytes);
+int ctx_finish_pending(lsd_ctx *ctx);  // api.cu: waits for deferred mapping work (no-op when there is none)
 int frame_ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need);  // api.cu: lazily builds planes (blocking)
 
 // pyramid.cu

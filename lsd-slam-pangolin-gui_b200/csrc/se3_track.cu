@@ -1569,10 +1569,14 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
   if (!live) rc = se3_launch(ctx, 0, n, traces != nullptr, st);
   if (rc) return rc;
   LSD_CUDA(cudaEventRecord(ctx->evB, st));
-  LSD_CUDA(cudaEventSynchronize(ctx->evB));
+  // one host synchronisation per call: the read-back of the states is queued behind the kernels and se3_collect waits for it;
+  // both events have completed by then
+  rc = se3_collect(ctx, n, refs, frames, results, traces, st, 0.0f);
+  if (rc) return rc;
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
-  return se3_collect(ctx, n, refs, frames, results, traces, st, ms);
+  ctx->lastKernelMs = ms;
+  return LSD_OK;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -63,6 +64,7 @@ struct lsd_slam_system {
   float kfMeanIdepth;
   bool kfMeanValid;
   int keepFinishedKeyframes;
+  bool pipelined;        // see lsd_slam_set_pipelined
   lsd_undistorter *und;  // optional: images arrive distorted, as at InputThread.cpp:59-62
   double stageSec[5];    // wall time spent in: frame ingest, reference import, tracking, updateKeyframe, keyframe switch
 };
@@ -89,6 +91,10 @@ int lsd_slam_create(lsd_ctx *ctx, lsd_slam_system **out) {
   s->kfMeanIdepth = 0;
   s->kfMeanValid = false;
   s->keepFinishedKeyframes = 1;
+  {
+    const char *e = std::getenv("LSD_B200_SLAM_PIPELINE");  // experiments: 0 = every stage synchronises on its own
+    s->pipelined = !(e && e[0] == '0');
+  }
   s->und = nullptr;
   for (double &v : s->stageSec) v = 0;
   int rc = lsd_depthmap_create(ctx, &s->dm);
@@ -99,6 +105,7 @@ int lsd_slam_create(lsd_ctx *ctx, lsd_slam_system **out) {
 
 int lsd_slam_destroy(lsd_slam_system *s) {
   if (!s) return LSD_OK;
+  ctx_finish_pending(s->ctx);
   if (s->ref) lsd_ref_release(s->ctx, s->ref);
   for (lsd_frame *f : s->keyframes) lsd_frame_release(s->ctx, f);
   if (s->kf) lsd_frame_release(s->ctx, s->kf);
@@ -110,6 +117,12 @@ int lsd_slam_destroy(lsd_slam_system *s) {
 int lsd_slam_set_keep_keyframes(lsd_slam_system *s, int keep) {
   LSD_ARG(s);
   s->keepFinishedKeyframes = keep;
+  return LSD_OK;
+}
+
+int lsd_slam_set_pipelined(lsd_slam_system *s, int enable) {
+  LSD_ARG(s);
+  s->pipelined = enable != 0;
   return LSD_OK;
 }
 
@@ -196,6 +209,16 @@ int lsd_slam_next_image(lsd_slam_system *s, int id, const uint8_t *image, size_t
     s->stageSec[k] += std::chrono::duration<double>(t1 - t0).count();
     t0 = t1;
   };
+  // Pipelined (default): frame ingest, reference import and the tracker are queued back to back and synchronised ONCE, by the
+  // tracker's result; updateKeyframe is queued and finished by the next call, AFTER that call has staged its image into pinned
+  // memory -- the mapping kernels of frame k run while the host copies frame k + 1.  Same kernels in the same stream order:
+  // not a bit changes.  The caller still sees blocking semantics: every entry point that reads a result of the mapping
+  // (or rewrites a table it reads) finishes it first (ctx_finish_pending).
+  struct DeferGuard {
+    lsd_ctx *ctx;
+    ~DeferGuard() { ctx->deferSync = false; }
+  } deferGuard = {ctx};
+  ctx->deferSync = s->pipelined;
   // a tracked frame needs image + gradient pyramids only; maxGradients(0) / gradients(0) are built lazily if it is promoted
   // to keyframe (propagateDepth asks for them)
   if ((rc = slam_new_frame(s, id, image, pitch, LSD_BUILD_TRACKING, &f))) return rc;

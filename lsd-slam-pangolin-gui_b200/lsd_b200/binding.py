@@ -137,6 +137,7 @@ SYMBOLS = {
     "lsd_slam_ref_frame_score": (_fp, [_fp, _fp]),
     "lsd_slam_destroy": (_ip, [_vp]),
     "lsd_slam_set_keep_keyframes": (_ip, [_vp, _ip]),
+    "lsd_slam_set_pipelined": (_ip, [_vp, _ip]),
     "lsd_slam_set_undistorter": (_ip, [_vp, _vp]),
     "lsd_slam_gt_depth_init": (_ip, [_vp, _ip, _vp, _sz, _vp, _vp]),
     "lsd_slam_random_init": (_ip, [_vp, _ip, _vp, _sz, _vp]),
@@ -759,6 +760,9 @@ class SlamSystem:
 
     def set_undistorter(self, und):
         _chk(self.ctx.L.lsd_slam_set_undistorter(self.p, und.p if und is not None else None))
+
+    def set_pipelined(self, enable):
+        _chk(self.ctx.L.lsd_slam_set_pipelined(self.p, int(bool(enable))))
 
     def _done(self, st):
         if st.tracked:

@@ -181,3 +181,42 @@ def test_batched_sequences_equal_separate_systems(lsd):
     for g in single + batch:
         g.close()
     ctx.close()
+
+
+def test_pipelined_driver_is_bit_identical_and_blocking_to_the_caller(lsd):
+    """lsd_slam_set_pipelined: with the stages of a frame queued back to back and updateKeyframe finished by the NEXT call
+    (csrc/slam.cu), every status and the final depth map equal the fully synchronous driver's bit for bit -- and a caller
+    that reads the keyframe's depth between two images (while the deferred mapping may still be in flight) sees the state
+    after that mapping, exactly as with blocking calls."""
+    w, h = 320, 240
+    K = synth.default_K(w, h)
+    room = synth.make_room(3)
+    traj = synth.trajectory(200, seed=3)[::4]
+    frames = [synth.render(room, w, h, K, R, t, noise_seed=i) for i, (R, t) in enumerate(traj)]
+    ctx = lsd.Context(w, h, K)
+    ctx.set_live_tracking(True)
+    runs = []
+    for pipelined in (True, False):
+        s = lsd.SlamSystem(ctx)
+        s.set_pipelined(pipelined)
+        sts = [s.gtDepthInit(frames[0][0].numpy(), 0, frames[0][1].numpy())]
+        mids = []
+        for i in range(1, len(frames)):
+            sts.append(s.nextImage(frames[i][0].numpy(), i))
+            if i % 7 == 0:  # a read between two images
+                kf = s.current_keyframe()
+                mids.append((kf.idepth(0).copy(), kf.idepthVar(1).copy(), kf.mean_idepth()))
+        kf = s.current_keyframe()
+        runs.append((sts, mids, [kf.idepth(l).copy() for l in range(5)], s.lines, s.counters()))
+        s.close()
+    a, b = runs
+    assert a[4] == b[4] and a[4]["keyframes"] >= 2 and a[4]["lost"] == 0
+    assert a[3] == b[3]
+    for x, y in zip(a[0], b[0]):
+        assert (x.tracked, x.isKeyframe, x.currentKeyframeId) == (y.tracked, y.isKeyframe, y.currentKeyframeId)
+        assert list(x.camToWorld) == list(y.camToWorld) and x.keyframeScore == y.keyframeScore
+    for (i0, v1, m), (j0, w1, n) in zip(a[1], b[1]):
+        assert np.array_equal(i0, j0, equal_nan=True) and np.array_equal(v1, w1, equal_nan=True) and m == n
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y, equal_nan=True)
+    ctx.close()
