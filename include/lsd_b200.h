@@ -109,13 +109,14 @@ int lsd_ctx_set_se3_work_item_records(lsd_ctx *ctx, int records);
 int lsd_ctx_set_se3_record_points(lsd_ctx *ctx, int points);
 /* Record size per pyramid level: points[l] for level l = 1 .. LSD_PYRAMID_LEVELS - 1 (points[0] is ignored: level 0 is never
  * tracked); 0 = the context-wide value of lsd_ctx_set_se3_record_points.  A live context wants every evaluation to be ONE
- * record per 128-thread group of its cluster with as few points per thread as the level allows, e.g. {0, 640, 256, 128, 128}
+ * record per 128-thread group of its cluster with as few points per thread as the level allows, e.g. {0, 768, 256, 128, 128}
  * at 640x480: a coarse level then costs one point per thread instead of four.  Like the context-wide value this defines the
  * summation order and nothing else. */
 int lsd_ctx_set_se3_record_points_per_level(lsd_ctx *ctx, const int *points);
 /* Convenience for the context of SlamSystem's tracking thread (one frame per call): picks the per-level record sizes for this
- * image size -- ceil(0.45 * pixels(level) / 64) rounded up to a multiple of 128, i.e. {640, 256, 128, 128} at 640x480 and
- * {2176, 640, 256, 128} at 1280x960.  enable = 0 returns to the context-wide record size. */
+ * image size -- ceil(0.6 * pixels(level) / 64) rounded up to a multiple of 128, i.e. {768, 256, 128, 128} at 640x480 and
+ * {2944, 768, 256, 128} at 1280x960: one record per 128-thread group of a 16-CTA cluster as long as at most 60 % of a level's
+ * pixels carry depth.  enable = 0 returns to the context-wide record size. */
 int lsd_ctx_set_live_tracking(lsd_ctx *ctx, int enable);
 /* SE3 tracking calls with at most `pairs` pairs run on the live kernel: ONE thread-block cluster per pair (16 CTAs x 512 threads
  * where the device co-schedules them, else 8), LM state in the leader CTA's shared memory, header and partial records exchanged

@@ -504,11 +504,11 @@ int lsd_ctx_set_live_tracking(lsd_ctx *ctx, int enable) {
     for (int &v : ctx->se3RecordPointsLvl) v = 0;
     return LSD_OK;
   }
-  // one record per 128-thread group of a 16-CTA cluster (64 groups) when about 45 % of a level's pixels carry depth -- the density
-  // of a semi-dense keyframe; a denser level simply takes a second round
+  // one record per 128-thread group of a 16-CTA cluster (64 groups) while at most 60 % of a level's pixels carry depth (a
+  // semi-dense keyframe of the bench scenes: 45 %); a denser level simply takes a second round
   for (int l = 1; l < NL; l++) {
     const long long px = (long long)ctx->K.w[l] * ctx->K.h[l];
-    long long p = (px * 45 / 100 + 63) / 64;
+    long long p = (px * 60 / 100 + 63) / 64;
     p = (p + 127) / 128 * 128;
     if (p < 128) p = 128;
     while ((px + p - 1) / p > 4096) p += 128;

@@ -600,84 +600,95 @@ __device__ __forceinline__ void eval_range(const RefPoint *__restrict__ pts, int
   cp_async_wait<0>();
 }
 
-// Block reduction through shared memory: every thread parks its 38 sums (column = thread), then warp w
-// reduces rows w, w+8, ...: 8 conflict-free LDS + one shuffle tree per row.  Fixed order => deterministic.
-struct SE3Red {
-  float f[SE3_NF][SE3_THREADS];
-  double d[SE3_ND][SE3_THREADS];
+// ---- the reduction of one record: 128 threads x (33 fp32 + 5 fp64) partial sums -> 38 numbers ------------------------------
+// Step 1, inside each warp, registers only: a PACKED butterfly.  A plain butterfly spends five shuffles per value (190 per
+// lane, most of them moving sums nobody needs); here, at the step with lane distance o, the two halves of every lane pair
+// split the values still to be reduced -- the lane with bit o clear keeps the even ones and hands over the odd ones, its
+// partner the other way round -- so the number of live values halves with every step: 17 + 9 + 5 + 3 + 2 shuffles for the 33
+// floats, 8 for the 5 doubles.  Every value still goes through the full tree (L, L^16), (.,.^8), (.,.^4), (.,.^2), (.,.^1), and
+// fp addition is commutative, so both lanes of a pair hold the same bits: the result is a pure function of the 32 inputs.
+// Step 2: the warps' sums meet in shared memory (688 bytes per group, double-buffered by record parity so that ONE barrier
+// per record suffices) and thread r adds them in warp order: v = (((0 + w0) + w1) + w2) + w3.
+// r03g: replaces a 22 KB parking area, 38 STS + 44 LDS + 65 SHFL per lane and three barriers (1.4 us per record of a live
+// evaluation).  Both tracker kernels use this one function, so they keep returning identical bits.
+template <typename T, int N, int O>
+__device__ __forceinline__ void packed_step(const T (&a)[N], const int (&ia)[N], T (&b)[(N + 1) / 2], int (&ib)[(N + 1) / 2], const bool upper) {
+#pragma unroll
+  for (int i = 0; i < N / 2; i++) {
+    const T keep = upper ? a[2 * i + 1] : a[2 * i];
+    const T give = upper ? a[2 * i] : a[2 * i + 1];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, give, O);
+    ib[i] = upper ? ia[2 * i + 1] : ia[2 * i];
+  }
+  if (N & 1) {  // the odd one out is kept by both halves
+    b[N / 2] = a[N - 1] + __shfl_xor_sync(0xffffffffu, a[N - 1], O);
+    ib[N / 2] = ia[N - 1];
+  }
+}
+
+// Warp-wide sums of N per-lane values: on return out[j] is the complete sum of value number row[j] (every value ends up on
+// at least one lane; lanes that hold the same value hold the same bits).
+template <typename T, int N>
+__device__ __forceinline__ void packed_warp_sum(const T (&v)[N], const int lane, T (&out)[(((((N + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2],
+                                                int (&row)[(((((N + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2]) {
+  constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2;
+  int i0[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) i0[i] = i;
+  T b1[N1], b2[N2], b3[N3], b4[N4];
+  int i1[N1], i2[N2], i3[N3], i4[N4];
+  packed_step<T, N, 16>(v, i0, b1, i1, (lane & 16) != 0);
+  packed_step<T, N1, 8>(b1, i1, b2, i2, (lane & 8) != 0);
+  packed_step<T, N2, 4>(b2, i2, b3, i3, (lane & 4) != 0);
+  packed_step<T, N3, 2>(b3, i3, b4, i4, (lane & 2) != 0);
+  packed_step<T, N4, 1>(b4, i4, out, row, (lane & 1) != 0);
+}
+
+struct SE3Red {  // per 128-thread group: the warps' sums of two consecutive records
+  float f[2][SE3_THREADS / 32][SE3_NF + 1];
+  double d[2][SE3_THREADS / 32][SE3_ND + 1];
 };
-// The tap slots of eval_range and the reduction scratch are never live at the same time (one CTA barrier separates them).
-union SE3Smem {
+struct SE3Smem {
   float4 taps[SE3_D * 4 * SE3_THREADS];  // [stage][tap][thread]: a warp's LDS.128 / cp.async rows are conflict-free
   SE3Red red;
 };
 
-// Rows of the parked sums one warp reduces: rows wid, wid + 4, ...  All of a warp's rows go through the steps TOGETHER
-// (loads of every row, then the four ordered adds of every row, then each level of the shuffle tree for every row), so the
-// dependent latencies of a row -- LDS, 4 FADD, 5 x (SHFL + FADD) -- are paid once per warp instead of once per row: 2.0 -> 0.3 us
-// per record.  Per row the operations and their order are exactly: v = (((0 + c0) + c1) + c2) + c3 over the four columns
-// lane + 32 k, then v += shfl_down(v, 16), 8, 4, 2, 1; lane 0 holds the row's sum.
-#define SE3_ROWS_PER_WARP ((SE3_NF + SE3_ND + SE3_THREADS / 32 - 1) / (SE3_THREADS / 32))
-__device__ __forceinline__ void reduce_rows(const SE3Red &sm, float *__restrict__ dst, const int lane, const int wid) {
+// `parity`: which half of the scratch this record uses (the caller alternates it record by record).
+// `Bar`: the barrier of the 128 threads that reduce the record (the CTA barrier in k_se3_track, a named one in k_se3_track_live).
+template <class Bar>
+__device__ __forceinline__ void reduce_record(const float (&acc)[SE3_NF], const double (&dacc)[SE3_ND], float *dst, SE3Red &sm, const int tid,
+                                              const int parity, Bar bar) {
+  const int lane = tid & 31, wid = tid >> 5;
   constexpr int NW = SE3_THREADS / 32;
-  constexpr int FR = (SE3_NF + NW - 1) / NW;  // float rows per warp (upper bound)
-  constexpr int DR = (SE3_ND + NW - 1) / NW;  // double rows per warp (upper bound)
-  float fv[FR];
-  double dv[DR];
-#pragma unroll
-  for (int i = 0; i < FR; i++) {
-    const int row = wid + NW * i;
+  {
+    float of[2];
+    int rf[2];
+    packed_warp_sum<float, SE3_NF>(acc, lane, of, rf);
+    sm.f[parity][wid][rf[0]] = of[0];
+    sm.f[parity][wid][rf[1]] = of[1];
+    double od[1];
+    int rd[1];
+    packed_warp_sum<double, SE3_ND>(dacc, lane, od, rd);
+    sm.d[parity][wid][rd[0]] = od[0];
+  }
+  bar();
+  if (tid < SE3_NF) {
     float v = 0.0f;
-    if (row < SE3_NF) {
 #pragma unroll
-      for (int k = 0; k < NW; k++) v += sm.f[row][lane + 32 * k];
-    }
-    fv[i] = v;
-  }
-  // double rows: row index SE3_NF + r is handled by warp (SE3_NF + r) % NW in the original layout (rows wid, wid + NW, ...)
-#pragma unroll
-  for (int i = 0; i < DR; i++) {
-    // the i-th double row of this warp: smallest r >= 0 with (SE3_NF + r) % NW == wid, then + NW * i
-    const int r = ((wid - SE3_NF % NW) + NW) % NW + NW * i;
+    for (int k = 0; k < NW; k++) v += sm.f[parity][k][tid];
+    dst[2 * SE3_ND + tid] = v;
+  } else if (tid < SE3_NF + SE3_ND) {
+    const int r = tid - SE3_NF;
     double v = 0.0;
-    if (r < SE3_ND) {
 #pragma unroll
-      for (int k = 0; k < NW; k++) v += sm.d[r][lane + 32 * k];
-    }
-    dv[i] = v;
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-#pragma unroll
-    for (int i = 0; i < FR; i++) fv[i] += __shfl_down_sync(0xffffffffu, fv[i], o);
-#pragma unroll
-    for (int i = 0; i < DR; i++) dv[i] += __shfl_down_sync(0xffffffffu, dv[i], o);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < FR; i++) {
-      const int row = wid + NW * i;
-      if (row < SE3_NF) dst[2 * SE3_ND + row] = fv[i];
-    }
-#pragma unroll
-    for (int i = 0; i < DR; i++) {
-      const int r = ((wid - SE3_NF % NW) + NW) % NW + NW * i;
-      if (r < SE3_ND) reinterpret_cast<double *>(dst)[r] = dv[i];
-    }
+    for (int k = 0; k < NW; k++) v += sm.d[parity][k][r];
+    reinterpret_cast<double *>(dst)[r] = v;
   }
 }
 
-__device__ __forceinline__ void block_reduce_store(const float acc[SE3_NF], const double dacc[SE3_ND], float *__restrict__ dst,
-                                                   SE3Smem &smu) {
-  SE3Red &sm = smu.red;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();  // every thread has left eval_range: the tap slots may be overwritten
-#pragma unroll
-  for (int j = 0; j < SE3_NF; j++) sm.f[j][threadIdx.x] = acc[j];
-#pragma unroll
-  for (int j = 0; j < SE3_ND; j++) sm.d[j][threadIdx.x] = dacc[j];
-  __syncthreads();
-  reduce_rows(sm, dst, lane, wid);
+__device__ __forceinline__ void block_reduce_store(const float (&acc)[SE3_NF], const double (&dacc)[SE3_ND], float *__restrict__ dst,
+                                                   SE3Smem &smu, const int parity) {
+  reduce_record(acc, dacc, dst, smu.red, threadIdx.x, parity, [] { __syncthreads(); });
   // No fence here: the record is published by the release-ordered completion ticket below (the CTA barrier
   // orders these stores before thread 0's gpu-scope release; a per-thread __threadfence would also flush L1
   // -- CCTL.IVALL -- after every record and throw away the tap locality of the next one).
@@ -782,7 +793,7 @@ k_se3_track(const SE3Pair *__restrict__ pairs, SE3State *states, float *partials
         const int end = min(n, begin + recPoints);
         eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps, threadIdx.x);
         float *dst = partials + ((size_t)pairIdx * prm.maxChunks + rec) * SE3_NRED;
-        block_reduce_store(acc, dacc, dst, sm);
+        block_reduce_store(acc, dacc, dst, sm, rec & 1);
       }
       if (nch > 1) {
         if (threadIdx.x == 0) sIsLast = (atom_add_acq_rel(&S->done, 1u) == (unsigned)(nch - 1));
@@ -882,7 +893,7 @@ __global__ void k_se3_init(const SE3Pair *__restrict__ pairs, SE3State *__restri
 // about 11 us of fixed latency per evaluation, 30 evaluations per frame.  Here the pair lives in one cluster:
 //   * the LM state sits in the leader CTA's shared memory; the other CTAs read the evaluation header from it over DSMEM;
 //   * a CTA is LIVE_GROUPS groups of SE3_THREADS threads; group g of CTA r takes records myGroup, myGroup + G, ... and
-//     reduces each with the SAME thread-strided order and the same tree as block_reduce_store (named barrier per group),
+//     reduces each with the SAME thread-strided order and the same reduction as k_se3_track (reduce_record, named barrier per group),
 //     into the CTA's own shared memory;
 //   * after one cluster barrier the leader gathers the records over DSMEM, sums them in record order and runs lm_step;
 //     a second cluster barrier publishes the next header.
@@ -897,24 +908,10 @@ __device__ __forceinline__ void group_bar(const int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(SE3_THREADS) : "memory");
 }
 
-// block_reduce_store for one group of a larger CTA: same parking layout, same row sums, same shuffle tree
-__device__ __forceinline__ void group_reduce_store(const float acc[SE3_NF], const double dacc[SE3_ND], float *dst, SE3Red &sm,
-                                                   const int tid, const int bar) {
-  const int lane = tid & 31, wid = tid >> 5;
-  group_bar(bar);  // every thread of the group has left eval_range: the tap slots may be overwritten
-#pragma unroll
-  for (int j = 0; j < SE3_NF; j++) sm.f[j][tid] = acc[j];
-#pragma unroll
-  for (int j = 0; j < SE3_ND; j++) sm.d[j][tid] = dacc[j];
-  group_bar(bar);
-  reduce_rows(sm, dst, lane, wid);
-  group_bar(bar);  // the scratch is free for the group's next record
-}
-
 #ifndef LIVE_NP
 #define LIVE_NP 2  // points of a thread whose record loads and taps are in flight TOGETHER (r03d: 4 spills at 128 registers, 0.268 vs 0.245 ms)
 #endif
-union LiveSmem {
+struct LiveSmem {
   float4 taps[LIVE_NP * 4 * SE3_THREADS];  // [point][tap][thread]
   SE3Red red;
 };
@@ -1030,8 +1027,6 @@ k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __gr
   }
   const int4 *leadHdr = reinterpret_cast<const int4 *>(dsmem_ptr(&sState, 0));
   const volatile int *leadNext = dsmem_ptr(&sNext, 0);
-  // the leader's view of every CTA's record slots is only needed by the leader, computed per use (mapa is one instruction)
-  const int CAP = (int)(sizeof(LiveSmem) * LIVE_GROUPS / (SE3_NRED * sizeof(float)));  // records the gather buffer (= the group scratch) holds
 
   LIVE_T(tStart);
   for (;;) {
@@ -1063,7 +1058,7 @@ k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __gr
 #ifdef SE3_LIVE_TIMING
       if (rec == myGroup) tE = global_timer_ns();
 #endif
-      group_reduce_store(acc, dacc, recs + (size_t)slot * SE3_NRED, gsm[g].red, tid, 1 + g);
+      reduce_record(acc, dacc, recs + (size_t)slot * SE3_NRED, gsm[g].red, tid, (slot / LIVE_GROUPS) & 1, [g] { group_bar(1 + g); });
 #ifdef SE3_LIVE_TIMING
       if (rec == myGroup) tR = global_timer_ns();
 #endif
@@ -1072,27 +1067,29 @@ k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __gr
     cluster_barrier();  // [B] every record of the evaluation is in its CTA's shared memory
     LIVE_T(tB);
     if (rank == 0) {
-      // gather (all threads, independent DSMEM loads) into the group scratch, then 38 threads sum their column in record order
+      // gather: every thread fetches ONE float4 of one record over DSMEM (a thread that issues several distributed-shared-memory
+      // loads gets them back one after the other -- r03h: 16 loads per thread cost 1.3 us, one load per thread 0.3 us) into the
+      // groups' scratch; then 38 threads sum their column in record order, 16 local loads in flight ahead of the adds
+      constexpr int CAP = (int)(sizeof(LiveSmem) * LIVE_GROUPS / (SE3_NRED * sizeof(float)));  // records the scratch holds
       float *buf = reinterpret_cast<float *>(dsm);
+      const int gShift = __ffs(G) - 1;  // G = 32 or 64
       double ds = 0.0;
       float fs = 0.0f;
       for (int r0 = 0; r0 < nRecs; r0 += CAP) {
         const int m = min(CAP, nRecs - r0);
-        for (int i = threadIdx.x; i < m * (SE3_NRED / 4); i += LIVE_THREADS) {  // one float4 per step
-          const int r = r0 + i / (SE3_NRED / 4), q4 = i % (SE3_NRED / 4);
-          const int grp = r % G, round = r / G;
-          const float *src = dsmem_ptr(recs, (unsigned)(grp / LIVE_GROUPS)) + (size_t)(round * LIVE_GROUPS + grp % LIVE_GROUPS) * SE3_NRED;
+        for (int i = threadIdx.x; i < m * (SE3_NRED / 4); i += LIVE_THREADS) {
+          const int rl = i / (SE3_NRED / 4), q4 = i - rl * (SE3_NRED / 4);
+          const int r = r0 + rl, grp = r & (G - 1), round = r >> gShift;
+          const float *src = dsmem_ptr(recs, (unsigned)(grp / LIVE_GROUPS)) + (round * LIVE_GROUPS + grp % LIVE_GROUPS) * SE3_NRED;
           reinterpret_cast<float4 *>(buf)[i] = reinterpret_cast<const float4 *>(src)[q4];
         }
         __syncthreads();
-        // strictly sequential adds (record order is the contract), but the loads of 16 records are requested before the first
-        // add of the batch needs them
         if (threadIdx.x < SE3_ND) {
           const double *src = reinterpret_cast<const double *>(buf) + threadIdx.x;
           for (int k0 = 0; k0 < m; k0 += 16) {
             double v[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = (k0 + k < m) ? src[(size_t)(k0 + k) * (SE3_NRED / 2)] : 0.0;
+            for (int k = 0; k < 16; k++) v[k] = (k0 + k < m) ? src[(k0 + k) * (SE3_NRED / 2)] : 0.0;
 #pragma unroll
             for (int k = 0; k < 16; k++)
               if (k0 + k < m) ds += v[k];
@@ -1102,13 +1099,13 @@ k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __gr
           for (int k0 = 0; k0 < m; k0 += 16) {
             float v[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = (k0 + k < m) ? src[(size_t)(k0 + k) * SE3_NRED] : 0.0f;
+            for (int k = 0; k < 16; k++) v[k] = (k0 + k < m) ? src[(k0 + k) * SE3_NRED] : 0.0f;
 #pragma unroll
             for (int k = 0; k < 16; k++)
               if (k0 + k < m) fs += v[k];
           }
         }
-        __syncthreads();
+        if (r0 + CAP < nRecs) __syncthreads();  // the scratch is refilled
       }
       if (threadIdx.x < SE3_ND) sdtot[threadIdx.x] = ds;
       else if (threadIdx.x < SE3_ND + SE3_NF) stot[threadIdx.x - SE3_ND] = fs;
@@ -1380,7 +1377,9 @@ static int live_smem_bytes(const SE3Params &prm, int cluster, int *recsPerCta) {
 static int se3_launch_live(lsd_ctx *ctx, int m, bool wantTrace, cudaStream_t st, int *used) {
   *used = 0;
   SE3Scratch *s = ctx->se3s;
-  const int limit = ctx->se3LivePairs < 0 ? 2 : ctx->se3LivePairs;
+  // default: up to two pairs, and only while level 1 is small enough for one cluster (r03h, 1280x960: level 1 has ~140 k points,
+  // 17 per thread of a 16-CTA cluster; the work-queue kernel spreads them over the whole device: 1892 vs 1811 fps)
+  const int limit = ctx->se3LivePairs < 0 ? (ctx->K.w[1] * ctx->K.h[1] <= 131072 ? 2 : 0) : ctx->se3LivePairs;
   if (m > limit || s->liveCluster == 0) return LSD_OK;
   SE3Params prm = make_params(ctx, m);
   cudaLaunchConfig_t cfg;
@@ -1667,7 +1666,7 @@ k_se3_eval_once(const SE3Pair *__restrict__ P, const SE3State *__restrict__ S, f
   const int begin = blockIdx.x * prm.recPointsLvl[level];
   const int end = min(n, begin + prm.recPointsLvl[level]);
   eval_range(P->pts[level], begin, end, P->fgrad[level], mask, c, acc, dacc, sm.taps, threadIdx.x);
-  block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sm);
+  block_reduce_store(acc, dacc, partials + (size_t)blockIdx.x * SE3_NRED, sm, 0);
 }
 
 int se3_eval_impl(lsd_ctx *ctx, lsd_ref *ref, lsd_frame *frame, const double refToFrame[7], int level, float a, float b,
