@@ -31,6 +31,7 @@
 
 #include "ctx.cuh"
 #include "lie_dev.cuh"
+#include "reduce.cuh"
 
 namespace lsd {
 
@@ -600,95 +601,17 @@ __device__ __forceinline__ void eval_range(const RefPoint *__restrict__ pts, int
   cp_async_wait<0>();
 }
 
-// ---- the reduction of one record: 128 threads x (33 fp32 + 5 fp64) partial sums -> 38 numbers ------------------------------
-// Step 1, inside each warp, registers only: a PACKED butterfly.  A plain butterfly spends five shuffles per value (190 per
-// lane, most of them moving sums nobody needs); here, at the step with lane distance o, the two halves of every lane pair
-// split the values still to be reduced -- the lane with bit o clear keeps the even ones and hands over the odd ones, its
-// partner the other way round -- so the number of live values halves with every step: 17 + 9 + 5 + 3 + 2 shuffles for the 33
-// floats, 8 for the 5 doubles.  Every value still goes through the full tree (L, L^16), (.,.^8), (.,.^4), (.,.^2), (.,.^1), and
-// fp addition is commutative, so both lanes of a pair hold the same bits: the result is a pure function of the 32 inputs.
-// Step 2: the warps' sums meet in shared memory (688 bytes per group, double-buffered by record parity so that ONE barrier
-// per record suffices) and thread r adds them in warp order: v = (((0 + w0) + w1) + w2) + w3.
-// r03g: replaces a 22 KB parking area, 38 STS + 44 LDS + 65 SHFL per lane and three barriers (1.4 us per record of a live
-// evaluation).  Both tracker kernels use this one function, so they keep returning identical bits.
-template <typename T, int N, int O>
-__device__ __forceinline__ void packed_step(const T (&a)[N], const int (&ia)[N], T (&b)[(N + 1) / 2], int (&ib)[(N + 1) / 2], const bool upper) {
-#pragma unroll
-  for (int i = 0; i < N / 2; i++) {
-    const T keep = upper ? a[2 * i + 1] : a[2 * i];
-    const T give = upper ? a[2 * i] : a[2 * i + 1];
-    b[i] = keep + __shfl_xor_sync(0xffffffffu, give, O);
-    ib[i] = upper ? ia[2 * i + 1] : ia[2 * i];
-  }
-  if (N & 1) {  // the odd one out is kept by both halves
-    b[N / 2] = a[N - 1] + __shfl_xor_sync(0xffffffffu, a[N - 1], O);
-    ib[N / 2] = ia[N - 1];
-  }
-}
-
-// Warp-wide sums of N per-lane values: on return out[j] is the complete sum of value number row[j] (every value ends up on
-// at least one lane; lanes that hold the same value hold the same bits).
-template <typename T, int N>
-__device__ __forceinline__ void packed_warp_sum(const T (&v)[N], const int lane, T (&out)[(((((N + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2],
-                                                int (&row)[(((((N + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2]) {
-  constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2;
-  int i0[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) i0[i] = i;
-  T b1[N1], b2[N2], b3[N3], b4[N4];
-  int i1[N1], i2[N2], i3[N3], i4[N4];
-  packed_step<T, N, 16>(v, i0, b1, i1, (lane & 16) != 0);
-  packed_step<T, N1, 8>(b1, i1, b2, i2, (lane & 8) != 0);
-  packed_step<T, N2, 4>(b2, i2, b3, i3, (lane & 4) != 0);
-  packed_step<T, N3, 2>(b3, i3, b4, i4, (lane & 2) != 0);
-  packed_step<T, N4, 1>(b4, i4, out, row, (lane & 1) != 0);
-}
-
-struct SE3Red {  // per 128-thread group: the warps' sums of two consecutive records
-  float f[2][SE3_THREADS / 32][SE3_NF + 1];
-  double d[2][SE3_THREADS / 32][SE3_ND + 1];
-};
+// The reduction of one record (reduce.cuh): 128 threads x (33 fp32 + 5 fp64) partial sums -> 38 numbers.  Both tracker kernels use
+// this one function, so they keep returning identical bits.
+typedef RecordRed<SE3_NF, SE3_ND, SE3_THREADS / 32> SE3Red;  // per 128-thread group: the warps' sums of two consecutive records
 struct SE3Smem {
   float4 taps[SE3_D * 4 * SE3_THREADS];  // [stage][tap][thread]: a warp's LDS.128 / cp.async rows are conflict-free
   SE3Red red;
 };
 
-// `parity`: which half of the scratch this record uses (the caller alternates it record by record).
-// `Bar`: the barrier of the 128 threads that reduce the record (the CTA barrier in k_se3_track, a named one in k_se3_track_live).
-template <class Bar>
-__device__ __forceinline__ void reduce_record(const float (&acc)[SE3_NF], const double (&dacc)[SE3_ND], float *dst, SE3Red &sm, const int tid,
-                                              const int parity, Bar bar) {
-  const int lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = SE3_THREADS / 32;
-  {
-    float of[2];
-    int rf[2];
-    packed_warp_sum<float, SE3_NF>(acc, lane, of, rf);
-    sm.f[parity][wid][rf[0]] = of[0];
-    sm.f[parity][wid][rf[1]] = of[1];
-    double od[1];
-    int rd[1];
-    packed_warp_sum<double, SE3_ND>(dacc, lane, od, rd);
-    sm.d[parity][wid][rd[0]] = od[0];
-  }
-  bar();
-  if (tid < SE3_NF) {
-    float v = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NW; k++) v += sm.f[parity][k][tid];
-    dst[2 * SE3_ND + tid] = v;
-  } else if (tid < SE3_NF + SE3_ND) {
-    const int r = tid - SE3_NF;
-    double v = 0.0;
-#pragma unroll
-    for (int k = 0; k < NW; k++) v += sm.d[parity][k][r];
-    reinterpret_cast<double *>(dst)[r] = v;
-  }
-}
-
 __device__ __forceinline__ void block_reduce_store(const float (&acc)[SE3_NF], const double (&dacc)[SE3_ND], float *__restrict__ dst,
                                                    SE3Smem &smu, const int parity) {
-  reduce_record(acc, dacc, dst, smu.red, threadIdx.x, parity, [] { __syncthreads(); });
+  reduce_record<SE3_NF, SE3_ND, SE3_THREADS / 32>(acc, dacc, dst, smu.red, threadIdx.x, parity, [] { __syncthreads(); });
   // No fence here: the record is published by the release-ordered completion ticket below (the CTA barrier
   // orders these stores before thread 0's gpu-scope release; a per-thread __threadfence would also flush L1
   // -- CCTL.IVALL -- after every record and throw away the tap locality of the next one).
@@ -1058,7 +981,7 @@ k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __gr
 #ifdef SE3_LIVE_TIMING
       if (rec == myGroup) tE = global_timer_ns();
 #endif
-      reduce_record(acc, dacc, recs + (size_t)slot * SE3_NRED, gsm[g].red, tid, (slot / LIVE_GROUPS) & 1, [g] { group_bar(1 + g); });
+      reduce_record<SE3_NF, SE3_ND, SE3_THREADS / 32>(acc, dacc, recs + (size_t)slot * SE3_NRED, gsm[g].red, tid, (slot / LIVE_GROUPS) & 1, [g] { group_bar(1 + g); });
 #ifdef SE3_LIVE_TIMING
       if (rec == myGroup) tR = global_timer_ns();
 #endif

@@ -28,6 +28,7 @@
 
 #include "ctx.cuh"
 #include "lie_dev.cuh"
+#include "reduce.cuh"
 
 namespace lsd {
 
@@ -104,6 +105,8 @@ struct S3State {
   S3Res lastErr, finalRes;
   float sums[41];  // A6, b6, A4, b4 of the evaluation the current outer iteration started from (undivided)
   int nc;
+  float Adiv[36];  // the same, assembled into the 7x7 system and divided by num_constraints: 28 upper-triangle entries (row-major)
+                   // + 7 right-hand sides -- kept so that a rejected step re-solves with a new lambda without re-dividing
   // outputs that accumulate over the track: kept here (the state is only ever read through L2) and written to Sim3Out once,
   // when the track finishes -- a read-modify-write of Sim3Out from whichever SM runs the LM step could hit a stale L1 line
   int n[NL], nRes[NL], nWarp[NL];
@@ -405,44 +408,16 @@ __device__ __forceinline__ void s3_eval_range(const RefPoint *__restrict__ pts, 
   s3_cp_async_wait<0>();
 }
 
-struct S3Red {
-  float f[S3_NF][S3_THREADS];
-  double d[S3_ND][S3_THREADS];
-};
-union S3Smem {  // staging slots and reduction scratch are never live at the same time (one CTA barrier separates them)
+typedef RecordRed<S3_NF, S3_ND, S3_THREADS / 32> S3Red;
+struct S3Smem {
   S3Slots slots;
   S3Red red;
 };
 
-// fixed-order block reduction of the per-thread sums into one partial record (same scheme as the SE3 tracker)
-__device__ __forceinline__ void s3_block_reduce_store(const float acc[S3_NF], const double dacc[S3_ND], float *__restrict__ dst, S3Smem &smu) {
-  S3Red &sm = smu.red;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < S3_NF; j++) sm.f[j][threadIdx.x] = acc[j];
-#pragma unroll
-  for (int j = 0; j < S3_ND; j++) sm.d[j][threadIdx.x] = dacc[j];
-  __syncthreads();
-  for (int row = wid; row < S3_NF + S3_ND; row += S3_THREADS / 32) {
-    if (row < S3_NF) {
-      float v = 0.0f;
-#pragma unroll
-      for (int k = 0; k < S3_THREADS / 32; k++) v += sm.f[row][lane + 32 * k];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) dst[2 * S3_ND + row] = v;
-    } else {
-      const int r = row - S3_NF;
-      double v = 0.0;
-#pragma unroll
-      for (int k = 0; k < S3_THREADS / 32; k++) v += sm.d[r][lane + 32 * k];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) reinterpret_cast<double *>(dst)[r] = v;
-    }
-  }
-  __syncthreads();
+// fixed-order block reduction of the per-thread sums into one partial record (reduce.cuh: the SE3 tracker's scheme)
+__device__ __forceinline__ void s3_block_reduce_store(const float (&acc)[S3_NF], const double (&dacc)[S3_ND], float *dst, S3Smem &smu) {
+  reduce_record<S3_NF, S3_ND, S3_THREADS / 32>(acc, dacc, dst, smu.red, threadIdx.x, 0, [] { __syncthreads(); });
+  __syncthreads();  // the record (shared or global memory) is complete for the whole CTA; the scratch is free again
 }
 
 __device__ __forceinline__ bool s3_too_few(int size, int lvl, const Sim3Params &prm) {
@@ -503,14 +478,80 @@ __device__ void s3_flush(const S3State &S, Sim3Out *O) {
   }
 }
 
+// What two other warps of the CTA compute WHILE thread 0 runs the LM decision logic of s3_step (same operations on the same
+// operands as the one-thread path, so not a bit changes; the serial tail of an evaluation gets shorter):
+//   pre[0..34]  = the 7x7 normal equations of THIS evaluation: ls6 + the remapped ls4 terms, divided by num_constraints
+//                 (28 upper-triangle entries row by row, then the 7 right-hand sides): helper warp 1, one or two entries per lane
+//   pre[36..37] = affine-lighting estimate (fp64 square root + four fp64 divisions): one lane of helper warp 2
+// `ready[k] == seq` publishes part k for LM step number `seq` of this CTA (seq only grows: no reset).
+struct S3Pre {
+  volatile float pre[40];
+  volatile int ready[2];
+};
+__device__ __forceinline__ void s3_affine(const double *dtot, float *aL, float *bL) {
+  const double sxx = dtot[0], syy = dtot[1], sx = dtot[2], sy = dtot[3], sw = dtot[4];
+  const double aLd = sqrt((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+  *aL = (float)aLd;
+  *bL = (float)((sy - aLd * sx) / sw);
+}
+// entry e of the divided system: e < 28 -> A(a, c) with a <= c in row-major upper-triangle order; e >= 28 -> rhs[e - 28]
+__device__ __forceinline__ float s3_system_entry(const float *sums, const int e, const float nc) {
+  int a, c;
+  if (e < 28) {
+    a = 0;
+    int rem = e;
+    while (rem >= 7 - a) { rem -= 7 - a; a++; }
+    c = a + rem;
+  } else {
+    a = c = e - 28;
+  }
+  // index of row / column x inside the 4-parameter system (2, 3, 4, 6 -> 0, 1, 2, 3), -1 when x is not part of it
+  const int m4a = a == 2 ? 0 : a == 3 ? 1 : a == 4 ? 2 : a == 6 ? 3 : -1;
+  const int m4c = c == 2 ? 0 : c == 3 ? 1 : c == 4 ? 2 : c == 6 ? 3 : -1;
+  float v = 0.0f;
+  if (e < 28) {
+    if (c < 6) v = sums[Q_A6 + a * 6 - a * (a - 1) / 2 + (c - a)];
+    if (m4a >= 0 && m4c >= 0) v += sums[Q_A4 + m4a * 4 - m4a * (m4a - 1) / 2 + (m4c - m4a)];
+  } else {
+    if (a < 6) v = sums[Q_B6 + a];
+    if (m4a >= 0) v += sums[Q_B4 + m4a];
+  }
+  return v / nc;
+}
+__device__ __forceinline__ void s3_prework(const float *tot, const double *dtot, S3Pre *P, const int seq, const int t) {
+  if (t >= 32 && t < 64) {
+    const int lane = t - 32;
+    const float nc = (float)(2 * (int)tot[Q_CNT]);
+    P->pre[lane] = s3_system_entry(tot, lane, nc);
+    if (lane + 32 < 35) P->pre[lane + 32] = s3_system_entry(tot, lane + 32, nc);
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) P->ready[0] = seq;
+  } else if (t == 64) {
+    float aL, bL;
+    s3_affine(dtot, &aL, &bL);
+    P->pre[36] = aL;
+    P->pre[37] = bL;
+    __threadfence_block();
+    P->ready[1] = seq;
+  }
+}
+
 __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *tot, const double *dtot, const Sim3Params &prm,
-                        lsd_trace_entry *trace, S3Cmd &next) {
+                        lsd_trace_entry *trace, S3Cmd &next, const S3Pre *P = nullptr, const int seq = 0) {
   const int lvl = S.level;
   const int size = (int)tot[Q_CNT];
   S.pointUsage = tot[Q_USAGE] / (float)S.n[lvl];
-  const double sxx = dtot[0], syy = dtot[1], sx = dtot[2], sy = dtot[3], sw = dtot[4];
-  const double aLd = sqrt((syy - sy * sy / sw) / (sxx - sx * sx / sw));
-  const float aL = (float)aLd, bL = (float)((sy - aLd * sx) / sw);
+  // the affine estimate is only consumed when the step is accepted (or the level starts): fetched from the helper at that point
+  auto affine = [&](float &aL, float &bL) {
+    if (P) {
+      while (P->ready[1] != seq) {}
+      aL = P->pre[36];
+      bL = P->pre[37];
+    } else {
+      s3_affine(dtot, &aL, &bL);
+    }
+  };
   S3Res err;
   err.sumResD = tot[Q_RD];
   err.sumResP = tot[Q_RP];
@@ -539,8 +580,7 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
   float traceLambda = S.lambda;
   if (S.phase == 0) {
     S.lastErr = err;
-    S.a = aL;
-    S.b = bL;
+    affine(S.a, S.b);
     S.lambda = prm.s.lambdaInitial[lvl];
     S.iteration = 0;
     S.upToDate = false;
@@ -555,8 +595,7 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
     for (int i = 0; i < 3; i++) S.t[i] = S.tt[i];
     S.s = S.st;
     S.upToDate = false;
-    S.a = aL;
-    S.b = bL;
+    affine(S.a, S.b);
     if (err.mean / S.lastErr.mean > prm.s.convergenceEps[lvl]) S.iteration = maxIts;
     S.finalRes = S.lastErr = err;
     if (S.lambda <= 0.2f) S.lambda = 0; else S.lambda *= prm.s.lambdaSuccessFac;
@@ -608,40 +647,28 @@ __device__ bool s3_step(const Sim3Job *J, S3State &S, Sim3Out *O, const float *t
     S.nWarp[lvl]++;
     S.incTry = 0;
     S.upToDate = true;
+    // A = ls7.A / num_constraints; b = -ls7.b / num_constraints (ls7 = ls6 + the remapped ls4 terms)
+    if (P) {
+      while (P->ready[0] != seq) {}
+#pragma unroll
+      for (int e = 0; e < 35; e++) S.Adiv[e] = P->pre[e];
+    } else {
+      const float nc = (float)S.nc;
+      for (int e = 0; e < 35; e++) S.Adiv[e] = s3_system_entry(S.sums, e, nc);
+    }
   }
-  // A = ls7.A / num_constraints; b = -ls7.b / num_constraints; A(i,i) *= 1 + lambda; inc = A.ldlt().solve(b)
+  // A(i,i) *= 1 + lambda; inc = A.ldlt().solve(b)
   float A[49], rhs[7], inc[7];
   {
-#pragma unroll
-    for (int i = 0; i < 49; i++) A[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 7; i++) rhs[i] = 0;
-    int k = 0;
-    for (int a = 0; a < 6; a++) {
-      for (int c = a; c < 6; c++, k++) A[a * 7 + c] = A[c * 7 + a] = S.sums[Q_A6 + k];
-      rhs[a] = S.sums[Q_B6 + a];
-    }
-    const int remap[4] = {2, 3, 4, 6};
-    k = 0;
-    for (int a = 0; a < 4; a++) {
-      for (int c = a; c < 4; c++, k++) {
-        A[remap[a] * 7 + remap[c]] += S.sums[Q_A4 + k];
-        if (c != a) A[remap[c] * 7 + remap[a]] += S.sums[Q_A4 + k];
-      }
-      rhs[remap[a]] += S.sums[Q_B4 + a];
-    }
-    const float nc = (float)S.nc;
-    // A is symmetric by construction (both triangles were filled with the same sums): 28 divisions instead of 49, same values
+    int e = 0;
 #pragma unroll
     for (int a = 0; a < 7; a++)
 #pragma unroll
-      for (int c = a; c < 7; c++) {
-        const float v = A[a * 7 + c] / nc;
-        A[a * 7 + c] = v;
-        A[c * 7 + a] = v;
-      }
-    for (int i = 0; i < 7; i++) rhs[i] = rhs[i] / nc;
+      for (int c = a; c < 7; c++, e++) A[a * 7 + c] = A[c * 7 + a] = S.Adiv[e];
+#pragma unroll
+    for (int i = 0; i < 7; i++) rhs[i] = S.Adiv[28 + i];
     const float lam1 = 1 + S.lambda;
+#pragma unroll
     for (int i = 0; i < 7; i++) A[i * 7 + i] *= lam1;
   }
   ldlt_solve<float, 7>(A, rhs, inc);
@@ -731,6 +758,9 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, S3Track *tracks, Sim3Out *outs, f
   __shared__ int sCode, sIsLast, sMore;
   __shared__ __align__(16) S3State sState;
   __shared__ __align__(16) S3Cmd sNext;
+  __shared__ S3Pre sPre;
+  int lmSeq = 0;  // LM steps this CTA has run (CTA-uniform)
+  if (threadIdx.x < 2) sPre.ready[threadIdx.x] = 0;
 
   unsigned ticket = 0;
   if (threadIdx.x == 0) ticket = atomicAdd(q.head, 1u);
@@ -825,12 +855,14 @@ k_sim3_track(const Sim3Job *__restrict__ jobs, S3Track *tracks, Sim3Out *outs, f
       }
       __syncthreads();
       haveState = true;
+      lmSeq++;
+      if (threadIdx.x != 0) s3_prework(stot, sdtot, &sPre, lmSeq, threadIdx.x);
       if (threadIdx.x == 0) {
         S3Cmd next;
         next.op = 1;
         next.nPts = 0;
         Sim3Out *O = outs + (size_t)sState.stage * q.nTracks + track;
-        bool more = s3_step(J, sState, O, stot, sdtot, prm, traces ? traces + (size_t)track * LSD_TRACE_CAP : nullptr, next);
+        bool more = s3_step(J, sState, O, stot, sdtot, prm, traces ? traces + (size_t)track * LSD_TRACE_CAP : nullptr, next, &sPre, lmSeq);
         if (more) {
           next.nPts = sState.n[next.level];
         } else {
