@@ -432,6 +432,10 @@ def leg_track_map(lsd, dev, local_rank, args, cpu):
     counts = [int(x) for x in args.multi.split(",") if x.strip()]
     nmax = max(counts) if counts else 0
     if nmax > 1:
+        # batches of sequences run on the work-queue tracker: one record size for every level (the per-level sizes of a live
+        # context would cut the coarse levels into more work items than a batch needs)
+        ctx.set_live_tracking(False)
+        ctx.set_se3_record_points(int(os.environ.get("LSD_B200_BENCH_MULTI_REC", "512")))
         seqs = [frames] + [render_sequence(W, H, K, n, 100 + s, dev)[0] for s in range(1, min(nmax, 8))]
         import torch
         for m in counts:
