@@ -597,6 +597,13 @@ int lsd_frame_create_batch(lsd_ctx *ctx, int n, const int *ids, const uint8_t *c
   for (int i = 0; i < n; i++) LSD_ARG(images[i]);
   static const bool trace = std::getenv("LSD_B200_TRACE") != nullptr;  // host-side timing of the ingest steps on stderr
   static int traced = 0, traced1 = 0;
+  // the pinned staging buffer is reused chunk by chunk: only a single-chunk call may leave its copy unsynchronised
+  struct DeferRestore {
+    lsd_ctx *ctx;
+    bool saved;
+    ~DeferRestore() { ctx->deferSync = saved; }
+  } deferRestore = {ctx, ctx->deferSync};
+  if (n > CH) ctx->deferSync = false;
   for (int i0 = 0; i0 < n; i0 += CH) {
     const int m = (n - i0) < CH ? (n - i0) : CH;
     const auto t0 = std::chrono::steady_clock::now();
@@ -911,9 +918,11 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
     if (!(keyframes[i]->built & FB_IDEPTH_PYR)) needPyr.push_back(keyframes[i]->slab);
   }
   if (!needPyr.empty()) {
-    int rc = upload_ptrs(ctx, needPyr, st);
+    // pipelined driver: offset 0 of the pinned table may still be read by the copy of the frame list queued just before
+    const size_t pyrOff = ctx->deferSync ? 16384 : 0;
+    int rc = upload_ptrs(ctx, needPyr, st, pyrOff);
     if (rc) return rc;
-    launch_idepth_pyramid(ctx, reinterpret_cast<uint8_t *const *>(ctx->d_table), (int)needPyr.size(), st);
+    launch_idepth_pyramid(ctx, reinterpret_cast<uint8_t *const *>((char *)ctx->d_table + pyrOff), (int)needPyr.size(), st);
     LSD_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < n; i++) keyframes[i]->built |= FB_IDEPTH_PYR;
   }
@@ -939,7 +948,7 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
     tab[2 * (size_t)n + i] = r->d_num;
   }
   // pipelined driver: the frame created just before may still be waiting for ITS pointer list at offset 0 of the pinned table
-  const size_t tabOff = ctx->deferSync ? 256 : 0;
+  const size_t tabOff = ctx->deferSync ? 8192 : 0;  // room for the pointers of 1024 frames in front
   int rc = upload_ptrs(ctx, tab, st, tabOff);
   if (rc) return rc;
   void **d = reinterpret_cast<void **>((char *)ctx->d_table + tabOff);

@@ -99,6 +99,9 @@ int lsd_slam_create(lsd_ctx *ctx, lsd_slam_system **out) {
   for (double &v : s->stageSec) v = 0;
   int rc = lsd_depthmap_create(ctx, &s->dm);
   if (rc) { delete s; return rc; }
+  // the pipelined driver keeps two pointer lists of a frame in flight in the context's pinned table (frames at offset 0,
+  // tracking references at 8192): sized here once, so that no list is ever moved while a copy still reads it
+  if ((rc = ensure_table(ctx, 65536))) { lsd_depthmap_destroy(ctx, s->dm); delete s; return rc; }
   *out = s;
   return LSD_OK;
 }
@@ -337,6 +340,15 @@ int lsd_slam_next_image_batch(int n, lsd_slam_system *const *sys, const int *ids
     t0 = t1;
   };
   int rc;
+  // pipelined like lsd_slam_next_image: one synchronisation (the tracker's) for ingest + import + tracking, and the batched
+  // updateKeyframe -- queued LAST, after the keyframe switches -- is finished by the next call, after it has staged its images
+  struct DeferGuard {
+    lsd_ctx *ctx;
+    ~DeferGuard() { ctx->deferSync = false; }
+  } deferGuard = {ctx};
+  bool pipelined = true;
+  for (int i = 0; i < n; i++) pipelined = pipelined && sys[i]->pipelined;
+  ctx->deferSync = pipelined;
   std::vector<lsd_frame *> fr(n, nullptr);
   struct Guard {  // frames that nobody has taken over are dropped on every exit
     lsd_ctx *ctx;
@@ -424,24 +436,7 @@ int lsd_slam_next_image_batch(int n, lsd_slam_system *const *sys, const int *ids
   }
   lap(3);
 
-  // ---- one blocking mapping iteration per sequence, batched by kind
-  if (!upd.empty()) {
-    std::vector<lsd_depthmap *> dms;
-    std::vector<lsd_frame *> frames;
-    std::vector<char> setsDepth;
-    for (int i : upd) {
-      dms.push_back(sys[i]->dm);
-      frames.push_back(fr[i]);
-      setsDepth.push_back(!sys[i]->kf->depthHasBeenUpdatedFlag);
-    }
-    if ((rc = lsd_depth_update_keyframe_batch(ctx, (int)upd.size(), dms.data(), frames.data()))) return rc;
-    for (size_t k = 0; k < upd.size(); k++) {
-      const int i = upd[k];
-      if (setsDepth[k]) sys[i]->kfMeanValid = false;
-      fill_status(sys[i], ids[i], 1, 0, &toKf[8 * (size_t)i], &res[i], score[i], &st[i]);
-    }
-    lap(3);
-  }
+  // ---- one mapping iteration per sequence, batched by kind: keyframe switches first (they synchronise), updates last (deferred)
   if (!sw.empty()) {
     std::vector<lsd_depthmap *> dms;
     std::vector<lsd_frame *> frames;
@@ -472,6 +467,23 @@ int lsd_slam_next_image_batch(int n, lsd_slam_system *const *sys, const int *ids
       st[i].keyframeRescale = f->thisToParent_raw[7];
     }
     lap(4);
+  }
+  if (!upd.empty()) {
+    std::vector<lsd_depthmap *> dms;
+    std::vector<lsd_frame *> frames;
+    std::vector<char> setsDepth;
+    for (int i : upd) {
+      dms.push_back(sys[i]->dm);
+      frames.push_back(fr[i]);
+      setsDepth.push_back(!sys[i]->kf->depthHasBeenUpdatedFlag);
+    }
+    if ((rc = lsd_depth_update_keyframe_batch(ctx, (int)upd.size(), dms.data(), frames.data()))) return rc;
+    for (size_t k = 0; k < upd.size(); k++) {
+      const int i = upd[k];
+      if (setsDepth[k]) sys[i]->kfMeanValid = false;
+      fill_status(sys[i], ids[i], 1, 0, &toKf[8 * (size_t)i], &res[i], score[i], &st[i]);
+    }
+    lap(3);
   }
   return LSD_OK;  // the guard releases every frame that did not become a keyframe
 }
