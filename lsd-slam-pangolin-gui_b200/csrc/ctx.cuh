@@ -87,6 +87,7 @@ struct IdepthMapSrc {  // hypothesis planes Frame::setDepth reads (depth.cuh lay
 };
 void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st,
                                   float *d_statOut2 = nullptr);
+void launch_set_depth_and_pyramid_one(lsd_ctx *ctx, uint8_t *slab, const IdepthMapSrc &src, cudaStream_t st, float *d_statOut2 = nullptr);
 void launch_set_depth_gt(lsd_ctx *ctx, uint8_t *slab, const float *d_depth, float cov, cudaStream_t st);
 void launch_mask_init(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
 void launch_idepth_stats(lsd_ctx *ctx, uint8_t *slab, float *d_out2, cudaStream_t st);

@@ -236,17 +236,18 @@ __device__ __forceinline__ void fuse4(const float id[4], const float var[4], flo
 #ifndef IDP_MINB
 #define IDP_MINB 8  // 32 registers, no spills: setDepth + pyramids 0.127 -> 0.110 ms per 64 keyframes (r02za)
 #endif
-template <bool FROM_MAP>
+template <bool FROM_MAP, bool ONE = false>
 __global__ void __launch_bounds__(256, IDP_MINB) k_idepth_pyramid(uint8_t *const *__restrict__ slabs, const IdepthMapSrc *__restrict__ srcs,
                                                         FrameLayout lay, int W, int H, uint8_t *__restrict__ statScratch, size_t statStride,
-                                                        float *__restrict__ statOut2) {
+                                                        float *__restrict__ statOut2, uint8_t *slab0, const IdepthMapSrc src0) {
+  // ONE: a single frame whose slab / map planes ride in the kernel parameters (per-frame setDepth: no pointer-table uploads)
   __shared__ float a1[TILE_H / 2][TILE_W / 2], b1[TILE_H / 2][TILE_W / 2];
   __shared__ double s_wsum[8];
   __shared__ int s_wcnt[8];
   __shared__ float a2[TILE_H / 4][TILE_W / 4], b2[TILE_H / 4][TILE_W / 4];
   __shared__ float a3[TILE_H / 8][TILE_W / 8], b3[TILE_H / 8][TILE_W / 8];
   const int f = blockIdx.z;
-  uint8_t *slab = slabs[f];
+  uint8_t *slab = ONE ? slab0 : slabs[f];
   const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
   const int t = threadIdx.x;
   {
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(256, IDP_MINB) k_idepth_pyramid(uint8_t *const
       const size_t base = (size_t)(2 * y) * W + 2 * x;
       float2 i0, i1, v0, v1;
       if (FROM_MAP) {
-        const IdepthMapSrc S = srcs[f];
+        const IdepthMapSrc S = ONE ? src0 : srcs[f];
         const uint2 m0 = *reinterpret_cast<const uint2 *>(S.meta + base), m1 = *reinterpret_cast<const uint2 *>(S.meta + base + W);
         i0 = *reinterpret_cast<const float2 *>(S.ids + base); i1 = *reinterpret_cast<const float2 *>(S.ids + base + W);
         v0 = *reinterpret_cast<const float2 *>(S.vars + base); v1 = *reinterpret_cast<const float2 *>(S.vars + base + W);
@@ -393,8 +394,9 @@ static size_t stats_stride(const lsd_ctx *ctx);
 // d_statOut2 != nullptr: Frame::setDepth's (meanIdepth, numPoints) of every frame as well (ensure_stats_scratch(ctx, n) first)
 void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st, float *d_statOut2) {
   dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
+  const IdepthMapSrc none = {nullptr, nullptr, nullptr};
   k_idepth_pyramid<false><<<grid, 256, 0, st>>>(d_slabs, nullptr, ctx->lay, ctx->w, ctx->h, d_statOut2 ? ctx->d_stats : nullptr,
-                                                stats_stride(ctx), d_statOut2);
+                                                stats_stride(ctx), d_statOut2, nullptr, none);
   ctx->launches++;
 }
 
@@ -402,8 +404,17 @@ void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStr
 void launch_set_depth_and_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, const IdepthMapSrc *d_srcs, int n, cudaStream_t st,
                                   float *d_statOut2) {
   dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, n);
+  const IdepthMapSrc none = {nullptr, nullptr, nullptr};
   k_idepth_pyramid<true><<<grid, 256, 0, st>>>(d_slabs, d_srcs, ctx->lay, ctx->w, ctx->h, d_statOut2 ? ctx->d_stats : nullptr,
-                                               stats_stride(ctx), d_statOut2);
+                                               stats_stride(ctx), d_statOut2, nullptr, none);
+  ctx->launches++;
+}
+
+// the same for ONE keyframe, slab and map planes passed in the kernel parameters (no pointer tables to upload)
+void launch_set_depth_and_pyramid_one(lsd_ctx *ctx, uint8_t *slab, const IdepthMapSrc &src, cudaStream_t st, float *d_statOut2) {
+  dim3 grid((ctx->w + TILE_W - 1) / TILE_W, (ctx->h + TILE_H - 1) / TILE_H, 1);
+  k_idepth_pyramid<true, true><<<grid, 256, 0, st>>>(nullptr, nullptr, ctx->lay, ctx->w, ctx->h, d_statOut2 ? ctx->d_stats : nullptr,
+                                               stats_stride(ctx), d_statOut2, slab, src);
   ctx->launches++;
 }
 

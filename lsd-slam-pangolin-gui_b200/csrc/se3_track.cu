@@ -1321,7 +1321,8 @@ static int se3_launch_live(lsd_ctx *ctx, int m, bool wantTrace, cudaStream_t st,
       int recsPerCta = 0;
       const int bytes = live_smem_bytes(prm, cl, &recsPerCta);
       if (bytes > 220 * 1024) continue;
-      if (cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) continue;
+      // the cap is set ONCE per context (= per device), to the most any image size may ask for: later launches do not touch it
+      if (cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) continue;
       cfg.gridDim = dim3(cl, 1, 1);
       cfg.dynamicSmemBytes = bytes;
       attr[0].val.clusterDim.x = cl;
@@ -1339,9 +1340,6 @@ static int se3_launch_live(lsd_ctx *ctx, int m, bool wantTrace, cudaStream_t st,
   int recsPerCta = 0;
   const int bytes = live_smem_bytes(prm, cl, &recsPerCta);
   if (bytes > 220 * 1024) return LSD_OK;  // a record size that small for this image size: the queue kernel takes it
-  // per device, cheap: set on every launch (a process may hold contexts on several devices)
-  LSD_CUDA(cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  LSD_CUDA(cudaFuncSetAttribute(k_se3_track_live, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   cfg.gridDim = dim3(cl * m, 1, 1);
   cfg.dynamicSmemBytes = bytes;
   attr[0].val.clusterDim.x = cl;
