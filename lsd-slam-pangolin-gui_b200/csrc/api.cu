@@ -199,6 +199,21 @@ int ensure_table(lsd_ctx *ctx, size_t bytes) {
   return LSD_OK;
 }
 
+#define LSD_PTR_TABLE_CAP 8192
+int ptr_table_register(lsd_ctx *ctx, const void *p) {
+  if (!ctx->d_ptrTable) LSD_CUDA(cudaMalloc(&ctx->d_ptrTable, sizeof(void *) * LSD_PTR_TABLE_CAP));
+  if (ctx->ptrTableCount >= LSD_PTR_TABLE_CAP) return LSD_OK;  // such a slab simply keeps using uploaded lists
+  const int idx = ctx->ptrTableCount++;
+  // blocking 8-byte copy: once per slab allocation, never on the per-frame path (slabs are pooled)
+  LSD_CUDA(cudaMemcpy(ctx->d_ptrTable + idx, &p, sizeof(void *), cudaMemcpyHostToDevice));
+  ctx->ptrIndex[p] = idx;
+  return LSD_OK;
+}
+void *const *ptr_table_entry(const lsd_ctx *ctx, const void *p) {
+  const auto it = ctx->ptrIndex.find(p);
+  return it == ctx->ptrIndex.end() ? nullptr : ctx->d_ptrTable + it->second;
+}
+
 static int alloc_frame_slab(lsd_ctx *ctx, uint8_t **out) {
   if (!ctx->frameSlabPool.empty()) {
     *out = ctx->frameSlabPool.back();
@@ -206,7 +221,7 @@ static int alloc_frame_slab(lsd_ctx *ctx, uint8_t **out) {
     return LSD_OK;
   }
   LSD_CUDA(cudaMalloc(out, ctx->lay.total));
-  return LSD_OK;
+  return ptr_table_register(ctx, *out);
 }
 
 static lsd_frame *new_frame(int id, uint8_t *slab) {
@@ -232,9 +247,8 @@ static int upload_ptrs(lsd_ctx *ctx, const std::vector<void *> &v, cudaStream_t 
   return LSD_OK;
 }
 
-// builds the requested planes of n frames whose slabs are listed in d_table[0..n)
-static void build_planes(lsd_ctx *ctx, int n, unsigned flags, cudaStream_t st) {
-  uint8_t *const *d_slabs = reinterpret_cast<uint8_t *const *>(ctx->d_table);
+// builds the requested planes of n frames whose slabs are listed in d_slabs[0..n)
+static void build_planes(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, unsigned flags, cudaStream_t st) {
   launch_gradients(ctx, d_slabs, n, (flags & LSD_BUILD_GRAD0) ? 0 : 1, NL - 1, st);
   if (flags & LSD_BUILD_MAXGRAD0) launch_maxgrad0(ctx, d_slabs, n, st);
 }
@@ -406,6 +420,8 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->imageStreamed = -1;
   ctx->streamWatchdogNs = 2000000000ull;
   ctx->d_stats = nullptr;
+  ctx->d_ptrTable = nullptr;
+  ctx->ptrTableCount = 0;
   ctx->statsFrames = 0;
   ctx->d_means = ctx->h_means = nullptr;
   ctx->meansCap = 0;
@@ -439,6 +455,7 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
   se3_scratch_free(ctx);
   sim3_scratch_free(ctx);
   delete ctx->pool;
+  if (ctx->d_ptrTable) cudaFree(ctx->d_ptrTable);
   for (auto p : ctx->frameSlabPool) cudaFree(p);
   for (auto p : ctx->refSlabPool) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -560,13 +577,17 @@ int lsd_frame_create_batch_device(lsd_ctx *ctx, int n, const int *ids, const voi
     tevMade = true;
   }
   const auto t0 = std::chrono::steady_clock::now();
-  int rc = upload_ptrs(ctx, slabs, st);
-  if (rc) return rc;
+  // one frame: its slab's entry in the device-resident pointer table; several: an uploaded list
+  uint8_t *const *d_slabs = n == 1 ? reinterpret_cast<uint8_t *const *>(ptr_table_entry(ctx, slabs[0])) : nullptr;
+  if (!d_slabs) {
+    int rc = upload_ptrs(ctx, slabs, st);
+    if (rc) return rc;
+    d_slabs = reinterpret_cast<uint8_t *const *>(ctx->d_table);
+  }
   if (trace) cudaEventRecord(tev[0], st);
-  launch_ingest(ctx, (const uint8_t *)d_images, ctx->w, (size_t)ctx->w * ctx->h, reinterpret_cast<uint8_t *const *>(ctx->d_table), n,
-                st);
+  launch_ingest(ctx, (const uint8_t *)d_images, ctx->w, (size_t)ctx->w * ctx->h, d_slabs, n, st);
   if (trace) cudaEventRecord(tev[1], st);
-  build_planes(ctx, n, flags, st);
+  build_planes(ctx, d_slabs, n, flags, st);
   if (trace) cudaEventRecord(tev[2], st);
   const auto t1 = std::chrono::steady_clock::now();
   if (!ctx->deferSync) LSD_CUDA(cudaStreamSynchronize(st));  // pipelined driver: the planes are consumed in stream order by the tracker
@@ -934,6 +955,9 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
       ctx->refSlabPool.pop_back();
     } else {
       LSD_CUDA(cudaMalloc(&slab, ctx->refSlabBytes));
+      int rcp = ptr_table_register(ctx, slab);
+      if (!rcp) rcp = ptr_table_register(ctx, slab + offNum);  // the reference's counters (lsd_ref::d_num)
+      if (rcp) return rcp;
     }
     lsd_ref *r = new lsd_ref();
     r->keyframe = keyframes[i];
@@ -948,12 +972,23 @@ int lsd_ref_create_batch(lsd_ctx *ctx, int n, lsd_frame *const *keyframes, lsd_r
     tab[2 * (size_t)n + i] = r->d_num;
   }
   // pipelined driver: the frame created just before may still be waiting for ITS pointer list at offset 0 of the pinned table
-  const size_t tabOff = ctx->deferSync ? 8192 : 0;  // room for the pointers of 1024 frames in front
-  int rc = upload_ptrs(ctx, tab, st, tabOff);
-  if (rc) return rc;
-  void **d = reinterpret_cast<void **>((char *)ctx->d_table + tabOff);
-  launch_make_pointcloud(ctx, reinterpret_cast<uint8_t *const *>(d), reinterpret_cast<uint8_t *const *>(d + n),
-                         reinterpret_cast<int *const *>(d + 2 * (size_t)n), n, offPts, offGrad, st);
+  void *const *eK = nullptr, *const *eR = nullptr, *const *eN = nullptr;
+  if (n == 1) {  // one reference: the three pointers are entries of the device-resident pointer table
+    eK = ptr_table_entry(ctx, tab[0]);
+    eR = ptr_table_entry(ctx, tab[1]);
+    eN = ptr_table_entry(ctx, tab[2]);
+  }
+  if (eK && eR && eN) {
+    launch_make_pointcloud(ctx, reinterpret_cast<uint8_t *const *>(eK), reinterpret_cast<uint8_t *const *>(eR), reinterpret_cast<int *const *>(eN), 1,
+                           offPts, offGrad, st);
+  } else {
+    const size_t tabOff = ctx->deferSync ? 8192 : 0;  // room for the pointers of 1024 frames in front
+    int rc = upload_ptrs(ctx, tab, st, tabOff);
+    if (rc) return rc;
+    void **d = reinterpret_cast<void **>((char *)ctx->d_table + tabOff);
+    launch_make_pointcloud(ctx, reinterpret_cast<uint8_t *const *>(d), reinterpret_cast<uint8_t *const *>(d + n),
+                           reinterpret_cast<int *const *>(d + 2 * (size_t)n), n, offPts, offGrad, st);
+  }
   if (!ctx->deferSync) LSD_CUDA(cudaStreamSynchronize(st));
   return LSD_OK;
 }

@@ -1,5 +1,7 @@
 // ctx.cuh -- lsd_ctx definition and kernel-launcher prototypes (internal).
 #pragma once
+#include <unordered_map>
+
 #include "common.cuh"
 
 struct SE3Scratch;   // se3_track.cu
@@ -35,6 +37,12 @@ struct lsd_ctx {
   std::vector<uint8_t *> frameSlabPool;
   std::vector<uint8_t *> refSlabPool;
   size_t refSlabBytes;
+  // Device-resident table of the slab pointers this context has allocated (entry written once, when the slab is created): a
+  // kernel that takes a pointer LIST (uint8_t *const *slabs) is handed the address of the one entry when it works on one frame --
+  // the per-frame path uploads no pointer lists at all.
+  void **d_ptrTable;
+  int ptrTableCount;
+  std::unordered_map<const void *, int> ptrIndex;
   // staging for uploads
   uint8_t *h_stage;  // pinned
   size_t h_stageBytes;
@@ -72,6 +80,8 @@ namespace lsd {
 
 int ensure_stage(lsd_ctx *ctx, size_t hostBytes, size_t devBytes);
 int ensure_table(lsd_ctx *ctx, size_t bytes);
+int ptr_table_register(lsd_ctx *ctx, const void *p);             // api.cu: after a cudaMalloc of a slab
+void *const *ptr_table_entry(const lsd_ctx *ctx, const void *p);  // device address of the entry holding p, or nullptr
 int ctx_finish_pending(lsd_ctx *ctx);  // api.cu: waits for deferred mapping work (no-op when there is none)
 int frame_ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need);  // api.cu: lazily builds planes (blocking)
 
@@ -106,7 +116,7 @@ void launch_make_pointcloud(lsd_ctx *ctx, uint8_t *const *d_kfSlabs, uint8_t *co
 int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
                          lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st);
 int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init, bool wantTrace,
-                cudaStream_t st);
+                cudaStream_t st, bool upload = true);
 int se3_launch(lsd_ctx *ctx, int i0, int m, bool wantTrace, cudaStream_t st);
 int se3_stream_begin(lsd_ctx *ctx, int n, cudaStream_t trackSt, cudaEvent_t armed);
 int se3_stream_feed(lsd_ctx *ctx, int i0, int m, int n, cudaStream_t st);

@@ -826,6 +826,10 @@ __global__ void k_se3_init(const SE3Pair *__restrict__ pairs, SE3State *__restri
 // ---------------------------------------------------------------------------------------------
 #define LIVE_GROUPS 4
 #define LIVE_THREADS (LIVE_GROUPS * SE3_THREADS)
+#define LIVE_MAX_PAIRS 8  // pairs of one live launch (their descriptors are kernel parameters)
+struct SE3PairPack {
+  SE3Pair p[LIVE_MAX_PAIRS];
+};
 
 __device__ __forceinline__ void group_bar(const int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(SE3_THREADS) : "memory");
@@ -918,7 +922,7 @@ template <typename T> __device__ __forceinline__ T *dsmem_ptr(T *p, const unsign
 
 // recsPerCta: record slots in every CTA's shared memory (>= ceil(maxChunks / (clusterSize * LIVE_GROUPS)) * LIVE_GROUPS)
 __global__ void __launch_bounds__(LIVE_THREADS, 1)
-k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __grid_constant__ SE3Params prm, lsd_trace_entry *traces,
+k_se3_track_live(const __grid_constant__ SE3PairPack pk, SE3State *states, const __grid_constant__ SE3Params prm, lsd_trace_entry *traces,
                  const int recsPerCta) {
   extern __shared__ __align__(16) unsigned char dsm[];
   LiveSmem *gsm = reinterpret_cast<LiveSmem *>(dsm);                                  // one per group
@@ -933,7 +937,7 @@ k_se3_track_live(const SE3Pair *__restrict__ pairs, SE3State *states, const __gr
 
   const unsigned CL = cluster_size(), rank = cluster_rank();
   const int pairIdx = blockIdx.x / CL;
-  const SE3Pair *P = pairs + pairIdx;
+  const SE3Pair *P = &pk.p[pairIdx];  // the pair descriptors ride in the kernel parameters: no upload before a live launch
   const int g = threadIdx.x / SE3_THREADS, tid = threadIdx.x % SE3_THREADS;
   const int G = (int)CL * LIVE_GROUPS, myGroup = (int)rank * LIVE_GROUPS + g;
 
@@ -1206,6 +1210,13 @@ static int init_masks(lsd_ctx *ctx, int n, lsd_frame *const *frames, cudaStream_
       frames[i]->built |= FB_MASK;
     }
   if (m == 0) return LSD_OK;
+  if (m == 1) {  // one frame: its slab's entry in the context's device-resident pointer table (no upload)
+    uint8_t *const *e = reinterpret_cast<uint8_t *const *>(ptr_table_entry(ctx, s->h_maskTab[0]));
+    if (e) {
+      launch_mask_init(ctx, e, 1, st);
+      return LSD_OK;
+    }
+  }
   LSD_CUDA(cudaMemcpyAsync(s->d_maskTab, s->h_maskTab, sizeof(uint8_t *) * (size_t)m, cudaMemcpyHostToDevice, st));
   launch_mask_init(ctx, s->d_maskTab, m, st);
   return LSD_OK;
@@ -1223,7 +1234,7 @@ __global__ void k_se3_reset(unsigned *ctrs, unsigned n, unsigned active) {
 // ---- the batch API in three steps, so that the host-image pipeline can queue several launches without a host
 // ---- synchronisation in between:  prepare (pair table for ALL n pairs, one upload)  ->  launch(i0, m) ...  ->  collect
 int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init, bool wantTrace,
-                cudaStream_t st) {
+                cudaStream_t st, bool upload) {
   LSD_ARG(n < (1 << 19));
   int rc = se3_scratch_ensure(ctx, n, wantTrace);
   if (rc) return rc;
@@ -1247,7 +1258,8 @@ int se3_prepare(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
       invert_pose_to_float(init + 7 * i, P.q0, P.t0);
     }
   }
-  LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
+  // (a live launch takes the descriptors as kernel parameters: se3_track_batch_impl uploads them only for the work-queue kernel)
+  if (upload) LSD_CUDA(cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
   return LSD_OK;
 }
 
@@ -1303,7 +1315,7 @@ static int se3_launch_live(lsd_ctx *ctx, int m, bool wantTrace, cudaStream_t st,
   // default: up to two pairs, and only while level 1 is small enough for one cluster (r03h, 1280x960: level 1 has ~140 k points,
   // 17 per thread of a 16-CTA cluster; the work-queue kernel spreads them over the whole device: 1892 vs 1811 fps)
   const int limit = ctx->se3LivePairs < 0 ? (ctx->K.w[1] * ctx->K.h[1] <= 131072 ? 2 : 0) : ctx->se3LivePairs;
-  if (m > limit || s->liveCluster == 0) return LSD_OK;
+  if (m > limit || m > LIVE_MAX_PAIRS || s->liveCluster == 0) return LSD_OK;
   SE3Params prm = make_params(ctx, m);
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
@@ -1345,9 +1357,11 @@ static int se3_launch_live(lsd_ctx *ctx, int m, bool wantTrace, cudaStream_t st,
   attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
   lsd_trace_entry *d_tr = wantTrace ? s->d_traces : nullptr;
-  const SE3Pair *d_pairs = s->d_pairs;
+  SE3PairPack pk;
+  std::memset(&pk, 0, sizeof(pk));
+  for (int i = 0; i < m; i++) pk.p[i] = s->h_pairs[i];
   SE3State *d_states = s->d_states;
-  LSD_CUDA(cudaLaunchKernelEx(&cfg, k_se3_track_live, d_pairs, d_states, prm, d_tr, recsPerCta));
+  LSD_CUDA(cudaLaunchKernelEx(&cfg, k_se3_track_live, pk, d_states, prm, d_tr, recsPerCta));
   ctx->launches += 1;
   *used = 1;
   return LSD_OK;
@@ -1476,7 +1490,7 @@ int se3_collect(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *fra
 int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *const *frames, const double *init,
                          lsd_se3_result *results, lsd_trace_entry *traces, cudaStream_t st) {
   if (n == 0) return LSD_OK;
-  int rc = se3_prepare(ctx, n, refs, frames, init, traces != nullptr, st);
+  int rc = se3_prepare(ctx, n, refs, frames, init, traces != nullptr, st, false);
   if (rc) return rc;
   if (!ctx->se3Permaref) {
     rc = init_masks(ctx, n, frames, st);
@@ -1486,7 +1500,10 @@ int se3_track_batch_impl(lsd_ctx *ctx, int n, lsd_ref *const *refs, lsd_frame *c
   int live = 0;
   rc = se3_launch_live(ctx, n, traces != nullptr, st, &live);
   if (rc) return rc;
-  if (!live) rc = se3_launch(ctx, 0, n, traces != nullptr, st);
+  if (!live) {
+    LSD_CUDA(cudaMemcpyAsync(ctx->se3s->d_pairs, ctx->se3s->h_pairs, sizeof(SE3Pair) * n, cudaMemcpyHostToDevice, st));
+    rc = se3_launch(ctx, 0, n, traces != nullptr, st);
+  }
   if (rc) return rc;
   LSD_CUDA(cudaEventRecord(ctx->evB, st));
   // one host synchronisation per call: the read-back of the states is queued behind the kernels and se3_collect waits for it;
