@@ -109,6 +109,9 @@ class Context {
     return cur;
   }
   void makeCurrent() { current() = this; }
+  // The context of SlamSystem's tracking thread (one frame per tracking call): per-level record sizes for the live tracker
+  // kernel -- one thread-block cluster per (reference, frame) pair (include/lsd_b200.h: lsd_ctx_set_live_tracking)
+  void setLiveTracking(bool on = true) { check(lsd_ctx_set_live_tracking(c_, on ? 1 : 0)); }
 
  private:
   lsd_ctx *c_ = nullptr;
@@ -415,7 +418,13 @@ struct KeyframePublisher {
 // [UP] lsd_slam::SlamSystem, lock-step (Conf().runRealTime == false): tools/LSD.cpp:102, lib/App/InputThread.cpp:71
 class SlamSystem {
  public:
-  explicit SlamSystem(Context &ctx) : ctx_(ctx) { check(lsd_slam_create(ctx.c(), &s_)); }
+  // a lock-step system tracks one frame per call: its context gets the live-tracker configuration
+  explicit SlamSystem(Context &ctx) : ctx_(ctx) {
+    ctx.setLiveTracking(true);
+    check(lsd_slam_create(ctx.c(), &s_));
+  }
+  // 0: every stage of nextImage synchronises on its own (default: stages queued back to back, updateKeyframe finished by the next call)
+  void setPipelined(bool on) { check(lsd_slam_set_pipelined(s_, on ? 1 : 0)); }
   ~SlamSystem() { lsd_slam_destroy(s_); }
   SlamSystem(const SlamSystem &) = delete;
   SlamSystem &operator=(const SlamSystem &) = delete;
