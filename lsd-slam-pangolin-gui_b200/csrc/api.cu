@@ -249,7 +249,7 @@ static int upload_ptrs(lsd_ctx *ctx, const std::vector<void *> &v, cudaStream_t 
 
 // builds the requested planes of n frames whose slabs are listed in d_slabs[0..n)
 static void build_planes(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, unsigned flags, cudaStream_t st) {
-  launch_gradients(ctx, d_slabs, n, (flags & LSD_BUILD_GRAD0) ? 0 : 1, NL - 1, st);
+  launch_gradients(ctx, d_slabs, n, (flags & LSD_BUILD_GRAD0) ? 0 : 1, NL - 1, st, true);  // + the refPixelWasGood plane (FB_MASK)
   if (flags & LSD_BUILD_MAXGRAD0) launch_maxgrad0(ctx, d_slabs, n, st);
 }
 
@@ -600,7 +600,7 @@ int lsd_frame_create_batch_device(lsd_ctx *ctx, int n, const int *ids, const voi
                  1e6 * std::chrono::duration<double>(t1 - t0).count(), 1e6 * std::chrono::duration<double>(t2 - t1).count(), 1e3 * msI, 1e3 * msG);
   }
   for (int i = 0; i < n; i++)
-    out[i]->built = FB_TRACKING | ((flags & LSD_BUILD_MAXGRAD0) ? FB_MAXGRAD0 : 0) | ((flags & LSD_BUILD_GRAD0) ? FB_GRAD0 : 0);
+    out[i]->built = FB_TRACKING | FB_MASK | ((flags & LSD_BUILD_MAXGRAD0) ? FB_MAXGRAD0 : 0) | ((flags & LSD_BUILD_GRAD0) ? FB_GRAD0 : 0);
   return LSD_OK;
 }
 

@@ -88,7 +88,7 @@ int frame_ensure_built(lsd_ctx *ctx, lsd_frame *f, unsigned need);  // api.cu: l
 // pyramid.cu
 void launch_ingest(lsd_ctx *ctx, const uint8_t *d_src, size_t srcPitch, size_t srcFrameStride, uint8_t *const *d_slabs, int n,
                    cudaStream_t st);
-void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st);
+void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st, bool initMask = false);
 void launch_maxgrad0(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st);
 void launch_idepth_pyramid(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, cudaStream_t st, float *d_statOut2 = nullptr);
 struct IdepthMapSrc {  // hypothesis planes Frame::setDepth reads (depth.cuh layout)

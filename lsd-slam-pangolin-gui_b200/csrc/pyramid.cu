@@ -89,7 +89,9 @@ struct LevelSpan {
   int lvlLo, lvlHi;
 };
 
-__global__ void __launch_bounds__(256) k_gradients(uint8_t *const *__restrict__ slabs, FrameLayout lay, Intrinsics K, LevelSpan sp) {
+// initMask: the level-1 threads also create the frame's refPixelWasGood plane (0xFF, Frame::refPixelWasGood()): a new frame
+// then needs no mask-initialisation launch before it is tracked
+__global__ void __launch_bounds__(256) k_gradients(uint8_t *const *__restrict__ slabs, FrameLayout lay, Intrinsics K, LevelSpan sp, int initMask) {
   const int f = blockIdx.y;
   uint8_t *slab = slabs[f];
   int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,9 +108,10 @@ __global__ void __launch_bounds__(256) k_gradients(uint8_t *const *__restrict__ 
     out.z = __ldg(I + i);
   }
   reinterpret_cast<float4 *>(slab + lay.grad[l])[i] = out;
+  if (initMask && l == 1) (slab + lay.mask)[i] = 0xFF;
 }
 
-void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st) {
+void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, int lvlHi, cudaStream_t st, bool initMask) {
   LevelSpan sp;
   sp.lvlLo = lvlLo;
   sp.lvlHi = lvlHi;
@@ -119,7 +122,7 @@ void launch_gradients(lsd_ctx *ctx, uint8_t *const *d_slabs, int n, int lvlLo, i
   }
   sp.start[lvlHi - lvlLo + 1] = acc;
   dim3 grid((acc + 255) / 256, n);
-  k_gradients<<<grid, 256, 0, st>>>(d_slabs, ctx->lay, ctx->K, sp);
+  k_gradients<<<grid, 256, 0, st>>>(d_slabs, ctx->lay, ctx->K, sp, (initMask && lvlLo <= 1 && lvlHi >= 1) ? 1 : 0);
   ctx->launches++;
 }
 
