@@ -201,11 +201,17 @@ int ensure_table(lsd_ctx *ctx, size_t bytes) {
 
 #define LSD_PTR_TABLE_CAP 8192
 int ptr_table_register(lsd_ctx *ctx, const void *p) {
-  if (!ctx->d_ptrTable) LSD_CUDA(cudaMalloc(&ctx->d_ptrTable, sizeof(void *) * LSD_PTR_TABLE_CAP));
+  if (!ctx->d_ptrTable) {
+    LSD_CUDA(cudaMalloc(&ctx->d_ptrTable, sizeof(void *) * LSD_PTR_TABLE_CAP));
+    LSD_CUDA(cudaMallocHost(&ctx->h_ptrTable, sizeof(void *) * LSD_PTR_TABLE_CAP));
+  }
   if (ctx->ptrTableCount >= LSD_PTR_TABLE_CAP) return LSD_OK;  // such a slab simply keeps using uploaded lists
   const int idx = ctx->ptrTableCount++;
-  // blocking 8-byte copy: once per slab allocation, never on the per-frame path (slabs are pooled)
-  LSD_CUDA(cudaMemcpy(ctx->d_ptrTable + idx, &p, sizeof(void *), cudaMemcpyHostToDevice));
+  // Once per slab allocation, never on the per-frame path (slabs are pooled).  Queued on the context's stream out of a pinned
+  // mirror that is never rewritten: every consumer of the entry runs on that stream, after the copy.  (A blocking cudaMemcpy from
+  // pageable memory may return before its DMA has landed, and nothing would order it against the context's non-blocking stream.)
+  ctx->h_ptrTable[idx] = const_cast<void *>(p);
+  LSD_CUDA(cudaMemcpyAsync(ctx->d_ptrTable + idx, ctx->h_ptrTable + idx, sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
   ctx->ptrIndex[p] = idx;
   return LSD_OK;
 }
@@ -421,6 +427,7 @@ int lsd_ctx_create(int device, int width, int height, const float K[4], void *st
   ctx->streamWatchdogNs = 2000000000ull;
   ctx->d_stats = nullptr;
   ctx->d_ptrTable = nullptr;
+  ctx->h_ptrTable = nullptr;
   ctx->ptrTableCount = 0;
   ctx->statsFrames = 0;
   ctx->d_means = ctx->h_means = nullptr;
@@ -456,6 +463,7 @@ int lsd_ctx_destroy(lsd_ctx *ctx) {
   sim3_scratch_free(ctx);
   delete ctx->pool;
   if (ctx->d_ptrTable) cudaFree(ctx->d_ptrTable);
+  if (ctx->h_ptrTable) cudaFreeHost(ctx->h_ptrTable);
   for (auto p : ctx->frameSlabPool) cudaFree(p);
   for (auto p : ctx->refSlabPool) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);

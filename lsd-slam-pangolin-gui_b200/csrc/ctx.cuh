@@ -40,7 +40,7 @@ struct lsd_ctx {
   // Device-resident table of the slab pointers this context has allocated (entry written once, when the slab is created): a
   // kernel that takes a pointer LIST (uint8_t *const *slabs) is handed the address of the one entry when it works on one frame --
   // the per-frame path uploads no pointer lists at all.
-  void **d_ptrTable;
+  void **d_ptrTable, **h_ptrTable;  // device table and its pinned mirror (an entry is written once and never changes)
   int ptrTableCount;
   std::unordered_map<const void *, int> ptrIndex;
   // staging for uploads

@@ -1210,7 +1210,8 @@ static int init_masks(lsd_ctx *ctx, int n, lsd_frame *const *frames, cudaStream_
       frames[i]->built |= FB_MASK;
     }
   if (m == 0) return LSD_OK;
-  if (m == 1) {  // one frame: its slab's entry in the context's device-resident pointer table (no upload)
+  if (m == 1 && st == ctx->stream) {  // one frame: its slab's entry in the context's device-resident pointer table (no upload;
+                                       // entries are written in the order of the context's own stream)
     uint8_t *const *e = reinterpret_cast<uint8_t *const *>(ptr_table_entry(ctx, s->h_maskTab[0]));
     if (e) {
       launch_mask_init(ctx, e, 1, st);
