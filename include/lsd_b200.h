@@ -122,7 +122,9 @@ int lsd_ctx_set_live_tracking(lsd_ctx *ctx, int enable);
  * where the device co-schedules them, else 8), LM state in the leader CTA's shared memory, header and partial records exchanged
  * over distributed shared memory, two cluster barriers per LM evaluation instead of the work queue's global-memory hand-offs.
  * This is the shape of SlamSystem::trackFrame (one frame at a time).  Same records, same summation order: for a given record
- * size both kernels return identical bits.  -1 = default (2), 0 = always the work-queue kernel. */
+ * size both kernels return identical bits.  -1 = default (2 while level 1 has at most 131072 pixels -- up to 724x724 images --,
+ * else 0: a larger level 1 is better spread over the whole device by the work-queue kernel), 0 = always the work-queue kernel;
+ * at most 8 pairs per live launch (larger batches take the work-queue kernel whatever the setting). */
 int lsd_ctx_set_se3_live_pairs(lsd_ctx *ctx, int pairs);
 /* Depth-map stencil kernels: bit 0 of `mask` = regularizeDepthMap, bit 1 = regularizeDepthMapFillHoles.  A set bit makes the
  * kernel fetch the halo tile of each CTA with the TMA unit (cp.async.bulk.tensor, out-of-map cells zero-filled by the
